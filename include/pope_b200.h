@@ -1,0 +1,153 @@
+/* pope_b200.h -- C ABI of libpope_b200.so: the B200-native (sm_100a) Matcher hot path of karltan0328/POPE.
+ *
+ * The reference is 100 % Python/PyTorch and has no FFI of its own; each entry point below replaces the
+ * PyTorch op sequence of one reference function (paths relative to the reference tree) and is what a
+ * ctypes binding from the reference side calls:
+ *
+ *   pope_coarse_match   <- CoarseMatching.forward + get_coarse_match
+ *                          src/matcher/utils/coarse_matching.py:87-148, :150-261 (helpers :8-25)
+ *   pope_fine_gather    <- FinePreprocess.forward, unfold + gather part
+ *                          src/matcher/loftr_module/fine_preprocess.py:29-47
+ *   pope_fine_match     <- FineMatching.forward + get_fine_match
+ *                          src/matcher/utils/fine_matching.py:15-74
+ *   pope_cosine_topk    <- F.cosine_similarity + running top-3 of the crop-retrieval loop
+ *                          eval_linemod_json.py:72-101 (token: segment_anything/segment_anything/dinov2_utils.py:106-111)
+ *   pope_pipeline_* / pope_match_pairs_host <- the pair loop of the eval drivers, batched
+ *                          eval_linemod_json.py:103-122 (Matcher.forward steps 3-5, src/matcher/matcher.py:71-79)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `const void*` / `void*` data pointer is a DEVICE pointer unless the
+ *     function name ends in `_host`; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - all buffers are caller-owned; the library keeps no global state, allocates nothing persistent and never
+ *     synchronises the device (the `_host` driver synchronises its own streams before returning).
+ *   - return value: 0 = ok; < 0 = argument error (pope_status_t); > 0 = a cudaError_t from a launch/copy.
+ *   - dtype: element type of the feature tensors (POPE_F32 or POPE_BF16).  All softmax / expectation arithmetic
+ *     is fp32 regardless; ids are int64, coordinates and confidences fp32, exactly as the reference emits them.
+ *   - there is no CPU fallback: on a machine without an sm_100 device every compute entry point returns a
+ *     cudaError_t.
+ */
+#ifndef POPE_B200_H_
+#define POPE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POPE_B200_ABI_VERSION 1
+
+typedef enum {
+  POPE_OK = 0,
+  POPE_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, thr outside (0,1], ... */
+  POPE_ERR_DTYPE = -2,         /* dtype not POPE_F32 / POPE_BF16 */
+  POPE_ERR_WORKSPACE = -3,     /* workspace smaller than pope_coarse_workspace_bytes() */
+  POPE_ERR_SHAPE = -4,         /* shape not supported by the requested implementation */
+  POPE_ERR_ALIGNMENT = -5,     /* pointer / stride not aligned as documented */
+  POPE_ERR_CAPACITY = -6       /* output capacity smaller than n_pairs * min(L, S) */
+} pope_status_t;
+
+typedef enum { POPE_F32 = 0, POPE_BF16 = 1 } pope_dtype_t;
+
+/* which coarse kernel family runs: AUTO picks TCGEN05 for bf16 with C % 64 == 0 && C <= 256, else SIMT */
+typedef enum { POPE_COARSE_AUTO = 0, POPE_COARSE_SIMT = 1, POPE_COARSE_TCGEN05 = 2 } pope_coarse_impl_t;
+
+/* bits of counts[n_pairs + 1] written by pope_coarse_match */
+#define POPE_FLAG_NONFINITE_LSE 1u   /* a row/column log-sum-exp was inf/nan (inputs contain inf/nan) */
+
+int pope_abi_version(void);
+const char* pope_status_string(int status);
+
+/* Which kernel family POPE_COARSE_AUTO resolves to for this problem: POPE_COARSE_SIMT or POPE_COARSE_TCGEN05. */
+int pope_coarse_auto_impl(int dtype, int L, int S, int C);
+
+/* Bytes of device scratch pope_coarse_match needs for this problem (row/col log-sum-exp + best-candidate keys). */
+size_t pope_coarse_workspace_bytes(int n_pairs, int L, int S);
+
+/* Coarse matching for n_pairs independent image pairs.
+ *   feat_c0 [n_pairs, L, C], feat_c1 [n_pairs, S, C]  contiguous, 16-byte aligned, L = h0c*w0c, S = h1c*w1c.
+ *   conf(i,j) = softmax_i(S)*softmax_j(S),  S = <f0_i, f1_j> / (C * temperature); a match is a cell with
+ *   conf > thr that is the maximum of its row and of its column (over the full matrix) and whose two cells are
+ *   at least `border_rm` cells away from their grid borders.  The L x S matrix is never written to memory.
+ *   pixel_scale = hw0_i[0] / hw0_c[0] (8 for the (8,2) backbone).
+ * Outputs (capacity >= n_pairs * min(L,S) entries each), matches sorted by (pair, i):
+ *   b_ids, i_ids, j_ids int64[capacity]; mconf float[capacity]; mkpts0_c, mkpts1_c float[capacity][2] (x, y);
+ *   counts int32[n_pairs + 2]: matches per pair, then counts[n_pairs] = total M, counts[n_pairs+1] = POPE_FLAG_* bits.
+ * Entries past M are left untouched. */
+int pope_coarse_match(const void* feat_c0, const void* feat_c1, int dtype,
+                      int n_pairs, int L, int S, int C,
+                      int h0c, int w0c, int h1c, int w1c,
+                      float pixel_scale, float temperature, float thr, int border_rm, int impl,
+                      void* workspace, size_t workspace_bytes,
+                      int64_t* b_ids, int64_t* i_ids, int64_t* j_ids,
+                      float* mconf, float* mkpts0_c, float* mkpts1_c,
+                      int32_t* counts, int64_t capacity, void* stream);
+
+/* Gather the W x W fine-level windows of every match from both fine feature maps (no unfold is materialised).
+ *   feat_f0 / feat_f1: logical [n_pairs, Cf, Hf, Wf] with arbitrary element strides (sN, sC, sH, sW); the fast
+ *   path is channels-last (sC == 1), plain NCHW works through a strided path.
+ *   window element ww = ky*W + kx of coarse cell (y, x) = feat[b, :, stride*y - W/2 + ky, stride*x - W/2 + kx],
+ *   zero outside the map; cell ids are row-major over a grid w0c (w1c) cells wide.
+ *   m_dev: optional device int32 holding the live match count (e.g. counts + n_pairs); when non-NULL, `M` is the
+ *   launch capacity and rows >= *m_dev are not touched, so no host sync is needed between coarse and fine.
+ * Outputs win0, win1: [M, W*W, Cf] contiguous, same dtype as the maps. */
+int pope_fine_gather(const void* feat_f0, const void* feat_f1, int dtype, int n_pairs, int Cf,
+                     int Hf0, int Wf0, const int64_t strides0[4],
+                     int Hf1, int Wf1, const int64_t strides1[4],
+                     int w0c, int w1c, int stride, int W,
+                     const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids,
+                     int64_t M, const int32_t* m_dev,
+                     void* win0, void* win1, void* stream);
+
+/* Fine matching: correlate the centre row of win0 with the WW rows of win1, softmax(./sqrt(Cf)), spatial
+ * expectation and std over the normalised W x W grid, then mkpts1_f = mkpts1_c + expec_xy * coord_scale with
+ * coord_scale = (W/2) * hw0_i[0]/hw0_f[0].
+ *   win0, win1 [M, WW, Cf] contiguous, 16-byte aligned, Cf == 128, WW == 25 (W == 5).
+ * Outputs expec_f float[M][3] = (E[x], E[y], std_x + std_y), mkpts1_f float[M][2]. */
+int pope_fine_match(const void* win0, const void* win1, int dtype, int64_t M, const int32_t* m_dev,
+                    int WW, int Cf, const float* mkpts1_c, float coord_scale,
+                    float* expec_f, float* mkpts1_f, void* stream);
+
+/* Retrieval: cosine similarity (x.y / (max(|x|,eps) * max(|y|,eps))) of one query token against R reference
+ * tokens, followed by the eval loop's slot-replacement top-k (slots start at 0; a score greater than any slot
+ * overwrites the first arg-min slot), evaluated in reference order so slot order matches the loop.
+ *   q [D], refs [R, D] contiguous.  Outputs scores float[R], slot_scores float[k], slot_idx int32[k] (-1 = empty). */
+int pope_cosine_topk(const void* q, const void* refs, int dtype, int R, int D, int k, float eps,
+                     float* scores, float* slot_scores, int32_t* slot_idx, void* stream);
+
+/* Pair-batching driver with HOST buffers (the end-to-end entry point): coarse match -> window gather -> fine
+ * match for n_pairs pairs, processed in chunks of `chunk_pairs` with host->device copies, kernels and
+ * device->host copies overlapped on three internal streams (double-buffered device slots).
+ * A pipeline is an opaque handle that owns the device slots and streams for one geometry; it is the only object
+ * the library ever allocates and it is not shared between host threads.
+ *   Inputs  : feat_c0 [n,L,C], feat_c1 [n,S,C]; feat_f0 [n,Hf0,Wf0,Cf], feat_f1 [n,Hf1,Wf1,Cf] (channels-last),
+ *             Hf = fine_stride*h_c, Wf = fine_stride*w_c.  Host buffers should be page-locked for full PCIe speed.
+ *   Outputs : per-pair slots of cap = min(L,S) entries: i_ids, j_ids int64[n][cap]; mconf float[n][cap];
+ *             mkpts0_f, mkpts1_f float[n][cap][2]; counts int32[n]; flags (optional, may be NULL) int32[1] = OR of the
+ *             POPE_FLAG_* bits of all chunks.  pope_pipeline_run returns after every copy has landed. */
+typedef struct pope_pipeline pope_pipeline_t;
+
+int pope_pipeline_create(pope_pipeline_t** out, int device, int dtype, int chunk_pairs, int C, int Cf,
+                         int h0c, int w0c, int h1c, int w1c, int fine_stride, int W,
+                         float pixel_scale, float fine_scale /* hw0_i[0]/hw0_f[0] */,
+                         float temperature, float thr, int border_rm, int impl);
+int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const void* feat_c1, const void* feat_f0,
+                      const void* feat_f1, int n_pairs,
+                      int64_t* i_ids, int64_t* j_ids, float* mconf, float* mkpts0_f, float* mkpts1_f,
+                      int32_t* counts, int32_t* flags);
+int pope_pipeline_destroy(pope_pipeline_t* pl);
+
+/* One-shot convenience: create + run + destroy. */
+int pope_match_pairs_host(const void* feat_c0, const void* feat_c1, const void* feat_f0, const void* feat_f1,
+                          int dtype, int n_pairs, int C, int Cf,
+                          int h0c, int w0c, int h1c, int w1c, int fine_stride, int W,
+                          float pixel_scale, float fine_scale, float temperature, float thr, int border_rm, int impl,
+                          int chunk_pairs, int device,
+                          int64_t* i_ids, int64_t* j_ids, float* mconf, float* mkpts0_f, float* mkpts1_f,
+                          int32_t* counts, int32_t* flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POPE_B200_H_ */

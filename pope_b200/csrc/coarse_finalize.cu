@@ -1,0 +1,129 @@
+// coarse_finalize.cu -- mutual-nearest test, border removal and ordered compaction of the coarse matches.
+//
+// Replaces src/matcher/utils/coarse_matching.py:176-196 and :239-259 (reference tree): after the sweeps every row
+// and column holds its best above-threshold candidate (value = log2 conf, index).  Because conf <= min(p_row,
+// p_col), any cell above the threshold beats every cell below it, so "== row max and == column max of the full
+// matrix" is "the row's best candidate is also (by value) its column's best candidate".  Border cells take part
+// in the maxima and are only removed afterwards, exactly like the reference (mask_border clears the threshold
+// mask only, :176-184, while :187-189 use the full conf matrix).
+// Output order is torch.where order: sorted by (pair, i), at most one match per row (:192-195).
+#include "common.cuh"
+
+namespace pope {
+namespace {
+
+constexpr int FT = 1024;
+
+struct Grid2 { int h, w, b; };
+__device__ __forceinline__ bool interior(int idx, Grid2 g) {
+  int y = idx / g.w, x = idx - y * g.w;
+  return y >= g.b && y < g.h - g.b && x >= g.b && x < g.w - g.b;
+}
+
+// is row i of pair n a match?  returns j and log2-conf
+__device__ __forceinline__ bool row_match(const u64* __restrict__ rowbest, const u64* __restrict__ colbest, int L,
+                                          int S, int i, Grid2 g0, Grid2 g1, int& j, float& t2) {
+  const u64 rb = rowbest[i];
+  if (rb == 0ull) return false;
+  j = best_index(rb);
+  if (static_cast<unsigned>(j) >= static_cast<unsigned>(S)) return false;
+  if (best_key(colbest[j]) != best_key(rb)) return false;   // some other row holds a larger value in column j
+  if (!interior(i, g0) || !interior(j, g1)) return false;
+  t2 = key_to_float(best_key(rb));
+  return true;
+}
+
+__device__ __forceinline__ int block_sum(int v, int* smem) {
+  // returns the block-wide sum to every thread (FT threads)
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  int t = (lane < FT / 32) ? smem[lane] : 0;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(kFullMask, t, o);
+  return t;
+}
+
+__global__ void __launch_bounds__(FT) count_kernel(const u64* __restrict__ rowbest, const u64* __restrict__ colbest,
+                                                  const float* __restrict__ lse_r, const float* __restrict__ lse_c,
+                                                  int L, int S, Grid2 g0, Grid2 g1, int32_t* __restrict__ counts,
+                                                  int n_pairs) {
+  __shared__ int smem[32];
+  const int n = blockIdx.x;
+  rowbest += size_t(n) * L; colbest += size_t(n) * S;
+  int c = 0, bad = 0;
+  for (int i = threadIdx.x; i < L; i += FT) {
+    int j; float t2;
+    c += row_match(rowbest, colbest, L, S, i, g0, g1, j, t2) ? 1 : 0;
+    bad |= !isfinite(lse_r[size_t(n) * L + i]);
+  }
+  for (int j = threadIdx.x; j < S; j += FT) bad |= !isfinite(lse_c[size_t(n) * S + j]);
+  c = block_sum(c, smem);
+  bad = block_sum(bad, smem);
+  if (threadIdx.x == 0) {
+    counts[n] = c;
+    if (bad) atomicOr(reinterpret_cast<unsigned*>(counts + n_pairs + 1), POPE_FLAG_NONFINITE_LSE);
+  }
+}
+
+__global__ void __launch_bounds__(FT) emit_kernel(const u64* __restrict__ rowbest, const u64* __restrict__ colbest, int L,
+                                                 int S, Grid2 g0, Grid2 g1, float pixel_scale,
+                                                 int32_t* __restrict__ counts, int n_pairs,
+                                                 int64_t* __restrict__ b_ids, int64_t* __restrict__ i_ids,
+                                                 int64_t* __restrict__ j_ids, float* __restrict__ mconf,
+                                                 float* __restrict__ mk0, float* __restrict__ mk1) {
+  __shared__ int smem[32];
+  __shared__ int warp_off[FT / 32];
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  rowbest += size_t(n) * L; colbest += size_t(n) * S;
+  // exclusive prefix of the per-pair counts = where this pair's matches start
+  int part = 0;
+  for (int p = threadIdx.x; p < n; p += FT) part += counts[p];
+  int base = block_sum(part, smem);
+  if (n == n_pairs - 1 && threadIdx.x == 0) counts[n_pairs] = base + counts[n];
+  for (int i0 = 0; i0 < L; i0 += FT) {
+    const int i = i0 + threadIdx.x;
+    int j = 0; float t2 = 0.f;
+    const bool hit = (i < L) && row_match(rowbest, colbest, L, S, i, g0, g1, j, t2);
+    const unsigned ballot = __ballot_sync(kFullMask, hit);
+    __syncthreads();
+    if (lane == 0) warp_off[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of the 32 warp totals
+      int v = warp_off[lane], incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+      }
+      warp_off[lane] = incl - v;
+      if (lane == 31) smem[0] = incl;
+    }
+    __syncthreads();
+    if (hit) {
+      const int64_t pos = base + warp_off[warp] + __popc(ballot & ((1u << lane) - 1u));
+      b_ids[pos] = n; i_ids[pos] = i; j_ids[pos] = j;
+      mconf[pos] = exp2f(t2);
+      mk0[2 * pos + 0] = float(i % g0.w) * pixel_scale; mk0[2 * pos + 1] = float(i / g0.w) * pixel_scale;
+      mk1[2 * pos + 0] = float(j % g1.w) * pixel_scale; mk1[2 * pos + 1] = float(j / g1.w) * pixel_scale;
+    }
+    base += smem[0];
+  }
+}
+
+}  // namespace
+
+cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, int64_t* b_ids, int64_t* i_ids,
+                                int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts,
+                                cudaStream_t st) {
+  Grid2 g0{p.h0c, p.w0c, p.border}, g1{p.h1c, p.w1c, p.border};
+  count_kernel<<<p.n, FT, 0, st>>>(w.rowbest, w.colbest, w.lse_r, w.lse_c, p.L, p.S, g0, g1, counts, p.n);
+  emit_kernel<<<p.n, FT, 0, st>>>(w.rowbest, w.colbest, p.L, p.S, g0, g1, p.pixel_scale, counts, p.n, b_ids, i_ids,
+                                  j_ids, mconf, mk0, mk1);
+  return cudaGetLastError();
+}
+
+}  // namespace pope

@@ -1,0 +1,86 @@
+// common.cuh -- shared device helpers and internal launcher declarations of libpope_b200.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pope_b200.h"
+
+namespace pope {
+
+typedef unsigned long long u64;
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---- order-preserving float <-> uint key (so that atomicMax on integers is a float max) -------------------
+__device__ __forceinline__ uint32_t ordered_key(float t) {
+  uint32_t b = __float_as_uint(t);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// Best-candidate record: high word = ordered log2-confidence, low word = ~index, so that atomicMax keeps the
+// largest confidence and, on exact ties, the smallest index.  0 means "no candidate".
+__device__ __forceinline__ u64 pack_best(float t2, int idx) {
+  return (static_cast<u64>(ordered_key(t2)) << 32) | static_cast<uint32_t>(~static_cast<uint32_t>(idx));
+}
+__device__ __forceinline__ int best_index(u64 rec) { return static_cast<int>(~static_cast<uint32_t>(rec)); }
+__device__ __forceinline__ uint32_t best_key(u64 rec) { return static_cast<uint32_t>(rec >> 32); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---- coarse-match scratch layout -------------------------------------------------------------------------
+struct CoarseScratch {
+  float* lse_r;   // [n, L]  log2-domain log-sum-exp of every row of S
+  float* lse_c;   // [n, S]  ... of every column
+  u64* rowbest;   // [n, L]  best above-threshold candidate of the row   (pack_best(t2, j))
+  u64* colbest;   // [n, S]  best above-threshold candidate of the column (pack_best(t2, i))
+  size_t bytes;
+};
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline CoarseScratch carve_coarse_scratch(void* base, int n, int L, int S) {
+  CoarseScratch w;
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  // the two key arrays are adjacent so one memset clears both
+  w.rowbest = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L, 256);
+  w.colbest = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * S, 256);
+  w.lse_r = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * L, 256);
+  w.lse_c = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * S, 256);
+  w.bytes = off;
+  return w;
+}
+
+struct CoarseProblem {
+  const void* f0;  // [n, L, C]
+  const void* f1;  // [n, S, C]
+  int dtype, n, L, S, C;
+  int h0c, w0c, h1c, w1c;
+  float scale_log2;  // log2(e) / (C * temperature): S in log2 units = <f0,f1> * scale_log2
+  float log2_thr;    // log2(float(thr))
+  int border;
+  float pixel_scale;
+};
+
+// coarse_simt.cu -- fp32-FMA kernels (fp32 or bf16 inputs): the fp32 product path and the cross-check for tcgen05
+cudaError_t coarse_simt_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
+// coarse_tc.cu -- tcgen05/TMEM/TMA kernels (bf16 inputs, C in {64,128,192,256})
+bool coarse_tc_supported(const CoarseProblem& p);
+cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
+// coarse_finalize.cu -- mutual test, border removal, ordered compaction
+cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, int64_t* b_ids, int64_t* i_ids,
+                                int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts,
+                                cudaStream_t st);
+
+}  // namespace pope

@@ -1,0 +1,258 @@
+// fine.cu -- fine-level window gather and fine matching (HBM-bound, no tensor cores).
+//
+// pope_fine_gather replaces F.unfold(5x5, stride 4, pad 2) + advanced indexing of
+//   src/matcher/loftr_module/fine_preprocess.py:40-47: only the M matched windows are read, straight from the
+//   feature maps; the 25x unfold blow-up (2 x 61 MB per 480x640 pair) is never materialised.
+// pope_fine_match replaces src/matcher/utils/fine_matching.py:43-57 and :62-74 (~10 small ATen kernels) with one
+//   warp per match: 128-bit loads, warp-shuffle transpose-reduce of the 25 dot products, softmax + expectation in
+//   registers.
+#include "common.cuh"
+
+namespace pope {
+namespace {
+
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_stream8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+struct MapDesc {
+  const char* base;
+  int H, W, wc;              // map height/width (fine cells), coarse grid width
+  int64_t sN, sC, sH, sW;    // element strides
+};
+
+// ---- channels-last gather: one warp per (match, image); a window pixel is one contiguous Cf-vector -----------
+// VEC = 16-byte vectors per pixel (Cf * sizeof(T) / 16): 32 for fp32, 16 for bf16 at Cf = 128.
+template <int VEC>
+__global__ void __launch_bounds__(256) gather_cl_kernel(MapDesc m0, MapDesc m1, int esize, int stride, int W,
+                                                       const int64_t* __restrict__ b_ids,
+                                                       const int64_t* __restrict__ i_ids,
+                                                       const int64_t* __restrict__ j_ids, int64_t M,
+                                                       const int32_t* __restrict__ m_dev, char* __restrict__ win0,
+                                                       char* __restrict__ win1) {
+  const int lane = threadIdx.x & 31;
+  const int64_t job = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);   // 2 jobs per match
+  const int64_t live = m_dev ? min(int64_t(*m_dev), M) : M;
+  const int64_t m = job >> 1;
+  if (m >= live) return;
+  const bool second = job & 1;
+  const MapDesc& md = second ? m1 : m0;
+  const int64_t cell = second ? j_ids[m] : i_ids[m];
+  const int64_t b = b_ids[m];
+  const int cy = int(cell / md.wc), cx = int(cell - int64_t(cy) * md.wc);
+  const int y0 = cy * stride - W / 2, x0 = cx * stride - W / 2;
+  const int WW = W * W;
+  constexpr int PIX_PER_IT = 32 / VEC;              // window pixels copied per warp iteration
+  const int sub = lane / VEC, v = lane % VEC;
+  char* out = (second ? win1 : win0) + size_t(m) * WW * VEC * 16;
+  const char* img = md.base + size_t(b) * md.sN * esize;
+  constexpr int UNROLL = 5;
+  for (int p0 = 0; p0 < WW; p0 += PIX_PER_IT * UNROLL) {
+    uint4 val[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int p = p0 + u * PIX_PER_IT + sub;
+      val[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (p < WW) {
+        const int ky = p / W, kx = p - ky * W;
+        const int y = y0 + ky, x = x0 + kx;
+        if (y >= 0 && y < md.H && x >= 0 && x < md.W)
+          val[u] = ld_stream16(img + (size_t(y) * md.sH + size_t(x) * md.sW) * esize + size_t(v) * 16);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int p = p0 + u * PIX_PER_IT + sub;
+      if (p < WW) *reinterpret_cast<uint4*>(out + (size_t(p) * VEC + v) * 16) = val[u];
+    }
+  }
+}
+
+// ---- generic strided gather (plain NCHW maps): one thread per output element, coalesced on the write side --------
+template <typename T>
+__global__ void __launch_bounds__(256) gather_strided_kernel(MapDesc m0, MapDesc m1, int Cf, int stride, int W,
+                                                            const int64_t* __restrict__ b_ids,
+                                                            const int64_t* __restrict__ i_ids,
+                                                            const int64_t* __restrict__ j_ids, int64_t M,
+                                                            const int32_t* __restrict__ m_dev, T* __restrict__ win0,
+                                                            T* __restrict__ win1) {
+  const int64_t live = m_dev ? min(int64_t(*m_dev), M) : M;
+  const int WW = W * W;
+  const int64_t per_img = live * WW * Cf;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < 2 * per_img;
+       e += int64_t(gridDim.x) * blockDim.x) {
+    const bool second = e >= per_img;
+    const int64_t r = second ? e - per_img : e;
+    const int c = int(r % Cf);
+    const int p = int((r / Cf) % WW);
+    const int64_t m = r / (int64_t(Cf) * WW);
+    const MapDesc& md = second ? m1 : m0;
+    const int64_t cell = second ? j_ids[m] : i_ids[m];
+    const int cy = int(cell / md.wc), cx = int(cell - int64_t(cy) * md.wc);
+    const int ky = p / W, kx = p - ky * W;
+    const int y = cy * stride - W / 2 + ky, x = cx * stride - W / 2 + kx;
+    T val = T(0.f);
+    if (y >= 0 && y < md.H && x >= 0 && x < md.W)
+      val = reinterpret_cast<const T*>(md.base)[b_ids[m] * md.sN + c * md.sC + y * md.sH + x * md.sW];
+    (second ? win1 : win0)[r] = val;
+  }
+}
+
+// ---- fine matching: one warp per match ---------------------------------------------------------------------------
+template <typename T> struct Row4;   // each lane owns 4 consecutive channels of the 128
+template <> struct Row4<float> {
+  static __device__ __forceinline__ float4 load(const float* row, int lane) {
+    uint4 u = ld_stream16(row + lane * 4);
+    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+  }
+};
+template <> struct Row4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* row, int lane) {
+    uint2 u = ld_stream8(row + lane * 4);
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fine_match_kernel(const T* __restrict__ win0, const T* __restrict__ win1,
+                                                        int64_t M, const int32_t* __restrict__ m_dev,
+                                                        const float* __restrict__ mkpts1_c, float inv_sqrt_c,
+                                                        float coord_scale, float* __restrict__ expec_f,
+                                                        float* __restrict__ mkpts1_f) {
+  constexpr int WW = 25, C = 128, WIN = 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t m = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t live = m_dev ? min(int64_t(*m_dev), M) : M;
+  if (m >= live) return;
+  const T* w0 = win0 + size_t(m) * WW * C;
+  const T* w1 = win1 + size_t(m) * WW * C;
+  // all 26 row loads are issued before the first use (memory-level parallelism; the kernel is HBM-bound)
+  const float4 ctr = Row4<T>::load(w0 + (WW / 2) * C, lane);
+  float4 rows[WW];
+#pragma unroll
+  for (int r = 0; r < WW; ++r) rows[r] = Row4<T>::load(w1 + r * C, lane);
+  float p[32];
+#pragma unroll
+  for (int r = 0; r < WW; ++r)
+    p[r] = fmaf(ctr.x, rows[r].x, fmaf(ctr.y, rows[r].y, fmaf(ctr.z, rows[r].z, ctr.w * rows[r].w)));
+#pragma unroll
+  for (int r = WW; r < 32; ++r) p[r] = 0.f;
+  // transpose-reduce: after the 5 steps lane r holds sum over lanes of p[r]   (31 shuffles instead of 25*5)
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = lane & off;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = upper ? p[k] : p[k + off];
+      const float keep = upper ? p[k + off] : p[k];
+      p[k] = keep + __shfl_xor_sync(kFullMask, send, off);
+    }
+  }
+  const bool on = lane < WW;
+  const float x = on ? p[0] * inv_sqrt_c : -INFINITY;
+  float mx = x;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+  const float e = on ? expf(x - mx) : 0.f;
+  const float h = e / warp_sum(e);
+  const float gx = -1.f + 0.5f * float(lane % WIN), gy = -1.f + 0.5f * float(lane / WIN);
+  const float ex = warp_sum(h * gx), ey = warp_sum(h * gy);
+  const float exx = warp_sum(h * gx * gx), eyy = warp_sum(h * gy * gy);
+  if (lane == 0) {
+    const float sd = sqrtf(fmaxf(exx - ex * ex, 1e-10f)) + sqrtf(fmaxf(eyy - ey * ey, 1e-10f));
+    expec_f[3 * m + 0] = ex; expec_f[3 * m + 1] = ey; expec_f[3 * m + 2] = sd;
+    mkpts1_f[2 * m + 0] = mkpts1_c[2 * m + 0] + ex * coord_scale;
+    mkpts1_f[2 * m + 1] = mkpts1_c[2 * m + 1] + ey * coord_scale;
+  }
+}
+
+}  // namespace
+}  // namespace pope
+
+using namespace pope;
+
+extern "C" int pope_fine_gather(const void* feat_f0, const void* feat_f1, int dtype, int n_pairs, int Cf, int Hf0,
+                                int Wf0, const int64_t strides0[4], int Hf1, int Wf1, const int64_t strides1[4],
+                                int w0c, int w1c, int stride, int W, const int64_t* b_ids, const int64_t* i_ids,
+                                const int64_t* j_ids, int64_t M, const int32_t* m_dev, void* win0, void* win1,
+                                void* stream) {
+  if (!feat_f0 || !feat_f1 || !strides0 || !strides1 || M < 0) return POPE_ERR_INVALID_ARG;
+  if (dtype != POPE_F32 && dtype != POPE_BF16) return POPE_ERR_DTYPE;
+  if (n_pairs <= 0 || Cf <= 0 || Hf0 <= 0 || Wf0 <= 0 || Hf1 <= 0 || Wf1 <= 0 || w0c <= 0 || w1c <= 0 || stride <= 0 ||
+      W <= 0 || (W & 1) == 0)
+    return POPE_ERR_INVALID_ARG;
+  if (M == 0) return POPE_OK;
+  if (!b_ids || !i_ids || !j_ids || !win0 || !win1) return POPE_ERR_INVALID_ARG;
+  const int esize = dtype == POPE_BF16 ? 2 : 4;
+  MapDesc m0{static_cast<const char*>(feat_f0), Hf0, Wf0, w0c, strides0[0], strides0[1], strides0[2], strides0[3]};
+  MapDesc m1{static_cast<const char*>(feat_f1), Hf1, Wf1, w1c, strides1[0], strides1[1], strides1[2], strides1[3]};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int vec = Cf * esize / 16;
+  auto vec_ok = [&](const MapDesc& m) {
+    return m.sC == 1 && (m.sW * esize) % 16 == 0 && (m.sH * esize) % 16 == 0 && (m.sN * esize) % 16 == 0 &&
+           (reinterpret_cast<uintptr_t>(m.base) & 15u) == 0;
+  };
+  const bool fast = (Cf * esize) % 16 == 0 && (vec == 32 || vec == 16) && vec_ok(m0) && vec_ok(m1) &&
+                    ((reinterpret_cast<uintptr_t>(win0) | reinterpret_cast<uintptr_t>(win1)) & 15u) == 0;
+  if (fast) {
+    const int warps = 8;
+    const unsigned blocks = unsigned((2 * M + warps - 1) / warps);
+    if (vec == 32)
+      gather_cl_kernel<32><<<blocks, warps * 32, 0, st>>>(m0, m1, esize, stride, W, b_ids, i_ids, j_ids, M, m_dev,
+                                                         static_cast<char*>(win0), static_cast<char*>(win1));
+    else
+      gather_cl_kernel<16><<<blocks, warps * 32, 0, st>>>(m0, m1, esize, stride, W, b_ids, i_ids, j_ids, M, m_dev,
+                                                         static_cast<char*>(win0), static_cast<char*>(win1));
+  } else {
+    const int64_t total = 2 * M * W * W * Cf;
+    const int64_t want = (total + 255) / 256;
+    const unsigned blocks = unsigned(want < 148 * 32 ? want : 148 * 32);
+    if (dtype == POPE_BF16)
+      gather_strided_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(m0, m1, Cf, stride, W, b_ids, i_ids, j_ids, M, m_dev,
+                                                                  static_cast<__nv_bfloat16*>(win0),
+                                                                  static_cast<__nv_bfloat16*>(win1));
+    else
+      gather_strided_kernel<float><<<blocks, 256, 0, st>>>(m0, m1, Cf, stride, W, b_ids, i_ids, j_ids, M, m_dev,
+                                                          static_cast<float*>(win0), static_cast<float*>(win1));
+  }
+  return int(cudaGetLastError());
+}
+
+extern "C" int pope_fine_match(const void* win0, const void* win1, int dtype, int64_t M, const int32_t* m_dev, int WW,
+                               int Cf, const float* mkpts1_c, float coord_scale, float* expec_f, float* mkpts1_f,
+                               void* stream) {
+  if (M < 0) return POPE_ERR_INVALID_ARG;
+  if (dtype != POPE_F32 && dtype != POPE_BF16) return POPE_ERR_DTYPE;
+  if (WW != 25 || Cf != 128) return POPE_ERR_SHAPE;
+  if (M == 0) return POPE_OK;
+  if (!win0 || !win1 || !mkpts1_c || !expec_f || !mkpts1_f) return POPE_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(win0) | reinterpret_cast<uintptr_t>(win1)) & 15u) return POPE_ERR_ALIGNMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int warps = 8;
+  const unsigned blocks = unsigned((M + warps - 1) / warps);
+  const float inv_sqrt_c = static_cast<float>(1.0 / sqrt(double(Cf)));
+  if (dtype == POPE_BF16)
+    fine_match_kernel<__nv_bfloat16><<<blocks, warps * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(win0),
+                                                                   static_cast<const __nv_bfloat16*>(win1), M, m_dev,
+                                                                   mkpts1_c, inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
+  else
+    fine_match_kernel<float><<<blocks, warps * 32, 0, st>>>(static_cast<const float*>(win0),
+                                                           static_cast<const float*>(win1), M, m_dev, mkpts1_c,
+                                                           inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
+  return int(cudaGetLastError());
+}

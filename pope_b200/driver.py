@@ -1,0 +1,161 @@
+"""Pair-batching driver: batches of independent image pairs through the hot path, on one GPU (chunked stream
+pipeline in libpope_b200.so) or sharded over the GPUs of one box with a single gather of the match lists.
+
+Replaces the batch-1 loops of the eval drivers (eval_linemod_json.py:103-122, eval_onepose_json.py:103-124,
+eval_ycb_json.py:86-105: three sequential `matcher(batch)` calls per test pair, `.cpu()` after each).
+Pairs are independent, so ranks share nothing on the data path; the only cross-GPU step is `gather_matches`
+(SURVEY.md section 8(e)).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, dtype_code, lib
+
+
+def _pin(t: torch.Tensor) -> torch.Tensor:
+    t = t.contiguous()
+    if t.device.type != "cpu":
+        raise _lib.PopeError("the host pipeline takes CPU (preferably pinned) tensors")
+    return t
+
+
+def _fine_to_nhwc(ff: torch.Tensor) -> torch.Tensor:
+    """logical [N, Cf, H, W] (any strides) -> memory [N, H, W, Cf]; free for channels-last inputs."""
+    return ff.permute(0, 2, 3, 1).contiguous()
+
+
+class Pipeline:
+    """Owns one `pope_pipeline_t` (device slots + streams for one geometry)."""
+
+    def __init__(self, dtype: torch.dtype, chunk_pairs: int, hw0_i: Sequence[int], hw0_c: Sequence[int],
+                 hw1_c: Sequence[int], C_coarse: int = 256, C_fine: int = 128, fine_stride: int = 4, W: int = 5,
+                 thr: float = 0.2, border_rm: int = 2, temperature: float = 0.1, impl: int = _lib.COARSE_AUTO,
+                 device: int = 0):
+        self.dtype, self.chunk, self.device = dtype, chunk_pairs, device
+        self.hw0_c, self.hw1_c = tuple(hw0_c), tuple(hw1_c)
+        self.L, self.S = hw0_c[0] * hw0_c[1], hw1_c[0] * hw1_c[1]
+        self.cap = min(self.L, self.S)
+        self.C, self.Cf, self.fstride, self.W = C_coarse, C_fine, fine_stride, W
+        self._h = C.c_void_p()
+        code = _lib.POPE_BF16 if dtype == torch.bfloat16 else _lib.POPE_F32
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise _lib.PopeError(f"unsupported dtype {dtype}")
+        pixel_scale = hw0_i[0] / hw0_c[0]
+        fine_scale = hw0_i[0] / (hw0_c[0] * fine_stride)
+        st = lib().pope_pipeline_create(C.byref(self._h), device, code, chunk_pairs, C_coarse, C_fine,
+                                        hw0_c[0], hw0_c[1], hw1_c[0], hw1_c[1], fine_stride, W,
+                                        float(pixel_scale), float(fine_scale), float(temperature), float(thr),
+                                        int(border_rm), int(impl))
+        check(st, "pope_pipeline_create")
+
+    def alloc_outputs(self, n: int, pinned: bool = True) -> Dict[str, torch.Tensor]:
+        kw = dict(pin_memory=pinned)
+        return {"i_ids": torch.empty(n, self.cap, dtype=torch.int64, **kw),
+                "j_ids": torch.empty(n, self.cap, dtype=torch.int64, **kw),
+                "mconf": torch.empty(n, self.cap, dtype=torch.float32, **kw),
+                "mkpts0_f": torch.empty(n, self.cap, 2, dtype=torch.float32, **kw),
+                "mkpts1_f": torch.empty(n, self.cap, 2, dtype=torch.float32, **kw),
+                "counts": torch.empty(n, dtype=torch.int32, **kw),
+                "flags": torch.zeros(1, dtype=torch.int32, **kw)}
+
+    def run(self, feat_c0, feat_c1, feat_f0_nhwc, feat_f1_nhwc, out: Optional[Dict[str, torch.Tensor]] = None):
+        """Inputs: CPU tensors feat_c* [n,L|S,C], feat_f*_nhwc [n,Hf,Wf,Cf] (memory order), same dtype."""
+        n = feat_c0.shape[0]
+        for t in (feat_c0, feat_c1, feat_f0_nhwc, feat_f1_nhwc):
+            if t.dtype != self.dtype or not t.is_contiguous() or t.device.type != "cpu":
+                raise _lib.PopeError("pipeline inputs must be contiguous CPU tensors of the pipeline dtype")
+        if out is None:
+            out = self.alloc_outputs(n)
+        st = lib().pope_pipeline_run(self._h, feat_c0.data_ptr(), feat_c1.data_ptr(), feat_f0_nhwc.data_ptr(),
+                                     feat_f1_nhwc.data_ptr(), n, out["i_ids"].data_ptr(), out["j_ids"].data_ptr(),
+                                     out["mconf"].data_ptr(), out["mkpts0_f"].data_ptr(), out["mkpts1_f"].data_ptr(),
+                                     out["counts"].data_ptr(), out["flags"].data_ptr())
+        check(st, "pope_pipeline_run")
+        return out
+
+    def close(self):
+        if self._h:
+            lib().pope_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def match_pairs_host(feat_c0, feat_c1, feat_f0, feat_f1, hw0_i, hw0_c, hw1_c, chunk_pairs: int = 16, device: int = 0,
+                     **kw) -> Dict[str, torch.Tensor]:
+    """One-shot host-buffer entry: feat_f* are logical [N, Cf, Hf, Wf] CPU tensors (channels-last is free)."""
+    n = feat_c0.shape[0]
+    pl = Pipeline(feat_c0.dtype, min(chunk_pairs, n), hw0_i, hw0_c, hw1_c, feat_c0.shape[2], feat_f0.shape[1],
+                  feat_f0.shape[2] // hw0_c[0], device=device, **kw)
+    try:
+        return pl.run(_pin(feat_c0), _pin(feat_c1), _fine_to_nhwc(feat_f0), _fine_to_nhwc(feat_f1))
+    finally:
+        pl.close()
+
+
+def flatten_slots(out: Dict[str, torch.Tensor], pair_offset: int = 0) -> Dict[str, torch.Tensor]:
+    """Per-pair slots [n, cap] -> the reference's packed lists sorted by (b, i)."""
+    counts = out["counts"].to(torch.int64)
+    n, cap = out["i_ids"].shape
+    live = torch.arange(cap)[None, :] < counts[:, None]
+    b = torch.arange(n)[:, None].expand(n, cap)[live] + pair_offset
+    return {"b_ids": b, "i_ids": out["i_ids"][live], "j_ids": out["j_ids"][live], "mconf": out["mconf"][live],
+            "mkpts0_f": out["mkpts0_f"][live], "mkpts1_f": out["mkpts1_f"][live], "counts": out["counts"]}
+
+
+# ---- multi-GPU sharding -----------------------------------------------------------------------------------------
+
+def shard_range(n_pairs: int, rank: int, world: int):
+    """Contiguous block partition of pair indices: rank r owns [lo, hi)."""
+    base, rem = divmod(n_pairs, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_matches(local: Dict[str, torch.Tensor], n_pairs: int, rank: int, world: int, group=None,
+                   device: Optional[torch.device] = None) -> Optional[Dict[str, torch.Tensor]]:
+    """THE one collective of a sharded run: every rank contributes the packed match lists of its pairs
+    (`flatten_slots(..., pair_offset=lo)`), rank 0 receives the concatenation, which is sorted by (b, i) because the
+    partition is contiguous.  One all_gather of the per-rank totals sizes a single padded all_gather of one packed
+    [max_M, 8] fp64-free record tensor (ids as int64, values as float32 bit patterns)."""
+    import torch.distributed as dist
+    dev = device or local["i_ids"].device
+    m = torch.tensor([local["i_ids"].numel()], dtype=torch.int64, device=dev)
+    totals = [torch.zeros_like(m) for _ in range(world)]
+    dist.all_gather(totals, m, group=group)
+    totals = [int(t.item()) for t in totals]
+    mx = max(max(totals), 1)
+    rec = torch.zeros(mx, 8, dtype=torch.int64, device=dev)
+    k = local["i_ids"].numel()
+    if k:
+        rec[:k, 0] = local["b_ids"].to(dev)
+        rec[:k, 1] = local["i_ids"].to(dev)
+        rec[:k, 2] = local["j_ids"].to(dev)
+        f = torch.cat([local["mconf"][:, None], local["mkpts0_f"], local["mkpts1_f"]], 1).to(dev).contiguous()
+        rec[:k, 3:8] = f.view(torch.int32).to(torch.int64)
+    bufs = [torch.zeros_like(rec) for _ in range(world)]
+    dist.all_gather(bufs, rec, group=group)
+    if rank != 0:
+        return None
+    allrec = torch.cat([b[:t] for b, t in zip(bufs, totals)], 0)
+    fl = allrec[:, 3:8].to(torch.int32).view(torch.float32)
+    return {"b_ids": allrec[:, 0], "i_ids": allrec[:, 1], "j_ids": allrec[:, 2], "mconf": fl[:, 0],
+            "mkpts0_f": fl[:, 1:3], "mkpts1_f": fl[:, 3:5], "per_rank_matches": totals}
+
+
+def run_sharded(n_pairs: int, rank: int, world: int, local_fn: Callable[[int, int], Dict[str, torch.Tensor]],
+                group=None, device: Optional[torch.device] = None):
+    """Shard `n_pairs` over `world` ranks, run `local_fn(lo, hi)` (returns packed lists with *global* b_ids) on each,
+    gather on rank 0.  No collective runs inside `local_fn`."""
+    lo, hi = shard_range(n_pairs, rank, world)
+    local = local_fn(lo, hi)
+    return gather_matches(local, n_pairs, rank, world, group, device)

@@ -1,0 +1,149 @@
+"""Functional wrappers over the C ABI (device tensors in, device tensors out).
+
+Each function is the CUDA replacement of one reference function (paths relative to the reference tree):
+  coarse_match  <- CoarseMatching.forward/get_coarse_match   src/matcher/utils/coarse_matching.py:87-261
+  fine_gather   <- FinePreprocess unfold + gather              src/matcher/loftr_module/fine_preprocess.py:40-47
+  fine_match    <- FineMatching.forward/get_fine_match         src/matcher/utils/fine_matching.py:15-74
+  cosine_topk   <- retrieval loop                              eval_linemod_json.py:72-101
+Nothing here computes on the CPU; tensors that are not on a CUDA device are rejected.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, dtype_code, lib, ptr, require_cuda, stream_ptr
+
+
+class CoarseResult(dict):
+    """dict of device tensors at full capacity plus `counts` (int32 [n+2] on device).  `.sliced()` performs the
+    one host sync (reads the total) and returns views of length M, in the reference's key order."""
+
+    def total(self) -> int:
+        return int(self["counts"][self["n_pairs"]].item())
+
+    def flags(self) -> int:
+        return int(self["counts"][self["n_pairs"] + 1].item())
+
+    def sliced(self) -> Dict[str, torch.Tensor]:
+        m = self.total()
+        out = {k: self[k][:m] for k in ("b_ids", "i_ids", "j_ids")}
+        mconf = self["mconf"][:m]
+        out["gt_mask"] = mconf == 0
+        out["m_bids"] = out["b_ids"]
+        out["mkpts0_c"] = self["mkpts0_c"][:m]
+        out["mkpts1_c"] = self["mkpts1_c"][:m]
+        out["mconf"] = mconf
+        return out
+
+
+def coarse_match(feat_c0: torch.Tensor, feat_c1: torch.Tensor, hw0_c: Sequence[int], hw1_c: Sequence[int],
+                 pixel_scale: float, thr: float = 0.2, border_rm: int = 2, temperature: float = 0.1,
+                 impl: int = _lib.COARSE_AUTO, workspace: Optional[torch.Tensor] = None) -> CoarseResult:
+    dev = require_cuda(feat_c0, feat_c1)
+    if feat_c0.dtype != feat_c1.dtype:
+        raise _lib.PopeError("feat_c0 and feat_c1 must have the same dtype")
+    feat_c0, feat_c1 = feat_c0.contiguous(), feat_c1.contiguous()
+    n, L, Cc = feat_c0.shape
+    S = feat_c1.shape[1]
+    if feat_c1.shape[0] != n or feat_c1.shape[2] != Cc:
+        raise _lib.PopeError(f"shape mismatch {tuple(feat_c0.shape)} vs {tuple(feat_c1.shape)}")
+    h = lib()
+    need = h.pope_coarse_workspace_bytes(n, L, S)
+    if workspace is None or workspace.numel() < need or workspace.device != dev:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    cap = n * min(L, S)
+    i64 = dict(dtype=torch.int64, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    res = CoarseResult(
+        b_ids=torch.empty(cap, **i64), i_ids=torch.empty(cap, **i64), j_ids=torch.empty(cap, **i64),
+        mconf=torch.empty(cap, **f32), mkpts0_c=torch.empty(cap, 2, **f32), mkpts1_c=torch.empty(cap, 2, **f32),
+        counts=torch.empty(n + 2, dtype=torch.int32, device=dev), n_pairs=n, workspace=workspace)
+    with torch.cuda.device(dev):
+        st = h.pope_coarse_match(ptr(feat_c0), ptr(feat_c1), dtype_code(feat_c0), n, L, S, Cc,
+                                 int(hw0_c[0]), int(hw0_c[1]), int(hw1_c[0]), int(hw1_c[1]),
+                                 float(pixel_scale), float(temperature), float(thr), int(border_rm), int(impl),
+                                 ptr(workspace), workspace.numel(),
+                                 ptr(res["b_ids"]), ptr(res["i_ids"]), ptr(res["j_ids"]), ptr(res["mconf"]),
+                                 ptr(res["mkpts0_c"]), ptr(res["mkpts1_c"]), ptr(res["counts"]), cap, stream_ptr(dev))
+    check(st, "pope_coarse_match")
+    return res
+
+
+def _strides4(t: torch.Tensor):
+    return (C.c_int64 * 4)(*t.stride())
+
+
+def fine_gather(feat_f0: torch.Tensor, feat_f1: torch.Tensor, b_ids: torch.Tensor, i_ids: torch.Tensor,
+                j_ids: torch.Tensor, w0c: int, w1c: int, stride: int, W: int = 5,
+                m_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (win0, win1) of shape [M, W*W, Cf] (M = len(b_ids); with `m_dev` rows >= *m_dev are left
+    uninitialised).  feat_f* are logical [N, Cf, Hf, Wf] with any strides (channels-last is the fast path)."""
+    dev = require_cuda(feat_f0, feat_f1, b_ids, i_ids, j_ids)
+    if feat_f0.dtype != feat_f1.dtype:
+        raise _lib.PopeError("feat_f0 and feat_f1 must have the same dtype")
+    n, Cf, Hf0, Wf0 = feat_f0.shape
+    _, _, Hf1, Wf1 = feat_f1.shape
+    M = b_ids.shape[0]
+    win0 = torch.empty(M, W * W, Cf, dtype=feat_f0.dtype, device=dev)
+    win1 = torch.empty(M, W * W, Cf, dtype=feat_f0.dtype, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().pope_fine_gather(ptr(feat_f0), ptr(feat_f1), dtype_code(feat_f0), n, Cf, Hf0, Wf0, _strides4(feat_f0),
+                                    Hf1, Wf1, _strides4(feat_f1), int(w0c), int(w1c), int(stride), int(W),
+                                    ptr(b_ids), ptr(i_ids), ptr(j_ids), M, ptr(m_dev), ptr(win0), ptr(win1),
+                                    stream_ptr(dev))
+    check(st, "pope_fine_gather")
+    return win0, win1
+
+
+def fine_match(win0: torch.Tensor, win1: torch.Tensor, mkpts1_c: torch.Tensor, coord_scale: float,
+               m_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (expec_f [M,3], mkpts1_f [M,2]);  coord_scale = (W//2) * hw0_i[0]/hw0_f[0]."""
+    dev = require_cuda(win0, win1, mkpts1_c)
+    if win0.dtype != win1.dtype or win0.shape != win1.shape:
+        raise _lib.PopeError("win0 and win1 must have the same dtype and shape")
+    win0, win1, mkpts1_c = win0.contiguous(), win1.contiguous(), mkpts1_c.contiguous().float()
+    M, WW, Cf = win0.shape
+    expec = torch.empty(M, 3, dtype=torch.float32, device=dev)
+    mk1f = torch.empty(M, 2, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().pope_fine_match(ptr(win0), ptr(win1), dtype_code(win0), M, ptr(m_dev), WW, Cf, ptr(mkpts1_c),
+                                   float(coord_scale), ptr(expec), ptr(mk1f), stream_ptr(dev))
+    check(st, "pope_fine_match")
+    return expec, mk1f
+
+
+def cosine_topk(q: torch.Tensor, refs: torch.Tensor, k: int = 3, eps: float = 1e-8):
+    """q [1,D] or [D], refs [R,D] -> (scores [R], slot_scores [k], slot_idx [k] int32; -1 = empty slot)."""
+    dev = require_cuda(q, refs)
+    q, refs = q.reshape(-1).contiguous(), refs.contiguous()
+    if q.dtype != refs.dtype or q.shape[0] != refs.shape[1]:
+        raise _lib.PopeError("q and refs must share dtype and feature dimension")
+    R, D = refs.shape
+    scores = torch.empty(R, dtype=torch.float32, device=dev)
+    slot_s = torch.empty(k, dtype=torch.float32, device=dev)
+    slot_i = torch.empty(k, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().pope_cosine_topk(ptr(q), ptr(refs), dtype_code(q), R, D, k, float(eps), ptr(scores), ptr(slot_s),
+                                    ptr(slot_i), stream_ptr(dev))
+    check(st, "pope_cosine_topk")
+    return scores, slot_s, slot_i
+
+
+def match_pairs_device(feat_c0, feat_c1, feat_f0, feat_f1, hw0_i, hw0_c, hw1_c, thr=0.2, border_rm=2,
+                       temperature=0.1, W=5, impl=_lib.COARSE_AUTO, workspace=None) -> CoarseResult:
+    """The hot path on device-resident inputs with NO host synchronisation: coarse match -> window gather ->
+    fine match, the match count staying on the device (`m_dev`).  Returns the capacity-sized CoarseResult
+    extended with `expec_f`, `mkpts0_f`, `mkpts1_f`, `win0`, `win1`."""
+    res = coarse_match(feat_c0, feat_c1, hw0_c, hw1_c, hw0_i[0] / hw0_c[0], thr, border_rm, temperature, impl, workspace)
+    n = res["n_pairs"]
+    m_dev = res["counts"][n:n + 1]
+    stride = feat_f0.shape[2] // hw0_c[0]
+    win0, win1 = fine_gather(feat_f0, feat_f1, res["b_ids"], res["i_ids"], res["j_ids"], hw0_c[1], hw1_c[1], stride, W,
+                             m_dev)
+    expec, mk1f = fine_match(win0, win1, res["mkpts1_c"], (W // 2) * (hw0_i[0] / feat_f0.shape[2]), m_dev)
+    res.update(win0=win0, win1=win1, expec_f=expec, mkpts0_f=res["mkpts0_c"], mkpts1_f=mk1f)
+    return res

@@ -1,0 +1,21 @@
+"""Reference-crop retrieval: cosine similarity of DINOv2 CLS tokens + the eval loop's running top-k, on device.
+
+Replaces the per-crop `F.cosine_similarity(ref_fea, fea, dim=1, eps=1e-8)` + `.item()` + slot update of
+eval_linemod_json.py:72-101 (token: segment_anything/segment_anything/dinov2_utils.py:106-111) by one call over
+all R crops.  The ViT forward that produces the tokens is outside the accelerated path."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+
+from . import ops
+
+
+def retrieve_topk(ref_fea: torch.Tensor, crop_feas: torch.Tensor, k: int = 3, eps: float = 1e-8
+                  ) -> Tuple[torch.Tensor, List[float], List[int]]:
+    """ref_fea [1,D] (the prompt image's token), crop_feas [R,D] in crop order.
+    Returns (scores [R] on device, slot_scores, slot_indices) -- the slots are what the eval loop leaves in
+    `similarity_score` / `top_images` (index -1: slot never filled, score stays 0)."""
+    scores, slot_s, slot_i = ops.cosine_topk(ref_fea, crop_feas, k, eps)
+    return scores, slot_s.tolist(), slot_i.tolist()

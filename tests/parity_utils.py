@@ -1,0 +1,67 @@
+"""Helpers for the parity tests: compare match lists bit-exactly, classifying any difference as a near-tie /
+near-threshold case (BASELINE.json north_star: pairs whose top-2 gap is below 1e-3 are reported separately)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import pope_oracle as O
+
+TIE_REL = 1e-3      # relative top-2 gap below which a row/column maximum is a tie
+THR_REL = 2e-3      # relative distance to the threshold below which `conf > thr` may flip
+
+
+def margins_from_conf(conf: torch.Tensor):
+    r = conf.topk(2, dim=2)[0]
+    c = conf.topk(2, dim=1)[0]
+    return dict(conf_rowmax=r[..., 0].numpy(), conf_row2nd=r[..., 1].numpy(),
+                conf_colmax=c[:, 0].numpy(), conf_col2nd=c[:, 1].numpy())
+
+
+def oracle_with_margins(f0, f1, hw0_i, hw0_c, hw1_c, thr=O.THR, border_rm=O.BORDER_RM, temperature=O.DSMAX_TEMPERATURE):
+    """Oracle match list + row/col top-2 margins, pair by pair (memory-bounded)."""
+    outs, margins = [], []
+    for b in range(f0.shape[0]):
+        conf = O.dual_softmax_conf(f0[b:b + 1].float(), f1[b:b + 1].float(), temperature)
+        o = O.coarse_match_from_conf(conf, hw0_i, hw0_c, hw1_c, thr, border_rm)
+        o["b_ids"] = o["b_ids"] + b
+        o["m_bids"] = o["m_bids"] + b
+        outs.append(o)
+        margins.append(margins_from_conf(conf))
+    out = {k: torch.cat([o[k] for o in outs]) for k in outs[0]}
+    mg = {k: np.concatenate([m[k] for m in margins]) for k in margins[0]}
+    return out, mg
+
+
+def _fragile(b, i, js, mg, thr):
+    rm, r2 = mg["conf_rowmax"][b, i], mg["conf_row2nd"][b, i]
+    if abs(rm - thr) <= THR_REL * thr or (rm - r2) <= TIE_REL * rm:
+        return True
+    for j in js:
+        if j is None:
+            continue
+        cm, c2 = mg["conf_colmax"][b, j], mg["conf_col2nd"][b, j]
+        if abs(cm - thr) <= THR_REL * thr or (cm - c2) <= TIE_REL * cm:
+            return True
+    return False
+
+
+def compare_match_lists(got, want, mg, thr=O.THR):
+    """got / want: dicts with b_ids, i_ids, j_ids (1-D int tensors).  Returns (n_same, near, bad) where `near` and
+    `bad` are lists of (b, i, j_got, j_want); `bad` must be empty for parity."""
+    g = {(int(b), int(i)): int(j) for b, i, j in zip(got["b_ids"].tolist(), got["i_ids"].tolist(), got["j_ids"].tolist())}
+    w = {(int(b), int(i)): int(j) for b, i, j in zip(want["b_ids"].tolist(), want["i_ids"].tolist(), want["j_ids"].tolist())}
+    same, near, bad = 0, [], []
+    for key in sorted(set(g) | set(w)):
+        jg, jw = g.get(key), w.get(key)
+        if jg == jw:
+            same += 1
+            continue
+        rec = (key[0], key[1], jg, jw)
+        (near if _fragile(key[0], key[1], (jg, jw), mg, thr) else bad).append(rec)
+    return same, near, bad
+
+
+def assert_sorted_by_pair_and_row(b_ids: torch.Tensor, i_ids: torch.Tensor, L: int):
+    key = b_ids.to(torch.int64) * L + i_ids.to(torch.int64)
+    assert bool((key[1:] > key[:-1]).all()), "matches are not strictly sorted by (b, i)"

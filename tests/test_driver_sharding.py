@@ -1,0 +1,77 @@
+"""The N>1 path on CPU: world_size-2 gloo processes shard pairs, the oracle stands in for the GPU hot path (it is
+the checker here, the thing under test is the partition + the single gather)."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pope_b200 import driver
+
+
+def test_shard_range_partitions_exactly():
+    for n in (1, 7, 64, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [driver.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_flatten_slots_orders_by_pair_then_row():
+    out = {"i_ids": torch.tensor([[3, 9, 0], [1, 0, 0]]), "j_ids": torch.tensor([[5, 2, 0], [7, 0, 0]]),
+           "mconf": torch.tensor([[.5, .6, 0], [.7, 0, 0]]), "mkpts0_f": torch.zeros(2, 3, 2), "mkpts1_f": torch.ones(2, 3, 2),
+           "counts": torch.tensor([2, 1], dtype=torch.int32)}
+    flat = driver.flatten_slots(out, pair_offset=10)
+    assert flat["b_ids"].tolist() == [10, 10, 11] and flat["i_ids"].tolist() == [3, 9, 1] and flat["j_ids"].tolist() == [5, 2, 7]
+
+
+def _worker(rank, world, port, n_pairs, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pope_oracle as O
+    from pope_b200 import synth
+    hw = (8, 10)
+
+    def local_fn(lo, hi):
+        f0, f1 = synth.coarse_features(5, n_pairs, 80, 80, 64, sigma=0.8)      # every rank regenerates, slices its shard
+        ff0, ff1 = synth.fine_feature_maps(6, n_pairs, 32, 40, 128, channels_last=False)
+        if hi == lo:
+            e = torch.empty(0)
+            return {"b_ids": e.long(), "i_ids": e.long(), "j_ids": e.long(), "mconf": e, "mkpts0_f": torch.empty(0, 2),
+                    "mkpts1_f": torch.empty(0, 2)}
+        o = O.match_pairs(f0[lo:hi], f1[lo:hi], ff0[lo:hi], ff1[lo:hi], (64, 80), hw, hw)
+        o["b_ids"] = o["b_ids"] + lo
+        return o
+
+    got = driver.run_sharded(n_pairs, rank, world, local_fn)
+    if rank == 0:
+        q.put({k: (v.clone() if torch.is_tensor(v) else v) for k, v in got.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_equals_single_process():
+    from oracle import pope_oracle as O
+    from pope_b200 import synth
+    n_pairs, world = 5, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_pairs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    f0, f1 = synth.coarse_features(5, n_pairs, 80, 80, 64, sigma=0.8)
+    ff0, ff1 = synth.fine_feature_maps(6, n_pairs, 32, 40, 128, channels_last=False)
+    want = O.match_pairs(f0, f1, ff0, ff1, (64, 80), (8, 10), (8, 10))
+    assert want["b_ids"].numel() > 20
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(got[k], want[k]), k
+    assert torch.equal(got["mconf"], want["mconf"])
+    assert torch.equal(got["mkpts1_f"], want["mkpts1_f"]) and torch.equal(got["mkpts0_f"], want["mkpts0_f"])
+    assert sum(got["per_rank_matches"]) == want["b_ids"].numel()

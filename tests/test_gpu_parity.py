@@ -1,0 +1,324 @@
+"""Parity of the CUDA path (through the C ABI) against the reference-generated golden fixtures and the oracle.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pope_oracle as O
+from oracle.gen_golden import COARSE_CASES, coarse_inputs
+from pope_b200 import _lib, ops, synth
+from tests.parity_utils import assert_sorted_by_pair_and_row, compare_match_lists, oracle_with_margins
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+IMPLS = {"simt": _lib.COARSE_SIMT, "tcgen05": _lib.COARSE_TCGEN05}
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def _tc_ok(C, dtype, L=4800, S=4800):
+    return dtype == torch.bfloat16 and _lib.tcgen05_available(L, S, C)
+
+
+def _need_tc(impl, C=256, L=4800, S=4800):
+    if impl == "tcgen05" and not _lib.tcgen05_available(L, S, C):
+        pytest.skip("tcgen05 kernels do not cover this shape")
+
+
+def _run_coarse(f0, f1, hw0_c, hw1_c, impl, dtype, **kw):
+    res = ops.coarse_match(f0.to(DEV, dtype), f1.to(DEV, dtype), hw0_c, hw1_c, 8.0, impl=impl, **kw)
+    assert res.flags() == 0
+    out = {k: v.cpu() for k, v in res.sliced().items()}
+    counts = res["counts"][: f0.shape[0]].cpu()
+    assert int(counts.sum()) == out["b_ids"].numel()
+    assert torch.equal(torch.bincount(out["b_ids"], minlength=f0.shape[0]).to(torch.int32), counts)
+    return out
+
+
+@pytest.mark.parametrize("impl", list(IMPLS))
+@pytest.mark.parametrize("name", list(COARSE_CASES))
+def test_coarse_golden(golden_dir, name, impl):
+    case = COARSE_CASES[name]
+    g = _load(golden_dir, name)
+    f0, f1 = coarse_inputs(case)            # fp32 values; for the bf16 case they are exactly bf16-representable
+    dtypes = [torch.bfloat16] if case["kind"] == "bf16" else [torch.float32]
+    for dtype in dtypes:
+        if impl == "tcgen05" and not _tc_ok(case["C"], dtype, case["hw0_c"][0] * case["hw0_c"][1],
+                                            case["hw1_c"][0] * case["hw1_c"][1]):
+            pytest.skip("tcgen05 path takes bf16 features with C in {64,128,192,256}")
+        out = _run_coarse(f0, f1, case["hw0_c"], case["hw1_c"], IMPLS[impl], dtype)
+        want = {k: torch.from_numpy(g[k]) for k in ("b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c")}
+        same, near, bad = compare_match_lists(out, want, g)
+        assert not bad, f"{name}/{impl}: index mismatches that are not near-ties: {bad[:5]}"
+        assert len(near) <= max(2, want["b_ids"].numel() // 200), near
+        if not near:
+            for k in ("b_ids", "i_ids", "j_ids"):
+                assert out[k].dtype == torch.int64 and torch.equal(out[k], want[k]), k
+            tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
+            np.testing.assert_allclose(out["mconf"].numpy(), g["mconf"], rtol=tol, atol=0)
+            np.testing.assert_array_equal(out["mkpts0_c"].numpy(), g["mkpts0_c"])
+            np.testing.assert_array_equal(out["mkpts1_c"].numpy(), g["mkpts1_c"])
+            assert out["gt_mask"].dtype == torch.bool and not out["gt_mask"].any()
+        L = case["hw0_c"][0] * case["hw0_c"][1]
+        if out["b_ids"].numel() > 1:
+            assert_sorted_by_pair_and_row(out["b_ids"], out["i_ids"], L)
+
+
+@pytest.mark.parametrize("impl", list(IMPLS))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_coarse_full_size_vs_oracle(impl, dtype):
+    """BASELINE configs[1] shape (480x640 -> 60x80 tokens, d=256), 3 pairs, against the oracle on the same
+    (bf16-rounded) values."""
+    if impl == "tcgen05" and dtype != torch.bfloat16:
+        pytest.skip("tcgen05 path is bf16-only")
+    _need_tc(impl)
+    f0, f1 = synth.coarse_features(41, 3, 4800, 4800, 256, dtype=dtype)
+    want, mg = oracle_with_margins(f0.float(), f1.float(), (480, 640), (60, 80), (60, 80))
+    out = _run_coarse(f0, f1, (60, 80), (60, 80), IMPLS[impl], dtype)
+    same, near, bad = compare_match_lists(out, want, mg)
+    assert not bad, bad[:5]
+    assert len(near) <= 8, near
+    assert same > 6000
+    if not near:
+        tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
+        assert torch.allclose(out["mconf"], want["mconf"], rtol=tol, atol=0)
+        assert torch.equal(out["mkpts1_c"], want["mkpts1_c"])
+
+
+@pytest.mark.parametrize("impl", list(IMPLS))
+def test_coarse_hard_set_bf16(impl):
+    """Exact duplicates, near-duplicates and x50 rows (|S| in the hundreds) on bf16-rounded inputs."""
+    _need_tc(impl, 256, 40 * 48, 36 * 56)
+    f0, f1 = synth.hard_coarse_features(43, 2, 40 * 48, 36 * 56, 256, sigma=0.9, dtype=torch.bfloat16)
+    want, mg = oracle_with_margins(f0.float(), f1.float(), (320, 384), (40, 48), (36, 56))
+    out = _run_coarse(f0, f1, (40, 48), (36, 56), IMPLS[impl], torch.bfloat16)
+    same, near, bad = compare_match_lists(out, want, mg)
+    assert not bad, bad[:5]
+    assert same > 100
+
+
+@pytest.mark.parametrize("impl", list(IMPLS))
+def test_coarse_permutation_property_full_size(impl):
+    """Size-independent property at the benchmark size: f1 = P f0 with large norm -> the matches are exactly the
+    interior cells with j = P(i), mconf -> 1; sorted by (b, i); every j used once."""
+    _need_tc(impl)
+    n, h, w, C = 4, 60, 80, 256
+    L = h * w
+    g = torch.Generator().manual_seed(5)
+    f0 = (3.0 * torch.randn(n, L, C, generator=g)).to(torch.bfloat16)
+    f1 = torch.empty_like(f0)
+    perms = []
+    for b in range(n):
+        p = torch.randperm(L, generator=g)
+        f1[b, p] = f0[b]
+        perms.append(p)
+    out = _run_coarse(f0, f1, (h, w), (h, w), IMPLS[impl], torch.bfloat16)
+    keep = O._interior(h, w, 2)
+    want_b, want_i, want_j = [], [], []
+    for b in range(n):
+        i = torch.nonzero(keep & keep[perms[b]]).flatten()
+        want_b.append(torch.full_like(i, b)); want_i.append(i); want_j.append(perms[b][i])
+    assert torch.equal(out["b_ids"], torch.cat(want_b))
+    assert torch.equal(out["i_ids"], torch.cat(want_i))
+    assert torch.equal(out["j_ids"], torch.cat(want_j))
+    assert float(out["mconf"].min()) > 0.999
+    assert_sorted_by_pair_and_row(out["b_ids"], out["i_ids"], L)
+
+
+def test_coarse_edge_cases():
+    # grid too small for the border -> no match, empty tensors of the right shapes/dtypes
+    f0, f1 = synth.coarse_features(1, 1, 16, 16, 64, sigma=2.0)
+    out = _run_coarse(f0, f1, (4, 4), (4, 4), _lib.COARSE_SIMT, torch.float32)
+    assert out["b_ids"].shape == (0,) and out["mkpts0_c"].shape == (0, 2) and out["mconf"].dtype == torch.float32
+    # border_rm = 0 keeps everything the mutual test keeps
+    out0 = _run_coarse(f0, f1, (4, 4), (4, 4), _lib.COARSE_SIMT, torch.float32, border_rm=0)
+    want = O.coarse_match(f0, f1, (32, 32), (4, 4), (4, 4), border_rm=0)
+    assert torch.equal(out0["i_ids"], want["i_ids"]) and torch.equal(out0["j_ids"], want["j_ids"])
+    # status codes on a live GPU
+    with pytest.raises(_lib.PopeError):
+        ops.coarse_match(torch.zeros(1, 16, 60, device=DEV), torch.zeros(1, 16, 60, device=DEV), (4, 4), (4, 4), 8.0)
+    with pytest.raises(_lib.PopeError):
+        ops.coarse_match(torch.zeros(1, 16, 64, device=DEV), torch.zeros(1, 16, 64, device=DEV), (4, 5), (4, 4), 8.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("channels_last", [True, False])
+def test_fine_gather_golden(golden_dir, dtype, channels_last):
+    g = _load(golden_dir, "fine_preprocess")
+    meta = json.loads(str(g["meta"]))
+    case = COARSE_CASES[meta["coarse_case"]]
+    c = _load(golden_dir, meta["coarse_case"])
+    b_ids, i_ids, j_ids = (torch.from_numpy(c[k]).to(DEV) for k in ("b_ids", "i_ids", "j_ids"))
+    hw = case["hw0_c"]
+    ff0, ff1 = synth.fine_feature_maps(meta["fine_seed"], case["n"], hw[0] * 4, hw[1] * 4, 128, channels_last=channels_last)
+    a, b = ff0.to(DEV, dtype), ff1.to(DEV, dtype)
+    if channels_last:
+        a, b = a.contiguous(memory_format=torch.channels_last), b.contiguous(memory_format=torch.channels_last)
+    w0, w1 = ops.fine_gather(a, b, b_ids, i_ids, j_ids, hw[1], hw[1], 4, 5)
+    assert w0.shape == (b_ids.numel(), 25, 128) and w0.dtype == dtype
+    if dtype == torch.float32:       # a gather is bit-exact
+        np.testing.assert_array_equal(w0[: meta["kept"]].cpu().numpy(), g["win0"])
+        np.testing.assert_array_equal(w1[: meta["kept"]].cpu().numpy(), g["win1"])
+        np.testing.assert_allclose(w0.sum((1, 2)).cpu().numpy(), g["win0_sum"], rtol=1e-5, atol=1e-4)
+    else:
+        want0 = torch.from_numpy(g["win0"]).to(torch.bfloat16)
+        assert torch.equal(w0[: meta["kept"]].cpu(), want0)
+        assert torch.equal(w1[: meta["kept"]].cpu(), torch.from_numpy(g["win1"]).to(torch.bfloat16))
+
+
+def test_fine_gather_ragged_maps_and_device_count():
+    """Different map sizes for the two images, windows hanging over every border, and the device-side count."""
+    h0, w0, h1, w1, n = 7, 9, 5, 6, 3
+    ff0, _ = synth.fine_feature_maps(3, n, h0 * 4, w0 * 4, 128)
+    ff1, _ = synth.fine_feature_maps(4, n, h1 * 4, w1 * 4, 128)
+    g = torch.Generator().manual_seed(9)
+    M = 200
+    b = torch.randint(0, n, (M,), generator=g).sort()[0]
+    i = torch.randint(0, h0 * w0, (M,), generator=g)
+    j = torch.randint(0, h1 * w1, (M,), generator=g)
+    i[:4] = torch.tensor([0, w0 - 1, (h0 - 1) * w0, h0 * w0 - 1])
+    want0, want1 = O.fine_windows(ff0, b, i), O.fine_windows(ff1, b, j)
+    live = torch.tensor([150], dtype=torch.int32, device=DEV)
+    w0_, w1_ = ops.fine_gather(ff0.to(DEV), ff1.to(DEV), b.to(DEV), i.to(DEV), j.to(DEV), w0, w1, 4, 5, m_dev=live)
+    assert torch.equal(w0_[:150].cpu(), want0[:150]) and torch.equal(w1_[:150].cpu(), want1[:150])
+    full0, full1 = ops.fine_gather(ff0.to(DEV), ff1.to(DEV), b.to(DEV), i.to(DEV), j.to(DEV), w0, w1, 4, 5)
+    assert torch.equal(full0.cpu(), want0) and torch.equal(full1.cpu(), want1)
+
+
+@pytest.mark.parametrize("name", ["fine_match_soft", "fine_match_peaked"])
+def test_fine_match_golden(golden_dir, name):
+    g = _load(golden_dir, name)
+    meta = json.loads(str(g["meta"]))
+    a, b = synth.fine_windows(meta["seed"], meta["M"], 25, 128, gain=meta["gain"])
+    expec, mk1f = ops.fine_match(a.to(DEV), b.to(DEV), torch.from_numpy(g["mkpts1_c"]).to(DEV), 4.0)
+    np.testing.assert_allclose(expec[:, :2].cpu().numpy(), g["expec_f"][:, :2], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(expec[:, 2].cpu().numpy(), g["expec_f"][:, 2], rtol=1e-4, atol=2e-3)   # cancellation
+    np.testing.assert_allclose(mk1f.cpu().numpy(), g["mkpts1_f"], rtol=1e-4, atol=1e-5)
+    # bf16 windows against the oracle on the rounded values
+    a16, b16 = a.to(torch.bfloat16), b.to(torch.bfloat16)
+    want = O.fine_match(a16.float(), b16.float(), torch.from_numpy(g["mkpts0_c"]), torch.from_numpy(g["mkpts1_c"]), 2.0)
+    expec, mk1f = ops.fine_match(a16.to(DEV), b16.to(DEV), torch.from_numpy(g["mkpts1_c"]).to(DEV), 4.0)
+    assert torch.allclose(expec[:, :2].cpu(), want["expec_f"][:, :2], rtol=1e-2, atol=1e-5)
+    assert torch.allclose(mk1f.cpu(), want["mkpts1_f"], rtol=1e-2, atol=1e-4)
+
+
+def test_fine_match_known_answers():
+    M, WW, C = 25, 25, 128
+    w0 = torch.zeros(M, WW, C); w1 = torch.zeros(M, WW, C)
+    w0[:, 12, 0] = 100.0
+    for r in range(25):
+        w1[r, r, 0] = 100.0
+    expec, mk1f = ops.fine_match(w0.to(DEV), w1.to(DEV), torch.zeros(M, 2, device=DEV), 4.0)
+    lin = torch.linspace(-1, 1, 5)
+    want = torch.stack([lin.repeat(5), lin.repeat_interleave(5)], 1)
+    assert torch.allclose(expec[:, :2].cpu(), want, atol=1e-6)
+    assert torch.allclose(mk1f.cpu(), want * 4.0, atol=1e-5)
+    expec, _ = ops.fine_match(torch.zeros(3, WW, C, device=DEV), torch.zeros(3, WW, C, device=DEV),
+                              torch.zeros(3, 2, device=DEV), 4.0)
+    assert torch.allclose(expec[:, :2].cpu(), torch.zeros(3, 2), atol=1e-7)
+    assert torch.allclose(expec[:, 2].cpu(), torch.full((3,), 2 * 0.5 ** 0.5), atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cosine_topk_vs_oracle(dtype):
+    q, refs = synth.retrieval_tokens(7, 256, 384, dtype=dtype)
+    want = O.cosine_scores(q, refs)
+    ws, wi = O.running_topk(want.tolist(), 3)
+    scores, slot_s, slot_i = ops.cosine_topk(q.to(DEV), refs.to(DEV), 3)
+    assert torch.allclose(scores.cpu(), want, rtol=1e-5, atol=1e-6)
+    assert slot_i.cpu().tolist() == wi
+    assert torch.allclose(slot_s.cpu(), torch.tensor(ws), rtol=1e-5, atol=1e-6)
+    # nothing positive -> all slots empty, like the loop that starts from zeros
+    _, s, i = ops.cosine_topk(q.to(DEV), (-q).repeat(5, 1).to(DEV), 3)
+    assert i.cpu().tolist() == [-1, -1, -1] and s.cpu().tolist() == [0.0, 0.0, 0.0]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_hot_path_end_to_end_vs_oracle(dtype):
+    h0, w0, h1, w1, n = 30, 40, 24, 32, 3
+    f0, f1 = synth.coarse_features(51, n, h0 * w0, h1 * w1, 256, sigma=0.9, dtype=dtype)
+    ff0, _ = synth.fine_feature_maps(52, n, h0 * 4, w0 * 4, 128, dtype=dtype)
+    ff1, _ = synth.fine_feature_maps(53, n, h1 * 4, w1 * 4, 128, dtype=dtype)
+    want = O.match_pairs(f0.float(), f1.float(), ff0.float(), ff1.float(), (h0 * 8, w0 * 8), (h0, w0), (h1, w1))
+    res = ops.match_pairs_device(f0.to(DEV), f1.to(DEV), ff0.to(DEV), ff1.to(DEV), (h0 * 8, w0 * 8), (h0, w0), (h1, w1))
+    m = res.total()
+    assert m == want["b_ids"].numel()
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(res[k][:m].cpu(), want[k])
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
+    assert torch.allclose(res["mconf"][:m].cpu(), want["mconf"], rtol=tol, atol=0)
+    assert torch.equal(res["mkpts0_f"][:m].cpu(), want["mkpts0_f"])
+    assert torch.allclose(res["mkpts1_f"][:m].cpu(), want["mkpts1_f"], rtol=tol, atol=1e-3)
+    assert torch.allclose(res["expec_f"][:m, :2].cpu(), want["expec_f"][:, :2], rtol=tol, atol=1e-4)
+
+
+def test_matcher_module_flow_matches_oracle():
+    """The drop-in modules chained as Matcher.forward chains them (steps 3-5), weights shared with a CPU copy."""
+    import copy
+    import pope_b200
+    torch.manual_seed(0)
+    m_gpu = pope_b200.Matcher(pope_b200.make_default_cfg()).eval()
+    m_cpu = copy.deepcopy(m_gpu)
+    m_gpu = m_gpu.to(DEV)
+    h, w, n = 20, 24, 2
+    f0, f1 = synth.coarse_features(61, n, h * w, h * w, 256, sigma=0.85)
+    ff0, ff1 = synth.fine_feature_maps(62, n, h * 4, w * 4, 128, channels_last=False)
+    data = {"hw0_i": torch.Size([h * 8, w * 8]), "hw1_i": torch.Size([h * 8, w * 8]), "hw0_c": torch.Size([h, w]),
+            "hw1_c": torch.Size([h, w]), "hw0_f": torch.Size([h * 4, w * 4]), "hw1_f": torch.Size([h * 4, w * 4]), "bs": n}
+    with torch.no_grad():
+        m_gpu.coarse_matching(f0.to(DEV), f1.to(DEV), data)
+        w0, w1 = m_gpu.fine_preprocess(ff0.to(DEV), ff1.to(DEV), f0.to(DEV), f1.to(DEV), data)
+        w0, w1 = m_gpu.loftr_fine(w0, w1)
+        m_gpu.fine_matching(w0, w1, data)
+        # CPU: oracle for the hot-path stages, the same torch modules for the Linears / transformer
+        want = O.coarse_match(f0, f1, data["hw0_i"], (h, w), (h, w))
+        c0, c1 = O.fine_windows(ff0, want["b_ids"], want["i_ids"]), O.fine_windows(ff1, want["b_ids"], want["j_ids"])
+        cw = m_cpu.fine_preprocess.down_proj(torch.cat([f0[want["b_ids"], want["i_ids"]], f1[want["b_ids"], want["j_ids"]]], 0))
+        mg = m_cpu.fine_preprocess.merge_feat(torch.cat([torch.cat([c0, c1], 0), cw[:, None].expand(-1, 25, -1)], -1))
+        c0, c1 = m_cpu.loftr_fine(*mg.chunk(2, 0))
+        wf = O.fine_match(c0, c1, want["mkpts0_c"], want["mkpts1_c"], 2.0)
+    keys = list(data.keys())
+    assert keys[7:] == ["b_ids", "i_ids", "j_ids", "gt_mask", "m_bids", "mkpts0_c", "mkpts1_c", "mconf", "W", "expec_f",
+                        "mkpts0_f", "mkpts1_f"]
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(data[k].cpu(), want[k])
+    assert data["W"] == 5
+    assert torch.allclose(data["mconf"].cpu(), want["mconf"], rtol=1e-4)
+    assert torch.allclose(data["mkpts1_f"].cpu(), wf["mkpts1_f"], rtol=1e-4, atol=2e-3)
+    assert torch.equal(data["mkpts0_f"].cpu(), wf["mkpts0_f"])
+
+
+def test_matcher_forward_images_and_empty_result():
+    import pope_b200
+    m = pope_b200.Matcher(pope_b200.make_default_cfg()).eval().to(DEV)
+    batch = {"image0": torch.rand(2, 1, 96, 128, device=DEV), "image1": torch.rand(2, 1, 64, 64, device=DEV)}
+    with torch.no_grad():
+        assert m(batch) is None
+    assert batch["mkpts0_f"].shape[1] == 2 and batch["mkpts0_f"].shape == batch["mkpts1_f"].shape
+    assert batch["expec_f"].shape[1] == 3 and batch["b_ids"].dtype == torch.int64
+    with torch.no_grad():
+        fc0, fc1 = m({"image0": batch["image0"], "image1": batch["image1"]}, only_att_fea=True)
+    assert fc0.shape == (2, 12 * 16, 256) and fc1.shape == (2, 8 * 8, 256)
+
+
+def test_host_pipeline_equals_device_path():
+    """pope_match_pairs_host (pinned host buffers, chunked streams) returns what the device path returns."""
+    from pope_b200 import driver
+    h, w, n = 20, 24, 5
+    f0, f1 = synth.coarse_features(71, n, h * w, h * w, 256, sigma=0.85, dtype=torch.bfloat16)
+    ff0, ff1 = synth.fine_feature_maps(72, n, h * 4, w * 4, 128, dtype=torch.bfloat16)
+    res = ops.match_pairs_device(f0.to(DEV), f1.to(DEV), ff0.to(DEV), ff1.to(DEV), (h * 8, w * 8), (h, w), (h, w))
+    m = res.total()
+    out = driver.match_pairs_host(f0, f1, ff0, ff1, (h * 8, w * 8), (h, w), (h, w), chunk_pairs=2, device=0)
+    assert int(out["counts"].sum()) == m
+    cat = driver.flatten_slots(out)
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(cat[k], res[k][:m].cpu()), k
+    assert torch.equal(cat["mconf"], res["mconf"][:m].cpu())
+    assert torch.equal(cat["mkpts0_f"], res["mkpts0_f"][:m].cpu())
+    assert torch.equal(cat["mkpts1_f"], res["mkpts1_f"][:m].cpu())

@@ -1,0 +1,105 @@
+"""Host-side logic that needs no GPU: drop-in surface, state-dict layout, C-ABI loading and argument checking."""
+import ctypes as C
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import pope_b200
+from pope_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def layout(golden_dir):
+    with open(os.path.join(golden_dir, "matcher_layout.json")) as f:
+        return json.load(f)
+
+
+def test_default_cfg_equals_reference(layout):
+    assert json.loads(json.dumps(pope_b200.default_cfg)) == layout["default_cfg"]
+
+
+def test_state_dict_layout_equals_reference(layout):
+    m = pope_b200.Matcher(pope_b200.make_default_cfg()).eval()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(layout["state_dict"].keys())
+    assert {k: list(v.shape) for k, v in sd.items()} == layout["state_dict"]
+    assert sum(p.numel() for p in m.parameters()) == layout["n_params"]
+    for name in ("backbone", "pos_encoding", "loftr_coarse", "coarse_matching", "fine_preprocess", "loftr_fine",
+                 "fine_matching"):
+        assert hasattr(m, name)
+
+
+def test_load_state_dict_strips_matcher_prefix():
+    a = pope_b200.Matcher(pope_b200.make_default_cfg())
+    b = pope_b200.Matcher(pope_b200.make_default_cfg())
+    sd = {"matcher." + k: v for k, v in a.state_dict().items()}
+    res = b.load_state_dict(sd, strict=False)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert all(torch.equal(v, b.state_dict()[k]) for k, v in a.state_dict().items())
+
+
+def test_matcher_constructor_does_not_mutate_config():
+    cfg = pope_b200.make_default_cfg()
+    before = json.dumps(cfg, sort_keys=True)
+    pope_b200.Matcher(cfg)
+    assert json.dumps(cfg, sort_keys=True) == before
+
+
+def test_hot_path_has_no_cpu_fallback():
+    cm = pope_b200.CoarseMatching(pope_b200.default_cfg["match_coarse"]).eval()
+    data = {"hw0_i": (64, 64), "hw0_c": (8, 8), "hw1_c": (8, 8)}
+    with pytest.raises(_lib.PopeError):
+        cm(torch.randn(1, 64, 256), torch.randn(1, 64, 256), data)           # CPU tensors are rejected
+    with pytest.raises(_lib.PopeError):
+        pope_b200.FineMatching().eval()(torch.randn(4, 25, 128), torch.randn(4, 25, 128),
+                                        {"hw0_i": (64, 64), "hw0_f": (32, 32), "mconf": torch.ones(4),
+                                         "mkpts0_c": torch.zeros(4, 2), "mkpts1_c": torch.zeros(4, 2)})
+    with pytest.raises(NotImplementedError):
+        cm(torch.randn(1, 64, 256), torch.randn(1, 64, 256), data, mask_c0=torch.ones(1, 64), mask_c1=torch.ones(1, 64))
+
+
+def test_product_package_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pope_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "ref_shim" not in src, f
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "pope_b200.h")).read()
+    declared = set(re.findall(r"\b(pope_[a-z_0-9]+)\s*\(", header))
+    declared -= {"pope_pipeline"}        # the opaque struct tag
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    h = _lib.lib()                        # raises if the .so is missing or lacks a symbol
+    for name in declared:
+        assert getattr(h, name) is not None
+    assert h.pope_abi_version() == 1
+    assert h.pope_status_string(0) == b"ok"
+
+
+def test_argument_errors_are_reported_before_touching_the_gpu():
+    h = _lib.lib()
+    assert h.pope_coarse_workspace_bytes(0, 10, 10) == 0
+    need = h.pope_coarse_workspace_bytes(2, 4800, 4800)
+    assert need >= 2 * 4800 * (8 + 8 + 4 + 4)
+    # null pointers / bad sizes / bad dtype: negative status, no CUDA call is made
+    args_ok = [1, 1, 0, 1, 64, 64, 256, 8, 8, 8, 8, 8.0, 0.1, 0.2, 2, 0, 1, need, 1, 1, 1, 1, 1, 1, 1, 64, None]
+    bad = list(args_ok); bad[0] = None
+    assert h.pope_coarse_match(*bad) == -1
+    bad = list(args_ok); bad[2] = 7
+    assert h.pope_coarse_match(*bad) == -2
+    bad = list(args_ok); bad[6] = 250
+    assert h.pope_coarse_match(*bad) == -4
+    bad = list(args_ok); bad[7] = 9           # h0c*w0c != L
+    assert h.pope_coarse_match(*bad) == -1
+    assert h.pope_fine_match(None, None, 0, 4, None, 25, 64, None, 4.0, None, None, None) == -4
+    assert h.pope_fine_match(None, None, 0, 0, None, 25, 128, None, 4.0, None, None, None) == 0     # M == 0 is a no-op
+    assert h.pope_cosine_topk(None, None, 0, 4, 4, 3, 1e-8, None, None, None, None) == -1
+    assert b"workspace" in h.pope_status_string(-3)
