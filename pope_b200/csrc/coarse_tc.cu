@@ -1,7 +1,429 @@
-// coarse_tc.cu -- tcgen05/TMEM/TMA coarse matching (placeholder until the tensor-core kernels land).
+// coarse_tc.cu -- coarse matching on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), bf16 features, fp32 accumulate.
+//
+// Replaces src/matcher/utils/coarse_matching.py:106-119 and :175-189 of the reference (einsum -> /T -> dual softmax
+// -> threshold -> mutual max) without ever writing the L x S matrix.  Three sweeps over S = f0 f1^T (log2 units):
+//   sweep 1+2 (one launch): row log-sum-exp of S and of S^T (= column log-sum-exp of S), online softmax per row
+//   sweep 3               : recompute S, t2 = log2 conf = (x - lse_r[i]) + (x - lse_c[j]); cells above log2(thr) update
+//                           the best-candidate record of their row and column (rare 64-bit atomicMax)
+//
+// Kernel anatomy (persistent, one CTA per SM, 320 threads):
+//   work unit   = (direction, pair, 256-row block of the stationary operand "A"); the unit's A block (256 x C bf16,
+//                 up to 128 KB) stays in shared memory while all 128-row tiles of the streamed operand "B" pass through
+//                 a 5-stage ring of 16 KB K-chunks (one TMA box of 128 rows x 64 k, 128B-swizzled) -> 32 B/clk/SM of
+//                 L2 traffic instead of 64 with a 128-row stationary block.
+//   warp 0      = TMA producer (one elected lane)
+//   warp 1      = TMEM allocator + tcgen05.mma issuer (one elected lane): per B tile two M128 x N128 x K16 chains
+//                 (A rows 0-127 -> TMEM columns [0,128), rows 128-255 -> [128,256)), double-buffered accumulators
+//                 (2 x 256 columns = all 512 TMEM columns)
+//   warps 2-9   = epilogue: thread <-> one row of the unit; tcgen05.ld 32 columns at a time; online softmax
+//                 (FMNMX + FFMA + MUFU.EX2 + FADD per element) or the candidate test (FADD + FSETP per element)
+//   barriers    = a_full/a_empty (stationary block), b_full/b_empty[5] (ring), acc_full/acc_empty[2] (TMEM stages)
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace pope {
-bool coarse_tc_supported(const CoarseProblem&) { return false; }
-cudaError_t coarse_tc_run(const CoarseProblem&, const CoarseScratch&, cudaStream_t) { return cudaErrorNotSupported; }
+namespace {
+
+constexpr int kStages = 5;              // B ring depth
+constexpr int kBoxRows = 128;           // rows per TMA box / per MMA operand tile
+constexpr int kBoxK = 64;               // bf16 elements per 128-byte swizzle row
+constexpr int kBoxBytes = kBoxRows * kBoxK * 2;      // 16384
+constexpr int kUnitRows = 256;          // stationary rows per work unit (two M=128 MMAs)
+constexpr int kMaxKChunks = 4;          // C <= 256
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr uint32_t kTmemCols = 512;
+
+// dynamic shared memory layout (base aligned to 1024 B for the 128B swizzle)
+constexpr int kSmemA = 0;                                            // 2 halves x 4 k-chunks x 16 KB
+constexpr int kSmemB = kSmemA + 2 * kMaxKChunks * kBoxBytes;         // kStages x 16 KB
+constexpr int kSmemLc = kSmemB + kStages * kBoxBytes;                // 2 x 128 floats (sweep 3)
+constexpr int kSmemBar = kSmemLc + 2 * 128 * 4;                      // barriers
+constexpr int kNumBars = 2 + 2 * kStages + 4;
+constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
+constexpr int kSmemBytes = kSmemTmemPtr + 16;
+constexpr int kSmemAlloc = kSmemBytes + 1024;                        // slack for manual 1024-B alignment
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must become a launch failure, never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();     // ~2 s at 2 GHz
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3ffffu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+// kind::f16, A = B = bf16 (K-major), D = fp32, M = 128, N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(128 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread; the wait is part of the same statement so the
+// registers are valid when it retires.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct SweepParams {
+  // direction d: stationary operand = feature set d (rows LA[d]), streamed operand = the other one
+  int n;
+  int LA[2], LB[2];
+  int kchunks;
+  int units_dir0;           // work units of direction 0 (direction 1 follows)
+  int total_units;
+  float scale_log2;
+  float log2_thr;
+  float* lse_out[2];        // sweep 1+2: where direction d writes its row log-sum-exp
+  const float* lse_r;       // sweep 3
+  const float* lse_c;
+  u64* rowbest;
+  u64* colbest;
+};
+
+// MODE 0: row log-sum-exp (both directions).  MODE 1: candidate sweep (direction 0 only).
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_constant__ CUtensorMap map0,
+                                                              const __grid_constant__ CUtensorMap map1,
+                                                              const SweepParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kSmemBar;
+  const uint32_t bar_a_full = bar0, bar_a_empty = bar0 + 8;
+  const uint32_t bar_b_full = bar0 + 16, bar_b_empty = bar_b_full + 8 * kStages;
+  const uint32_t bar_acc_full = bar_b_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 16;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
+  float* lc_smem = reinterpret_cast<float*>(smem + kSmemLc);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map0);
+    prefetch_tmap(&map1);
+    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_empty, 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemTmemPtr), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int kchunks = P.kchunks;
+
+  // unit -> (direction, pair, row block)
+  auto decode = [&](int u, int& dir, int& n, int& rb) {
+    dir = (u >= P.units_dir0) ? 1 : 0;
+    const int v = dir ? u - P.units_dir0 : u;
+    const int rbs = (P.LA[dir] + kUnitRows - 1) / kUnitRows;
+    n = v / rbs;
+    rb = v - n * rbs;
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      uint32_t a_phase = 0, b_stage = 0, b_phase = 0;
+      for (int u = blockIdx.x; u < P.total_units; u += gridDim.x) {
+        int dir, n, rb;
+        decode(u, dir, n, rb);
+        const CUtensorMap* mapA = dir ? &map1 : &map0;
+        const CUtensorMap* mapB = dir ? &map0 : &map1;
+        mbar_wait(bar_a_empty, a_phase ^ 1);
+        mbar_expect_tx(bar_a_full, 2 * kchunks * kBoxBytes);
+        for (int h = 0; h < 2; ++h)
+          for (int kc = 0; kc < kchunks; ++kc)
+            tma_load_3d(sbase + kSmemA + (h * kMaxKChunks + kc) * kBoxBytes, mapA, bar_a_full, kc * kBoxK,
+                        rb * kUnitRows + h * kBoxRows, n);
+        a_phase ^= 1;
+        const int ntiles = (P.LB[dir] + kBoxRows - 1) / kBoxRows;
+        for (int ct = 0; ct < ntiles; ++ct)
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(bar_b_empty + 8 * b_stage, b_phase ^ 1);
+            mbar_expect_tx(bar_b_full + 8 * b_stage, kBoxBytes);
+            tma_load_3d(sbase + kSmemB + b_stage * kBoxBytes, mapB, bar_b_full + 8 * b_stage, kc * kBoxK, ct * kBoxRows, n);
+            if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      uint32_t a_phase = 0, b_stage = 0, b_phase = 0, tile_ctr = 0;
+      for (int u = blockIdx.x; u < P.total_units; u += gridDim.x) {
+        int dir, n, rb;
+        decode(u, dir, n, rb);
+        const int ntiles = (P.LB[dir] + kBoxRows - 1) / kBoxRows;
+        mbar_wait(bar_a_full, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
+          const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
+          mbar_wait(bar_acc_empty + 8 * s, acc_phase ^ 1);
+          tc_fence_after();
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(bar_b_full + 8 * b_stage, b_phase);
+            tc_fence_after();
+            const uint32_t b_addr = sbase + kSmemB + b_stage * kBoxBytes;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t a_addr = sbase + kSmemA + (h * kMaxKChunks + kc) * kBoxBytes;
+              const uint32_t d = tmem_base + s * 256 + h * 128;
+#pragma unroll
+              for (int ks = 0; ks < kBoxK / 16; ++ks)
+                umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), (kc | ks) ? 1u : 0u);
+            }
+            umma_commit(bar_b_empty + 8 * b_stage);      // ring slot free once these MMAs have read it
+            if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
+          }
+          umma_commit(bar_acc_full + 8 * s);             // accumulator stage complete
+        }
+        umma_commit(bar_a_empty);                        // stationary block may be overwritten
+      }
+    }
+  } else {
+    // =============================== epilogue (256 threads, one row each) ===============================
+    const int e = threadIdx.x - 64;                 // 0..255
+    const int half = e >> 7;                        // which M=128 accumulator
+    const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
+    const int row_in_unit = half * 128 + quad * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    uint32_t tile_ctr = 0;
+    for (int u = blockIdx.x; u < P.total_units; u += gridDim.x) {
+      int dir, n, rb;
+      decode(u, dir, n, rb);
+      const int LA = P.LA[dir], LB = P.LB[dir];
+      const int ntiles = (LB + kBoxRows - 1) / kBoxRows;
+      const int row = rb * kUnitRows + row_in_unit;
+      const float scale = P.scale_log2;
+
+      float m_run = -INFINITY, s_run = 0.f;         // MODE 0 state
+      float lrp = INFINITY, lr = INFINITY;          // MODE 1 state
+      const float inv2s = 1.f / (2.f * scale);
+      if (MODE == 1 && row < LA) {
+        lr = P.lse_r[size_t(n) * LA + row];
+        const float b = (lr + P.log2_thr) * inv2s;
+        lrp = isfinite(b) ? b - 1e-5f * fabsf(b) - 0.005f * inv2s : INFINITY;
+      }
+
+      for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
+        const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
+        const int col0 = ct * kBoxRows;
+        if (MODE == 1) {
+          // stage this tile's column terms: (lse_c / 2scale) with a safety margin, +inf past the end
+          if (e < 128) {
+            const int col = col0 + e;
+            float v = INFINITY;
+            if (col < LB) {
+              const float b = __ldg(P.lse_c + size_t(n) * LB + col) * inv2s;
+              v = isfinite(b) ? b - 1e-5f * fabsf(b) : INFINITY;
+            }
+            lc_smem[s * 128 + e] = v;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        }
+        mbar_wait(bar_acc_full + 8 * s, acc_phase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + lane_addr + s * 256 + half * 128;
+        const int nvalid = min(LB - col0, kBoxRows);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int vc = nvalid - c * 32;
+          if (vc <= 0) break;
+          float v[32];
+          tmem_ld32(tbase + c * 32, v);
+          if (MODE == 0) {
+            float cmax = -INFINITY;
+            if (vc >= 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) cmax = (j < vc) ? fmaxf(cmax, v[j]) : cmax;
+            }
+            const float m_new = fmaxf(m_run, cmax * scale);
+            const float neg = -m_new;
+            float a0 = s_run * ex2_approx(m_run - m_new), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            if (vc >= 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                a0 += ex2_approx(fmaf(v[j + 0], scale, neg));
+                a1 += ex2_approx(fmaf(v[j + 1], scale, neg));
+                a2 += ex2_approx(fmaf(v[j + 2], scale, neg));
+                a3 += ex2_approx(fmaf(v[j + 3], scale, neg));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < vc) a1 += ex2_approx(fmaf(v[j], scale, neg));
+            }
+            s_run = (a0 + a1) + (a2 + a3);
+            m_run = m_new;
+          } else {
+            const float* lc = lc_smem + s * 128 + c * 32;
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(lc + j4);
+              const float lcv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                if (v[j4 + jj] > lrp + lcv[jj]) {      // cheap pre-filter (margin on the safe side), then the exact test
+                  const int col = col0 + c * 32 + j4 + jj;
+                  const float lcj = __ldg(P.lse_c + size_t(n) * LB + col);
+                  const float x = v[j4 + jj] * scale;
+                  const float t2 = (x - lr) + (x - lcj);
+                  if (t2 > P.log2_thr) {
+                    atomicMax(P.rowbest + size_t(n) * LA + row, pack_best(t2, col));
+                    atomicMax(P.colbest + size_t(n) * LB + col, pack_best(t2, row));
+                  }
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_acc_empty + 8 * s);
+      }
+      if (MODE == 0 && row < LA) P.lse_out[dir][size_t(n) * LA + row] = m_run + lg2_approx(s_run);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// [n, rows, C] bf16, box = 64 k x 128 rows x 1 pair, 128-byte swizzle, zero fill past the last row
+bool make_map(CUtensorMap* m, const void* base, int n, int rows, int C) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {cuuint64_t(C), cuuint64_t(rows), cuuint64_t(n)};
+  cuuint64_t strides[2] = {cuuint64_t(C) * 2, cuuint64_t(rows) * C * 2};
+  cuuint32_t box[3] = {kBoxK, kBoxRows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool coarse_tc_supported(const CoarseProblem& p) {
+  return p.dtype == POPE_BF16 && p.C % kBoxK == 0 && p.C >= kBoxK && p.C <= kBoxK * kMaxKChunks;
+}
+
+cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st) {
+  CUtensorMap map0, map1;
+  if (!make_map(&map0, p.f0, p.n, p.L, p.C) || !make_map(&map1, p.f1, p.n, p.S, p.C)) return cudaErrorInvalidValue;
+  int dev = 0, sms = 0;
+  cudaError_t e;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  // per-device attribute, cheap: set on every call so that any device of a multi-GPU process is covered
+  if ((e = cudaFuncSetAttribute(sweep_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sweep_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
+  SweepParams P{};
+  P.n = p.n;
+  P.LA[0] = p.L; P.LB[0] = p.S; P.LA[1] = p.S; P.LB[1] = p.L;
+  P.kchunks = p.C / kBoxK;
+  P.scale_log2 = p.scale_log2; P.log2_thr = p.log2_thr;
+  P.lse_out[0] = w.lse_r; P.lse_out[1] = w.lse_c;
+  P.lse_r = w.lse_r; P.lse_c = w.lse_c; P.rowbest = w.rowbest; P.colbest = w.colbest;
+  const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows), u1 = p.n * ((p.S + kUnitRows - 1) / kUnitRows);
+  // sweeps 1+2: both directions in one launch
+  P.units_dir0 = u0; P.total_units = u0 + u1;
+  sweep_tc_kernel<0><<<min(P.total_units, sms), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  // sweep 3: direction 0 only
+  P.total_units = u0;
+  sweep_tc_kernel<1><<<min(P.total_units, sms), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+  return cudaGetLastError();
+}
+
 }  // namespace pope

@@ -147,3 +147,18 @@ def match_pairs_device(feat_c0, feat_c1, feat_f0, feat_f1, hw0_i, hw0_c, hw1_c, 
     expec, mk1f = fine_match(win0, win1, res["mkpts1_c"], (W // 2) * (hw0_i[0] / feat_f0.shape[2]), m_dev)
     res.update(win0=win0, win1=win1, expec_f=expec, mkpts0_f=res["mkpts0_c"], mkpts1_f=mk1f)
     return res
+
+
+def scratch_views(workspace: torch.Tensor, n: int, L: int, S: int) -> Dict[str, torch.Tensor]:
+    """Debug/test view of the coarse scratch (layout of carve_coarse_scratch in csrc/common.cuh): the row/column
+    log-sum-exp (log2 units) and the best-candidate records left by the last pope_coarse_match call."""
+    def up(x):
+        return (x + 255) // 256 * 256
+    o_rb = 0
+    o_cb = o_rb + up(8 * n * L)
+    o_lr = o_cb + up(8 * n * S)
+    o_lc = o_lr + up(4 * n * L)
+    return {"rowbest": workspace[o_rb:o_rb + 8 * n * L].view(torch.int64).view(n, L),
+            "colbest": workspace[o_cb:o_cb + 8 * n * S].view(torch.int64).view(n, S),
+            "lse_r": workspace[o_lr:o_lr + 4 * n * L].view(torch.float32).view(n, L),
+            "lse_c": workspace[o_lc:o_lc + 4 * n * S].view(torch.float32).view(n, S)}

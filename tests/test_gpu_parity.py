@@ -60,6 +60,10 @@ def test_coarse_golden(golden_dir, name, impl):
             for k in ("b_ids", "i_ids", "j_ids"):
                 assert out[k].dtype == torch.int64 and torch.equal(out[k], want[k]), k
             tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
+            if case["kind"] == "hard":
+                # |S| reaches several hundred here: one fp32 ulp of S is ~3e-5 and conf = exp(2S - lse_r - lse_c)
+                # inherits it on BOTH sides (the reference's fp32 einsum included), so 1e-4 is not attainable
+                tol = 5e-4
             np.testing.assert_allclose(out["mconf"].numpy(), g["mconf"], rtol=tol, atol=0)
             np.testing.assert_array_equal(out["mkpts0_c"].numpy(), g["mkpts0_c"])
             np.testing.assert_array_equal(out["mkpts1_c"].numpy(), g["mkpts1_c"])
