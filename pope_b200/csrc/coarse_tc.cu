@@ -6,7 +6,7 @@
 //   sweep 3               : recompute S, t2 = log2 conf = (x - lse_r[i]) + (x - lse_c[j]); cells above log2(thr) update
 //                           the best-candidate record of their row and column (rare 64-bit atomicMax)
 //
-// Kernel anatomy (persistent, one CTA per SM, 320 threads):
+// Kernel anatomy (persistent, one CTA per SM, 576 threads):
 //   work unit   = (direction, pair, 256-row block of the stationary operand "A"); the unit's A block (256 x C bf16,
 //                 up to 128 KB) stays in shared memory while all 128-row tiles of the streamed operand "B" pass through
 //                 a 5-stage ring of 16 KB K-chunks (one TMA box of 128 rows x 64 k, 128B-swizzled) -> 32 B/clk/SM of
@@ -15,8 +15,9 @@
 //   warp 1      = TMEM allocator + tcgen05.mma issuer (one elected lane): per B tile two M128 x N128 x K16 chains
 //                 (A rows 0-127 -> TMEM columns [0,128), rows 128-255 -> [128,256)), double-buffered accumulators
 //                 (2 x 256 columns = all 512 TMEM columns)
-//   warps 2-9   = epilogue: thread <-> one row of the unit; tcgen05.ld 32 columns at a time; online softmax
-//                 (FMNMX + FFMA + MUFU.EX2 + FADD per element) or the candidate test (FADD + FSETP per element)
+//   warps 2-17  = epilogue: two threads per row of the unit (64 of the tile's 128 columns each); tcgen05.ld 32 columns
+//                 at a time; online softmax (FMNMX + FFMA + MUFU.EX2 + FADD per element) or the candidate test
+//                 (FADD + FSETP per element, one warp vote per 32x32 block)
 //   barriers    = a_full/a_empty (stationary block), b_full/b_empty[5] (ring), acc_full/acc_empty[2] (TMEM stages)
 #include <cuda.h>
 
@@ -31,15 +32,16 @@ constexpr int kBoxK = 64;               // bf16 elements per 128-byte swizzle ro
 constexpr int kBoxBytes = kBoxRows * kBoxK * 2;      // 16384
 constexpr int kUnitRows = 256;          // stationary rows per work unit (two M=128 MMAs)
 constexpr int kMaxKChunks = 4;          // C <= 256
-constexpr int kThreads = 320;
-constexpr int kEpiThreads = 256;
+constexpr int kEpiThreads = 512;       // 16 epilogue warps: 4 per scheduler keep the MUFU pipe fed
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kTmemCols = 512;
 
 // dynamic shared memory layout (base aligned to 1024 B for the 128B swizzle)
 constexpr int kSmemA = 0;                                            // 2 halves x 4 k-chunks x 16 KB
 constexpr int kSmemB = kSmemA + 2 * kMaxKChunks * kBoxBytes;         // kStages x 16 KB
-constexpr int kSmemLc = kSmemB + kStages * kBoxBytes;                // 2 x 128 floats (sweep 3)
-constexpr int kSmemBar = kSmemLc + 2 * 128 * 4;                      // barriers
+constexpr int kSmemLc = kSmemB + kStages * kBoxBytes;                // sweep 3: 2 stages x 128 x {bound, exact} floats
+constexpr int kSmemMerge = kSmemLc + 2 * 2 * 128 * 4;                // sweep 1+2: 256 x (max, sum)
+constexpr int kSmemBar = kSmemMerge + 256 * 8;                       // barriers
 constexpr int kNumBars = 2 + 2 * kStages + 4;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
 constexpr int kSmemBytes = kSmemTmemPtr + 16;
@@ -127,18 +129,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 struct SweepParams {
   // direction d: stationary operand = feature set d (rows LA[d]), streamed operand = the other one
   int n;
-  int LA[2], LB[2];
+  int L0, L1;               // rows of feature set 0 / 1; direction d has LA = L_d, LB = L_(1-d)
   int kchunks;
   int units_dir0;           // work units of direction 0 (direction 1 follows)
   int total_units;
   float scale_log2;
   float log2_thr;
-  float* lse_out[2];        // sweep 1+2: where direction d writes its row log-sum-exp
+  float* lse_out0;          // sweep 1+2: where direction 0 / 1 writes its row log-sum-exp
+  float* lse_out1;
   const float* lse_r;       // sweep 3
   const float* lse_c;
   u64* rowbest;
   u64* colbest;
 };
+
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
+  return __uint_as_float(r);
+}
 
 // MODE 0: row log-sum-exp (both directions).  MODE 1: candidate sweep (direction 0 only).
 template <int MODE>
@@ -153,7 +162,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   const uint32_t bar_b_full = bar0 + 16, bar_b_empty = bar_b_full + 8 * kStages;
   const uint32_t bar_acc_full = bar_b_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 16;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
-  float* lc_smem = reinterpret_cast<float*>(smem + kSmemLc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   auto decode = [&](int u, int& dir, int& n, int& rb) {
     dir = (u >= P.units_dir0) ? 1 : 0;
     const int v = dir ? u - P.units_dir0 : u;
-    const int rbs = (P.LA[dir] + kUnitRows - 1) / kUnitRows;
+    const int rbs = ((dir ? P.L1 : P.L0) + kUnitRows - 1) / kUnitRows;
     n = v / rbs;
     rb = v - n * rbs;
   };
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
             tma_load_3d(sbase + kSmemA + (h * kMaxKChunks + kc) * kBoxBytes, mapA, bar_a_full, kc * kBoxK,
                         rb * kUnitRows + h * kBoxRows, n);
         a_phase ^= 1;
-        const int ntiles = (P.LB[dir] + kBoxRows - 1) / kBoxRows;
+        const int ntiles = ((dir ? P.L0 : P.L1) + kBoxRows - 1) / kBoxRows;
         for (int ct = 0; ct < ntiles; ++ct)
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(bar_b_empty + 8 * b_stage, b_phase ^ 1);
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
       for (int u = blockIdx.x; u < P.total_units; u += gridDim.x) {
         int dir, n, rb;
         decode(u, dir, n, rb);
-        const int ntiles = (P.LB[dir] + kBoxRows - 1) / kBoxRows;
+        const int ntiles = ((dir ? P.L0 : P.L1) + kBoxRows - 1) / kBoxRows;
         mbar_wait(bar_a_full, a_phase);
         a_phase ^= 1;
         tc_fence_after();
@@ -248,17 +256,22 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
       }
     }
   } else {
-    // =============================== epilogue (256 threads, one row each) ===============================
-    const int e = threadIdx.x - 64;                 // 0..255
-    const int half = e >> 7;                        // which M=128 accumulator
+    // =============================== epilogue (16 warps; two threads per row, 64 columns of the tile each) ==========
+    const int e = threadIdx.x - 64;                 // 0..511
+    const int grp = (warp - 2) >> 2;                // 4 consecutive warps = one full set of TMEM lane quadrants
+    const int half = grp & 1;                       // which M=128 accumulator (rows 0-127 / 128-255 of the unit)
+    const int colhalf = grp >> 1;                   // which 64 of the tile's 128 columns
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
     const int row_in_unit = half * 128 + quad * 32 + lane;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    float* lc_bound = reinterpret_cast<float*>(smem + kSmemLc);          // [2][128] pre-filter bounds
+    float* lc_exact = lc_bound + 2 * 128;                                // [2][128] exact column log-sum-exp
+    float2* merge = reinterpret_cast<float2*>(smem + kSmemMerge);        // [256] (max, sum) of the upper column half
     uint32_t tile_ctr = 0;
     for (int u = blockIdx.x; u < P.total_units; u += gridDim.x) {
       int dir, n, rb;
       decode(u, dir, n, rb);
-      const int LA = P.LA[dir], LB = P.LB[dir];
+      const int LA = dir ? P.L1 : P.L0, LB = dir ? P.L0 : P.L1;
       const int ntiles = (LB + kBoxRows - 1) / kBoxRows;
       const int row = rb * kUnitRows + row_in_unit;
       const float scale = P.scale_log2;
@@ -266,25 +279,28 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
       float m_run = -INFINITY, s_run = 0.f;         // MODE 0 state
       float lrp = INFINITY, lr = INFINITY;          // MODE 1 state
       const float inv2s = 1.f / (2.f * scale);
-      if (MODE == 1 && row < LA) {
-        lr = P.lse_r[size_t(n) * LA + row];
-        const float b = (lr + P.log2_thr) * inv2s;
-        lrp = isfinite(b) ? b - 1e-5f * fabsf(b) - 0.005f * inv2s : INFINITY;
+      float lc_next = INFINITY;
+      if (MODE == 1) {
+        if (row < LA) {
+          lr = P.lse_r[size_t(n) * LA + row];
+          const float b = (lr + P.log2_thr) * inv2s;
+          lrp = isfinite(b) ? b - 1e-5f * fabsf(b) - 0.005f * inv2s : INFINITY;
+        }
+        if (e < 128 && e < LB) lc_next = __ldg(P.lse_c + size_t(n) * LB + e);
       }
 
       for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
         const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
         const int col0 = ct * kBoxRows;
         if (MODE == 1) {
-          // stage this tile's column terms: (lse_c / 2scale) with a safety margin, +inf past the end
+          // stage this tile's column terms (fetched one tile ahead): exact value and a pre-filter bound
+          // (lse_c / 2scale, margin on the safe side); +inf past the last column
           if (e < 128) {
-            const int col = col0 + e;
-            float v = INFINITY;
-            if (col < LB) {
-              const float b = __ldg(P.lse_c + size_t(n) * LB + col) * inv2s;
-              v = isfinite(b) ? b - 1e-5f * fabsf(b) : INFINITY;
-            }
-            lc_smem[s * 128 + e] = v;
+            const float b = lc_next * inv2s;
+            lc_exact[s * 128 + e] = lc_next;
+            lc_bound[s * 128 + e] = isfinite(b) ? b - 1e-5f * fabsf(b) : INFINITY;
+            const int coln = col0 + kBoxRows + e;
+            lc_next = (coln < LB) ? __ldg(P.lse_c + size_t(n) * LB + coln) : INFINITY;
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
@@ -293,17 +309,23 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         const uint32_t tbase = tmem_base + lane_addr + s * 256 + half * 128;
         const int nvalid = min(LB - col0, kBoxRows);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = colhalf * 2 + cc;
           const int vc = nvalid - c * 32;
           if (vc <= 0) break;
           float v[32];
           tmem_ld32(tbase + c * 32, v);
           if (MODE == 0) {
-            float cmax = -INFINITY;
+            float cmax;
             if (vc >= 32) {
+              float q0 = v[0], q1 = v[1], q2 = v[2], q3 = v[3];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
+              for (int j = 4; j < 32; j += 4) {
+                q0 = fmaxf(q0, v[j]); q1 = fmaxf(q1, v[j + 1]); q2 = fmaxf(q2, v[j + 2]); q3 = fmaxf(q3, v[j + 3]);
+              }
+              cmax = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
             } else {
+              cmax = -INFINITY;
 #pragma unroll
               for (int j = 0; j < 32; ++j) cmax = (j < vc) ? fmaxf(cmax, v[j]) : cmax;
             }
@@ -326,19 +348,31 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
             s_run = (a0 + a1) + (a2 + a3);
             m_run = m_new;
           } else {
-            const float* lc = lc_smem + s * 128 + c * 32;
+            // fast path: FADD + FSETP per element, one warp vote per 32x32 block; no per-element branches
+            const float* lb = lc_bound + s * 128 + c * 32;
+            bool any = false;
 #pragma unroll
             for (int j4 = 0; j4 < 32; j4 += 4) {
-              const float4 l4 = *reinterpret_cast<const float4*>(lc + j4);
-              const float lcv[4] = {l4.x, l4.y, l4.z, l4.w};
+              const float4 l4 = *reinterpret_cast<const float4*>(lb + j4);
+              any |= (v[j4 + 0] > lrp + l4.x) | (v[j4 + 1] > lrp + l4.y) | (v[j4 + 2] > lrp + l4.z) | (v[j4 + 3] > lrp + l4.w);
+            }
+            if (__any_sync(kFullMask, any)) {
+              // rare path (a block holds a candidate ~1 time in 4): warp-uniform loop over the flagged columns, the
+              // accumulator column is re-read from TMEM so the code stays small
+              uint32_t mask = 0;
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                if (v[j4 + jj] > lrp + lcv[jj]) {      // cheap pre-filter (margin on the safe side), then the exact test
-                  const int col = col0 + c * 32 + j4 + jj;
-                  const float lcj = __ldg(P.lse_c + size_t(n) * LB + col);
-                  const float x = v[j4 + jj] * scale;
-                  const float t2 = (x - lr) + (x - lcj);
+              for (int j = 0; j < 32; ++j) mask |= (v[j] > lrp + lb[j]) ? (1u << j) : 0u;
+              uint32_t all = __reduce_or_sync(kFullMask, mask);
+              const float* le = lc_exact + s * 128 + c * 32;
+              while (all) {
+                const int j = __ffs(all) - 1;
+                all &= all - 1;
+                const float vj = tmem_ld1(tbase + c * 32 + j);
+                if ((mask >> j) & 1u) {
+                  const float x = vj * scale;
+                  const float t2 = (x - lr) + (x - le[j]);
                   if (t2 > P.log2_thr) {
+                    const int col = col0 + c * 32 + j;
                     atomicMax(P.rowbest + size_t(n) * LA + row, pack_best(t2, col));
                     atomicMax(P.colbest + size_t(n) * LB + col, pack_best(t2, row));
                   }
@@ -350,7 +384,18 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         tc_fence_before();
         mbar_arrive(bar_acc_empty + 8 * s);
       }
-      if (MODE == 0 && row < LA) P.lse_out[dir][size_t(n) * LA + row] = m_run + lg2_approx(s_run);
+      if (MODE == 0) {
+        // the two column halves of a row merge their (max, sum) through shared memory
+        if (colhalf == 1) merge[row_in_unit] = make_float2(m_run, s_run);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (colhalf == 0 && row < LA) {
+          const float2 o = merge[row_in_unit];
+          const float m = fmaxf(m_run, o.x);
+          const float sum = s_run * ex2_approx(m_run - m) + o.y * ex2_approx(o.x - m);
+          (dir ? P.lse_out1 : P.lse_out0)[size_t(n) * LA + row] = m + lg2_approx(sum);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      }
     }
   }
 
@@ -410,10 +455,10 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, cudaSt
   if ((e = cudaFuncSetAttribute(sweep_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   SweepParams P{};
   P.n = p.n;
-  P.LA[0] = p.L; P.LB[0] = p.S; P.LA[1] = p.S; P.LB[1] = p.L;
+  P.L0 = p.L; P.L1 = p.S;
   P.kchunks = p.C / kBoxK;
   P.scale_log2 = p.scale_log2; P.log2_thr = p.log2_thr;
-  P.lse_out[0] = w.lse_r; P.lse_out[1] = w.lse_c;
+  P.lse_out0 = w.lse_r; P.lse_out1 = w.lse_c;
   P.lse_r = w.lse_r; P.lse_c = w.lse_c; P.rowbest = w.rowbest; P.colbest = w.colbest;
   const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows), u1 = p.n * ((p.S + kUnitRows - 1) / kUnitRows);
   // sweeps 1+2: both directions in one launch
