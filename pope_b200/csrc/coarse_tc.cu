@@ -6,19 +6,22 @@
 //   sweep 3               : recompute S, t2 = log2 conf = (x - lse_r[i]) + (x - lse_c[j]); cells above log2(thr) update
 //                           the best-candidate record of their row and column (rare 64-bit atomicMax)
 //
-// Kernel anatomy (persistent, one CTA per SM, 576 threads):
-//   work unit   = (direction, pair, 256-row block of the stationary operand "A"); the unit's A block (256 x C bf16,
-//                 up to 128 KB) stays in shared memory while all 128-row tiles of the streamed operand "B" pass through
-//                 a 5-stage ring of 16 KB K-chunks (one TMA box of 128 rows x 64 k, 128B-swizzled) -> 32 B/clk/SM of
-//                 L2 traffic instead of 64 with a 128-row stationary block.
-//   warp 0      = TMA producer (one elected lane)
-//   warp 1      = TMEM allocator + tcgen05.mma issuer (one elected lane): per B tile two M128 x N128 x K16 chains
-//                 (A rows 0-127 -> TMEM columns [0,128), rows 128-255 -> [128,256)), double-buffered accumulators
-//                 (2 x 256 columns = all 512 TMEM columns)
-//   warps 2-17  = epilogue: two threads per row of the unit (64 of the tile's 128 columns each); tcgen05.ld 32 columns
-//                 at a time; online softmax (FMNMX + FFMA + MUFU.EX2 + FADD per element) or the candidate test
-//                 (FADD + FSETP per element, one warp vote per 32x32 block)
-//   barriers    = a_full/a_empty (stationary block), b_full/b_empty[5] (ring), acc_full/acc_empty[2] (TMEM stages)
+// Kernel anatomy (persistent, one CTA PAIR per two SMs, cta_group::2, 576 threads per CTA):
+//   work unit   = (direction, pair, 256-row block of the stationary operand "A"); CTA r of the pair keeps rows
+//                 [128r, 128r+128) of the block (64 KB) in its shared memory for the whole unit while 256-row tiles of
+//                 the streamed operand "B" pass through an 8-stage ring: per stage each CTA TMA-loads ITS half of the
+//                 tile (128 rows x 64 k, 16 KB, 128B-swizzled).  One tcgen05.mma.cta_group::2 (M=256, N=256, K=16)
+//                 reads A and half of B from each SM: 64 B/clk of shared-memory reads and 32 B/clk of L2 traffic per
+//                 SM (a single-CTA M=128 x N=128 tile needs 128 B/clk of shared-memory reads, i.e. all of it).
+//   warp 0      = TMA producer (one elected lane, both CTAs; transaction bytes land on the leader's barrier)
+//   warp 1      = TMEM allocator (both CTAs) + tcgen05.mma issuer (leader CTA, one elected lane); accumulators are
+//                 128 lanes x 256 fp32 columns per CTA, double-buffered (2 x 256 = all 512 TMEM columns); commits are
+//                 multicast to the barriers of both CTAs
+//   warps 2-17  = epilogue: four threads per row (64 of the tile's 256 columns each); tcgen05.ld 32 columns at a time;
+//                 online softmax (FMNMX + FFMA + MUFU.EX2 + FADD per element) or the candidate test (FADD + FSETP per
+//                 element, one warp vote per 32x32 block)
+//   barriers    = a_full/a_empty (stationary block), b_full/b_empty[8] (ring), acc_full/acc_empty[2] (TMEM stages);
+//                 *_full of the operands and acc_empty live in the leader CTA (the issuer waits on them)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -26,22 +29,25 @@
 namespace pope {
 namespace {
 
-constexpr int kStages = 5;              // B ring depth
-constexpr int kBoxRows = 128;           // rows per TMA box / per MMA operand tile
+constexpr int kStages = 8;              // B ring depth
+constexpr int kBoxRows = 128;           // rows per TMA box = rows of A / of the B half held by one CTA
 constexpr int kBoxK = 64;               // bf16 elements per 128-byte swizzle row
 constexpr int kBoxBytes = kBoxRows * kBoxK * 2;      // 16384
-constexpr int kUnitRows = 256;          // stationary rows per work unit (two M=128 MMAs)
+constexpr int kUnitRows = 256;          // stationary rows per work unit (128 per CTA of the pair)
+constexpr int kTileCols = 256;          // streamed rows per tile (= MMA N; 128 loaded by each CTA)
 constexpr int kMaxKChunks = 4;          // C <= 256
-constexpr int kEpiThreads = 512;       // 16 epilogue warps: 4 per scheduler keep the MUFU pipe fed
+constexpr int kEpiWarps = 16;           // 4 per scheduler keep the MUFU pipe fed
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
-// dynamic shared memory layout (base aligned to 1024 B for the 128B swizzle)
-constexpr int kSmemA = 0;                                            // 2 halves x 4 k-chunks x 16 KB
-constexpr int kSmemB = kSmemA + 2 * kMaxKChunks * kBoxBytes;         // kStages x 16 KB
-constexpr int kSmemLc = kSmemB + kStages * kBoxBytes;                // sweep 3: 2 stages x 128 x {bound, exact} floats
-constexpr int kSmemMerge = kSmemLc + 2 * 2 * 128 * 4;                // sweep 1+2: 256 x (max, sum)
-constexpr int kSmemBar = kSmemMerge + 256 * 8;                       // barriers
+// dynamic shared memory layout (base aligned to 1024 B for the 128B swizzle); identical in both CTAs of a pair
+constexpr int kSmemA = 0;                                            // 4 k-chunks x 16 KB
+constexpr int kSmemB = kSmemA + kMaxKChunks * kBoxBytes;             // kStages x 16 KB
+constexpr int kSmemLc = kSmemB + kStages * kBoxBytes;                // sweep 3: 2 stages x 256 x {bound, exact} floats
+constexpr int kSmemMerge = kSmemLc + 2 * 2 * kTileCols * 4;          // sweep 1+2: 3 x 128 x (max, sum)
+constexpr int kSmemBar = kSmemMerge + 3 * 128 * 8;                   // barriers
 constexpr int kNumBars = 2 + 2 * kStages + 4;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
 constexpr int kSmemBytes = kSmemTmemPtr + 16;
@@ -81,10 +87,24 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+// 2-SM TMA load: data lands in the executing CTA's shared memory, the transaction bytes are credited to the
+// LEADER CTA's barrier (rank bit cleared)
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// arrive on the leader CTA's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -95,18 +115,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return uint64_t((smem_addr & 0x3ffffu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
          (uint64_t(2) << 61);
 }
-// kind::f16, A = B = bf16 (K-major), D = fp32, M = 128, N = 128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(128 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+// kind::f16, A = B = bf16 (K-major), D = fp32, M = 256 (128 per CTA), N = 256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kTileCols >> 3) << 17) | (uint32_t(256 >> 4) << 24);
 
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// arrives on the barrier at this offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(uint16_t(3)) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread; the wait is part of the same statement so the
 // registers are valid when it retires.
@@ -151,9 +173,8 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
 
 // MODE 0: row log-sum-exp (both directions).  MODE 1: candidate sweep (direction 0 only).
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_constant__ CUtensorMap map0,
-                                                              const __grid_constant__ CUtensorMap map1,
-                                                              const SweepParams P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const SweepParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -164,23 +185,30 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map0);
     prefetch_tmap(&map1);
+    // operand "full" barriers: one arrival (the leader's expect_tx) + the bytes of both CTAs' TMA loads
     mbar_init(bar_a_full, 1);
-    mbar_init(bar_a_empty, 1);
+    mbar_init(bar_a_empty, 1);                       // one multicast tcgen05.commit
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, kEpiThreads); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_acc_full + 8 * s, 1);            // one multicast tcgen05.commit
+      mbar_init(bar_acc_empty + 8 * s, 2 * kEpiWarps);   // one arrival per epilogue warp of BOTH CTAs (leader's copy)
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemTmemPtr), "r"(kTmemCols)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemTmemPtr), "r"(kTmemCols)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int kchunks = P.kchunks;
@@ -195,39 +223,39 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   };
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
+    // =============================== TMA producer (both CTAs) ===============================
     if (lane == 0) {
       uint32_t a_phase = 0, b_stage = 0, b_phase = 0;
-      for (int u = blockIdx.x; u < P.total_units; u += gridDim.x) {
+      for (int u = pair; u < P.total_units; u += npairs) {
         int dir, n, rb;
         decode(u, dir, n, rb);
         const CUtensorMap* mapA = dir ? &map1 : &map0;
         const CUtensorMap* mapB = dir ? &map0 : &map1;
         mbar_wait(bar_a_empty, a_phase ^ 1);
-        mbar_expect_tx(bar_a_full, 2 * kchunks * kBoxBytes);
-        for (int h = 0; h < 2; ++h)
-          for (int kc = 0; kc < kchunks; ++kc)
-            tma_load_3d(sbase + kSmemA + (h * kMaxKChunks + kc) * kBoxBytes, mapA, bar_a_full, kc * kBoxK,
-                        rb * kUnitRows + h * kBoxRows, n);
+        if (rank == 0) mbar_expect_tx(bar_a_full, 2 * kchunks * kBoxBytes);
+        for (int kc = 0; kc < kchunks; ++kc)
+          tma_load_3d_2sm(sbase + kSmemA + kc * kBoxBytes, mapA, bar_a_full, kc * kBoxK,
+                          rb * kUnitRows + int(rank) * kBoxRows, n);
         a_phase ^= 1;
-        const int ntiles = ((dir ? P.L0 : P.L1) + kBoxRows - 1) / kBoxRows;
+        const int ntiles = ((dir ? P.L0 : P.L1) + kTileCols - 1) / kTileCols;
         for (int ct = 0; ct < ntiles; ++ct)
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(bar_b_empty + 8 * b_stage, b_phase ^ 1);
-            mbar_expect_tx(bar_b_full + 8 * b_stage, kBoxBytes);
-            tma_load_3d(sbase + kSmemB + b_stage * kBoxBytes, mapB, bar_b_full + 8 * b_stage, kc * kBoxK, ct * kBoxRows, n);
+            if (rank == 0) mbar_expect_tx(bar_b_full + 8 * b_stage, 2 * kBoxBytes);
+            tma_load_3d_2sm(sbase + kSmemB + b_stage * kBoxBytes, mapB, bar_b_full + 8 * b_stage, kc * kBoxK,
+                            ct * kTileCols + int(rank) * kBoxRows, n);
             if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
           }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // =============================== MMA issuer (leader CTA only) ===============================
+    if (rank == 0 && lane == 0) {
       uint32_t a_phase = 0, b_stage = 0, b_phase = 0, tile_ctr = 0;
-      for (int u = blockIdx.x; u < P.total_units; u += gridDim.x) {
+      for (int u = pair; u < P.total_units; u += npairs) {
         int dir, n, rb;
         decode(u, dir, n, rb);
-        const int ntiles = ((dir ? P.L0 : P.L1) + kBoxRows - 1) / kBoxRows;
+        const int ntiles = ((dir ? P.L0 : P.L1) + kTileCols - 1) / kTileCols;
         mbar_wait(bar_a_full, a_phase);
         a_phase ^= 1;
         tc_fence_after();
@@ -235,45 +263,40 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
           const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
           mbar_wait(bar_acc_empty + 8 * s, acc_phase ^ 1);
           tc_fence_after();
+          const uint32_t d = tmem_base + s * kTileCols;
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(bar_b_full + 8 * b_stage, b_phase);
             tc_fence_after();
+            const uint32_t a_addr = sbase + kSmemA + kc * kBoxBytes;
             const uint32_t b_addr = sbase + kSmemB + b_stage * kBoxBytes;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t a_addr = sbase + kSmemA + (h * kMaxKChunks + kc) * kBoxBytes;
-              const uint32_t d = tmem_base + s * 256 + h * 128;
-#pragma unroll
-              for (int ks = 0; ks < kBoxK / 16; ++ks)
-                umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), (kc | ks) ? 1u : 0u);
-            }
-            umma_commit(bar_b_empty + 8 * b_stage);      // ring slot free once these MMAs have read it
+            for (int ks = 0; ks < kBoxK / 16; ++ks)
+              umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), (kc | ks) ? 1u : 0u);
+            umma_commit_2sm(bar_b_empty + 8 * b_stage);  // ring slot free in both CTAs once these MMAs have read it
             if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
           }
-          umma_commit(bar_acc_full + 8 * s);             // accumulator stage complete
+          umma_commit_2sm(bar_acc_full + 8 * s);         // accumulator stage complete (both CTAs' epilogues)
         }
-        umma_commit(bar_a_empty);                        // stationary block may be overwritten
+        umma_commit_2sm(bar_a_empty);                    // stationary blocks may be overwritten
       }
     }
   } else {
-    // =============================== epilogue (16 warps; two threads per row, 64 columns of the tile each) ==========
+    // =============================== epilogue (16 warps; four threads per row, 64 columns of the tile each) =========
     const int e = threadIdx.x - 64;                 // 0..511
-    const int grp = (warp - 2) >> 2;                // 4 consecutive warps = one full set of TMEM lane quadrants
-    const int half = grp & 1;                       // which M=128 accumulator (rows 0-127 / 128-255 of the unit)
-    const int colhalf = grp >> 1;                   // which 64 of the tile's 128 columns
+    const int colq = (warp - 2) >> 2;               // which 64 of the tile's 256 columns (4 consecutive warps = 4 quadrants)
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
-    const int row_in_unit = half * 128 + quad * 32 + lane;
+    const int row_in_cta = quad * 32 + lane;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    float* lc_bound = reinterpret_cast<float*>(smem + kSmemLc);          // [2][128] pre-filter bounds
-    float* lc_exact = lc_bound + 2 * 128;                                // [2][128] exact column log-sum-exp
-    float2* merge = reinterpret_cast<float2*>(smem + kSmemMerge);        // [256] (max, sum) of the upper column half
+    float* lc_bound = reinterpret_cast<float*>(smem + kSmemLc);          // [2][256] pre-filter bounds
+    float* lc_exact = lc_bound + 2 * kTileCols;                          // [2][256] exact column log-sum-exp
+    float2* merge = reinterpret_cast<float2*>(smem + kSmemMerge);        // [3][128] (max, sum) of column quarters 1..3
     uint32_t tile_ctr = 0;
-    for (int u = blockIdx.x; u < P.total_units; u += gridDim.x) {
+    for (int u = pair; u < P.total_units; u += npairs) {
       int dir, n, rb;
       decode(u, dir, n, rb);
       const int LA = dir ? P.L1 : P.L0, LB = dir ? P.L0 : P.L1;
-      const int ntiles = (LB + kBoxRows - 1) / kBoxRows;
-      const int row = rb * kUnitRows + row_in_unit;
+      const int ntiles = (LB + kTileCols - 1) / kTileCols;
+      const int row = rb * kUnitRows + int(rank) * kBoxRows + row_in_cta;
       const float scale = P.scale_log2;
 
       float m_run = -INFINITY, s_run = 0.f;         // MODE 0 state
@@ -286,35 +309,34 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
           const float b = (lr + P.log2_thr) * inv2s;
           lrp = isfinite(b) ? b - 1e-5f * fabsf(b) - 0.005f * inv2s : INFINITY;
         }
-        if (e < 128 && e < LB) lc_next = __ldg(P.lse_c + size_t(n) * LB + e);
+        if (e < kTileCols && e < LB) lc_next = __ldg(P.lse_c + size_t(n) * LB + e);
       }
 
       for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
         const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
-        const int col0 = ct * kBoxRows;
+        const int col0 = ct * kTileCols;
         if (MODE == 1) {
           // stage this tile's column terms (fetched one tile ahead): exact value and a pre-filter bound
           // (lse_c / 2scale, margin on the safe side); +inf past the last column
-          if (e < 128) {
+          if (e < kTileCols) {
             const float b = lc_next * inv2s;
-            lc_exact[s * 128 + e] = lc_next;
-            lc_bound[s * 128 + e] = isfinite(b) ? b - 1e-5f * fabsf(b) : INFINITY;
-            const int coln = col0 + kBoxRows + e;
+            lc_exact[s * kTileCols + e] = lc_next;
+            lc_bound[s * kTileCols + e] = isfinite(b) ? b - 1e-5f * fabsf(b) : INFINITY;
+            const int coln = col0 + kTileCols + e;
             lc_next = (coln < LB) ? __ldg(P.lse_c + size_t(n) * LB + coln) : INFINITY;
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
         mbar_wait(bar_acc_full + 8 * s, acc_phase);
         tc_fence_after();
-        const uint32_t tbase = tmem_base + lane_addr + s * 256 + half * 128;
-        const int nvalid = min(LB - col0, kBoxRows);
+        const uint32_t tbase = tmem_base + lane_addr + s * kTileCols + colq * 64;
+        const int nvalid = min(LB - col0, kTileCols) - colq * 64;      // valid columns from this thread's first one
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
-          const int c = colhalf * 2 + cc;
-          const int vc = nvalid - c * 32;
+          const int vc = nvalid - cc * 32;
           if (vc <= 0) break;
           float v[32];
-          tmem_ld32(tbase + c * 32, v);
+          tmem_ld32(tbase + cc * 32, v);
           if (MODE == 0) {
             float cmax;
             if (vc >= 32) {
@@ -349,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
             m_run = m_new;
           } else {
             // fast path: FADD + FSETP per element, one warp vote per 32x32 block; no per-element branches
-            const float* lb = lc_bound + s * 128 + c * 32;
+            const float* lb = lc_bound + s * kTileCols + colq * 64 + cc * 32;
             bool any = false;
 #pragma unroll
             for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -363,16 +385,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
 #pragma unroll
               for (int j = 0; j < 32; ++j) mask |= (v[j] > lrp + lb[j]) ? (1u << j) : 0u;
               uint32_t all = __reduce_or_sync(kFullMask, mask);
-              const float* le = lc_exact + s * 128 + c * 32;
+              const float* le = lc_exact + s * kTileCols + colq * 64 + cc * 32;
               while (all) {
                 const int j = __ffs(all) - 1;
                 all &= all - 1;
-                const float vj = tmem_ld1(tbase + c * 32 + j);
+                const float vj = tmem_ld1(tbase + cc * 32 + j);
                 if ((mask >> j) & 1u) {
                   const float x = vj * scale;
                   const float t2 = (x - lr) + (x - le[j]);
                   if (t2 > P.log2_thr) {
-                    const int col = col0 + c * 32 + j;
+                    const int col = col0 + colq * 64 + cc * 32 + j;
                     atomicMax(P.rowbest + size_t(n) * LA + row, pack_best(t2, col));
                     atomicMax(P.colbest + size_t(n) * LB + col, pack_best(t2, row));
                   }
@@ -381,17 +403,24 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
             }
           }
         }
+        // this warp is done with accumulator stage s: one arrival per warp on the LEADER's barrier
         tc_fence_before();
-        mbar_arrive(bar_acc_empty + 8 * s);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
       }
       if (MODE == 0) {
-        // the two column halves of a row merge their (max, sum) through shared memory
-        if (colhalf == 1) merge[row_in_unit] = make_float2(m_run, s_run);
+        // the four column quarters of a row merge their (max, sum) through shared memory
+        if (colq > 0) merge[(colq - 1) * 128 + row_in_cta] = make_float2(m_run, s_run);
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        if (colhalf == 0 && row < LA) {
-          const float2 o = merge[row_in_unit];
-          const float m = fmaxf(m_run, o.x);
-          const float sum = s_run * ex2_approx(m_run - m) + o.y * ex2_approx(o.x - m);
+        if (colq == 0 && row < LA) {
+          float m = m_run, sum = s_run;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float2 o = merge[q * 128 + row_in_cta];
+            const float mm = fmaxf(m, o.x);
+            sum = sum * ex2_approx(m - mm) + o.y * ex2_approx(o.x - mm);
+            m = mm;
+          }
           (dir ? P.lse_out1 : P.lse_out0)[size_t(n) * LA + row] = m + lg2_approx(sum);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
@@ -401,9 +430,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                // the peer may still be signalling / reading this CTA's memory
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -463,11 +493,12 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, cudaSt
   const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows), u1 = p.n * ((p.S + kUnitRows - 1) / kUnitRows);
   // sweeps 1+2: both directions in one launch
   P.units_dir0 = u0; P.total_units = u0 + u1;
-  sweep_tc_kernel<0><<<min(P.total_units, sms), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+  const int max_pairs = sms / 2;
+  sweep_tc_kernel<0><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   // sweep 3: direction 0 only
   P.total_units = u0;
-  sweep_tc_kernel<1><<<min(P.total_units, sms), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+  sweep_tc_kernel<1><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
   return cudaGetLastError();
 }
 
