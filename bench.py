@@ -13,6 +13,7 @@ Workload (BASELINE.json configs[1]): a batch of 64 synthetic 480x640 pairs per G
   e2e   : the same metric through the C-ABI host entry (pope_pipeline_run): pinned host buffers in, pinned host
           buffers out, host<->device copies inside the timed region.
   roofline : the coarse stage (dominant) against the measured bf16 tensor peak; algorithmic work 2*L*S*C per pair.
+             roofline_fine: the fused window-gather + fine-match kernel against the measured HBM copy bandwidth.
   cpu_baseline : the oracle port (same op sequence as the reference, torch CPU) on a bounded sample, rank 0.
 """
 from __future__ import annotations
@@ -186,11 +187,11 @@ def main():
         res = ops.coarse_match(d_f0, d_f1, (HC, WC), (HC, WC), 8.0, impl=impl, workspace=ws)
         if ev: ev[1].record()
         m_dev = res["counts"][n:n + 1]
-        w0, w1 = ops.fine_gather(ff0, ff1, res["b_ids"], res["i_ids"], res["j_ids"], WC, WC, FINE_STRIDE, WIN, m_dev)
+        # fused window gather + fine match (the hot-path-only pipeline has no fine transformer in between)
+        expec, mk1f = ops.fine_match_maps(ff0, ff1, res["b_ids"], res["i_ids"], res["j_ids"], res["mkpts1_c"], WC, WC,
+                                          FINE_STRIDE, (WIN // 2) * 2.0, WIN, m_dev)
         if ev: ev[2].record()
-        expec, mk1f = ops.fine_match(w0, w1, res["mkpts1_c"], (WIN // 2) * 2.0, m_dev)
-        if ev: ev[3].record()
-        res.update(mkpts1_f=mk1f, mkpts0_f=res["mkpts0_c"])
+        res.update(mkpts1_f=mk1f, mkpts0_f=res["mkpts0_c"], expec_f=expec)
         return res
 
     def gather_step(res):
@@ -210,7 +211,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         gather_step(step_device())
     barrier()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
@@ -228,8 +229,7 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * n * args.steps / (total_ms / 1e3)
     coarse_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    gather_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
-    fine_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+    fine_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
     M = res.total()
     flags = res.flags()
 
@@ -271,8 +271,7 @@ def main():
     hbm, tf_burst, tf_sus, peak_src = measured_peaks()
     flops = n * 2.0 * L * L * C_COARSE
     ach = flops / (coarse_ms / 1e3) / 1e12
-    fine_bytes = M * ((1 + 25) * C_FINE * esize + 8 + 12 + 8)
-    gather_bytes = M * 2 * 25 * C_FINE * esize * 2
+    fine_bytes = M * ((1 + 25) * C_FINE * esize + 3 * 8 + 8 + 12 + 8)     # 26 feature rows + ids + coords in/out
     tc = impl == _lib.COARSE_TCGEN05 or (impl == _lib.COARSE_AUTO and dtype == torch.bfloat16 and _lib.tcgen05_available())
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -285,15 +284,15 @@ def main():
                    "l2_policy": "inputs_exceed_l2 (2.8 GB of features per step vs 126 MB L2)",
                    "matches_per_step": M, "flags": flags, "gather": "nccl all_gather of match lists per step" if world > 1 else "none"},
         "clocks": clk.summary(),
-        "stage_ms": {"coarse": coarse_ms, "fine_gather": gather_ms, "fine_match": fine_ms},
+        "stage_ms": {"coarse": coarse_ms, "fine_gather_match_fused": fine_ms},
         "roofline": {"kernel": "coarse stage (row/col log-sum-exp sweeps + candidate sweep + compaction)", "bound": "tensor",
                      "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "algorithmic_flops_per_launch": flops},
-        "roofline_fine_match": {"bound": "hbm", "achieved": fine_bytes / (fine_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
-                                "frac": fine_bytes / (fine_ms / 1e3) / 1e9 / hbm, "traffic": None},
-        "roofline_fine_gather": {"bound": "hbm", "achieved": gather_bytes / (gather_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
-                                 "frac": gather_bytes / (gather_ms / 1e3) / 1e9 / hbm, "traffic": None},
-        "gpu_launches": args.steps * _lib.KERNELS_PER_STEP,
+        "roofline_fine": {"kernel": "fine_match_maps_kernel (fused 5x5 window gather + correlation + softmax expectation)",
+                          "bound": "hbm", "achieved": fine_bytes / (fine_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                          "frac": fine_bytes / (fine_ms / 1e3) / 1e9 / hbm, "traffic": None,
+                          "algorithmic_bytes_per_launch": fine_bytes},
+        "gpu_launches": args.steps * _lib.KERNELS_PER_STEP["tcgen05" if tc else "simt"],
     }
     if e2e:
         line["e2e"] = e2e

@@ -10,6 +10,7 @@
  *                          src/matcher/loftr_module/fine_preprocess.py:29-47
  *   pope_fine_match     <- FineMatching.forward + get_fine_match
  *                          src/matcher/utils/fine_matching.py:15-74
+ *   pope_fine_match_maps <- the two above back to back (fine_preprocess.py:40-47 + fine_matching.py:15-74), fused
  *   pope_cosine_topk    <- F.cosine_similarity + running top-3 of the crop-retrieval loop
  *                          eval_linemod_json.py:72-101 (token: segment_anything/segment_anything/dinov2_utils.py:106-111)
  *   pope_pipeline_* / pope_match_pairs_host <- the pair loop of the eval drivers, batched
@@ -108,6 +109,18 @@ int pope_fine_gather(const void* feat_f0, const void* feat_f1, int dtype, int n_
 int pope_fine_match(const void* win0, const void* win1, int dtype, int64_t M, const int32_t* m_dev,
                     int WW, int Cf, const float* mkpts1_c, float coord_scale,
                     float* expec_f, float* mkpts1_f, void* stream);
+
+/* Fused form of pope_fine_gather + pope_fine_match for pipelines that run nothing between the two (the hot-path-only
+ * pipeline; inside Matcher.forward the fine transformer sits between them and the two-call form is used): the centre
+ * pixel of window 0 and the W*W pixels of window 1 are read straight from the CHANNELS-LAST maps (strides[1] == 1,
+ * else POPE_ERR_SHAPE), the windows are never written.  Same results as the two calls.  Cf == 128, W == 5. */
+int pope_fine_match_maps(const void* feat_f0, const void* feat_f1, int dtype, int n_pairs, int Cf,
+                         int Hf0, int Wf0, const int64_t strides0[4],
+                         int Hf1, int Wf1, const int64_t strides1[4],
+                         int w0c, int w1c, int stride, int W,
+                         const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids,
+                         int64_t M, const int32_t* m_dev, const float* mkpts1_c, float coord_scale,
+                         float* expec_f, float* mkpts1_f, void* stream);
 
 /* Retrieval: cosine similarity (x.y / (max(|x|,eps) * max(|y|,eps))) of one query token against R reference
  * tokens, followed by the eval loop's slot-replacement top-k (slots start at 0; a score greater than any slot

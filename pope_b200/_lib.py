@@ -28,6 +28,8 @@ SIGNATURES = {
     "pope_fine_gather": (_i, [_p, _p, _i, _i, _i, _i, _i, C.POINTER(_i64), _i, _i, C.POINTER(_i64),
                               _i, _i, _i, _i, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "pope_fine_match": (_i, [_p, _p, _i, _i64, _p, _i, _i, _p, _f, _p, _p, _p]),
+    "pope_fine_match_maps": (_i, [_p, _p, _i, _i, _i, _i, _i, C.POINTER(_i64), _i, _i, C.POINTER(_i64),
+                                  _i, _i, _i, _i, _p, _p, _p, _i64, _p, _p, _f, _p, _p, _p]),
     "pope_cosine_topk": (_i, [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "pope_pipeline_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i]),
     "pope_pipeline_run": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
@@ -36,9 +38,9 @@ SIGNATURES = {
                                    _i, _i, _p, _p, _p, _p, _p, _p, _p]),
 }
 
-# kernels launched by one hot-path step (bench.py `gpu_launches`): 2 log-sum-exp sweeps + 1 candidate sweep +
-# count + emit (coarse) + window gather + fine match
-KERNELS_PER_STEP = 7
+# kernels launched by one hot-path step (bench.py `gpu_launches`): log-sum-exp sweep(s) + candidate sweep + count +
+# emit (coarse; the tcgen05 path does both log-sum-exp directions in one launch, the SIMT path in two) + fused fine match
+KERNELS_PER_STEP = {"tcgen05": 5, "simt": 6}
 
 _lib: Optional[C.CDLL] = None
 

@@ -23,6 +23,7 @@
 //   barriers    = a_full/a_empty (stationary block), b_full/b_empty[8] (ring), acc_full/acc_empty[2] (TMEM stages);
 //                 *_full of the operands and acc_empty live in the leader CTA (the issuer waits on them)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -163,6 +164,7 @@ struct SweepParams {
   const float* lse_c;
   u64* rowbest;
   u64* colbest;
+  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path
 };
 
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
@@ -335,6 +337,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         for (int cc = 0; cc < 2; ++cc) {
           const int vc = nvalid - cc * 32;
           if (vc <= 0) break;
+          if (P.debug & 1) break;
           float v[32];
           tmem_ld32(tbase + cc * 32, v);
           if (MODE == 0) {
@@ -378,7 +381,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               const float4 l4 = *reinterpret_cast<const float4*>(lb + j4);
               any |= (v[j4 + 0] > lrp + l4.x) | (v[j4 + 1] > lrp + l4.y) | (v[j4 + 2] > lrp + l4.z) | (v[j4 + 3] > lrp + l4.w);
             }
-            if (__any_sync(kFullMask, any)) {
+            if (__any_sync(kFullMask, any) && !(P.debug & 2)) {
               // rare path (a block holds a candidate ~1 time in 4): warp-uniform loop over the flagged columns, the
               // accumulator column is re-read from TMEM so the code stays small
               uint32_t mask = 0;
@@ -484,6 +487,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, cudaSt
   if ((e = cudaFuncSetAttribute(sweep_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sweep_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   SweepParams P{};
+  if (const char* dbg = getenv("POPE_TC_DEBUG")) P.debug = atoi(dbg);
   P.n = p.n;
   P.L0 = p.L; P.L1 = p.S;
   P.kchunks = p.C / kBoxK;

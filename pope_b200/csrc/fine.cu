@@ -128,30 +128,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) fine_match_kernel(const T* __restrict__ win0, const T* __restrict__ win1,
-                                                        int64_t M, const int32_t* __restrict__ m_dev,
-                                                        const float* __restrict__ mkpts1_c, float inv_sqrt_c,
-                                                        float coord_scale, float* __restrict__ expec_f,
-                                                        float* __restrict__ mkpts1_f) {
-  constexpr int WW = 25, C = 128, WIN = 5;
-  const int lane = threadIdx.x & 31;
-  const int64_t m = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t live = m_dev ? min(int64_t(*m_dev), M) : M;
-  if (m >= live) return;
-  const T* w0 = win0 + size_t(m) * WW * C;
-  const T* w1 = win1 + size_t(m) * WW * C;
-  // all 26 row loads are issued before the first use (memory-level parallelism; the kernel is HBM-bound)
-  const float4 ctr = Row4<T>::load(w0 + (WW / 2) * C, lane);
-  float4 rows[WW];
-#pragma unroll
-  for (int r = 0; r < WW; ++r) rows[r] = Row4<T>::load(w1 + r * C, lane);
-  float p[32];
-#pragma unroll
-  for (int r = 0; r < WW; ++r)
-    p[r] = fmaf(ctr.x, rows[r].x, fmaf(ctr.y, rows[r].y, fmaf(ctr.z, rows[r].z, ctr.w * rows[r].w)));
-#pragma unroll
-  for (int r = WW; r < 32; ++r) p[r] = 0.f;
+// Shared by both fine-match kernels: 25 per-lane partial dot products -> expectation / std / refined coordinate.
+__device__ __forceinline__ void fine_match_finish(float (&p)[32], int lane, int64_t m, const float* __restrict__ mkpts1_c,
+                                                  float inv_sqrt_c, float coord_scale, float* __restrict__ expec_f,
+                                                  float* __restrict__ mkpts1_f) {
+  constexpr int WW = 25, WIN = 5;
   // transpose-reduce: after the 5 steps lane r holds sum over lanes of p[r]   (31 shuffles instead of 25*5)
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -179,6 +160,72 @@ __global__ void __launch_bounds__(256) fine_match_kernel(const T* __restrict__ w
     mkpts1_f[2 * m + 0] = mkpts1_c[2 * m + 0] + ex * coord_scale;
     mkpts1_f[2 * m + 1] = mkpts1_c[2 * m + 1] + ey * coord_scale;
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fine_match_kernel(const T* __restrict__ win0, const T* __restrict__ win1,
+                                                        int64_t M, const int32_t* __restrict__ m_dev,
+                                                        const float* __restrict__ mkpts1_c, float inv_sqrt_c,
+                                                        float coord_scale, float* __restrict__ expec_f,
+                                                        float* __restrict__ mkpts1_f) {
+  constexpr int WW = 25, C = 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t m = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t live = m_dev ? min(int64_t(*m_dev), M) : M;
+  if (m >= live) return;
+  const T* w0 = win0 + size_t(m) * WW * C;
+  const T* w1 = win1 + size_t(m) * WW * C;
+  // all 26 row loads are issued before the first use (memory-level parallelism; the kernel is HBM-bound)
+  const float4 ctr = Row4<T>::load(w0 + (WW / 2) * C, lane);
+  float4 rows[WW];
+#pragma unroll
+  for (int r = 0; r < WW; ++r) rows[r] = Row4<T>::load(w1 + r * C, lane);
+  float p[32];
+#pragma unroll
+  for (int r = 0; r < WW; ++r)
+    p[r] = fmaf(ctr.x, rows[r].x, fmaf(ctr.y, rows[r].y, fmaf(ctr.z, rows[r].z, ctr.w * rows[r].w)));
+#pragma unroll
+  for (int r = WW; r < 32; ++r) p[r] = 0.f;
+  fine_match_finish(p, lane, m, mkpts1_c, inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
+}
+
+// Fused window gather + fine match for the pipeline that has nothing between the two (no fine transformer): the
+// centre pixel of window 0 and the 25 pixels of window 1 are read straight from the channels-last feature maps, the
+// [M,25,128] windows are never written.  Same arithmetic as gather_cl_kernel + fine_match_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) fine_match_maps_kernel(MapDesc m0, MapDesc m1, int stride,
+                                                             const int64_t* __restrict__ b_ids,
+                                                             const int64_t* __restrict__ i_ids,
+                                                             const int64_t* __restrict__ j_ids, int64_t M,
+                                                             const int32_t* __restrict__ m_dev,
+                                                             const float* __restrict__ mkpts1_c, float inv_sqrt_c,
+                                                             float coord_scale, float* __restrict__ expec_f,
+                                                             float* __restrict__ mkpts1_f) {
+  constexpr int WW = 25, WIN = 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t m = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t live = m_dev ? min(int64_t(*m_dev), M) : M;
+  if (m >= live) return;
+  const int64_t b = b_ids[m], ci = i_ids[m], cj = j_ids[m];
+  const int y0c = int(ci / m0.wc) * stride, x0c = int(ci % m0.wc) * stride;          // centre pixel of window 0
+  const int y1 = int(cj / m1.wc) * stride - WIN / 2, x1 = int(cj % m1.wc) * stride - WIN / 2;
+  const T* img0 = reinterpret_cast<const T*>(m0.base) + b * m0.sN;
+  const T* img1 = reinterpret_cast<const T*>(m1.base) + b * m1.sN;
+  const float4 ctr = Row4<T>::load(img0 + int64_t(y0c) * m0.sH + int64_t(x0c) * m0.sW, lane);
+  float4 rows[WW];
+#pragma unroll
+  for (int r = 0; r < WW; ++r) {
+    const int y = y1 + r / WIN, x = x1 + r % WIN;
+    rows[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < m1.H && x >= 0 && x < m1.W) rows[r] = Row4<T>::load(img1 + int64_t(y) * m1.sH + int64_t(x) * m1.sW, lane);
+  }
+  float p[32];
+#pragma unroll
+  for (int r = 0; r < WW; ++r)
+    p[r] = fmaf(ctr.x, rows[r].x, fmaf(ctr.y, rows[r].y, fmaf(ctr.z, rows[r].z, ctr.w * rows[r].w)));
+#pragma unroll
+  for (int r = WW; r < 32; ++r) p[r] = 0.f;
+  fine_match_finish(p, lane, m, mkpts1_c, inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
 }
 
 }  // namespace
@@ -254,5 +301,37 @@ extern "C" int pope_fine_match(const void* win0, const void* win1, int dtype, in
     fine_match_kernel<float><<<blocks, warps * 32, 0, st>>>(static_cast<const float*>(win0),
                                                            static_cast<const float*>(win1), M, m_dev, mkpts1_c,
                                                            inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
+  return int(cudaGetLastError());
+}
+
+extern "C" int pope_fine_match_maps(const void* feat_f0, const void* feat_f1, int dtype, int n_pairs, int Cf, int Hf0,
+                                    int Wf0, const int64_t strides0[4], int Hf1, int Wf1, const int64_t strides1[4],
+                                    int w0c, int w1c, int stride, int W, const int64_t* b_ids, const int64_t* i_ids,
+                                    const int64_t* j_ids, int64_t M, const int32_t* m_dev, const float* mkpts1_c,
+                                    float coord_scale, float* expec_f, float* mkpts1_f, void* stream) {
+  if (!feat_f0 || !feat_f1 || !strides0 || !strides1 || M < 0) return POPE_ERR_INVALID_ARG;
+  if (dtype != POPE_F32 && dtype != POPE_BF16) return POPE_ERR_DTYPE;
+  if (n_pairs <= 0 || Hf0 <= 0 || Wf0 <= 0 || Hf1 <= 0 || Wf1 <= 0 || w0c <= 0 || w1c <= 0 || stride <= 0)
+    return POPE_ERR_INVALID_ARG;
+  if (W != 5 || Cf != 128) return POPE_ERR_SHAPE;
+  if (strides0[1] != 1 || strides1[1] != 1) return POPE_ERR_SHAPE;        // channels-last maps only
+  if (M == 0) return POPE_OK;
+  if (!b_ids || !i_ids || !j_ids || !mkpts1_c || !expec_f || !mkpts1_f) return POPE_ERR_INVALID_ARG;
+  const int esize = dtype == POPE_BF16 ? 2 : 4;
+  for (int k = 0; k < 4; ++k)
+    if (k != 1 && ((strides0[k] * esize) % 16 != 0 || (strides1[k] * esize) % 16 != 0)) return POPE_ERR_ALIGNMENT;
+  if ((reinterpret_cast<uintptr_t>(feat_f0) | reinterpret_cast<uintptr_t>(feat_f1)) & 15u) return POPE_ERR_ALIGNMENT;
+  MapDesc m0{static_cast<const char*>(feat_f0), Hf0, Wf0, w0c, strides0[0], strides0[1], strides0[2], strides0[3]};
+  MapDesc m1{static_cast<const char*>(feat_f1), Hf1, Wf1, w1c, strides1[0], strides1[1], strides1[2], strides1[3]};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int warps = 8;
+  const unsigned blocks = unsigned((M + warps - 1) / warps);
+  const float inv_sqrt_c = static_cast<float>(1.0 / sqrt(double(Cf)));
+  if (dtype == POPE_BF16)
+    fine_match_maps_kernel<__nv_bfloat16><<<blocks, warps * 32, 0, st>>>(m0, m1, stride, b_ids, i_ids, j_ids, M, m_dev,
+                                                                        mkpts1_c, inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
+  else
+    fine_match_maps_kernel<float><<<blocks, warps * 32, 0, st>>>(m0, m1, stride, b_ids, i_ids, j_ids, M, m_dev, mkpts1_c,
+                                                                inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
   return int(cudaGetLastError());
 }

@@ -3,7 +3,7 @@
 // Replaces the batch-1 loop of the eval drivers (eval_linemod_json.py:103-122: three sequential matcher(batch)
 // calls per test pair, each followed by three .cpu() syncs) by a chunked, double-buffered stream pipeline:
 //   copy stream   : host -> device copies of chunk k+1
-//   compute stream: coarse match -> window gather -> fine match -> per-pair slotting of chunk k   (no host sync:
+//   compute stream: coarse match -> fused window gather + fine match -> per-pair slotting of chunk k (no host sync:
 //                   the match count stays on the device and gates the fine kernels)
 //   drain stream  : device -> host copies of chunk k-1
 // One host synchronisation at the very end.
@@ -105,7 +105,7 @@ extern "C" int pope_pipeline_create(pope_pipeline_t** out, int device, int dtype
   pl->pixel_scale = pixel_scale; pl->fine_scale = fine_scale; pl->temperature = temperature; pl->thr = thr;
   pl->ws_bytes = pope_coarse_workspace_bytes(chunk_pairs, pl->L, pl->S);
   {
-    const size_t n = chunk_pairs, e = pl->esize, capt = n * pl->cap, WW = size_t(W) * W;
+    const size_t n = chunk_pairs, e = pl->esize, capt = n * pl->cap;
     const size_t f0px = size_t(h0c) * fine_stride * w0c * fine_stride, f1px = size_t(h1c) * fine_stride * w1c * fine_stride;
     PL_CUDA(cudaSetDevice(device));
     PL_CUDA(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
@@ -117,8 +117,6 @@ extern "C" int pope_pipeline_create(pope_pipeline_t** out, int device, int dtype
       PL_CUDA(cudaMalloc(&s.ff0, n * f0px * Cf * e));
       PL_CUDA(cudaMalloc(&s.ff1, n * f1px * Cf * e));
       PL_CUDA(cudaMalloc(&s.ws, pl->ws_bytes));
-      PL_CUDA(cudaMalloc(&s.win0, capt * WW * Cf * e));
-      PL_CUDA(cudaMalloc(&s.win1, capt * WW * Cf * e));
       PL_CUDA(cudaMalloc(&s.b_ids, capt * 8)); PL_CUDA(cudaMalloc(&s.i_ids, capt * 8)); PL_CUDA(cudaMalloc(&s.j_ids, capt * 8));
       PL_CUDA(cudaMalloc(&s.o_i, capt * 8)); PL_CUDA(cudaMalloc(&s.o_j, capt * 8));
       PL_CUDA(cudaMalloc(&s.mconf, capt * 4)); PL_CUDA(cudaMalloc(&s.o_conf, capt * 4));
@@ -178,11 +176,9 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
                            pl->pixel_scale, pl->temperature, pl->thr, pl->border, pl->impl, s.ws, pl->ws_bytes, s.b_ids,
                            s.i_ids, s.j_ids, s.mconf, s.mk0, s.mk1, s.counts, int64_t(capt), pl->s_comp);
     if (rc) goto fail;
-    rc = pope_fine_gather(s.ff0, s.ff1, pl->dtype, n, pl->Cf, Hf0, Wf0, st0, Hf1, Wf1, st1, pl->w0c, pl->w1c, pl->fstride,
-                          pl->W, s.b_ids, s.i_ids, s.j_ids, int64_t(capt), s.counts + n, s.win0, s.win1, pl->s_comp);
-    if (rc) goto fail;
-    rc = pope_fine_match(s.win0, s.win1, pl->dtype, int64_t(capt), s.counts + n, pl->W * pl->W, pl->Cf, s.mk1, coord_scale,
-                         s.expec, s.mk1f, pl->s_comp);
+    rc = pope_fine_match_maps(s.ff0, s.ff1, pl->dtype, n, pl->Cf, Hf0, Wf0, st0, Hf1, Wf1, st1, pl->w0c, pl->w1c,
+                              pl->fstride, pl->W, s.b_ids, s.i_ids, s.j_ids, int64_t(capt), s.counts + n, s.mk1,
+                              coord_scale, s.expec, s.mk1f, pl->s_comp);
     if (rc) goto fail;
     slot_kernel<<<n, 256, 0, pl->s_comp>>>(s.counts, int(cap), s.i_ids, s.j_ids, s.mconf, s.mk0, s.mk1f, s.o_i, s.o_j,
                                            s.o_conf, s.o_mk0, s.o_mk1);

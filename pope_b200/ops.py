@@ -116,6 +116,27 @@ def fine_match(win0: torch.Tensor, win1: torch.Tensor, mkpts1_c: torch.Tensor, c
     return expec, mk1f
 
 
+def fine_match_maps(feat_f0: torch.Tensor, feat_f1: torch.Tensor, b_ids, i_ids, j_ids, mkpts1_c: torch.Tensor,
+                    w0c: int, w1c: int, stride: int, coord_scale: float, W: int = 5,
+                    m_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused fine_gather + fine_match on channels-last maps (no windows materialised); same results."""
+    dev = require_cuda(feat_f0, feat_f1, b_ids, i_ids, j_ids, mkpts1_c)
+    if feat_f0.dtype != feat_f1.dtype:
+        raise _lib.PopeError("feat_f0 and feat_f1 must have the same dtype")
+    n, Cf, Hf0, Wf0 = feat_f0.shape
+    _, _, Hf1, Wf1 = feat_f1.shape
+    M = b_ids.shape[0]
+    expec = torch.empty(M, 3, dtype=torch.float32, device=dev)
+    mk1f = torch.empty(M, 2, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().pope_fine_match_maps(ptr(feat_f0), ptr(feat_f1), dtype_code(feat_f0), n, Cf, Hf0, Wf0,
+                                        _strides4(feat_f0), Hf1, Wf1, _strides4(feat_f1), int(w0c), int(w1c),
+                                        int(stride), int(W), ptr(b_ids), ptr(i_ids), ptr(j_ids), M, ptr(m_dev),
+                                        ptr(mkpts1_c), float(coord_scale), ptr(expec), ptr(mk1f), stream_ptr(dev))
+    check(st, "pope_fine_match_maps")
+    return expec, mk1f
+
+
 def cosine_topk(q: torch.Tensor, refs: torch.Tensor, k: int = 3, eps: float = 1e-8):
     """q [1,D] or [D], refs [R,D] -> (scores [R], slot_scores [k], slot_idx [k] int32; -1 = empty slot)."""
     dev = require_cuda(q, refs)
@@ -134,18 +155,26 @@ def cosine_topk(q: torch.Tensor, refs: torch.Tensor, k: int = 3, eps: float = 1e
 
 
 def match_pairs_device(feat_c0, feat_c1, feat_f0, feat_f1, hw0_i, hw0_c, hw1_c, thr=0.2, border_rm=2,
-                       temperature=0.1, W=5, impl=_lib.COARSE_AUTO, workspace=None) -> CoarseResult:
+                       temperature=0.1, W=5, impl=_lib.COARSE_AUTO, workspace=None, fused_fine=None) -> CoarseResult:
     """The hot path on device-resident inputs with NO host synchronisation: coarse match -> window gather ->
     fine match, the match count staying on the device (`m_dev`).  Returns the capacity-sized CoarseResult
-    extended with `expec_f`, `mkpts0_f`, `mkpts1_f`, `win0`, `win1`."""
+    extended with `expec_f`, `mkpts0_f`, `mkpts1_f` (and `win0`, `win1` on the unfused route)."""
     res = coarse_match(feat_c0, feat_c1, hw0_c, hw1_c, hw0_i[0] / hw0_c[0], thr, border_rm, temperature, impl, workspace)
     n = res["n_pairs"]
     m_dev = res["counts"][n:n + 1]
     stride = feat_f0.shape[2] // hw0_c[0]
-    win0, win1 = fine_gather(feat_f0, feat_f1, res["b_ids"], res["i_ids"], res["j_ids"], hw0_c[1], hw1_c[1], stride, W,
-                             m_dev)
-    expec, mk1f = fine_match(win0, win1, res["mkpts1_c"], (W // 2) * (hw0_i[0] / feat_f0.shape[2]), m_dev)
-    res.update(win0=win0, win1=win1, expec_f=expec, mkpts0_f=res["mkpts0_c"], mkpts1_f=mk1f)
+    coord_scale = (W // 2) * (hw0_i[0] / feat_f0.shape[2])
+    if fused_fine is None:      # fused kernel needs channels-last maps; plain NCHW takes the two-kernel route
+        fused_fine = feat_f0.stride(1) == 1 and feat_f1.stride(1) == 1 and feat_f0.shape[1] == 128 and W == 5
+    if fused_fine:
+        expec, mk1f = fine_match_maps(feat_f0, feat_f1, res["b_ids"], res["i_ids"], res["j_ids"], res["mkpts1_c"],
+                                      hw0_c[1], hw1_c[1], stride, coord_scale, W, m_dev)
+    else:
+        win0, win1 = fine_gather(feat_f0, feat_f1, res["b_ids"], res["i_ids"], res["j_ids"], hw0_c[1], hw1_c[1],
+                                 stride, W, m_dev)
+        expec, mk1f = fine_match(win0, win1, res["mkpts1_c"], coord_scale, m_dev)
+        res.update(win0=win0, win1=win1)
+    res.update(expec_f=expec, mkpts0_f=res["mkpts0_c"], mkpts1_f=mk1f)
     return res
 
 

@@ -249,16 +249,42 @@ def test_hot_path_end_to_end_vs_oracle(dtype):
     ff0, _ = synth.fine_feature_maps(52, n, h0 * 4, w0 * 4, 128, dtype=dtype)
     ff1, _ = synth.fine_feature_maps(53, n, h1 * 4, w1 * 4, 128, dtype=dtype)
     want = O.match_pairs(f0.float(), f1.float(), ff0.float(), ff1.float(), (h0 * 8, w0 * 8), (h0, w0), (h1, w1))
-    res = ops.match_pairs_device(f0.to(DEV), f1.to(DEV), ff0.to(DEV), ff1.to(DEV), (h0 * 8, w0 * 8), (h0, w0), (h1, w1))
-    m = res.total()
-    assert m == want["b_ids"].numel()
-    for k in ("b_ids", "i_ids", "j_ids"):
-        assert torch.equal(res[k][:m].cpu(), want[k])
-    tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
-    assert torch.allclose(res["mconf"][:m].cpu(), want["mconf"], rtol=tol, atol=0)
-    assert torch.equal(res["mkpts0_f"][:m].cpu(), want["mkpts0_f"])
-    assert torch.allclose(res["mkpts1_f"][:m].cpu(), want["mkpts1_f"], rtol=tol, atol=1e-3)
-    assert torch.allclose(res["expec_f"][:m, :2].cpu(), want["expec_f"][:, :2], rtol=tol, atol=1e-4)
+    for fused in (True, False):
+        res = ops.match_pairs_device(f0.to(DEV), f1.to(DEV), ff0.to(DEV), ff1.to(DEV), (h0 * 8, w0 * 8), (h0, w0),
+                                     (h1, w1), fused_fine=fused)
+        m = res.total()
+        assert m == want["b_ids"].numel()
+        for k in ("b_ids", "i_ids", "j_ids"):
+            assert torch.equal(res[k][:m].cpu(), want[k])
+        tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
+        assert torch.allclose(res["mconf"][:m].cpu(), want["mconf"], rtol=tol, atol=0)
+        assert torch.equal(res["mkpts0_f"][:m].cpu(), want["mkpts0_f"])
+        assert torch.allclose(res["mkpts1_f"][:m].cpu(), want["mkpts1_f"], rtol=tol, atol=1e-3)
+        assert torch.allclose(res["expec_f"][:m, :2].cpu(), want["expec_f"][:, :2], rtol=tol, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_fused_fine_equals_gather_then_match(dtype):
+    """pope_fine_match_maps == pope_fine_gather + pope_fine_match, bit for bit, including border windows."""
+    h0, w0, h1, w1, n, M = 9, 11, 7, 8, 3, 500
+    ff0, _ = synth.fine_feature_maps(81, n, h0 * 4, w0 * 4, 128, dtype=dtype)
+    ff1, _ = synth.fine_feature_maps(82, n, h1 * 4, w1 * 4, 128, dtype=dtype)
+    g = torch.Generator().manual_seed(83)
+    b = torch.randint(0, n, (M,), generator=g).sort()[0].to(DEV)
+    i = torch.randint(0, h0 * w0, (M,), generator=g).to(DEV)
+    j = torch.randint(0, h1 * w1, (M,), generator=g).to(DEV)
+    j[:4] = torch.tensor([0, w1 - 1, (h1 - 1) * w1, h1 * w1 - 1])
+    mk1 = (torch.randint(0, 64, (M, 2), generator=g) * 8).float().to(DEV)
+    a, c = ff0.to(DEV), ff1.to(DEV)
+    w0_, w1_ = ops.fine_gather(a, c, b, i, j, w0, w1, 4, 5)
+    e_ref, k_ref = ops.fine_match(w0_, w1_, mk1, 4.0)
+    e_fused, k_fused = ops.fine_match_maps(a, c, b, i, j, mk1, w0, w1, 4, 4.0)
+    assert torch.equal(e_ref, e_fused) and torch.equal(k_ref, k_fused)
+    live = torch.tensor([123], dtype=torch.int32, device=DEV)
+    e_part, _ = ops.fine_match_maps(a, c, b, i, j, mk1, w0, w1, 4, 4.0, m_dev=live)
+    assert torch.equal(e_part[:123], e_ref[:123])
+    with pytest.raises(_lib.PopeError):     # plain NCHW maps are not accepted by the fused kernel
+        ops.fine_match_maps(a.contiguous(), c.contiguous(), b, i, j, mk1, w0, w1, 4, 4.0)
 
 
 def test_matcher_module_flow_matches_oracle():
