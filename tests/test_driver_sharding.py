@@ -58,7 +58,10 @@ def test_two_rank_gather_equals_single_process():
     n_pairs, world = 5, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
+    import socket
+    with socket.socket() as sk:          # a free port chosen by the kernel (fixed ports collide between test runs)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_pairs, q)) for r in range(world)]
     for p in procs:
         p.start()
