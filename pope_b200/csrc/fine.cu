@@ -45,9 +45,9 @@ __global__ void __launch_bounds__(256) gather_cl_kernel(MapDesc m0, MapDesc m1, 
   if (m >= live) return;
   const bool second = job & 1;
   const MapDesc& md = second ? m1 : m0;
-  const int64_t cell = second ? j_ids[m] : i_ids[m];
+  const int cell = int(second ? j_ids[m] : i_ids[m]);
   const int64_t b = b_ids[m];
-  const int cy = int(cell / md.wc), cx = int(cell - int64_t(cy) * md.wc);
+  const int cy = cell / md.wc, cx = cell - cy * md.wc;
   const int y0 = cy * stride - W / 2, x0 = cx * stride - W / 2;
   const int WW = W * W;
   constexpr int PIX_PER_IT = 32 / VEC;              // window pixels copied per warp iteration
@@ -189,9 +189,50 @@ __global__ void __launch_bounds__(256) fine_match_kernel(const T* __restrict__ w
   fine_match_finish(p, lane, m, mkpts1_c, inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
 }
 
+// softmax over the 25 window positions + expectation / std / refined coordinate; lane holds position r (on = r < 25)
+__device__ __forceinline__ void fine_match_tail(float sim, int r, bool on, int lane, int64_t m,
+                                                const float* __restrict__ mkpts1_c, float inv_sqrt_c, float coord_scale,
+                                                float* __restrict__ expec_f, float* __restrict__ mkpts1_f) {
+  constexpr int WIN = 5;
+  const float x = on ? sim * inv_sqrt_c : -INFINITY;
+  float mx = x;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+  const float e = on ? expf(x - mx) : 0.f;
+  const float h = e / warp_sum(e);
+  const float gx = -1.f + 0.5f * float(r % WIN), gy = -1.f + 0.5f * float(r / WIN);
+  const float ex = warp_sum(h * gx), ey = warp_sum(h * gy);
+  const float exx = warp_sum(h * gx * gx), eyy = warp_sum(h * gy * gy);
+  if (lane == 0) {
+    const float sd = sqrtf(fmaxf(exx - ex * ex, 1e-10f)) + sqrtf(fmaxf(eyy - ey * ey, 1e-10f));
+    expec_f[3 * m + 0] = ex; expec_f[3 * m + 1] = ey; expec_f[3 * m + 2] = sd;
+    mkpts1_f[2 * m + 0] = mkpts1_c[2 * m + 0] + ex * coord_scale;
+    mkpts1_f[2 * m + 1] = mkpts1_c[2 * m + 1] + ey * coord_scale;
+  }
+}
+
+template <typename T> struct Vec16;      // 16 bytes of channels -> floats
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void unpack(const uint4& u, float (&f)[4]) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void unpack(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { f[2 * k] = __uint_as_float(w[k] << 16); f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+  }
+};
+
 // Fused window gather + fine match for the pipeline that has nothing between the two (no fine transformer): the
 // centre pixel of window 0 and the 25 pixels of window 1 are read straight from the channels-last feature maps, the
-// [M,25,128] windows are never written.  Same arithmetic as gather_cl_kernel + fine_match_kernel.
+// [M,25,128] windows are never written.  One warp per match; a pixel (128 channels) is LPP = 128*sizeof(T)/16 lanes
+// x 16 bytes, so a warp covers 32/LPP pixels per load instruction (2 for bf16, 1 for fp32).  Loads are unconditional
+// from clamped coordinates (out-of-map pixels contribute 0, like the reference's zero padding) so that all of them
+// are in flight together.  Same arithmetic per channel as gather_cl_kernel + fine_match_kernel.
 template <typename T>
 __global__ void __launch_bounds__(256) fine_match_maps_kernel(MapDesc m0, MapDesc m1, int stride,
                                                              const int64_t* __restrict__ b_ids,
@@ -201,31 +242,59 @@ __global__ void __launch_bounds__(256) fine_match_maps_kernel(MapDesc m0, MapDes
                                                              const float* __restrict__ mkpts1_c, float inv_sqrt_c,
                                                              float coord_scale, float* __restrict__ expec_f,
                                                              float* __restrict__ mkpts1_f) {
-  constexpr int WW = 25, WIN = 5;
-  const int lane = threadIdx.x & 31;
+  constexpr int WW = 25, WIN = 5, C = 128;
+  constexpr int NCH = Vec16<T>::N;            // channels per lane
+  constexpr int LPP = C / NCH;                // lanes per pixel: 32 (fp32) or 16 (bf16)
+  constexpr int PPI = 32 / LPP;               // pixels per warp-wide load
+  constexpr int IT = (WW + PPI - 1) / PPI;    // 25 or 13
+  const int lane = threadIdx.x & 31, sub = lane / LPP, v = lane % LPP;
   const int64_t m = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t live = m_dev ? min(int64_t(*m_dev), M) : M;
   if (m >= live) return;
-  const int64_t b = b_ids[m], ci = i_ids[m], cj = j_ids[m];
-  const int y0c = int(ci / m0.wc) * stride, x0c = int(ci % m0.wc) * stride;          // centre pixel of window 0
-  const int y1 = int(cj / m1.wc) * stride - WIN / 2, x1 = int(cj % m1.wc) * stride - WIN / 2;
+  const int64_t b = b_ids[m];
+  const int ci = int(i_ids[m]), cj = int(j_ids[m]);                                   // 32-bit: no 64-bit divisions
+  const int y0c = (ci / m0.wc) * stride, x0c = (ci % m0.wc) * stride;                // centre pixel of window 0
+  const int y1 = (cj / m1.wc) * stride - WIN / 2, x1 = (cj % m1.wc) * stride - WIN / 2;
   const T* img0 = reinterpret_cast<const T*>(m0.base) + b * m0.sN;
   const T* img1 = reinterpret_cast<const T*>(m1.base) + b * m1.sN;
-  const float4 ctr = Row4<T>::load(img0 + int64_t(y0c) * m0.sH + int64_t(x0c) * m0.sW, lane);
-  float4 rows[WW];
+  const uint4 craw = ld_stream16(img0 + int64_t(y0c) * m0.sH + int64_t(x0c) * m0.sW + v * NCH);
+  uint4 raw[IT];
+  bool ok[IT];
 #pragma unroll
-  for (int r = 0; r < WW; ++r) {
+  for (int k = 0; k < IT; ++k) {
+    const int r = k * PPI + sub;
     const int y = y1 + r / WIN, x = x1 + r % WIN;
-    rows[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y >= 0 && y < m1.H && x >= 0 && x < m1.W) rows[r] = Row4<T>::load(img1 + int64_t(y) * m1.sH + int64_t(x) * m1.sW, lane);
+    ok[k] = r < WW && y >= 0 && y < m1.H && x >= 0 && x < m1.W;
+    const int yc = min(max(y, 0), m1.H - 1), xc = min(max(x, 0), m1.W - 1);
+    raw[k] = ld_stream16(img1 + int64_t(yc) * m1.sH + int64_t(xc) * m1.sW + v * NCH);
   }
-  float p[32];
+  float ctr[NCH];
+  Vec16<T>::unpack(craw, ctr);
+  float p[LPP];
 #pragma unroll
-  for (int r = 0; r < WW; ++r)
-    p[r] = fmaf(ctr.x, rows[r].x, fmaf(ctr.y, rows[r].y, fmaf(ctr.z, rows[r].z, ctr.w * rows[r].w)));
+  for (int k = 0; k < IT; ++k) {
+    float f[NCH];
+    Vec16<T>::unpack(raw[k], f);
+    float d = 0.f;
 #pragma unroll
-  for (int r = WW; r < 32; ++r) p[r] = 0.f;
-  fine_match_finish(p, lane, m, mkpts1_c, inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
+    for (int c = NCH - 1; c >= 0; --c) d = fmaf(ctr[c], f[c], d);
+    p[k] = ok[k] ? d : 0.f;
+  }
+#pragma unroll
+  for (int k = IT; k < LPP; ++k) p[k] = 0.f;
+  // transpose-reduce inside each group of LPP lanes: afterwards lane v of the group holds slot v = pixel v*PPI + sub
+#pragma unroll
+  for (int off = LPP / 2; off >= 1; off >>= 1) {
+    const bool upper = v & off;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = upper ? p[k] : p[k + off];
+      const float keep = upper ? p[k + off] : p[k];
+      p[k] = keep + __shfl_xor_sync(kFullMask, send, off);
+    }
+  }
+  const int r = v * PPI + sub;
+  fine_match_tail(p[0], r, r < WW, lane, m, mkpts1_c, inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
 }
 
 }  // namespace
