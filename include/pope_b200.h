@@ -113,7 +113,8 @@ int pope_fine_match(const void* win0, const void* win1, int dtype, int64_t M, co
 /* Fused form of pope_fine_gather + pope_fine_match for pipelines that run nothing between the two (the hot-path-only
  * pipeline; inside Matcher.forward the fine transformer sits between them and the two-call form is used): the centre
  * pixel of window 0 and the W*W pixels of window 1 are read straight from the CHANNELS-LAST maps (strides[1] == 1,
- * else POPE_ERR_SHAPE), the windows are never written.  Same results as the two calls.  Cf == 128, W == 5. */
+ * else POPE_ERR_SHAPE), the windows are never written.  Same results as the two calls up to fp32 summation order.
+ * Cf == 128, W == 5. */
 int pope_fine_match_maps(const void* feat_f0, const void* feat_f1, int dtype, int n_pairs, int Cf,
                          int Hf0, int Wf0, const int64_t strides0[4],
                          int Hf1, int Wf1, const int64_t strides1[4],

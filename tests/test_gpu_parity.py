@@ -265,7 +265,8 @@ def test_hot_path_end_to_end_vs_oracle(dtype):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_fused_fine_equals_gather_then_match(dtype):
-    """pope_fine_match_maps == pope_fine_gather + pope_fine_match, bit for bit, including border windows."""
+    """pope_fine_match_maps == pope_fine_gather + pope_fine_match, including border windows (bit for bit for fp32;
+    for bf16 the fused kernel sums 8 channels per lane instead of 4, so only to fp32 rounding)."""
     h0, w0, h1, w1, n, M = 9, 11, 7, 8, 3, 500
     ff0, _ = synth.fine_feature_maps(81, n, h0 * 4, w0 * 4, 128, dtype=dtype)
     ff1, _ = synth.fine_feature_maps(82, n, h1 * 4, w1 * 4, 128, dtype=dtype)
@@ -279,10 +280,13 @@ def test_fused_fine_equals_gather_then_match(dtype):
     w0_, w1_ = ops.fine_gather(a, c, b, i, j, w0, w1, 4, 5)
     e_ref, k_ref = ops.fine_match(w0_, w1_, mk1, 4.0)
     e_fused, k_fused = ops.fine_match_maps(a, c, b, i, j, mk1, w0, w1, 4, 4.0)
-    assert torch.equal(e_ref, e_fused) and torch.equal(k_ref, k_fused)
+    if dtype == torch.float32:
+        assert torch.equal(e_ref, e_fused) and torch.equal(k_ref, k_fused)
+    else:
+        assert torch.allclose(e_ref, e_fused, rtol=1e-5, atol=2e-6) and torch.allclose(k_ref, k_fused, rtol=1e-6, atol=1e-5)
     live = torch.tensor([123], dtype=torch.int32, device=DEV)
     e_part, _ = ops.fine_match_maps(a, c, b, i, j, mk1, w0, w1, 4, 4.0, m_dev=live)
-    assert torch.equal(e_part[:123], e_ref[:123])
+    assert torch.equal(e_part[:123], e_fused[:123])
     with pytest.raises(_lib.PopeError):     # plain NCHW maps are not accepted by the fused kernel
         ops.fine_match_maps(a.contiguous(), c.contiguous(), b, i, j, mk1, w0, w1, 4, 4.0)
 
