@@ -65,49 +65,60 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled in the background from before the warm-up until the end of the
+    run; `summary(t0, t1)` reports the samples that fall inside the timed region (wall-clock window)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
-
-    def __enter__(self):
+    def __init__(self, index: int, period_ms: int = 20):
+        import threading
+        self.samples, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", str(period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
         except OSError:
             self.proc = None
-        return self
 
-    def __exit__(self, *a):
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.samples.append((time.time(), ln))
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc is not None and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self):
         if self.proc is not None:
-            time.sleep(0.15)
             self.proc.terminate()
             try:
-                out, _ = self.proc.communicate(timeout=5)
+                self.proc.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-                out, _ = self.proc.communicate()
-            self.lines = [ln for ln in out.splitlines() if ln.strip()]
 
-    def summary(self):
-        sm, mx, reasons = [], 0.0, set()
+    def summary(self, t0: float, t1: float):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        rows = []
+        for ts, ln in list(self.samples):
             f = [x.strip() for x in ln.split(",")]
             try:
-                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+                rows.append((ts, float(f[0]), float(f[1]), float(f[2]), [nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
             except (ValueError, IndexError):
                 continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
-        busy = [s for s in sm if s >= 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if t0 - 0.03 <= r[0] <= t1 + 0.03]
+        scope = "timed region"
+        if not inside:       # region shorter than one sampling period: fall back to the samples taken under load
+            pmax = max(r[3] for r in rows)
+            inside = [r for r in rows if r[3] >= 0.6 * pmax]
+            scope = "samples under load (timed region shorter than the sampling period)"
+        reasons = sorted({x for r in inside for x in r[4]})
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in rows),
+                "power_w_max": max(r[3] for r in inside), "reasons": reasons, "samples": len(inside), "scope": scope}
 
 
 def cpu_reference_pairs_per_sec(n_sample: int, repeats: int = 1):
@@ -195,12 +206,9 @@ def main():
         return res
 
     def gather_step(res):
-        if world == 1:
-            return
-        m = res.total()
-        loc = {"b_ids": res["b_ids"][:m] + rank * n, "i_ids": res["i_ids"][:m], "j_ids": res["j_ids"][:m],
-               "mconf": res["mconf"][:m], "mkpts0_f": res["mkpts0_f"][:m], "mkpts1_f": res["mkpts1_f"][:m]}
-        driver.gather_matches(loc, n * world, rank, world, device=dev)
+        # the one cross-GPU step: all ranks' match lists land on every rank (padded records + counts, no host sync)
+        if world > 1:
+            driver.gather_matches_padded(res, n, rank, world)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -208,19 +216,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    clk = ClockSampler(local)
+    clk.wait_first()
     for _ in range(max(args.warmup, 3)):
         gather_step(step_device())
     barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier()
-        t_beg.record()
-        for k in range(args.steps):
-            res = step_device(evs[k])
-            gather_step(res)
-        t_end.record()
-        barrier()
+    barrier()
+    wall0 = time.time()
+    t_beg.record()
+    for k in range(args.steps):
+        res = step_device(evs[k])
+        gather_step(res)
+    t_end.record()
+    barrier()
+    wall1 = time.time()
     total_ms = t_beg.elapsed_time(t_end)
     t = torch.tensor([total_ms], device=dev)
     if world > 1:
@@ -263,6 +274,8 @@ def main():
         assert int(out["counts"].sum()) == M, (int(out["counts"].sum()), M)
         pl.close()
 
+    clk.stop()
+    clocks = clk.summary(wall0, wall1)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -283,7 +296,7 @@ def main():
                    "window": WIN, "coarse_impl": "tcgen05" if tc else "simt-fp32fma", "fine_map_layout": "channels_last",
                    "l2_policy": "inputs_exceed_l2 (2.8 GB of features per step vs 126 MB L2)",
                    "matches_per_step": M, "flags": flags, "gather": "nccl all_gather of match lists per step" if world > 1 else "none"},
-        "clocks": clk.summary(),
+        "clocks": clocks,
         "stage_ms": {"coarse": coarse_ms, "fine_gather_match_fused": fine_ms},
         "roofline": {"kernel": "coarse stage (row/col log-sum-exp sweeps + candidate sweep + compaction)", "bound": "tensor",
                      "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,

@@ -152,6 +152,23 @@ def gather_matches(local: Dict[str, torch.Tensor], n_pairs: int, rank: int, worl
             "mkpts0_f": fl[:, 1:3], "mkpts1_f": fl[:, 3:5], "per_rank_matches": totals}
 
 
+def gather_matches_padded(res, n_local: int, rank: int, world: int, group=None):
+    """Sync-free form of the single gather for a steady-state loop: every rank contributes its capacity-sized result
+    as one packed int32 record tensor [cap, 8] = (b_global, i, j, mconf, x0, y0, x1, y1; floats as bit patterns) plus
+    its per-pair counts; two NCCL all-gathers, no host read.  Returns (records [world, cap, 8], counts [world, n+2]);
+    rank r's live records are records[r, :counts[r, n]] and are sorted by (b, i)."""
+    import torch.distributed as dist
+    cap = res["i_ids"].shape[0]
+    rec = torch.cat([(res["b_ids"] + rank * n_local).to(torch.int32)[:, None], res["i_ids"].to(torch.int32)[:, None],
+                     res["j_ids"].to(torch.int32)[:, None], res["mconf"].view(torch.int32)[:, None],
+                     res["mkpts0_f"].view(torch.int32), res["mkpts1_f"].view(torch.int32)], 1)
+    out = torch.empty(world, cap, 8, dtype=torch.int32, device=rec.device)
+    cnt = torch.empty(world, res["counts"].numel(), dtype=torch.int32, device=rec.device)
+    dist.all_gather_into_tensor(out, rec, group=group)
+    dist.all_gather_into_tensor(cnt, res["counts"], group=group)
+    return out, cnt
+
+
 def run_sharded(n_pairs: int, rank: int, world: int, local_fn: Callable[[int, int], Dict[str, torch.Tensor]],
                 group=None, device: Optional[torch.device] = None):
     """Shard `n_pairs` over `world` ranks, run `local_fn(lo, hi)` (returns packed lists with *global* b_ids) on each,
