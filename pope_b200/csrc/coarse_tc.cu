@@ -164,7 +164,7 @@ struct SweepParams {
   const float* lse_c;
   u64* rowbest;
   u64* colbest;
-  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path
+  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once
 };
 
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
@@ -233,12 +233,14 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         decode(u, dir, n, rb);
         const CUtensorMap* mapA = dir ? &map1 : &map0;
         const CUtensorMap* mapB = dir ? &map0 : &map1;
-        mbar_wait(bar_a_empty, a_phase ^ 1);
-        if (rank == 0) mbar_expect_tx(bar_a_full, 2 * kchunks * kBoxBytes);
-        for (int kc = 0; kc < kchunks; ++kc)
-          tma_load_3d_2sm(sbase + kSmemA + kc * kBoxBytes, mapA, bar_a_full, kc * kBoxK,
-                          rb * kUnitRows + int(rank) * kBoxRows, n);
-        a_phase ^= 1;
+        if (!(P.debug & 4) || u == pair) {            // debug bit2: timing experiment, the stationary block is loaded once
+          mbar_wait(bar_a_empty, a_phase ^ 1);
+          if (rank == 0) mbar_expect_tx(bar_a_full, 2 * kchunks * kBoxBytes);
+          for (int kc = 0; kc < kchunks; ++kc)
+            tma_load_3d_2sm(sbase + kSmemA + kc * kBoxBytes, mapA, bar_a_full, kc * kBoxK,
+                            rb * kUnitRows + int(rank) * kBoxRows, n);
+          a_phase ^= 1;
+        }
         const int ntiles = ((dir ? P.L0 : P.L1) + kTileCols - 1) / kTileCols;
         for (int ct = 0; ct < ntiles; ++ct)
           for (int kc = 0; kc < kchunks; ++kc) {
@@ -258,8 +260,10 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         int dir, n, rb;
         decode(u, dir, n, rb);
         const int ntiles = ((dir ? P.L0 : P.L1) + kTileCols - 1) / kTileCols;
-        mbar_wait(bar_a_full, a_phase);
-        a_phase ^= 1;
+        if (!(P.debug & 4) || u == pair) {
+          mbar_wait(bar_a_full, a_phase);
+          a_phase ^= 1;
+        }
         tc_fence_after();
         for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
           const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
@@ -279,7 +283,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           }
           umma_commit_2sm(bar_acc_full + 8 * s);         // accumulator stage complete (both CTAs' epilogues)
         }
-        umma_commit_2sm(bar_a_empty);                    // stationary blocks may be overwritten
+        if (!(P.debug & 4)) umma_commit_2sm(bar_a_empty);   // stationary blocks may be overwritten
       }
     }
   } else {
