@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpope_b200.so")
 POPE_F32, POPE_BF16 = 0, 1
 COARSE_AUTO, COARSE_SIMT, COARSE_TCGEN05 = 0, 1, 2
 FLAG_NONFINITE_LSE = 1
+FLAG_CAND_OVERFLOW = 2
 
 _p, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
@@ -38,9 +39,9 @@ SIGNATURES = {
                                    _i, _i, _p, _p, _p, _p, _p, _p, _p]),
 }
 
-# kernels launched by one hot-path step (bench.py `gpu_launches`): log-sum-exp sweep(s) + candidate sweep + count +
-# emit (coarse; the tcgen05 path does both log-sum-exp directions in one launch, the SIMT path in two) + fused fine match
-KERNELS_PER_STEP = {"tcgen05": 5, "simt": 6}
+# kernels launched by one hot-path step (bench.py `gpu_launches`).  tcgen05 (thr > 0.15): row sweep, column sweep,
+# candidate evaluation, count, emit, fused fine match.  SIMT: 2 log-sum-exp sweeps, candidate sweep, count, emit, fine.
+KERNELS_PER_STEP = {"tcgen05": 6, "simt": 6}
 
 _lib: Optional[C.CDLL] = None
 

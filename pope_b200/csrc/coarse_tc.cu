@@ -164,16 +164,33 @@ struct SweepParams {
   const float* lse_c;
   u64* rowbest;
   u64* colbest;
-  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once
+  const float* lse_other;   // two-sweep path, sweep 2: log-sum-exp of the streamed operand's rows (from sweep 1)
+  int* cand_cnt;            //   per streamed row: cells with p_row > thr seen so far
+  u64* cand;                //   [.., kCandSlots] (raw accumulator bits << 32 | stationary row)
+  int32_t* flags;
+  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps
 };
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+  return r;
+}
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
   uint32_t r;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
   return __uint_as_float(r);
 }
 
-// MODE 0: row log-sum-exp (both directions).  MODE 1: candidate sweep (direction 0 only).
+// MODE 0: row log-sum-exp of the stationary operand's rows.
+// MODE 1: candidate sweep of the three-sweep path (needs both log-sum-exps; direction 0 only).
+// MODE 2: MODE 0 + while streaming, every cell whose STREAMED-row softmax exceeds thr is appended to that row's
+//         candidate list (two-sweep path: run in direction 1 after a MODE 0 sweep in direction 0).
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const SweepParams P) {
@@ -288,13 +305,15 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     }
   } else {
     // =============================== epilogue (16 warps; four threads per row, 64 columns of the tile each) =========
+    constexpr bool kLse = (MODE == 0 || MODE == 2);      // online log-sum-exp of the thread's row
+    constexpr bool kStage = (MODE == 1 || MODE == 2);    // per-column terms staged in shared memory, vote-based test
     const int e = threadIdx.x - 64;                 // 0..511
     const int colq = (warp - 2) >> 2;               // which 64 of the tile's 256 columns (4 consecutive warps = 4 quadrants)
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
     const int row_in_cta = quad * 32 + lane;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     float* lc_bound = reinterpret_cast<float*>(smem + kSmemLc);          // [2][256] pre-filter bounds
-    float* lc_exact = lc_bound + 2 * kTileCols;                          // [2][256] exact column log-sum-exp
+    float* lc_exact = lc_bound + 2 * kTileCols;                          // [2][256] exact column log-sum-exp (MODE 1)
     float2* merge = reinterpret_cast<float2*>(smem + kSmemMerge);        // [3][128] (max, sum) of column quarters 1..3
     uint32_t tile_ctr = 0;
     for (int u = pair; u < P.total_units; u += npairs) {
@@ -304,32 +323,36 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       const int ntiles = (LB + kTileCols - 1) / kTileCols;
       const int row = rb * kUnitRows + int(rank) * kBoxRows + row_in_cta;
       const float scale = P.scale_log2;
+      // MODE 1: per-column term = lse_c (this thread's row term lse_r is added per thread);
+      // MODE 2: per-column term = lse of the STREAMED operand's row (the test has no per-thread term)
+      const float* col_term = (MODE == 2) ? P.lse_other : P.lse_c;
+      const float inv_s = (MODE == 2) ? 1.f / scale : 1.f / (2.f * scale);
 
-      float m_run = -INFINITY, s_run = 0.f;         // MODE 0 state
-      float lrp = INFINITY, lr = INFINITY;          // MODE 1 state
-      const float inv2s = 1.f / (2.f * scale);
+      float m_run = -INFINITY, s_run = 0.f;         // log-sum-exp state
+      float lrp = (MODE == 2) ? 0.f : INFINITY, lr = INFINITY;
       float lc_next = INFINITY;
-      if (MODE == 1) {
-        if (row < LA) {
+      if (kStage) {
+        if (MODE == 1 && row < LA) {
           lr = P.lse_r[size_t(n) * LA + row];
-          const float b = (lr + P.log2_thr) * inv2s;
-          lrp = isfinite(b) ? b - 1e-5f * fabsf(b) - 0.005f * inv2s : INFINITY;
+          const float b = (lr + P.log2_thr) * inv_s;
+          lrp = isfinite(b) ? b - 1e-5f * fabsf(b) - 0.005f * inv_s : INFINITY;
         }
-        if (e < kTileCols && e < LB) lc_next = __ldg(P.lse_c + size_t(n) * LB + e);
+        if (e < kTileCols && e < LB) lc_next = __ldg(col_term + size_t(n) * LB + e);
       }
 
       for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
         const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
         const int col0 = ct * kTileCols;
-        if (MODE == 1) {
-          // stage this tile's column terms (fetched one tile ahead): exact value and a pre-filter bound
-          // (lse_c / 2scale, margin on the safe side); +inf past the last column
+        if (kStage) {
+          // stage this tile's column terms (fetched one tile ahead) as pre-filter bounds in raw-accumulator units,
+          // margin on the safe side, +inf past the last column
           if (e < kTileCols) {
-            const float b = lc_next * inv2s;
-            lc_exact[s * kTileCols + e] = lc_next;
-            lc_bound[s * kTileCols + e] = isfinite(b) ? b - 1e-5f * fabsf(b) : INFINITY;
+            const float b = (MODE == 2) ? (lc_next + P.log2_thr) * inv_s : lc_next * inv_s;
+            const float margin = (MODE == 2) ? 1e-5f * fabsf(b) + 0.005f * inv_s : 1e-5f * fabsf(b);
+            if (MODE == 1) lc_exact[s * kTileCols + e] = lc_next;
+            lc_bound[s * kTileCols + e] = isfinite(b) ? b - margin : INFINITY;
             const int coln = col0 + kTileCols + e;
-            lc_next = (coln < LB) ? __ldg(P.lse_c + size_t(n) * LB + coln) : INFINITY;
+            lc_next = (coln < LB) ? __ldg(col_term + size_t(n) * LB + coln) : INFINITY;
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
@@ -344,7 +367,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           if (P.debug & 1) break;
           float v[32];
           tmem_ld32(tbase + cc * 32, v);
-          if (MODE == 0) {
+          if (kLse) {
             float cmax;
             if (vc >= 32) {
               float q0 = v[0], q1 = v[1], q2 = v[2], q3 = v[3];
@@ -376,13 +399,14 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             }
             s_run = (a0 + a1) + (a2 + a3);
             m_run = m_new;
-          } else {
-            // fast path: FADD + FSETP per element, one warp vote per 32x32 block; no per-element branches
-            const float* lb = lc_bound + s * kTileCols + colq * 64 + cc * 32;
+          }
+          if (kStage) {
+            // fast path: (FADD +) FSETP per element, one warp vote per 32x32 block; no per-element branches
+            const uint32_t lb = sbase + kSmemLc + (s * kTileCols + colq * 64 + cc * 32) * 4;
             bool any = false;
 #pragma unroll
             for (int j4 = 0; j4 < 32; j4 += 4) {
-              const float4 l4 = *reinterpret_cast<const float4*>(lb + j4);
+              const float4 l4 = lds128(lb + j4 * 4);
               any |= (v[j4 + 0] > lrp + l4.x) | (v[j4 + 1] > lrp + l4.y) | (v[j4 + 2] > lrp + l4.z) | (v[j4 + 3] > lrp + l4.w);
             }
             if (__any_sync(kFullMask, any) && !(P.debug & 2)) {
@@ -390,20 +414,29 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               // accumulator column is re-read from TMEM so the code stays small
               uint32_t mask = 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) mask |= (v[j] > lrp + lb[j]) ? (1u << j) : 0u;
+              for (int j = 0; j < 32; ++j) mask |= (v[j] > lrp + lds32(lb + j * 4)) ? (1u << j) : 0u;
+              if (row >= LA) mask = 0;
               uint32_t all = __reduce_or_sync(kFullMask, mask);
-              const float* le = lc_exact + s * kTileCols + colq * 64 + cc * 32;
               while (all) {
                 const int j = __ffs(all) - 1;
                 all &= all - 1;
                 const float vj = tmem_ld1(tbase + cc * 32 + j);
                 if ((mask >> j) & 1u) {
-                  const float x = vj * scale;
-                  const float t2 = (x - lr) + (x - le[j]);
-                  if (t2 > P.log2_thr) {
-                    const int col = col0 + colq * 64 + cc * 32 + j;
-                    atomicMax(P.rowbest + size_t(n) * LA + row, pack_best(t2, col));
-                    atomicMax(P.colbest + size_t(n) * LB + col, pack_best(t2, row));
+                  const int col = col0 + colq * 64 + cc * 32 + j;
+                  if (MODE == 1) {
+                    const float x = vj * scale;
+                    const float t2 = (x - lr) + (x - lc_exact[s * kTileCols + colq * 64 + cc * 32 + j]);
+                    if (t2 > P.log2_thr) {
+                      atomicMax(P.rowbest + size_t(n) * LA + row, pack_best(t2, col));
+                      atomicMax(P.colbest + size_t(n) * LB + col, pack_best(t2, row));
+                    }
+                  } else {
+                    // the streamed operand's row `col` has p_row(col, row) > thr (up to the margin): remember the cell;
+                    // its confidence is evaluated by cand_eval_kernel once this sweep has produced the other LSE
+                    const size_t r = size_t(n) * LB + col;
+                    const int slot = atomicAdd(P.cand_cnt + r, 1);
+                    if (slot < kCandSlots) P.cand[r * kCandSlots + slot] = (u64(__float_as_uint(vj)) << 32) | uint32_t(row);
+                    else atomicOr(reinterpret_cast<unsigned*>(P.flags), POPE_FLAG_CAND_OVERFLOW);
                   }
                 }
               }
@@ -415,7 +448,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
       }
-      if (MODE == 0) {
+      if (kLse) {
         // the four column quarters of a row merge their (max, sum) through shared memory
         if (colq > 0) merge[(colq - 1) * 128 + row_in_cta] = make_float2(m_run, s_run);
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
@@ -474,13 +507,39 @@ bool make_map(CUtensorMap* m, const void* base, int n, int rows, int C) {
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// One thread per row i: evaluate the (at most kCandSlots) cells with p_row > thr found by the column sweep.
+__global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
+                                                       const float* __restrict__ lse_r, const float* __restrict__ lse_c,
+                                                       int n_pairs, int L, int S, float scale, float log2_thr,
+                                                       u64* __restrict__ rowbest, u64* __restrict__ colbest) {
+  const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= size_t(n_pairs) * L) return;
+  const int n = int(r / L), i = int(r - size_t(n) * L);
+  const int c = min(cand_cnt[r], kCandSlots);
+  if (c == 0) return;
+  const float lr = lse_r[r];
+  u64 best = 0;
+  for (int k = 0; k < c; ++k) {
+    const u64 rec = cand[r * kCandSlots + k];
+    const int j = int(uint32_t(rec));
+    const float x = __uint_as_float(uint32_t(rec >> 32)) * scale;
+    const float t2 = (x - lr) + (x - lse_c[size_t(n) * S + j]);
+    if (t2 > log2_thr) {
+      const u64 mine = pack_best(t2, j);
+      best = mine > best ? mine : best;
+      atomicMax(colbest + size_t(n) * S + j, pack_best(t2, i));
+    }
+  }
+  rowbest[r] = best;
+}
+
 }  // namespace
 
 bool coarse_tc_supported(const CoarseProblem& p) {
   return p.dtype == POPE_BF16 && p.C % kBoxK == 0 && p.C >= kBoxK && p.C <= kBoxK * kMaxKChunks;
 }
 
-cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st) {
+cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
   CUtensorMap map0, map1;
   if (!make_map(&map0, p.f0, p.n, p.L, p.C) || !make_map(&map1, p.f1, p.n, p.S, p.C)) return cudaErrorInvalidValue;
   int dev = 0, sms = 0;
@@ -490,6 +549,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, cudaSt
   // per-device attribute, cheap: set on every call so that any device of a multi-GPU process is covered
   if ((e = cudaFuncSetAttribute(sweep_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sweep_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(sweep_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   SweepParams P{};
   if (const char* dbg = getenv("POPE_TC_DEBUG")) P.debug = atoi(dbg);
   P.n = p.n;
@@ -498,13 +558,28 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, cudaSt
   P.scale_log2 = p.scale_log2; P.log2_thr = p.log2_thr;
   P.lse_out0 = w.lse_r; P.lse_out1 = w.lse_c;
   P.lse_r = w.lse_r; P.lse_c = w.lse_c; P.rowbest = w.rowbest; P.colbest = w.colbest;
+  P.lse_other = w.lse_r; P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags;
   const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows), u1 = p.n * ((p.S + kUnitRows - 1) / kUnitRows);
-  // sweeps 1+2: both directions in one launch
-  P.units_dir0 = u0; P.total_units = u0 + u1;
   const int max_pairs = sms / 2;
+  // A cell with conf > thr has p_row > thr, and a row has fewer than 1/thr such cells: with thr > 1/kCandSlots the
+  // column sweep can list them and the third (candidate) sweep is not needed.
+  const bool two_sweeps = exp2f(p.log2_thr) * float(kCandSlots) > 1.2f && !(P.debug & 8);
+  if (two_sweeps) {
+    P.units_dir0 = u0; P.total_units = u0;                        // sweep 1: rows of S -> lse_r
+    sweep_tc_kernel<0><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    P.units_dir0 = 0; P.total_units = u1;                         // sweep 2: columns of S -> lse_c + candidate lists
+    sweep_tc_kernel<2><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const size_t rows = size_t(p.n) * p.L;
+    cand_eval_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S,
+                                                                  p.scale_log2, p.log2_thr, w.rowbest, w.colbest);
+    return cudaGetLastError();
+  }
+  // three sweeps (small thresholds): both log-sum-exp directions in one launch, then the candidate sweep
+  P.units_dir0 = u0; P.total_units = u0 + u1;
   sweep_tc_kernel<0><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  // sweep 3: direction 0 only
   P.total_units = u0;
   sweep_tc_kernel<1><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
   return cudaGetLastError();

@@ -41,11 +41,16 @@ __device__ __forceinline__ float lg2_approx(float x) {
 }
 
 // ---- coarse-match scratch layout -------------------------------------------------------------------------
+constexpr int kCandSlots = 8;   // per-row candidate slots of the two-sweep tcgen05 path (thr > 1/8 => at most 7 pass)
+
 struct CoarseScratch {
   float* lse_r;   // [n, L]  log2-domain log-sum-exp of every row of S
   float* lse_c;   // [n, S]  ... of every column
   u64* rowbest;   // [n, L]  best above-threshold candidate of the row   (pack_best(t2, j))
   u64* colbest;   // [n, S]  best above-threshold candidate of the column (pack_best(t2, i))
+  int* cand_cnt;  // [n, L]  two-sweep path: number of cells of the row with p_row > thr found by the column sweep
+  u64* cand;      // [n, L, kCandSlots]  (raw accumulator bits << 32 | column)
+  size_t zero_bytes;   // rowbest, colbest, cand_cnt are adjacent and cleared by one memset
   size_t bytes;
 };
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -53,11 +58,13 @@ inline CoarseScratch carve_coarse_scratch(void* base, int n, int L, int S) {
   CoarseScratch w;
   char* p = static_cast<char*>(base);
   size_t off = 0;
-  // the two key arrays are adjacent so one memset clears both
   w.rowbest = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L, 256);
   w.colbest = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * S, 256);
+  w.cand_cnt = reinterpret_cast<int*>(p + off); off += align_up(sizeof(int) * size_t(n) * L, 256);
+  w.zero_bytes = off;
   w.lse_r = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * L, 256);
   w.lse_c = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * S, 256);
+  w.cand = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L * kCandSlots, 256);
   w.bytes = off;
   return w;
 }
@@ -77,7 +84,7 @@ struct CoarseProblem {
 cudaError_t coarse_simt_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
 // coarse_tc.cu -- tcgen05/TMEM/TMA kernels (bf16 inputs, C in {64,128,192,256})
 bool coarse_tc_supported(const CoarseProblem& p);
-cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
+cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st);
 // coarse_finalize.cu -- mutual test, border removal, ordered compaction
 cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, int64_t* b_ids, int64_t* i_ids,
                                 int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts,

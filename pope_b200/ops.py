@@ -185,7 +185,8 @@ def scratch_views(workspace: torch.Tensor, n: int, L: int, S: int) -> Dict[str, 
         return (x + 255) // 256 * 256
     o_rb = 0
     o_cb = o_rb + up(8 * n * L)
-    o_lr = o_cb + up(8 * n * S)
+    o_cc = o_cb + up(8 * n * S)
+    o_lr = o_cc + up(4 * n * L)
     o_lc = o_lr + up(4 * n * L)
     return {"rowbest": workspace[o_rb:o_rb + 8 * n * L].view(torch.int64).view(n, L),
             "colbest": workspace[o_cb:o_cb + 8 * n * S].view(torch.int64).view(n, S),

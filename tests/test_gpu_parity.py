@@ -107,6 +107,21 @@ def test_coarse_hard_set_bf16(impl):
 
 
 @pytest.mark.parametrize("impl", list(IMPLS))
+@pytest.mark.parametrize("thr", [0.1, 0.3])
+def test_coarse_other_thresholds(impl, thr):
+    """thr = 0.1 takes the tcgen05 three-sweep path (too many candidates per row for the list), 0.3 the two-sweep one."""
+    _need_tc(impl, 256, 1200, 1024)
+    f0, f1 = synth.coarse_features(45, 2, 1200, 1024, 256, sigma=0.85, dtype=torch.bfloat16)
+    want, mg = oracle_with_margins(f0.float(), f1.float(), (240, 320), (30, 40), (32, 32), thr=thr)
+    out = _run_coarse(f0, f1, (30, 40), (32, 32), IMPLS[impl], torch.bfloat16, thr=thr)
+    same, near, bad = compare_match_lists(out, want, mg, thr=thr)
+    assert not bad, bad[:5]
+    assert len(near) <= 3 and same > 100
+    if not near:
+        assert torch.allclose(out["mconf"], want["mconf"], rtol=1e-2, atol=0)
+
+
+@pytest.mark.parametrize("impl", list(IMPLS))
 def test_coarse_permutation_property_full_size(impl):
     """Size-independent property at the benchmark size: f1 = P f0 with large norm -> the matches are exactly the
     interior cells with j = P(i), mconf -> 1; sorted by (b, i); every j used once."""
