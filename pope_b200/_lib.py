@@ -39,9 +39,10 @@ SIGNATURES = {
                                    _i, _i, _p, _p, _p, _p, _p, _p, _p]),
 }
 
-# kernels launched by one hot-path step (bench.py `gpu_launches`).  tcgen05 (thr > 0.15): row sweep, column sweep,
-# candidate evaluation, count, emit, fused fine match.  SIMT: 2 log-sum-exp sweeps, candidate sweep, count, emit, fine.
-KERNELS_PER_STEP = {"tcgen05": 6, "simt": 6}
+# kernels launched by one hot-path step (bench.py `gpu_launches`).  tcgen05 (thr > 0.15): row sweep, candidate bounds,
+# column sweep, candidate evaluation, count, emit, fused fine match.  SIMT: 2 log-sum-exp sweeps, candidate sweep, count,
+# emit, fused fine match.
+KERNELS_PER_STEP = {"tcgen05": 7, "simt": 6}
 
 _lib: Optional[C.CDLL] = None
 

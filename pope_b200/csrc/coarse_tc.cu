@@ -164,7 +164,8 @@ struct SweepParams {
   const float* lse_c;
   u64* rowbest;
   u64* colbest;
-  const float* lse_other;   // two-sweep path, sweep 2: log-sum-exp of the streamed operand's rows (from sweep 1)
+  const float* cbound;      // two-sweep path, sweep 2: per streamed row, raw-accumulator bound for p_row > thr
+  const float* cminb;       //   minimum of cbound over each aligned group of 32 streamed rows
   int* cand_cnt;            //   per streamed row: cells with p_row > thr seen so far
   u64* cand;                //   [.., kCandSlots] (raw accumulator bits << 32 | stationary row)
   int32_t* flags;
@@ -185,6 +186,50 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
   uint32_t r;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
   return __uint_as_float(r);
+}
+
+// online log-sum-exp update of one row with 32 more raw accumulators (vc of them valid)
+__device__ __forceinline__ float lse_update(const float (&v)[32], int vc, float scale, float& m_run, float& s_run) {
+  float cmax;
+  if (vc >= 32) {
+    float q0 = v[0], q1 = v[1], q2 = v[2], q3 = v[3];
+#pragma unroll
+    for (int j = 4; j < 32; j += 4) {
+      q0 = fmaxf(q0, v[j]); q1 = fmaxf(q1, v[j + 1]); q2 = fmaxf(q2, v[j + 2]); q3 = fmaxf(q3, v[j + 3]);
+    }
+    cmax = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
+  } else {
+    cmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) cmax = (j < vc) ? fmaxf(cmax, v[j]) : cmax;
+  }
+  const float m_new = fmaxf(m_run, cmax * scale);
+  const float neg = -m_new;
+  float a0 = s_run * ex2_approx(m_run - m_new), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (vc >= 32) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      a0 += ex2_approx(fmaf(v[j + 0], scale, neg));
+      a1 += ex2_approx(fmaf(v[j + 1], scale, neg));
+      a2 += ex2_approx(fmaf(v[j + 2], scale, neg));
+      a3 += ex2_approx(fmaf(v[j + 3], scale, neg));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < vc) a1 += ex2_approx(fmaf(v[j], scale, neg));
+  }
+  s_run = (a0 + a1) + (a2 + a3);
+  m_run = m_new;
+  return cmax;      // raw-accumulator units
+}
+
+// two-sweep path: remember that streamed row `r` (global index over pairs) has p_row > thr at stationary row `row`
+__device__ __noinline__ void cand_emit(int* __restrict__ cand_cnt, u64* __restrict__ cand, int32_t* __restrict__ flags,
+                                       size_t r, float v, int row) {
+  const int slot = atomicAdd(cand_cnt + r, 1);
+  if (slot < kCandSlots) cand[r * kCandSlots + slot] = (u64(__float_as_uint(v)) << 32) | uint32_t(row);
+  else atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_CAND_OVERFLOW);
 }
 
 // MODE 0: row log-sum-exp of the stationary operand's rows.
@@ -306,7 +351,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   } else {
     // =============================== epilogue (16 warps; four threads per row, 64 columns of the tile each) =========
     constexpr bool kLse = (MODE == 0 || MODE == 2);      // online log-sum-exp of the thread's row
-    constexpr bool kStage = (MODE == 1 || MODE == 2);    // per-column terms staged in shared memory, vote-based test
+    constexpr bool kStage = (MODE == 1);                 // per-column terms staged in shared memory (three-sweep path)
     const int e = threadIdx.x - 64;                 // 0..511
     const int colq = (warp - 2) >> 2;               // which 64 of the tile's 256 columns (4 consecutive warps = 4 quadrants)
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
@@ -323,13 +368,12 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       const int ntiles = (LB + kTileCols - 1) / kTileCols;
       const int row = rb * kUnitRows + int(rank) * kBoxRows + row_in_cta;
       const float scale = P.scale_log2;
-      // MODE 1: per-column term = lse_c (this thread's row term lse_r is added per thread);
-      // MODE 2: per-column term = lse of the STREAMED operand's row (the test has no per-thread term)
-      const float* col_term = (MODE == 2) ? P.lse_other : P.lse_c;
-      const float inv_s = (MODE == 2) ? 1.f / scale : 1.f / (2.f * scale);
+      const float* col_term = P.lse_c;      // MODE 1: per-column term lse_c, this thread's row term lse_r added per thread
+      const float inv_s = 1.f / (2.f * scale);
+      const int nchunks = (LB + 31) / 32;   // MODE 2: 32-row groups of the streamed operand
 
       float m_run = -INFINITY, s_run = 0.f;         // log-sum-exp state
-      float lrp = (MODE == 2) ? 0.f : INFINITY, lr = INFINITY;
+      float lrp = INFINITY, lr = INFINITY;
       float lc_next = INFINITY;
       if (kStage) {
         if (MODE == 1 && row < LA) {
@@ -347,61 +391,32 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           // stage this tile's column terms (fetched one tile ahead) as pre-filter bounds in raw-accumulator units,
           // margin on the safe side, +inf past the last column
           if (e < kTileCols) {
-            const float b = (MODE == 2) ? (lc_next + P.log2_thr) * inv_s : lc_next * inv_s;
-            const float margin = (MODE == 2) ? 1e-5f * fabsf(b) + 0.005f * inv_s : 1e-5f * fabsf(b);
-            if (MODE == 1) lc_exact[s * kTileCols + e] = lc_next;
-            lc_bound[s * kTileCols + e] = isfinite(b) ? b - margin : INFINITY;
+            const float b = lc_next * inv_s;
+            lc_exact[s * kTileCols + e] = lc_next;
+            lc_bound[s * kTileCols + e] = isfinite(b) ? b - 1e-5f * fabsf(b) : INFINITY;
             const int coln = col0 + kTileCols + e;
             lc_next = (coln < LB) ? __ldg(col_term + size_t(n) * LB + coln) : INFINITY;
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
+        float minb0 = INFINITY, minb1 = INFINITY;    // MODE 2: fetched before the wait so the latency is hidden
+        if (MODE == 2) {
+          const int c0 = (col0 >> 5) + colq * 2;
+          if (c0 < nchunks) minb0 = __ldg(P.cminb + size_t(n) * nchunks + c0);
+          if (c0 + 1 < nchunks) minb1 = __ldg(P.cminb + size_t(n) * nchunks + c0 + 1);
+        }
         mbar_wait(bar_acc_full + 8 * s, acc_phase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + lane_addr + s * kTileCols + colq * 64;
         const int nvalid = min(LB - col0, kTileCols) - colq * 64;      // valid columns from this thread's first one
+        if (MODE == 1) {
+          // ---- three-sweep path: candidate test against both log-sum-exps; flagged columns re-read from TMEM ----
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int vc = nvalid - cc * 32;
-          if (vc <= 0) break;
-          if (P.debug & 1) break;
-          float v[32];
-          tmem_ld32(tbase + cc * 32, v);
-          if (kLse) {
-            float cmax;
-            if (vc >= 32) {
-              float q0 = v[0], q1 = v[1], q2 = v[2], q3 = v[3];
-#pragma unroll
-              for (int j = 4; j < 32; j += 4) {
-                q0 = fmaxf(q0, v[j]); q1 = fmaxf(q1, v[j + 1]); q2 = fmaxf(q2, v[j + 2]); q3 = fmaxf(q3, v[j + 3]);
-              }
-              cmax = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
-            } else {
-              cmax = -INFINITY;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) cmax = (j < vc) ? fmaxf(cmax, v[j]) : cmax;
-            }
-            const float m_new = fmaxf(m_run, cmax * scale);
-            const float neg = -m_new;
-            float a0 = s_run * ex2_approx(m_run - m_new), a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            if (vc >= 32) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                a0 += ex2_approx(fmaf(v[j + 0], scale, neg));
-                a1 += ex2_approx(fmaf(v[j + 1], scale, neg));
-                a2 += ex2_approx(fmaf(v[j + 2], scale, neg));
-                a3 += ex2_approx(fmaf(v[j + 3], scale, neg));
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < vc) a1 += ex2_approx(fmaf(v[j], scale, neg));
-            }
-            s_run = (a0 + a1) + (a2 + a3);
-            m_run = m_new;
-          }
-          if (kStage) {
-            // fast path: (FADD +) FSETP per element, one warp vote per 32x32 block; no per-element branches
+          for (int cc = 0; cc < 2; ++cc) {
+            const int vc = nvalid - cc * 32;
+            if (vc <= 0 || (P.debug & 1)) break;
+            float v[32];
+            tmem_ld32(tbase + cc * 32, v);
             const uint32_t lb = sbase + kSmemLc + (s * kTileCols + colq * 64 + cc * 32) * 4;
             bool any = false;
 #pragma unroll
@@ -410,12 +425,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               any |= (v[j4 + 0] > lrp + l4.x) | (v[j4 + 1] > lrp + l4.y) | (v[j4 + 2] > lrp + l4.z) | (v[j4 + 3] > lrp + l4.w);
             }
             if (__any_sync(kFullMask, any) && !(P.debug & 2)) {
-              // rare path (a block holds a candidate ~1 time in 4): warp-uniform loop over the flagged columns, the
-              // accumulator column is re-read from TMEM so the code stays small
               uint32_t mask = 0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) mask |= (v[j] > lrp + lds32(lb + j * 4)) ? (1u << j) : 0u;
-              if (row >= LA) mask = 0;
               uint32_t all = __reduce_or_sync(kFullMask, mask);
               while (all) {
                 const int j = __ffs(all) - 1;
@@ -423,30 +435,70 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
                 const float vj = tmem_ld1(tbase + cc * 32 + j);
                 if ((mask >> j) & 1u) {
                   const int col = col0 + colq * 64 + cc * 32 + j;
-                  if (MODE == 1) {
-                    const float x = vj * scale;
-                    const float t2 = (x - lr) + (x - lc_exact[s * kTileCols + colq * 64 + cc * 32 + j]);
-                    if (t2 > P.log2_thr) {
-                      atomicMax(P.rowbest + size_t(n) * LA + row, pack_best(t2, col));
-                      atomicMax(P.colbest + size_t(n) * LB + col, pack_best(t2, row));
-                    }
-                  } else {
-                    // the streamed operand's row `col` has p_row(col, row) > thr (up to the margin): remember the cell;
-                    // its confidence is evaluated by cand_eval_kernel once this sweep has produced the other LSE
-                    const size_t r = size_t(n) * LB + col;
-                    const int slot = atomicAdd(P.cand_cnt + r, 1);
-                    if (slot < kCandSlots) P.cand[r * kCandSlots + slot] = (u64(__float_as_uint(vj)) << 32) | uint32_t(row);
-                    else atomicOr(reinterpret_cast<unsigned*>(P.flags), POPE_FLAG_CAND_OVERFLOW);
+                  const float x = vj * scale;
+                  const float t2 = (x - lr) + (x - lc_exact[s * kTileCols + colq * 64 + cc * 32 + j]);
+                  if (t2 > P.log2_thr) {
+                    atomicMax(P.rowbest + size_t(n) * LA + row, pack_best(t2, col));
+                    atomicMax(P.colbest + size_t(n) * LB + col, pack_best(t2, row));
                   }
                 }
               }
             }
           }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
+        } else {
+          // ---- log-sum-exp sweeps: the accumulator stage is handed back to the MMA issuer as soon as this warp's
+          //      last TMEM load has retired; the second chunk's arithmetic and every atomic run after the hand-back ----
+          float pend_v = 0.f;
+          int pend_col = -1;                         // MODE 2: one deferred candidate of chunk 0
+          auto scan = [&](const float (&v)[32], int cc, float cmax, bool defer) {
+            // MODE 2: does this 32x32 block hold a cell with p_row > thr?  group-level bound first (1 compare + vote),
+            // the per-element test only where it can succeed (~1 block in 4); bounds come from cand_bounds_kernel
+            const int chunk = colq * 2 + cc;
+            const bool maybe = cmax > (cc ? minb1 : minb0);
+            if (__any_sync(kFullMask, maybe && row < LA) && !(P.debug & 2)) {
+              // bound rows are padded to a multiple of 32 with +inf, so every processed chunk is fully readable/aligned
+              const float4* lb = reinterpret_cast<const float4*>(P.cbound + (size_t(n) * nchunks << 5) + col0 + chunk * 32);
+              uint32_t mask = 0;
+#pragma unroll
+              for (int j4 = 0; j4 < 32; j4 += 4) {
+                const float4 l4 = __ldg(lb + (j4 >> 2));
+                mask |= (v[j4 + 0] > l4.x ? 1u : 0u) << j4 | (v[j4 + 1] > l4.y ? 2u : 0u) << j4 |
+                        (v[j4 + 2] > l4.z ? 4u : 0u) << j4 | (v[j4 + 3] > l4.w ? 8u : 0u) << j4;
+              }
+              if (row >= LA) mask = 0;
+              if (mask) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if ((mask >> j) & 1u) {
+                    const int col = col0 + chunk * 32 + j;
+                    if (defer && pend_col < 0) { pend_v = v[j]; pend_col = col; }
+                    else cand_emit(P.cand_cnt, P.cand, P.flags, size_t(n) * LB + col, v[j], row);
+                  }
+                }
+              }
+            }
+          };
+          const int vc0 = nvalid, vc1 = nvalid - 32;
+          const bool skip = (P.debug & 1) != 0;
+          float v[32];
+          if (vc0 > 0 && !skip) {
+            tmem_ld32(tbase, v);
+            const float cmax = lse_update(v, vc0, scale, m_run, s_run);
+            if (MODE == 2) scan(v, 0, cmax, true);
+          }
+          if (vc1 > 0 && !skip) tmem_ld32(tbase + 32, v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
+          if (vc1 > 0 && !skip) {
+            const float cmax = lse_update(v, vc1, scale, m_run, s_run);
+            if (MODE == 2) scan(v, 1, cmax, false);
+          }
+          if (MODE == 2 && pend_col >= 0) cand_emit(P.cand_cnt, P.cand, P.flags, size_t(n) * LB + pend_col, pend_v, row);
         }
-        // this warp is done with accumulator stage s: one arrival per warp on the LEADER's barrier
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
       }
       if (kLse) {
         // the four column quarters of a row merge their (max, sum) through shared memory
@@ -507,6 +559,30 @@ bool make_map(CUtensorMap* m, const void* base, int n, int rows, int C) {
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Two-sweep path, between the sweeps: cell (i, j) can only have conf > thr if p_row(i, j) > thr, i.e. if its raw
+// accumulator exceeds (lse_r[i] + log2 thr) / scale.  One warp per aligned group of 32 rows writes that bound (margin on
+// the safe side, +inf for non-finite lse) and the group's minimum.
+__global__ void __launch_bounds__(256) cand_bounds_kernel(const float* __restrict__ lse_r, int n_pairs, int L, float scale,
+                                                         float log2_thr, float* __restrict__ cbound,
+                                                         float* __restrict__ cminb) {
+  const int lane = threadIdx.x & 31;
+  const int nchunks = (L + 31) / 32;
+  const size_t g = size_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= size_t(n_pairs) * nchunks) return;
+  const int n = int(g / nchunks), i = int(g - size_t(n) * nchunks) * 32 + lane;
+  float bound = INFINITY;
+  if (i < L) {
+    const float inv_s = 1.f / scale;
+    const float b = (lse_r[size_t(n) * L + i] + log2_thr) * inv_s;
+    if (isfinite(b)) bound = b - (1e-5f * fabsf(b) + 0.005f * inv_s);
+  }
+  cbound[g * 32 + lane] = bound;        // rows padded to a multiple of 32 with +inf
+  float mb = bound;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mb = fminf(mb, __shfl_xor_sync(kFullMask, mb, o));
+  if (lane == 0) cminb[g] = mb;
+}
+
 // One thread per row i: evaluate the (at most kCandSlots) cells with p_row > thr found by the column sweep.
 __global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
                                                        const float* __restrict__ lse_r, const float* __restrict__ lse_c,
@@ -558,7 +634,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   P.scale_log2 = p.scale_log2; P.log2_thr = p.log2_thr;
   P.lse_out0 = w.lse_r; P.lse_out1 = w.lse_c;
   P.lse_r = w.lse_r; P.lse_c = w.lse_c; P.rowbest = w.rowbest; P.colbest = w.colbest;
-  P.lse_other = w.lse_r; P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags;
+  P.cbound = w.cbound; P.cminb = w.cminb; P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags;
   const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows), u1 = p.n * ((p.S + kUnitRows - 1) / kUnitRows);
   const int max_pairs = sms / 2;
   // A cell with conf > thr has p_row > thr, and a row has fewer than 1/thr such cells: with thr > 1/kCandSlots the
@@ -567,6 +643,9 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   if (two_sweeps) {
     P.units_dir0 = u0; P.total_units = u0;                        // sweep 1: rows of S -> lse_r
     sweep_tc_kernel<0><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const size_t groups = size_t(p.n) * ((p.L + 31) / 32);
+    cand_bounds_kernel<<<unsigned((groups + 7) / 8), 256, 0, st>>>(w.lse_r, p.n, p.L, p.scale_log2, p.log2_thr, w.cbound, w.cminb);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     P.units_dir0 = 0; P.total_units = u1;                         // sweep 2: columns of S -> lse_c + candidate lists
     sweep_tc_kernel<2><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);

@@ -50,6 +50,8 @@ struct CoarseScratch {
   u64* colbest;   // [n, S]  best above-threshold candidate of the column (pack_best(t2, i))
   int* cand_cnt;  // [n, L]  two-sweep path: number of cells of the row with p_row > thr found by the column sweep
   u64* cand;      // [n, L, kCandSlots]  (raw accumulator bits << 32 | column)
+  float* cbound;  // [n, 32*ceil(L/32)]  two-sweep path: raw-accumulator bound above which a cell of row i has p_row > thr
+  float* cminb;   // [n, ceil(L/32)]  minimum of cbound over each group of 32 rows
   size_t zero_bytes;   // rowbest, colbest, cand_cnt are adjacent and cleared by one memset
   size_t bytes;
 };
@@ -65,6 +67,8 @@ inline CoarseScratch carve_coarse_scratch(void* base, int n, int L, int S) {
   w.lse_r = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * L, 256);
   w.lse_c = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * S, 256);
   w.cand = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L * kCandSlots, 256);
+  w.cbound = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32) * 32, 256);
+  w.cminb = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32), 256);
   w.bytes = off;
   return w;
 }

@@ -88,7 +88,7 @@ def test_argument_errors_are_reported_before_touching_the_gpu():
     h = _lib.lib()
     assert h.pope_coarse_workspace_bytes(0, 10, 10) == 0
     need = h.pope_coarse_workspace_bytes(2, 4800, 4800)
-    assert need >= 2 * 4800 * (8 + 8 + 4 + 4 + 4 + 8 * 8)
+    assert need >= 2 * 4800 * (8 + 8 + 4 + 4 + 4 + 8 * 8 + 4)
     # null pointers / bad sizes / bad dtype: negative status, no CUDA call is made
     args_ok = [1, 1, 0, 1, 64, 64, 256, 8, 8, 8, 8, 8.0, 0.1, 0.2, 2, 0, 1, need, 1, 1, 1, 1, 1, 1, 1, 64, None]
     bad = list(args_ok); bad[0] = None
