@@ -41,6 +41,8 @@ constexpr int kEpiWarps = 16;           // 4 per scheduler keep the MUFU pipe fe
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kTmemCols = 512;
+constexpr bool kLoadBoth = false;                    // (measured slower: 64 live accumulators spill at the 96-register cap)
+constexpr bool kPolyExp = false;                     // every 4th exp2 on the FMA pipe (measured slower: +2.5 instr/element)
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
 // dynamic shared memory layout (base aligned to 1024 B for the 128B swizzle); identical in both CTAs of a pair
@@ -188,6 +190,21 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
   return __uint_as_float(r);
 }
 
+// 2^x for x <= 0 on the FMA/ALU pipes (Cody-Waite split + degree-4 minimax polynomial, max rel. error 2.7e-6): one
+// element in four goes this way so that the MUFU pipe (16 ex2/clk/SM, exactly the MMA rate at one exponential per
+// accumulator element) is no longer the co-bottleneck of the log-sum-exp sweeps.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                 // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);           // [-0.5, 0.5]
+  float p = 0.009570101276040077f;
+  p = fmaf(p, f, 0.05591785907745361f);
+  p = fmaf(p, f, 0.240247443318367f);
+  p = fmaf(p, f, 0.6931217908859253f);
+  p = fmaf(p, f, 0.9999992847442627f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // online log-sum-exp update of one row with 32 more raw accumulators (vc of them valid)
 __device__ __forceinline__ float lse_update(const float (&v)[32], int vc, float scale, float& m_run, float& s_run) {
   float cmax;
@@ -212,7 +229,7 @@ __device__ __forceinline__ float lse_update(const float (&v)[32], int vc, float 
       a0 += ex2_approx(fmaf(v[j + 0], scale, neg));
       a1 += ex2_approx(fmaf(v[j + 1], scale, neg));
       a2 += ex2_approx(fmaf(v[j + 2], scale, neg));
-      a3 += ex2_approx(fmaf(v[j + 3], scale, neg));
+      a3 += kPolyExp ? ex2_poly(fmaf(v[j + 3], scale, neg)) : ex2_approx(fmaf(v[j + 3], scale, neg));
     }
   } else {
 #pragma unroll
@@ -483,21 +500,39 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           };
           const int vc0 = nvalid, vc1 = nvalid - 32;
           const bool skip = (P.debug & 1) != 0;
-          float v[32];
-          if (vc0 > 0 && !skip) {
-            tmem_ld32(tbase, v);
-            const float cmax = lse_update(v, vc0, scale, m_run, s_run);
-            if (MODE == 2) scan(v, 0, cmax, true);
+          if (kLoadBoth) {
+            // both 32-column chunks are pulled into registers first, the stage is handed back, then all arithmetic
+            float v0[32], v1[32];
+            if (vc0 > 0 && !skip) tmem_ld32(tbase, v0);
+            if (vc1 > 0 && !skip) tmem_ld32(tbase + 32, v1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
+            if (vc0 > 0 && !skip) {
+              const float cmax = lse_update(v0, vc0, scale, m_run, s_run);
+              if (MODE == 2) scan(v0, 0, cmax, false);
+            }
+            if (vc1 > 0 && !skip) {
+              const float cmax = lse_update(v1, vc1, scale, m_run, s_run);
+              if (MODE == 2) scan(v1, 1, cmax, false);
+            }
+          } else {
+            float v[32];
+            if (vc0 > 0 && !skip) {
+              tmem_ld32(tbase, v);
+              const float cmax = lse_update(v, vc0, scale, m_run, s_run);
+              if (MODE == 2) scan(v, 0, cmax, true);
+            }
+            if (vc1 > 0 && !skip) tmem_ld32(tbase + 32, v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
+            if (vc1 > 0 && !skip) {
+              const float cmax = lse_update(v, vc1, scale, m_run, s_run);
+              if (MODE == 2) scan(v, 1, cmax, false);
+            }
+            if (MODE == 2 && pend_col >= 0) cand_emit(P.cand_cnt, P.cand, P.flags, size_t(n) * LB + pend_col, pend_v, row);
           }
-          if (vc1 > 0 && !skip) tmem_ld32(tbase + 32, v);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
-          if (vc1 > 0 && !skip) {
-            const float cmax = lse_update(v, vc1, scale, m_run, s_run);
-            if (MODE == 2) scan(v, 1, cmax, false);
-          }
-          if (MODE == 2 && pend_col >= 0) cand_emit(P.cand_cnt, P.cand, P.flags, size_t(n) * LB + pend_col, pend_v, row);
         }
       }
       if (kLse) {

@@ -35,6 +35,10 @@ class FinePreprocess(nn.Module):
         if b_ids.shape[0] == 0:
             empty = torch.empty(0, W * W, self.d_model_f, device=feat_f0.device)
             return empty, empty.clone()
+        # the CUDA gather is coalesced on channels-last maps (a window pixel = one contiguous Cf-vector); the stock
+        # backbone emits NCHW, so re-layout once per call (one pass over the map, far cheaper than F.unfold's 25x blow-up)
+        feat_f0 = feat_f0.contiguous(memory_format=torch.channels_last)
+        feat_f1 = feat_f1.contiguous(memory_format=torch.channels_last)
         win0, win1 = ops.fine_gather(feat_f0, feat_f1, b_ids, i_ids, j_ids, data["hw0_c"][1], data["hw1_c"][1],
                                      stride, W)
         if self.cat_c_feat:
