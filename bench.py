@@ -266,7 +266,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        h2d = sum(x.numel() * x.element_size() for x in (h_f0, h_f1, h_ff0, h_ff1))
+        h2d = pl.last_h2d_bytes      # bulk copies + the centre pixels of image 0 read in place from pinned memory
         d2h = sum(out[k].numel() * out[k].element_size() for k in ("i_ids", "j_ids", "mconf", "mkpts0_f", "mkpts1_f", "counts")) + 4 * ((n + chunk - 1) // chunk)
         e2e = {"value": world * n * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": k_e2e, "ms_per_step": 1e3 * dt / k_e2e, "matches": int(out["counts"].sum()),

@@ -152,6 +152,10 @@ int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const void* feat
                       int64_t* i_ids, int64_t* j_ids, float* mconf, float* mkpts0_f, float* mkpts1_f,
                       int32_t* counts, int32_t* flags);
 int pope_pipeline_destroy(pope_pipeline_t* pl);
+/* Bytes that crossed the host link towards the device during the last pope_pipeline_run: the bulk copies plus, when
+ * feat_f0 is page-locked, the centre pixels the fine kernel read directly from host memory (one Cf-vector per match;
+ * the rest of image 0's fine map is never needed by this pipeline and is not transferred). */
+int64_t pope_pipeline_last_h2d_bytes(const pope_pipeline_t* pl);
 
 /* One-shot convenience: create + run + destroy. */
 int pope_match_pairs_host(const void* feat_c0, const void* feat_c1, const void* feat_f0, const void* feat_f1,

@@ -57,6 +57,7 @@ struct pope_pipeline {
   int device, dtype, chunk, C, Cf, h0c, w0c, h1c, w1c, fstride, W, L, S, cap, esize, impl, border;
   float pixel_scale, fine_scale, temperature, thr;
   size_t ws_bytes;
+  int64_t last_h2d_bytes = 0;      // bytes that crossed the host link towards the device in the last run
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_drain = nullptr;
   Slot slot[2];
 };
@@ -152,6 +153,19 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
   const int64_t st0[4] = {int64_t(Hf0) * Wf0 * int64_t(Cf), 1, int64_t(Wf0) * int64_t(Cf), int64_t(Cf)};
   const int64_t st1[4] = {int64_t(Hf1) * Wf1 * int64_t(Cf), 1, int64_t(Wf1) * int64_t(Cf), int64_t(Cf)};
   const float coord_scale = float(pl->W / 2) * pl->fine_scale;
+  // Of image 0's fine map the pipeline only ever reads the centre pixel of each MATCHED cell (window 0 contributes its
+  // centre row to the fine correlation, fine_matching.py:43).  When the caller's buffer is page-locked (device-
+  // addressable under UVA) the fused fine kernel fetches those pixels straight from host memory (M x 256 B per chunk
+  // instead of copying the whole 1/2-resolution map); pageable buffers fall back to the bulk copy.
+  const char* f0_dev_view = nullptr;
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, feat_f0) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      f0_dev_view = static_cast<const char*>(attr.devicePointer);
+    else
+      cudaGetLastError();   // clear the "invalid value" some drivers report for pageable pointers
+  }
+  int64_t h2d = 0;
   int32_t flag_acc = 0;
   int n_chunks = (n_pairs + pl->chunk - 1) / pl->chunk;
   PL_CUDA(cudaSetDevice(pl->device));
@@ -168,7 +182,9 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
     }
     PL_CUDA(cudaMemcpyAsync(s.fc0, static_cast<const char*>(feat_c0) + p0 * fc0_pair, n * fc0_pair, cudaMemcpyHostToDevice, pl->s_copy));
     PL_CUDA(cudaMemcpyAsync(s.fc1, static_cast<const char*>(feat_c1) + p0 * fc1_pair, n * fc1_pair, cudaMemcpyHostToDevice, pl->s_copy));
-    PL_CUDA(cudaMemcpyAsync(s.ff0, static_cast<const char*>(feat_f0) + p0 * ff0_pair, n * ff0_pair, cudaMemcpyHostToDevice, pl->s_copy));
+    if (!f0_dev_view)
+      PL_CUDA(cudaMemcpyAsync(s.ff0, static_cast<const char*>(feat_f0) + p0 * ff0_pair, n * ff0_pair, cudaMemcpyHostToDevice, pl->s_copy));
+    h2d += int64_t(n) * int64_t(fc0_pair + fc1_pair + ff1_pair + (f0_dev_view ? 0 : ff0_pair));
     PL_CUDA(cudaMemcpyAsync(s.ff1, static_cast<const char*>(feat_f1) + p0 * ff1_pair, n * ff1_pair, cudaMemcpyHostToDevice, pl->s_copy));
     PL_CUDA(cudaEventRecord(s.uploaded, pl->s_copy));
     PL_CUDA(cudaStreamWaitEvent(pl->s_comp, s.uploaded, 0));
@@ -176,7 +192,7 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
                            pl->pixel_scale, pl->temperature, pl->thr, pl->border, pl->impl, s.ws, pl->ws_bytes, s.b_ids,
                            s.i_ids, s.j_ids, s.mconf, s.mk0, s.mk1, s.counts, int64_t(capt), pl->s_comp);
     if (rc) goto fail;
-    rc = pope_fine_match_maps(s.ff0, s.ff1, pl->dtype, n, pl->Cf, Hf0, Wf0, st0, Hf1, Wf1, st1, pl->w0c, pl->w1c,
+    rc = pope_fine_match_maps(f0_dev_view ? static_cast<const void*>(f0_dev_view + p0 * ff0_pair) : s.ff0, s.ff1, pl->dtype, n, pl->Cf, Hf0, Wf0, st0, Hf1, Wf1, st1, pl->w0c, pl->w1c,
                               pl->fstride, pl->W, s.b_ids, s.i_ids, s.j_ids, int64_t(capt), s.counts + n, s.mk1,
                               coord_scale, s.expec, s.mk1f, pl->s_comp);
     if (rc) goto fail;
@@ -197,6 +213,12 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
   PL_CUDA(cudaStreamSynchronize(pl->s_drain));
   for (int k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k) flag_acc |= pl->slot[k & 1].h_counts[pl->chunk + 1];
   if (flags) *flags = flag_acc;
+  if (f0_dev_view) {        // the centre pixels fetched by the fine kernel also crossed the host link
+    int64_t m = 0;
+    for (int p = 0; p < n_pairs; ++p) m += counts[p];
+    h2d += m * int64_t(Cf * e);
+  }
+  pl->last_h2d_bytes = h2d;
   return POPE_OK;
 fail:
   cudaStreamSynchronize(pl->s_copy); cudaStreamSynchronize(pl->s_comp); cudaStreamSynchronize(pl->s_drain);
@@ -221,3 +243,5 @@ extern "C" int pope_match_pairs_host(const void* feat_c0, const void* feat_c1, c
   pope_pipeline_destroy(pl);
   return rc;
 }
+
+extern "C" int64_t pope_pipeline_last_h2d_bytes(const pope_pipeline_t* pl) { return pl ? pl->last_h2d_bytes : 0; }

@@ -76,6 +76,7 @@ class Pipeline:
                                      out["mconf"].data_ptr(), out["mkpts0_f"].data_ptr(), out["mkpts1_f"].data_ptr(),
                                      out["counts"].data_ptr(), out["flags"].data_ptr())
         check(st, "pope_pipeline_run")
+        self.last_h2d_bytes = int(lib().pope_pipeline_last_h2d_bytes(self._h))
         return out
 
     def close(self):

@@ -363,11 +363,20 @@ def test_host_pipeline_equals_device_path():
     ff0, ff1 = synth.fine_feature_maps(72, n, h * 4, w * 4, 128, dtype=torch.bfloat16)
     res = ops.match_pairs_device(f0.to(DEV), f1.to(DEV), ff0.to(DEV), ff1.to(DEV), (h * 8, w * 8), (h, w), (h, w))
     m = res.total()
+    # pageable host buffers (bulk copies of everything) ...
     out = driver.match_pairs_host(f0, f1, ff0, ff1, (h * 8, w * 8), (h, w), (h, w), chunk_pairs=2, device=0)
-    assert int(out["counts"].sum()) == m
-    cat = driver.flatten_slots(out)
-    for k in ("b_ids", "i_ids", "j_ids"):
-        assert torch.equal(cat[k], res[k][:m].cpu()), k
-    assert torch.equal(cat["mconf"], res["mconf"][:m].cpu())
-    assert torch.equal(cat["mkpts0_f"], res["mkpts0_f"][:m].cpu())
-    assert torch.equal(cat["mkpts1_f"], res["mkpts1_f"][:m].cpu())
+    # ... and page-locked ones (image 0's centre pixels are read in place by the fine kernel, its map is not copied)
+    pl = driver.Pipeline(torch.bfloat16, 2, (h * 8, w * 8), (h, w), (h, w), device=0)
+    nhwc0, nhwc1 = ff0.permute(0, 2, 3, 1).contiguous().pin_memory(), ff1.permute(0, 2, 3, 1).contiguous().pin_memory()
+    out_pinned = pl.run(f0.pin_memory(), f1.pin_memory(), nhwc0, nhwc1)
+    full = sum(t.numel() * t.element_size() for t in (f0, f1, nhwc0, nhwc1))
+    assert pl.last_h2d_bytes == full - nhwc0.numel() * 2 + m * 128 * 2
+    pl.close()
+    for o in (out, out_pinned):
+        assert int(o["counts"].sum()) == m
+        cat = driver.flatten_slots(o)
+        for k in ("b_ids", "i_ids", "j_ids"):
+            assert torch.equal(cat[k], res[k][:m].cpu()), k
+        assert torch.equal(cat["mconf"], res["mconf"][:m].cpu())
+        assert torch.equal(cat["mkpts0_f"], res["mkpts0_f"][:m].cpu())
+        assert torch.equal(cat["mkpts1_f"], res["mkpts1_f"][:m].cpu())

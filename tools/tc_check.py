@@ -8,7 +8,9 @@ from pope_b200 import _lib, ops, synth
 dev = torch.device("cuda:0")
 cases = [(1, (12, 16), (12, 16), 256), (2, (12, 16), (12, 16), 64), (3, (10, 14), (8, 9), 128), (2, (30, 40), (32, 32), 256),
          (1, (5, 5), (40, 50), 192), (2, (60, 80), (60, 80), 256)]
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and sys.argv[1] == "hires":      # BASELINE configs[3]: 960x1280 -> 19,200 coarse tokens per image
+    cases = [(1, (120, 160), (120, 160), 256), (2, (120, 160), (120, 160), 256)]
+elif len(sys.argv) > 1:
     cases = cases[: int(sys.argv[1])]
 bad = 0
 for n, hw0, hw1, C in cases:
