@@ -153,6 +153,78 @@ def gather_matches(local: Dict[str, torch.Tensor], n_pairs: int, rank: int, worl
             "mkpts0_f": fl[:, 1:3], "mkpts1_f": fl[:, 3:5], "per_rank_matches": totals}
 
 
+def pack_records(res, pair_offset: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Capacity-sized result -> packed int32 records [cap, 8] = (b_global, i, j, mconf, x0, y0, x1, y1; floats as bit
+    patterns); rows past the live count are garbage.  No host sync."""
+    rec = torch.cat([(res["b_ids"] + pair_offset).to(torch.int32)[:, None], res["i_ids"].to(torch.int32)[:, None],
+                     res["j_ids"].to(torch.int32)[:, None], res["mconf"].view(torch.int32)[:, None],
+                     res["mkpts0_f"].view(torch.int32), res["mkpts1_f"].view(torch.int32)], 1, out=out)
+    return rec
+
+
+class JobGather:
+    """The single cross-GPU step of a sharded job: every rank appends the packed records of
+    each of its steps to a device buffer (no sync, no collective); `finish()` runs once at the end of the job -- one
+    host read of the per-step totals, one all-gather of the totals and one all-gather of the live records."""
+
+    def __init__(self, steps: int, cap: int, device):
+        self.rec = torch.empty(steps, cap, 8, dtype=torch.int32, device=device)
+        self.tot = torch.zeros(steps, dtype=torch.int32, device=device)
+        self.k = 0
+
+    def add(self, res, pair_offset: int):
+        pack_records(res, pair_offset, out=self.rec[self.k])
+        n = res["n_pairs"]
+        self.tot[self.k:self.k + 1].copy_(res["counts"][n:n + 1])
+        self.k += 1
+
+    def finish(self, rank: int, world: int, group=None):
+        import torch.distributed as dist
+        tot = self.tot[: self.k].tolist()                       # the job's one host read
+        live = torch.cat([self.rec[k, :m] for k, m in enumerate(tot)], 0) if sum(tot) else self.rec[0, :0]
+        mine = torch.tensor([live.shape[0]], dtype=torch.int64, device=live.device)
+        if world == 1:
+            self.k = 0
+            return live, [int(mine)]
+        sizes = torch.empty(world, dtype=torch.int64, device=live.device)
+        dist.all_gather_into_tensor(sizes, mine, group=group)
+        sizes = sizes.tolist()
+        mx = max(max(sizes), 1)
+        padded = torch.zeros(mx, 8, dtype=torch.int32, device=live.device)
+        padded[: live.shape[0]] = live
+        out = torch.empty(world * mx, 8, dtype=torch.int32, device=live.device)     # concatenation along dim 0
+        dist.all_gather_into_tensor(out, padded, group=group)
+        out = out.view(world, mx, 8)
+        self.k = 0
+        return out, sizes                                       # rank r's records: out[r, :sizes[r]], sorted by (b, i)
+
+
+def bind_host_to_gpu(device_index: int):
+    """Pin this process to the CPUs next to its GPU while it allocates page-locked staging buffers, so that they land
+    on the GPU's NUMA node (with 4-8 ranks the host link otherwise saturates on one socket).  Returns the previous
+    affinity (restore with os.sched_setaffinity(0, prev)) or None if NVML is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {c for c in range(ncpu) if (words[c // 64] >> (c % 64)) & 1}
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return prev
+    except Exception:
+        pass
+    return None
+
+
 def gather_matches_padded(res, n_local: int, rank: int, world: int, group=None):
     """Sync-free form of the single gather for a steady-state loop: every rank contributes its capacity-sized result
     as one packed int32 record tensor [cap, 8] = (b_global, i, j, mconf, x0, y0, x1, y1; floats as bit patterns) plus
@@ -160,14 +232,12 @@ def gather_matches_padded(res, n_local: int, rank: int, world: int, group=None):
     rank r's live records are records[r, :counts[r, n]] and are sorted by (b, i)."""
     import torch.distributed as dist
     cap = res["i_ids"].shape[0]
-    rec = torch.cat([(res["b_ids"] + rank * n_local).to(torch.int32)[:, None], res["i_ids"].to(torch.int32)[:, None],
-                     res["j_ids"].to(torch.int32)[:, None], res["mconf"].view(torch.int32)[:, None],
-                     res["mkpts0_f"].view(torch.int32), res["mkpts1_f"].view(torch.int32)], 1)
-    out = torch.empty(world, cap, 8, dtype=torch.int32, device=rec.device)
-    cnt = torch.empty(world, res["counts"].numel(), dtype=torch.int32, device=rec.device)
+    rec = pack_records(res, rank * n_local)
+    out = torch.empty(world * cap, 8, dtype=torch.int32, device=rec.device)
+    cnt = torch.empty(world * res["counts"].numel(), dtype=torch.int32, device=rec.device)
     dist.all_gather_into_tensor(out, rec, group=group)
     dist.all_gather_into_tensor(cnt, res["counts"], group=group)
-    return out, cnt
+    return out.view(world, cap, 8), cnt.view(world, -1)
 
 
 def run_sharded(n_pairs: int, rank: int, world: int, local_fn: Callable[[int, int], Dict[str, torch.Tensor]],

@@ -46,8 +46,27 @@ def _worker(rank, world, port, n_pairs, q):
         return o
 
     got = driver.run_sharded(n_pairs, rank, world, local_fn)
+    # the job-level gather used by bench.py for N > 1: two "steps" per rank, one collective at the end
+    lo, hi = driver.shard_range(n_pairs, rank, world)
+    loc = local_fn(lo, hi)
+    m = loc["i_ids"].numel()
+    cap = 2 * m + 8
+    res = {"b_ids": torch.zeros(cap, dtype=torch.int64), "i_ids": torch.zeros(cap, dtype=torch.int64),
+           "j_ids": torch.zeros(cap, dtype=torch.int64), "mconf": torch.zeros(cap), "mkpts0_f": torch.zeros(cap, 2),
+           "mkpts1_f": torch.zeros(cap, 2), "n_pairs": hi - lo, "counts": torch.zeros(hi - lo + 2, dtype=torch.int32)}
+    for k in ("b_ids", "i_ids", "j_ids", "mconf", "mkpts0_f", "mkpts1_f"):
+        res[k][:m] = loc[k] if k != "b_ids" else loc[k] - lo
+    res["counts"][hi - lo] = m
+    job = driver.JobGather(2, cap, torch.device("cpu"))
+    job.add(res, lo)
+    job.add(res, lo)
+    recs, sizes = job.finish(rank, world)
     if rank == 0:
-        q.put({k: (v.clone() if torch.is_tensor(v) else v) for k, v in got.items()})
+        payload = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in got.items()}
+        payload["job_sizes"] = sizes
+        payload["job_b"] = torch.cat([recs[r, :sizes[r], 0] for r in range(world)]).clone()
+        payload["job_conf"] = torch.cat([recs[r, :sizes[r], 3] for r in range(world)]).view(torch.float32).clone()
+        q.put(payload)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -78,3 +97,10 @@ def test_two_rank_gather_equals_single_process():
     assert torch.equal(got["mconf"], want["mconf"])
     assert torch.equal(got["mkpts1_f"], want["mkpts1_f"]) and torch.equal(got["mkpts0_f"], want["mkpts0_f"])
     assert sum(got["per_rank_matches"]) == want["b_ids"].numel()
+    # job-level gather: each rank contributed its matches twice (two identical steps)
+    assert got["job_sizes"] == [2 * x for x in got["per_rank_matches"]]
+    per = torch.tensor(got["per_rank_matches"])
+    off = torch.cat([torch.zeros(1, dtype=torch.long), per.cumsum(0)])
+    want_b = torch.cat([want["b_ids"][off[r]:off[r + 1]].repeat(2) for r in range(2)]).to(torch.int32)
+    want_c = torch.cat([want["mconf"][off[r]:off[r + 1]].repeat(2) for r in range(2)])
+    assert torch.equal(got["job_b"], want_b) and torch.equal(got["job_conf"], want_c)
