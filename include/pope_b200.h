@@ -114,15 +114,25 @@ int pope_fine_match(const void* win0, const void* win1, int dtype, int64_t M, co
 /* Fused form of pope_fine_gather + pope_fine_match for pipelines that run nothing between the two (the hot-path-only
  * pipeline; inside Matcher.forward the fine transformer sits between them and the two-call form is used): the centre
  * pixel of window 0 and the W*W pixels of window 1 are read straight from the CHANNELS-LAST maps (strides[1] == 1,
- * else POPE_ERR_SHAPE), the windows are never written.  Same results as the two calls up to fp32 summation order.
+ * else POPE_ERR_SHAPE), the windows are never written.  `order` (may be NULL) = processing order from
+ * pope_match_order_by_ref.  Same results as the two calls up to fp32 summation order.
  * Cf == 128, W == 5. */
 int pope_fine_match_maps(const void* feat_f0, const void* feat_f1, int dtype, int n_pairs, int Cf,
                          int Hf0, int Wf0, const int64_t strides0[4],
                          int Hf1, int Wf1, const int64_t strides1[4],
                          int w0c, int w1c, int stride, int W,
                          const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids,
-                         int64_t M, const int32_t* m_dev, const float* mkpts1_c, float coord_scale,
+                         int64_t M, const int32_t* m_dev, const int32_t* order,
+                         const float* mkpts1_c, float coord_scale,
                          float* expec_f, float* mkpts1_f, void* stream);
+
+/* Optional processing order for pope_fine_match_maps: order[k] = index of the k-th match when the matches of each
+ * pair are sorted by their reference cell j (counting sort, one CTA per pair).  The coarse stage emits matches sorted by
+ * (pair, i), whose reference cells are scattered over image 1; processed in (pair, j) order, neighbouring warps gather
+ * adjacent / overlapping windows of the fine map.  Results are written at the match's own index, so outputs do not
+ * depend on the order.  counts: the int32[n_pairs+2] array written by pope_coarse_match; order: int32[capacity]. */
+int pope_match_order_by_ref(const int32_t* counts, int n_pairs, int S, const int64_t* j_ids, int32_t* order,
+                            void* stream);
 
 /* Retrieval: cosine similarity (x.y / (max(|x|,eps) * max(|y|,eps))) of one query token against R reference
  * tokens, followed by the eval loop's slot-replacement top-k (slots start at 0; a score greater than any slot

@@ -189,6 +189,57 @@ __global__ void __launch_bounds__(256) fine_match_kernel(const T* __restrict__ w
   fine_match_finish(p, lane, m, mkpts1_c, inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
 }
 
+// Processing order for the fine stage: matches come out of the coarse stage sorted by (pair, i); their reference
+// cells j are scattered over image 1, so consecutive warps would gather windows from random places of the fine map.
+// One CTA per pair counting-sorts its matches by j (histogram over the S cells in shared memory, block scan, scatter):
+// order[k] = index of the k-th match in (pair, j) order.  Neighbouring warps then read overlapping / adjacent windows.
+__global__ void __launch_bounds__(1024) order_by_ref_kernel(const int32_t* __restrict__ counts, int n_pairs, int S,
+                                                           const int64_t* __restrict__ j_ids, int32_t* __restrict__ order) {
+  extern __shared__ int hist[];            // [S] counts, then exclusive offsets
+  __shared__ int warp_tot[32];
+  __shared__ int s_base;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    int base = 0;
+    for (int p = 0; p < b; ++p) base += counts[p];
+    s_base = base;
+  }
+  for (int j = tid; j < S; j += 1024) hist[j] = 0;
+  __syncthreads();
+  const int base = s_base, cnt = counts[b];
+  for (int r = tid; r < cnt; r += 1024) atomicAdd(&hist[int(j_ids[base + r])], 1);
+  __syncthreads();
+  // exclusive scan of hist[0..S): each thread owns a contiguous slice
+  const int per = (S + 1023) / 1024, lo = min(tid * per, S), hi = min(lo + per, S);
+  int sum = 0;
+  for (int j = lo; j < hi; ++j) sum += hist[j];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFullMask, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = warp_tot[lane], inc2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFullMask, inc2, o);
+      if (lane >= o) inc2 += t;
+    }
+    warp_tot[lane] = inc2 - v;
+  }
+  __syncthreads();
+  int run = warp_tot[warp] + incl - sum;
+  for (int j = lo; j < hi; ++j) { const int c = hist[j]; hist[j] = run; run += c; }
+  __syncthreads();
+  for (int r = tid; r < cnt; r += 1024) {
+    const int slot = atomicAdd(&hist[int(j_ids[base + r])], 1);
+    order[base + slot] = base + r;
+  }
+}
+
 // softmax over the 25 window positions + expectation / std / refined coordinate; lane holds position r (on = r < 25)
 __device__ __forceinline__ void fine_match_tail(float sim, int r, bool on, int lane, int64_t m,
                                                 const float* __restrict__ mkpts1_c, float inv_sqrt_c, float coord_scale,
@@ -239,6 +290,7 @@ __global__ void __launch_bounds__(256) fine_match_maps_kernel(MapDesc m0, MapDes
                                                              const int64_t* __restrict__ i_ids,
                                                              const int64_t* __restrict__ j_ids, int64_t M,
                                                              const int32_t* __restrict__ m_dev,
+                                                             const int32_t* __restrict__ order,
                                                              const float* __restrict__ mkpts1_c, float inv_sqrt_c,
                                                              float coord_scale, float* __restrict__ expec_f,
                                                              float* __restrict__ mkpts1_f) {
@@ -248,9 +300,10 @@ __global__ void __launch_bounds__(256) fine_match_maps_kernel(MapDesc m0, MapDes
   constexpr int PPI = 32 / LPP;               // pixels per warp-wide load
   constexpr int IT = (WW + PPI - 1) / PPI;    // 25 or 13
   const int lane = threadIdx.x & 31, sub = lane / LPP, v = lane % LPP;
-  const int64_t m = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t w = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t live = m_dev ? min(int64_t(*m_dev), M) : M;
-  if (m >= live) return;
+  if (w >= live) return;
+  const int64_t m = order ? int64_t(order[w]) : w;      // optional processing order (sorted by reference cell)
   const int64_t b = b_ids[m];
   const int ci = int(i_ids[m]), cj = int(j_ids[m]);                                   // 32-bit: no 64-bit divisions
   const int y0c = (ci / m0.wc) * stride, x0c = (ci % m0.wc) * stride;                // centre pixel of window 0
@@ -376,8 +429,9 @@ extern "C" int pope_fine_match(const void* win0, const void* win1, int dtype, in
 extern "C" int pope_fine_match_maps(const void* feat_f0, const void* feat_f1, int dtype, int n_pairs, int Cf, int Hf0,
                                     int Wf0, const int64_t strides0[4], int Hf1, int Wf1, const int64_t strides1[4],
                                     int w0c, int w1c, int stride, int W, const int64_t* b_ids, const int64_t* i_ids,
-                                    const int64_t* j_ids, int64_t M, const int32_t* m_dev, const float* mkpts1_c,
-                                    float coord_scale, float* expec_f, float* mkpts1_f, void* stream) {
+                                    const int64_t* j_ids, int64_t M, const int32_t* m_dev, const int32_t* order,
+                                    const float* mkpts1_c, float coord_scale, float* expec_f, float* mkpts1_f,
+                                    void* stream) {
   if (!feat_f0 || !feat_f1 || !strides0 || !strides1 || M < 0) return POPE_ERR_INVALID_ARG;
   if (dtype != POPE_F32 && dtype != POPE_BF16) return POPE_ERR_DTYPE;
   if (n_pairs <= 0 || Hf0 <= 0 || Wf0 <= 0 || Hf1 <= 0 || Wf1 <= 0 || w0c <= 0 || w1c <= 0 || stride <= 0)
@@ -398,9 +452,21 @@ extern "C" int pope_fine_match_maps(const void* feat_f0, const void* feat_f1, in
   const float inv_sqrt_c = static_cast<float>(1.0 / sqrt(double(Cf)));
   if (dtype == POPE_BF16)
     fine_match_maps_kernel<__nv_bfloat16><<<blocks, warps * 32, 0, st>>>(m0, m1, stride, b_ids, i_ids, j_ids, M, m_dev,
-                                                                        mkpts1_c, inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
+                                                                        order, mkpts1_c, inv_sqrt_c, coord_scale,
+                                                                        expec_f, mkpts1_f);
   else
-    fine_match_maps_kernel<float><<<blocks, warps * 32, 0, st>>>(m0, m1, stride, b_ids, i_ids, j_ids, M, m_dev, mkpts1_c,
-                                                                inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
+    fine_match_maps_kernel<float><<<blocks, warps * 32, 0, st>>>(m0, m1, stride, b_ids, i_ids, j_ids, M, m_dev, order,
+                                                                mkpts1_c, inv_sqrt_c, coord_scale, expec_f, mkpts1_f);
+  return int(cudaGetLastError());
+}
+
+extern "C" int pope_match_order_by_ref(const int32_t* counts, int n_pairs, int S, const int64_t* j_ids, int32_t* order,
+                                       void* stream) {
+  if (!counts || !j_ids || !order || n_pairs <= 0 || S <= 0) return POPE_ERR_INVALID_ARG;
+  const size_t smem = size_t(S) * sizeof(int);
+  if (smem > 200 * 1024) return POPE_ERR_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(order_by_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return int(e);
+  order_by_ref_kernel<<<n_pairs, 1024, smem, static_cast<cudaStream_t>(stream)>>>(counts, n_pairs, S, j_ids, order);
   return int(cudaGetLastError());
 }

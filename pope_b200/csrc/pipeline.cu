@@ -193,7 +193,7 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
                            s.i_ids, s.j_ids, s.mconf, s.mk0, s.mk1, s.counts, int64_t(capt), pl->s_comp);
     if (rc) goto fail;
     rc = pope_fine_match_maps(f0_dev_view ? static_cast<const void*>(f0_dev_view + p0 * ff0_pair) : s.ff0, s.ff1, pl->dtype, n, pl->Cf, Hf0, Wf0, st0, Hf1, Wf1, st1, pl->w0c, pl->w1c,
-                              pl->fstride, pl->W, s.b_ids, s.i_ids, s.j_ids, int64_t(capt), s.counts + n, s.mk1,
+                              pl->fstride, pl->W, s.b_ids, s.i_ids, s.j_ids, int64_t(capt), s.counts + n, nullptr, s.mk1,
                               coord_scale, s.expec, s.mk1f, pl->s_comp);
     if (rc) goto fail;
     slot_kernel<<<n, 256, 0, pl->s_comp>>>(s.counts, int(cap), s.i_ids, s.j_ids, s.mconf, s.mk0, s.mk1f, s.o_i, s.o_j,

@@ -302,6 +302,14 @@ def test_fused_fine_equals_gather_then_match(dtype):
     live = torch.tensor([123], dtype=torch.int32, device=DEV)
     e_part, _ = ops.fine_match_maps(a, c, b, i, j, mk1, w0, w1, 4, 4.0, m_dev=live)
     assert torch.equal(e_part[:123], e_fused[:123])
+    # processing order sorted by reference cell: a permutation within each pair, results unchanged
+    counts = torch.cat([torch.bincount(b, minlength=n).to(torch.int32), torch.tensor([M, 0], dtype=torch.int32, device=DEV)])
+    order = ops.match_order_by_ref(counts, n, h1 * w1, j)
+    assert sorted(order.tolist()) == list(range(M))
+    key = (b[order.long()] * (h1 * w1) + j[order.long()]).cpu()
+    assert bool((key[1:] >= key[:-1]).all())
+    e_ord, k_ord = ops.fine_match_maps(a, c, b, i, j, mk1, w0, w1, 4, 4.0, order=order)
+    assert torch.equal(e_ord, e_fused) and torch.equal(k_ord, k_fused)
     with pytest.raises(_lib.PopeError):     # plain NCHW maps are not accepted by the fused kernel
         ops.fine_match_maps(a.contiguous(), c.contiguous(), b, i, j, mk1, w0, w1, 4, 4.0)
 
