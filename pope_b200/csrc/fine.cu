@@ -285,7 +285,7 @@ template <> struct Vec16<__nv_bfloat16> {
 // from clamped coordinates (out-of-map pixels contribute 0, like the reference's zero padding) so that all of them
 // are in flight together.  Same arithmetic per channel as gather_cl_kernel + fine_match_kernel.
 template <typename T>
-__global__ void __launch_bounds__(256) fine_match_maps_kernel(MapDesc m0, MapDesc m1, int stride,
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) fine_match_maps_kernel(MapDesc m0, MapDesc m1, int stride,
                                                              const int64_t* __restrict__ b_ids,
                                                              const int64_t* __restrict__ i_ids,
                                                              const int64_t* __restrict__ j_ids, int64_t M,
@@ -313,13 +313,29 @@ __global__ void __launch_bounds__(256) fine_match_maps_kernel(MapDesc m0, MapDes
   const uint4 craw = ld_stream16(img0 + int64_t(y0c) * m0.sH + int64_t(x0c) * m0.sW + v * NCH);
   uint4 raw[IT];
   bool ok[IT];
+  if (y1 >= 0 && x1 >= 0 && y1 + WIN <= m1.H && x1 + WIN <= m1.W) {
+    // window entirely inside the map (always the case when border_rm >= 1): no clamping, the pixel offset advances
+    // incrementally (r -> r + PPI wraps to the next window row every 5 pixels)
+    const T* p1 = img1 + int64_t(y1) * m1.sH + int64_t(x1) * m1.sW + v * NCH;
+    int kx = sub;                                  // r = k * PPI + sub, (ky, kx) = divmod(r, 5); sub < 5
+    int64_t off = int64_t(sub) * m1.sW;
+    const int64_t wrap = m1.sH - int64_t(WIN) * m1.sW;
 #pragma unroll
-  for (int k = 0; k < IT; ++k) {
-    const int r = k * PPI + sub;
-    const int y = y1 + r / WIN, x = x1 + r % WIN;
-    ok[k] = r < WW && y >= 0 && y < m1.H && x >= 0 && x < m1.W;
-    const int yc = min(max(y, 0), m1.H - 1), xc = min(max(x, 0), m1.W - 1);
-    raw[k] = ld_stream16(img1 + int64_t(yc) * m1.sH + int64_t(xc) * m1.sW + v * NCH);
+    for (int k = 0; k < IT; ++k) {
+      ok[k] = k * PPI + sub < WW;
+      raw[k] = ld_stream16(p1 + (ok[k] ? off : 0));
+      kx += PPI; off += int64_t(PPI) * m1.sW;
+      if (kx >= WIN) { kx -= WIN; off += wrap; }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < IT; ++k) {
+      const int r = k * PPI + sub;
+      const int y = y1 + r / WIN, x = x1 + r % WIN;
+      ok[k] = r < WW && y >= 0 && y < m1.H && x >= 0 && x < m1.W;
+      const int yc = min(max(y, 0), m1.H - 1), xc = min(max(x, 0), m1.W - 1);
+      raw[k] = ld_stream16(img1 + int64_t(yc) * m1.sH + int64_t(xc) * m1.sW + v * NCH);
+    }
   }
   float ctr[NCH];
   Vec16<T>::unpack(craw, ctr);
