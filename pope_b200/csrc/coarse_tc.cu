@@ -37,11 +37,15 @@ constexpr int kBoxBytes = kBoxRows * kBoxK * 2;      // 16384
 constexpr int kUnitRows = 256;          // stationary rows per work unit (128 per CTA of the pair)
 constexpr int kTileCols = 256;          // streamed rows per tile (= MMA N; 128 loaded by each CTA)
 constexpr int kMaxKChunks = 4;          // C <= 256
-constexpr int kEpiWarps = 16;           // 4 per scheduler keep the MUFU pipe fed
+constexpr int kEpiWarps = 16;           // epilogue warps (multiple of 4: one per TMEM lane quadrant and column group)
+constexpr int kColGroups = kEpiWarps / 4;            // threads per row
+constexpr int kChunks = (256 / 32) / kColGroups;     // 32-column chunks per thread and tile
+constexpr int kSpan = kChunks * 32;                  // columns per thread and tile
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kTmemCols = 512;
-constexpr bool kLoadBoth = false;                    // (measured slower: 64 live accumulators spill at the 96-register cap)
+constexpr bool kLoadAll = (kEpiWarps == 8);          // all chunks TMEM -> registers before any arithmetic (needs the
+                                                     // 204-register budget of the 8-warp layout; spills with 16 warps)
 constexpr bool kPolyExp = false;                     // every 4th exp2 on the FMA pipe (measured slower: +2.5 instr/element)
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
@@ -370,7 +374,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     constexpr bool kLse = (MODE == 0 || MODE == 2);      // online log-sum-exp of the thread's row
     constexpr bool kStage = (MODE == 1);                 // per-column terms staged in shared memory (three-sweep path)
     const int e = threadIdx.x - 64;                 // 0..511
-    const int colq = (warp - 2) >> 2;               // which 64 of the tile's 256 columns (4 consecutive warps = 4 quadrants)
+    const int colq = (warp - 2) >> 2;               // which kSpan of the tile's 256 columns (4 consecutive warps = 4 quadrants)
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
     const int row_in_cta = quad * 32 + lane;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
@@ -416,25 +420,26 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
-        float minb0 = INFINITY, minb1 = INFINITY;    // MODE 2: fetched before the wait so the latency is hidden
-        if (MODE == 2) {
-          const int c0 = (col0 >> 5) + colq * 2;
-          if (c0 < nchunks) minb0 = __ldg(P.cminb + size_t(n) * nchunks + c0);
-          if (c0 + 1 < nchunks) minb1 = __ldg(P.cminb + size_t(n) * nchunks + c0 + 1);
+        float minb[kChunks];                         // MODE 2: fetched before the wait so the latency is hidden
+#pragma unroll
+        for (int cc = 0; cc < kChunks; ++cc) {
+          minb[cc] = INFINITY;
+          const int c0 = (col0 >> 5) + colq * kChunks + cc;
+          if (MODE == 2 && c0 < nchunks) minb[cc] = __ldg(P.cminb + size_t(n) * nchunks + c0);
         }
         mbar_wait(bar_acc_full + 8 * s, acc_phase);
         tc_fence_after();
-        const uint32_t tbase = tmem_base + lane_addr + s * kTileCols + colq * 64;
-        const int nvalid = min(LB - col0, kTileCols) - colq * 64;      // valid columns from this thread's first one
+        const uint32_t tbase = tmem_base + lane_addr + s * kTileCols + colq * kSpan;
+        const int nvalid = min(LB - col0, kTileCols) - colq * kSpan;   // valid columns from this thread's first one
         if (MODE == 1) {
           // ---- three-sweep path: candidate test against both log-sum-exps; flagged columns re-read from TMEM ----
 #pragma unroll 1
-          for (int cc = 0; cc < 2; ++cc) {
+          for (int cc = 0; cc < kChunks; ++cc) {
             const int vc = nvalid - cc * 32;
             if (vc <= 0 || (P.debug & 1)) break;
             float v[32];
             tmem_ld32(tbase + cc * 32, v);
-            const uint32_t lb = sbase + kSmemLc + (s * kTileCols + colq * 64 + cc * 32) * 4;
+            const uint32_t lb = sbase + kSmemLc + (s * kTileCols + colq * kSpan + cc * 32) * 4;
             bool any = false;
 #pragma unroll
             for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -451,9 +456,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
                 all &= all - 1;
                 const float vj = tmem_ld1(tbase + cc * 32 + j);
                 if ((mask >> j) & 1u) {
-                  const int col = col0 + colq * 64 + cc * 32 + j;
+                  const int col = col0 + colq * kSpan + cc * 32 + j;
                   const float x = vj * scale;
-                  const float t2 = (x - lr) + (x - lc_exact[s * kTileCols + colq * 64 + cc * 32 + j]);
+                  const float t2 = (x - lr) + (x - lc_exact[s * kTileCols + colq * kSpan + cc * 32 + j]);
                   if (t2 > P.log2_thr) {
                     atomicMax(P.rowbest + size_t(n) * LA + row, pack_best(t2, col));
                     atomicMax(P.colbest + size_t(n) * LB + col, pack_best(t2, row));
@@ -473,8 +478,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           auto scan = [&](const float (&v)[32], int cc, float cmax, bool defer) {
             // MODE 2: does this 32x32 block hold a cell with p_row > thr?  group-level bound first (1 compare + vote),
             // the per-element test only where it can succeed (~1 block in 4); bounds come from cand_bounds_kernel
-            const int chunk = colq * 2 + cc;
-            const bool maybe = cmax > (cc ? minb1 : minb0);
+            const int chunk = colq * kChunks + cc;
+            const bool maybe = cmax > minb[cc];
             if (__any_sync(kFullMask, maybe && row < LA) && !(P.debug & 2)) {
               // bound rows are padded to a multiple of 32 with +inf, so every processed chunk is fully readable/aligned
               const float4* lb = reinterpret_cast<const float4*>(P.cbound + (size_t(n) * nchunks << 5) + col0 + chunk * 32);
@@ -498,25 +503,27 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               }
             }
           };
-          const int vc0 = nvalid, vc1 = nvalid - 32;
           const bool skip = (P.debug & 1) != 0;
-          if (kLoadBoth) {
-            // both 32-column chunks are pulled into registers first, the stage is handed back, then all arithmetic
-            float v0[32], v1[32];
-            if (vc0 > 0 && !skip) tmem_ld32(tbase, v0);
-            if (vc1 > 0 && !skip) tmem_ld32(tbase + 32, v1);
+          if (kLoadAll) {
+            // every chunk of the thread is pulled into registers first, the stage is handed back, then all arithmetic
+            float v[kChunks][32];
+#pragma unroll
+            for (int cc = 0; cc < kChunks; ++cc)
+              if (nvalid - cc * 32 > 0 && !skip) tmem_ld32(tbase + cc * 32, v[cc]);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
-            if (vc0 > 0 && !skip) {
-              const float cmax = lse_update(v0, vc0, scale, m_run, s_run);
-              if (MODE == 2) scan(v0, 0, cmax, false);
-            }
-            if (vc1 > 0 && !skip) {
-              const float cmax = lse_update(v1, vc1, scale, m_run, s_run);
-              if (MODE == 2) scan(v1, 1, cmax, false);
+#pragma unroll
+            for (int cc = 0; cc < kChunks; ++cc) {
+              const int vc = nvalid - cc * 32;
+              if (vc > 0 && !skip) {
+                const float cmax = lse_update(v[cc], vc, scale, m_run, s_run);
+                if (MODE == 2) scan(v[cc], cc, cmax, false);
+              }
             }
           } else {
+            static_assert(kLoadAll || kChunks == 2, "the chunk-by-chunk epilogue is written for two chunks per thread");
+            const int vc0 = nvalid, vc1 = nvalid - 32;
             float v[32];
             if (vc0 > 0 && !skip) {
               tmem_ld32(tbase, v);
@@ -542,7 +549,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         if (colq == 0 && row < LA) {
           float m = m_run, sum = s_run;
 #pragma unroll
-          for (int q = 0; q < 3; ++q) {
+          for (int q = 0; q < kColGroups - 1; ++q) {
             const float2 o = merge[q * 128 + row_in_cta];
             const float mm = fmaxf(m, o.x);
             sum = sum * ex2_approx(m - mm) + o.y * ex2_approx(o.x - mm);

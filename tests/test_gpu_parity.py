@@ -149,6 +149,20 @@ def test_coarse_permutation_property_full_size(impl):
     assert_sorted_by_pair_and_row(out["b_ids"], out["i_ids"], L)
 
 
+def test_coarse_high_res_tcgen05_equals_fp32_fma():
+    """BASELINE configs[3]: 960x1280 -> 19,200 coarse tokens per image.  The CPU oracle needs 7 GB for this shape, so
+    the tensor-core path is held to the fp32-FMA kernels (themselves held to the oracle at the smaller sizes)."""
+    _need_tc("tcgen05", 256, 19200, 19200)
+    f0, f1 = synth.coarse_features(47, 1, 19200, 19200, 256, dtype=torch.bfloat16)
+    a = _run_coarse(f0, f1, (120, 160), (120, 160), _lib.COARSE_SIMT, torch.bfloat16)
+    b = _run_coarse(f0, f1, (120, 160), (120, 160), _lib.COARSE_TCGEN05, torch.bfloat16)
+    assert a["b_ids"].numel() > 50
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.allclose(a["mconf"], b["mconf"], rtol=1e-4, atol=0)
+    assert torch.equal(a["mkpts1_c"], b["mkpts1_c"])
+
+
 def test_coarse_edge_cases():
     # grid too small for the border -> no match, empty tensors of the right shapes/dtypes
     f0, f1 = synth.coarse_features(1, 1, 16, 16, 64, sigma=2.0)
