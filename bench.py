@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--coarse-impl", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-sample-pairs", type=int, default=2)
+    ap.add_argument("--in-matcher", type=int, default=0, metavar="PAIRS",
+                    help="also time steps 3-5 of Matcher.forward on PAIRS pairs with the PyTorch FinePreprocess Linears and "
+                         "fine transformer between the CUDA stages (fp32, SURVEY 8(d) 'in-Matcher' figure)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -136,6 +139,47 @@ def cpu_reference_pairs_per_sec(n_sample: int, repeats: int = 1):
         best = min(best, time.perf_counter() - t0)
         m = out["b_ids"].numel()
     return n_sample / best, best, m, torch.get_num_threads()
+
+
+def in_matcher_figure(n_pairs: int, dev):
+    """Steps 3-5 of Matcher.forward (src/matcher/matcher.py:71-79) with the drop-in modules: CUDA coarse match -> CUDA
+    window gather -> torch Linears -> torch fine transformer -> CUDA fine match, fp32 features like the reference."""
+    import pope_b200
+    from pope_b200 import synth
+    torch.manual_seed(0)
+    m = pope_b200.Matcher(pope_b200.make_default_cfg()).eval().to(dev)
+    f0, f1 = synth.coarse_features(99, n_pairs, L, L, C_COARSE)
+    g = torch.Generator(device=dev).manual_seed(98)
+    hf, wf = HC * FINE_STRIDE, WC * FINE_STRIDE
+    ff0 = torch.randn(n_pairs, hf, wf, C_FINE, device=dev, generator=g).permute(0, 3, 1, 2)
+    ff1 = torch.randn(n_pairs, hf, wf, C_FINE, device=dev, generator=g).permute(0, 3, 1, 2)
+    f0, f1 = f0.to(dev), f1.to(dev)
+    shapes = {"hw0_i": torch.Size([H, W_IMG]), "hw1_i": torch.Size([H, W_IMG]), "hw0_c": torch.Size([HC, WC]),
+              "hw1_c": torch.Size([HC, WC]), "hw0_f": torch.Size([hf, wf]), "hw1_f": torch.Size([hf, wf]), "bs": n_pairs}
+
+    def run():
+        data = dict(shapes)
+        with torch.no_grad():
+            m.coarse_matching(f0, f1, data)
+            w0, w1 = m.fine_preprocess(ff0, ff1, f0, f1, data)
+            if w0.size(0):
+                w0, w1 = m.loftr_fine(w0, w1)
+            m.fine_matching(w0, w1, data)
+        return data
+
+    for _ in range(2):
+        data = run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        data = run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 3
+    return {"value": n_pairs / (ms / 1e3), "unit": UNIT, "pairs": n_pairs, "ms": ms, "matches": int(data["mconf"].numel()),
+            "dtype": "f32", "note": "CUDA coarse (fp32-FMA path) + CUDA gather + torch Linears + torch fine transformer + CUDA "
+                                    "fine match; the fine transformer (SURVEY 8(f) next row 1) dominates"}
 
 
 def run_reference(args):
@@ -319,6 +363,8 @@ def main():
                           "algorithmic_bytes_per_launch": fine_bytes},
         "gpu_launches": args.steps * _lib.KERNELS_PER_STEP["tcgen05" if tc else "simt"],
     }
+    if args.in_matcher > 0:
+        line["in_matcher"] = in_matcher_figure(args.in_matcher, dev)
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu:
