@@ -33,6 +33,7 @@ SIGNATURES = {
                                   _i, _i, _i, _i, _p, _p, _p, _i64, _p, _p, _p, _f, _p, _p, _p]),
     "pope_match_order_by_ref": (_i, [_p, _i, _i, _p, _p, _p]),
     "pope_cosine_topk": (_i, [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
+    "pope_debug_trace_read": (_i, [_p, _i]),
     "pope_pipeline_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i]),
     "pope_pipeline_run": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "pope_pipeline_destroy": (_i, [_p]),

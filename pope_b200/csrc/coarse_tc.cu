@@ -47,6 +47,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr bool kLoadAll = (kEpiWarps == 8);          // all chunks TMEM -> registers before any arithmetic (needs the
                                                      // 204-register budget of the 8-warp layout; spills with 16 warps)
 constexpr bool kPolyExp = false;                     // every 4th exp2 on the FMA pipe (measured slower: +2.5 instr/element)
+constexpr int kTraceTiles = 512;                      // developer diagnostics: tiles of CTA pair 0 that get clock stamps
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
 // dynamic shared memory layout (base aligned to 1024 B for the 128B swizzle); identical in both CTAs of a pair
@@ -175,6 +176,7 @@ struct SweepParams {
   int* cand_cnt;            //   per streamed row: cells with p_row > thr seen so far
   u64* cand;                //   [.., kCandSlots] (raw accumulator bits << 32 | stationary row)
   int32_t* flags;
+  unsigned long long* trace;   // developer diagnostics (POPE_TC_TRACE): clock stamps of CTA pair 0, or nullptr
   int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps
 };
 
@@ -350,11 +352,16 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         tc_fence_after();
         for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
           const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
+          const bool tr = P.trace && pair == 0 && tile_ctr < kTraceTiles;
+          unsigned long long* rec = P.trace + size_t(tile_ctr) * 8;
+          if (tr) rec[0] = clock64() | ((unsigned long long)(ct == 0) << 63);   // top bit: first tile of a unit
           mbar_wait(bar_acc_empty + 8 * s, acc_phase ^ 1);
+          if (tr) rec[1] = clock64();
           tc_fence_after();
           const uint32_t d = tmem_base + s * kTileCols;
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(bar_b_full + 8 * b_stage, b_phase);
+            if (tr && kc == 0) rec[2] = clock64();
             tc_fence_after();
             const uint32_t a_addr = sbase + kSmemA + kc * kBoxBytes;
             const uint32_t b_addr = sbase + kSmemB + b_stage * kBoxBytes;
@@ -362,9 +369,11 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             for (int ks = 0; ks < kBoxK / 16; ++ks)
               umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), (kc | ks) ? 1u : 0u);
             umma_commit_2sm(bar_b_empty + 8 * b_stage);  // ring slot free in both CTAs once these MMAs have read it
+            if (tr && kc < 4) rec[4 + kc] = clock64();    // this chunk's four MMAs and its commit are issued
             if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
           }
           umma_commit_2sm(bar_acc_full + 8 * s);         // accumulator stage complete (both CTAs' epilogues)
+          if (tr) rec[3] = clock64();
         }
         if (!(P.debug & 4)) umma_commit_2sm(bar_a_empty);   // stationary blocks may be overwritten
       }
@@ -427,7 +436,11 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           const int c0 = (col0 >> 5) + colq * kChunks + cc;
           if (MODE == 2 && c0 < nchunks) minb[cc] = __ldg(P.cminb + size_t(n) * nchunks + c0);
         }
+        const bool etr = P.trace && pair == 0 && rank == 0 && warp == 2 && lane == 0 && tile_ctr < kTraceTiles;
+        unsigned long long* erec = P.trace + size_t(kTraceTiles + tile_ctr) * 8;
+        if (etr) erec[0] = clock64();
         mbar_wait(bar_acc_full + 8 * s, acc_phase);
+        if (etr) erec[1] = clock64();
         tc_fence_after();
         const uint32_t tbase = tmem_base + lane_addr + s * kTileCols + colq * kSpan;
         const int nvalid = min(LB - col0, kTileCols) - colq * kSpan;   // valid columns from this thread's first one
@@ -534,11 +547,13 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
+            if (etr) erec[2] = clock64();
             if (vc1 > 0 && !skip) {
               const float cmax = lse_update(v, vc1, scale, m_run, s_run);
               if (MODE == 2) scan(v, 1, cmax, false);
             }
             if (MODE == 2 && pend_col >= 0) cand_emit(P.cand_cnt, P.cand, P.flags, size_t(n) * LB + pend_col, pend_v, row);
+            if (etr) erec[3] = clock64();
           }
         }
       }
@@ -625,6 +640,8 @@ __global__ void __launch_bounds__(256) cand_bounds_kernel(const float* __restric
   if (lane == 0) cminb[g] = mb;
 }
 
+unsigned long long* g_trace = nullptr;     // developer diagnostics buffer (allocated on first use of POPE_TC_TRACE)
+
 // One thread per row i: evaluate the (at most kCandSlots) cells with p_row > thr found by the column sweep.
 __global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
                                                        const float* __restrict__ lse_r, const float* __restrict__ lse_c,
@@ -651,7 +668,9 @@ __global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ 
   rowbest[r] = best;
 }
 
+unsigned long long* trace_get() { return g_trace; }
 }  // namespace
+unsigned long long* trace_buffer() { return trace_get(); }
 
 bool coarse_tc_supported(const CoarseProblem& p) {
   return p.dtype == POPE_BF16 && p.C % kBoxK == 0 && p.C >= kBoxK && p.C <= kBoxK * kMaxKChunks;
@@ -670,6 +689,12 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   if ((e = cudaFuncSetAttribute(sweep_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   SweepParams P{};
   if (const char* dbg = getenv("POPE_TC_DEBUG")) P.debug = atoi(dbg);
+  const char* trace_env = getenv("POPE_TC_TRACE");         // developer diagnostics: "0" / "2" = trace that sweep mode
+  const int trace_mode = trace_env ? atoi(trace_env) : -1;
+  if (trace_mode >= 0 && !g_trace) {
+    if ((e = cudaMalloc(&g_trace, sizeof(unsigned long long) * 8 * 2 * kTraceTiles)) != cudaSuccess) return e;
+    if ((e = cudaMemset(g_trace, 0, sizeof(unsigned long long) * 8 * 2 * kTraceTiles)) != cudaSuccess) return e;
+  }
   P.n = p.n;
   P.L0 = p.L; P.L1 = p.S;
   P.kchunks = p.C / kBoxK;
@@ -684,12 +709,14 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   const bool two_sweeps = exp2f(p.log2_thr) * float(kCandSlots) > 1.2f && !(P.debug & 8);
   if (two_sweeps) {
     P.units_dir0 = u0; P.total_units = u0;                        // sweep 1: rows of S -> lse_r
+    P.trace = trace_mode == 0 ? g_trace : nullptr;
     sweep_tc_kernel<0><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const size_t groups = size_t(p.n) * ((p.L + 31) / 32);
     cand_bounds_kernel<<<unsigned((groups + 7) / 8), 256, 0, st>>>(w.lse_r, p.n, p.L, p.scale_log2, p.log2_thr, w.cbound, w.cminb);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     P.units_dir0 = 0; P.total_units = u1;                         // sweep 2: columns of S -> lse_c + candidate lists
+    P.trace = trace_mode == 2 ? g_trace : nullptr;
     sweep_tc_kernel<2><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const size_t rows = size_t(p.n) * p.L;
@@ -707,3 +734,13 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
 }
 
 }  // namespace pope
+
+// Developer diagnostics: copies the clock stamps written under POPE_TC_TRACE (8 x u64 per tile: MMA-issuer records
+// first, then epilogue-warp records) to the host; returns the number of u64 copied (0 when tracing is off).
+extern "C" int pope_debug_trace_read(unsigned long long* out, int max_u64) {
+  const int n = 8 * 2 * 512;
+  unsigned long long* src = pope::trace_buffer();
+  if (!out || max_u64 < n || !src) return 0;
+  if (cudaMemcpy(out, src, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return n;
+}
