@@ -44,8 +44,8 @@ SIGNATURES = {
 
 # kernels launched by one hot-path step (bench.py `gpu_launches`).  tcgen05 (thr > 0.15): row sweep, candidate bounds,
 # column sweep, candidate evaluation, count, emit, fused fine match.  SIMT: 2 log-sum-exp sweeps, candidate sweep, count,
-# emit, fused fine match.
-KERNELS_PER_STEP = {"tcgen05": 7, "simt": 6}
+# emit, fused fine match (both families use the two-sweep scheme for thr > 0.15).
+KERNELS_PER_STEP = {"tcgen05": 7, "simt": 7}
 
 _lib: Optional[C.CDLL] = None
 

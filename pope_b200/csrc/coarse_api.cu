@@ -70,7 +70,7 @@ extern "C" int pope_coarse_match(const void* feat_c0, const void* feat_c1, int d
   // clear the best-candidate records + candidate counters (adjacent) and the total/flag words
   if ((e = cudaMemsetAsync(w.rowbest, 0, w.zero_bytes, st)) != cudaSuccess) return int(e);
   if ((e = cudaMemsetAsync(counts + n_pairs, 0, 2 * sizeof(int32_t), st)) != cudaSuccess) return int(e);
-  e = use_tc ? coarse_tc_run(p, w, counts + n_pairs + 1, st) : coarse_simt_run(p, w, st);
+  e = use_tc ? coarse_tc_run(p, w, counts + n_pairs + 1, st) : coarse_simt_run(p, w, counts + n_pairs + 1, st);
   if (e != cudaSuccess) return int(e);
   e = coarse_finalize_run(p, w, b_ids, i_ids, j_ids, mconf, mkpts0_c, mkpts1_c, counts, st);
   return int(e);

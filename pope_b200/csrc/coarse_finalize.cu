@@ -114,7 +114,71 @@ __global__ void __launch_bounds__(FT) emit_kernel(const u64* __restrict__ rowbes
   }
 }
 
+// Two-sweep path, between the sweeps: cell (i, j) can only have conf > thr if p_row(i, j) > thr, i.e. if its raw
+// accumulator exceeds (lse_r[i] + log2 thr) / scale.  One warp per aligned group of 32 rows writes that bound (margin on
+// the safe side, +inf for non-finite lse) and the group's minimum.
+__global__ void __launch_bounds__(256) cand_bounds_kernel(const float* __restrict__ lse_r, int n_pairs, int L, float scale,
+                                                         float log2_thr, float* __restrict__ cbound,
+                                                         float* __restrict__ cminb) {
+  const int lane = threadIdx.x & 31;
+  const int nchunks = (L + 31) / 32;
+  const size_t g = size_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= size_t(n_pairs) * nchunks) return;
+  const int n = int(g / nchunks), i = int(g - size_t(n) * nchunks) * 32 + lane;
+  float bound = INFINITY;
+  if (i < L) {
+    const float inv_s = 1.f / scale;
+    const float b = (lse_r[size_t(n) * L + i] + log2_thr) * inv_s;
+    if (isfinite(b)) bound = b - (1e-5f * fabsf(b) + 0.005f * inv_s);
+  }
+  cbound[g * 32 + lane] = bound;        // rows padded to a multiple of 32 with +inf
+  float mb = bound;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mb = fminf(mb, __shfl_xor_sync(kFullMask, mb, o));
+  if (lane == 0) cminb[g] = mb;
+}
+
+// One thread per row i: evaluate the (at most kCandSlots) cells with p_row > thr found by the column sweep.
+__global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
+                                                       const float* __restrict__ lse_r, const float* __restrict__ lse_c,
+                                                       int n_pairs, int L, int S, float scale, float log2_thr,
+                                                       u64* __restrict__ rowbest, u64* __restrict__ colbest) {
+  const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= size_t(n_pairs) * L) return;
+  const int n = int(r / L), i = int(r - size_t(n) * L);
+  const int c = min(cand_cnt[r], kCandSlots);
+  if (c == 0) return;
+  const float lr = lse_r[r];
+  u64 best = 0;
+  for (int k = 0; k < c; ++k) {
+    const u64 rec = cand[r * kCandSlots + k];
+    const int j = int(uint32_t(rec));
+    const float x = __uint_as_float(uint32_t(rec >> 32)) * scale;
+    const float t2 = (x - lr) + (x - lse_c[size_t(n) * S + j]);
+    if (t2 > log2_thr) {
+      const u64 mine = pack_best(t2, j);
+      best = mine > best ? mine : best;
+      atomicMax(colbest + size_t(n) * S + j, pack_best(t2, i));
+    }
+  }
+  rowbest[r] = best;
+}
+
+
 }  // namespace
+
+cudaError_t cand_bounds_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st) {
+  const size_t groups = size_t(p.n) * ((p.L + 31) / 32);
+  cand_bounds_kernel<<<unsigned((groups + 7) / 8), 256, 0, st>>>(w.lse_r, p.n, p.L, p.scale_log2, p.log2_thr, w.cbound, w.cminb);
+  return cudaGetLastError();
+}
+
+cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st) {
+  const size_t rows = size_t(p.n) * p.L;
+  cand_eval_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S,
+                                                                p.scale_log2, p.log2_thr, w.rowbest, w.colbest);
+  return cudaGetLastError();
+}
 
 cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, int64_t* b_ids, int64_t* i_ids,
                                 int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts,

@@ -7,6 +7,7 @@
 //   sweep 2: row log-sum-exp of  S^T = f1 f0^T * scale      (= column log-sum-exp of S)
 //   sweep 3: recompute S, t2 = (x - lse_r[i]) + (x - lse_c[j]) = log2 conf(i,j); cells with t2 > log2(thr) update
 //            the best-candidate record of their row and column (64-bit atomicMax, rare).
+// For thr > 0.15 sweep 3 is replaced by candidate lists filled during sweep 2 (see coarse_tc.cu / coarse_finalize.cu).
 // This is the product path for fp32 inputs (tcgen05 has no true-fp32 MMA) and the on-device cross-check for
 // the tensor-core path.  All quantities are in log2 units (x = <f0,f1> * log2(e)/(C*T)).
 #include "common.cuh"
@@ -83,10 +84,14 @@ __device__ __forceinline__ void tile_gemm(const T* __restrict__ A, int LA, int r
 __device__ __forceinline__ int frag_index(int t, int r) { return (r < 4) ? (t * 4 + r) : (64 + t * 4 + (r - 4)); }
 
 // lse_out[n, row] = log2 sum_j 2^(x(row, j)),  x = <A_row, B_j> * scale_log2
-template <typename T>
+// EMIT (two-sweep path, second sweep: A = f1, B = f0): every cell whose raw dot product exceeds the B row's bound
+// (p_row > thr, see cand_bounds_kernel) is appended to that B row's candidate list.
+template <typename T, bool EMIT>
 __global__ void __launch_bounds__(NT) rowlse_simt_kernel(const T* __restrict__ A_all, const T* __restrict__ B_all,
                                                         int LA, int LB, int C, float scale_log2,
-                                                        float* __restrict__ lse_out) {
+                                                        float* __restrict__ lse_out, const float* __restrict__ cbound,
+                                                        int* __restrict__ cand_cnt, u64* __restrict__ cand,
+                                                        int32_t* __restrict__ flags) {
   __shared__ __align__(16) float As[BK][BM + LDS_PAD];
   __shared__ __align__(16) float Bs[BK][BN + LDS_PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -99,6 +104,25 @@ __global__ void __launch_bounds__(NT) rowlse_simt_kernel(const T* __restrict__ A
   float acc[8][8];
   for (int col0 = 0; col0 < LB; col0 += BN) {
     tile_gemm<T>(A, LA, row0, B, LB, col0, C, As, Bs, acc, tid);
+    if (EMIT) {
+      const size_t bpad = size_t((LB + 31) / 32) * 32;       // bound rows are padded to a multiple of 32 with +inf
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = col0 + frag_index(tx, c);
+        if (col >= LB) continue;
+        const float bound = __ldg(cbound + size_t(n) * bpad + col);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int row = row0 + frag_index(ty, r);
+          if (acc[r][c] > bound && row < LA) {
+            const size_t rr = size_t(n) * LB + col;
+            const int slot = atomicAdd(cand_cnt + rr, 1);
+            if (slot < kCandSlots) cand[rr * kCandSlots + slot] = (u64(__float_as_uint(acc[r][c])) << 32) | uint32_t(row);
+            else atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_CAND_OVERFLOW);
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       float tmax = -INFINITY;
@@ -171,12 +195,20 @@ __global__ void __launch_bounds__(NT) candidates_simt_kernel(const T* __restrict
 }
 
 template <typename T>
-cudaError_t run_typed(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st) {
+cudaError_t run_typed(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
   const T* f0 = static_cast<const T*>(p.f0);
   const T* f1 = static_cast<const T*>(p.f1);
   dim3 gr((p.L + BM - 1) / BM, p.n), gc((p.S + BM - 1) / BM, p.n);
-  rowlse_simt_kernel<T><<<gr, NT, 0, st>>>(f0, f1, p.L, p.S, p.C, p.scale_log2, w.lse_r);
-  rowlse_simt_kernel<T><<<gc, NT, 0, st>>>(f1, f0, p.S, p.L, p.C, p.scale_log2, w.lse_c);
+  rowlse_simt_kernel<T, false><<<gr, NT, 0, st>>>(f0, f1, p.L, p.S, p.C, p.scale_log2, w.lse_r, nullptr, nullptr, nullptr, nullptr);
+  if (two_sweeps_possible(p)) {
+    // same two-sweep scheme as the tcgen05 path: the column sweep lists the cells with p_row > thr
+    cudaError_t e;
+    if ((e = cand_bounds_run(p, w, st)) != cudaSuccess) return e;
+    rowlse_simt_kernel<T, true><<<gc, NT, 0, st>>>(f1, f0, p.S, p.L, p.C, p.scale_log2, w.lse_c, w.cbound, w.cand_cnt, w.cand, flags);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return cand_eval_run(p, w, st);
+  }
+  rowlse_simt_kernel<T, false><<<gc, NT, 0, st>>>(f1, f0, p.S, p.L, p.C, p.scale_log2, w.lse_c, nullptr, nullptr, nullptr, nullptr);
   candidates_simt_kernel<T><<<gr, NT, 0, st>>>(f0, f1, p.L, p.S, p.C, p.scale_log2, p.log2_thr, w.lse_r, w.lse_c,
                                                 w.rowbest, w.colbest);
   return cudaGetLastError();
@@ -184,8 +216,8 @@ cudaError_t run_typed(const CoarseProblem& p, const CoarseScratch& w, cudaStream
 
 }  // namespace
 
-cudaError_t coarse_simt_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st) {
-  return p.dtype == POPE_BF16 ? run_typed<__nv_bfloat16>(p, w, st) : run_typed<float>(p, w, st);
+cudaError_t coarse_simt_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
+  return p.dtype == POPE_BF16 ? run_typed<__nv_bfloat16>(p, w, flags, st) : run_typed<float>(p, w, flags, st);
 }
 
 }  // namespace pope

@@ -259,7 +259,8 @@ __device__ __noinline__ void cand_emit(int* __restrict__ cand_cnt, u64* __restri
 // MODE 1: candidate sweep of the three-sweep path (needs both log-sum-exps; direction 0 only).
 // MODE 2: MODE 0 + while streaming, every cell whose STREAMED-row softmax exceeds thr is appended to that row's
 //         candidate list (two-sweep path: run in direction 1 after a MODE 0 sweep in direction 0).
-template <int MODE>
+// TRACE: developer diagnostics instantiation (clock stamps of CTA pair 0); the product launches use TRACE = false.
+template <int MODE, bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const SweepParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -352,7 +353,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         tc_fence_after();
         for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
           const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
-          const bool tr = P.trace && pair == 0 && tile_ctr < kTraceTiles;
+          const bool tr = TRACE && P.trace && pair == 0 && tile_ctr < kTraceTiles;
           unsigned long long* rec = P.trace + size_t(tile_ctr) * 8;
           if (tr) rec[0] = clock64() | ((unsigned long long)(ct == 0) << 63);   // top bit: first tile of a unit
           mbar_wait(bar_acc_empty + 8 * s, acc_phase ^ 1);
@@ -436,7 +437,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           const int c0 = (col0 >> 5) + colq * kChunks + cc;
           if (MODE == 2 && c0 < nchunks) minb[cc] = __ldg(P.cminb + size_t(n) * nchunks + c0);
         }
-        const bool etr = P.trace && pair == 0 && rank == 0 && warp == 2 && lane == 0 && tile_ctr < kTraceTiles;
+        const bool etr = TRACE && P.trace && pair == 0 && rank == 0 && warp == 2 && lane == 0 && tile_ctr < kTraceTiles;
         unsigned long long* erec = P.trace + size_t(kTraceTiles + tile_ctr) * 8;
         if (etr) erec[0] = clock64();
         mbar_wait(bar_acc_full + 8 * s, acc_phase);
@@ -616,57 +617,7 @@ bool make_map(CUtensorMap* m, const void* base, int n, int rows, int C) {
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Two-sweep path, between the sweeps: cell (i, j) can only have conf > thr if p_row(i, j) > thr, i.e. if its raw
-// accumulator exceeds (lse_r[i] + log2 thr) / scale.  One warp per aligned group of 32 rows writes that bound (margin on
-// the safe side, +inf for non-finite lse) and the group's minimum.
-__global__ void __launch_bounds__(256) cand_bounds_kernel(const float* __restrict__ lse_r, int n_pairs, int L, float scale,
-                                                         float log2_thr, float* __restrict__ cbound,
-                                                         float* __restrict__ cminb) {
-  const int lane = threadIdx.x & 31;
-  const int nchunks = (L + 31) / 32;
-  const size_t g = size_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (g >= size_t(n_pairs) * nchunks) return;
-  const int n = int(g / nchunks), i = int(g - size_t(n) * nchunks) * 32 + lane;
-  float bound = INFINITY;
-  if (i < L) {
-    const float inv_s = 1.f / scale;
-    const float b = (lse_r[size_t(n) * L + i] + log2_thr) * inv_s;
-    if (isfinite(b)) bound = b - (1e-5f * fabsf(b) + 0.005f * inv_s);
-  }
-  cbound[g * 32 + lane] = bound;        // rows padded to a multiple of 32 with +inf
-  float mb = bound;
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) mb = fminf(mb, __shfl_xor_sync(kFullMask, mb, o));
-  if (lane == 0) cminb[g] = mb;
-}
-
 unsigned long long* g_trace = nullptr;     // developer diagnostics buffer (allocated on first use of POPE_TC_TRACE)
-
-// One thread per row i: evaluate the (at most kCandSlots) cells with p_row > thr found by the column sweep.
-__global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
-                                                       const float* __restrict__ lse_r, const float* __restrict__ lse_c,
-                                                       int n_pairs, int L, int S, float scale, float log2_thr,
-                                                       u64* __restrict__ rowbest, u64* __restrict__ colbest) {
-  const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (r >= size_t(n_pairs) * L) return;
-  const int n = int(r / L), i = int(r - size_t(n) * L);
-  const int c = min(cand_cnt[r], kCandSlots);
-  if (c == 0) return;
-  const float lr = lse_r[r];
-  u64 best = 0;
-  for (int k = 0; k < c; ++k) {
-    const u64 rec = cand[r * kCandSlots + k];
-    const int j = int(uint32_t(rec));
-    const float x = __uint_as_float(uint32_t(rec >> 32)) * scale;
-    const float t2 = (x - lr) + (x - lse_c[size_t(n) * S + j]);
-    if (t2 > log2_thr) {
-      const u64 mine = pack_best(t2, j);
-      best = mine > best ? mine : best;
-      atomicMax(colbest + size_t(n) * S + j, pack_best(t2, i));
-    }
-  }
-  rowbest[r] = best;
-}
 
 unsigned long long* trace_get() { return g_trace; }
 }  // namespace
@@ -684,13 +635,16 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   // per-device attribute, cheap: set on every call so that any device of a multi-GPU process is covered
-  if ((e = cudaFuncSetAttribute(sweep_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(sweep_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(sweep_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
-  SweepParams P{};
-  if (const char* dbg = getenv("POPE_TC_DEBUG")) P.debug = atoi(dbg);
+  auto k0 = sweep_tc_kernel<0, false>, k1 = sweep_tc_kernel<1, false>, k2 = sweep_tc_kernel<2, false>;
   const char* trace_env = getenv("POPE_TC_TRACE");         // developer diagnostics: "0" / "2" = trace that sweep mode
   const int trace_mode = trace_env ? atoi(trace_env) : -1;
+  if (trace_mode == 0) k0 = sweep_tc_kernel<0, true>;
+  if (trace_mode == 2) k2 = sweep_tc_kernel<2, true>;
+  if ((e = cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
+  SweepParams P{};
+  if (const char* dbg = getenv("POPE_TC_DEBUG")) P.debug = atoi(dbg);
   if (trace_mode >= 0 && !g_trace) {
     if ((e = cudaMalloc(&g_trace, sizeof(unsigned long long) * 8 * 2 * kTraceTiles)) != cudaSuccess) return e;
     if ((e = cudaMemset(g_trace, 0, sizeof(unsigned long long) * 8 * 2 * kTraceTiles)) != cudaSuccess) return e;
@@ -706,30 +660,25 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   const int max_pairs = sms / 2;
   // A cell with conf > thr has p_row > thr, and a row has fewer than 1/thr such cells: with thr > 1/kCandSlots the
   // column sweep can list them and the third (candidate) sweep is not needed.
-  const bool two_sweeps = exp2f(p.log2_thr) * float(kCandSlots) > 1.2f && !(P.debug & 8);
+  const bool two_sweeps = two_sweeps_possible(p) && !(P.debug & 8);
   if (two_sweeps) {
     P.units_dir0 = u0; P.total_units = u0;                        // sweep 1: rows of S -> lse_r
     P.trace = trace_mode == 0 ? g_trace : nullptr;
-    sweep_tc_kernel<0><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+    k0<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    const size_t groups = size_t(p.n) * ((p.L + 31) / 32);
-    cand_bounds_kernel<<<unsigned((groups + 7) / 8), 256, 0, st>>>(w.lse_r, p.n, p.L, p.scale_log2, p.log2_thr, w.cbound, w.cminb);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = cand_bounds_run(p, w, st)) != cudaSuccess) return e;
     P.units_dir0 = 0; P.total_units = u1;                         // sweep 2: columns of S -> lse_c + candidate lists
     P.trace = trace_mode == 2 ? g_trace : nullptr;
-    sweep_tc_kernel<2><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+    k2<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    const size_t rows = size_t(p.n) * p.L;
-    cand_eval_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S,
-                                                                  p.scale_log2, p.log2_thr, w.rowbest, w.colbest);
-    return cudaGetLastError();
+    return cand_eval_run(p, w, st);
   }
   // three sweeps (small thresholds): both log-sum-exp directions in one launch, then the candidate sweep
   P.units_dir0 = u0; P.total_units = u0 + u1;
-  sweep_tc_kernel<0><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+  k0<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   P.total_units = u0;
-  sweep_tc_kernel<1><<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+  k1<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
   return cudaGetLastError();
 }
 

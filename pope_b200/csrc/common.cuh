@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "pope_b200.h"
@@ -85,10 +86,16 @@ struct CoarseProblem {
 };
 
 // coarse_simt.cu -- fp32-FMA kernels (fp32 or bf16 inputs): the fp32 product path and the cross-check for tcgen05
-cudaError_t coarse_simt_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
+cudaError_t coarse_simt_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st);
 // coarse_tc.cu -- tcgen05/TMEM/TMA kernels (bf16 inputs, C in {64,128,192,256})
 bool coarse_tc_supported(const CoarseProblem& p);
 cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st);
+// coarse_finalize.cu -- two-sweep helpers (shared by both kernel families): per-row bounds for the column sweep's
+// candidate test, and the evaluation of the listed candidates
+cudaError_t cand_bounds_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
+cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
+// a thr large enough that a row's cells with p_row > thr fit its kCandSlots candidate slots
+inline bool two_sweeps_possible(const CoarseProblem& p) { return exp2f(p.log2_thr) * float(kCandSlots) > 1.2f; }
 // coarse_finalize.cu -- mutual test, border removal, ordered compaction
 cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, int64_t* b_ids, int64_t* i_ids,
                                 int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts,

@@ -1,0 +1,30 @@
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck): both coarse paths on ragged
+shapes, both thresholds paths, gather (channels-last and NCHW), fine match (fused and unfused), retrieval, host pipeline."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from pope_b200 import _lib, driver, ops, synth
+dev = torch.device("cuda:0")
+for (n, hw0, hw1, C, dtype, impl, thr) in [(2, (12, 16), (10, 9), 256, torch.bfloat16, _lib.COARSE_TCGEN05, 0.2),
+                                           (1, (20, 24), (18, 28), 128, torch.bfloat16, _lib.COARSE_TCGEN05, 0.1),
+                                           (2, (12, 16), (10, 9), 64, torch.float32, _lib.COARSE_SIMT, 0.2)]:
+    L, S = hw0[0] * hw0[1], hw1[0] * hw1[1]
+    f0, f1 = synth.coarse_features(5, n, L, S, C, sigma=0.8, dtype=dtype)
+    ff0, _ = synth.fine_feature_maps(6, n, hw0[0] * 4, hw0[1] * 4, 128, dtype=dtype)
+    ff1, _ = synth.fine_feature_maps(7, n, hw1[0] * 4, hw1[1] * 4, 128, dtype=dtype)
+    for fused in (True, False):
+        res = ops.match_pairs_device(f0.to(dev), f1.to(dev), ff0.to(dev), ff1.to(dev), (hw0[0] * 8, hw0[1] * 8), hw0, hw1,
+                                     thr=thr, impl=impl, fused_fine=fused)
+        print("impl", impl, "thr", thr, "fused", fused, "M", res.total(), "flags", res.flags())
+    m = res.total()
+    w0, w1 = ops.fine_gather(ff0.contiguous().to(dev), ff1.contiguous().to(dev), res["b_ids"][:m], res["i_ids"][:m],
+                             res["j_ids"][:m], hw0[1], hw1[1], 4, 5)     # NCHW path
+    order = ops.match_order_by_ref(res["counts"], n, S, res["j_ids"])
+q, refs = synth.retrieval_tokens(3, 100, 384)
+print("topk", ops.cosine_topk(q.to(dev), refs.to(dev), 3)[2].tolist())
+f0, f1 = synth.coarse_features(8, 3, 192, 192, 256, sigma=0.8, dtype=torch.bfloat16)
+ff0, ff1 = synth.fine_feature_maps(9, 3, 48, 64, 128, dtype=torch.bfloat16)
+out = driver.match_pairs_host(f0, f1, ff0, ff1, (96, 128), (12, 16), (12, 16), chunk_pairs=2, device=0)
+print("pipeline", int(out["counts"].sum()))
+torch.cuda.synchronize()
+print("sanitize_run done")
