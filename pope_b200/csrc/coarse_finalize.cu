@@ -164,6 +164,39 @@ __global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ 
   rowbest[r] = best;
 }
 
+// tcgen05 two-sweep path: one thread per row i evaluates the cells its four epilogue threads listed during the row
+// sweep (a superset of the cells with p_row > thr: the test there ran against the RUNNING log-sum-exp, which only
+// grows).  Same arithmetic as cand_eval_kernel.
+__global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
+                                                             const float* __restrict__ lse_r,
+                                                             const float* __restrict__ lse_c, int n_pairs, int L, int S,
+                                                             float scale, float log2_thr, u64* __restrict__ rowbest,
+                                                             u64* __restrict__ colbest) {
+  const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= size_t(n_pairs) * L) return;
+  const uint32_t c4 = uint32_t(cand_cnt[r]);
+  if (c4 == 0) return;
+  const int n = int(r / L), i = int(r - size_t(n) * L);
+  const float lr = lse_r[r];
+  u64 best = 0;
+#pragma unroll
+  for (int q = 0; q < kListGroups; ++q) {
+    const int c = min(int((c4 >> (8 * q)) & 0xffu), kCandSlots);
+    for (int k = 0; k < c; ++k) {
+      const u64 rec = cand[(r * kListGroups + q) * kCandSlots + k];
+      const int j = int(uint32_t(rec));
+      const float x = __uint_as_float(uint32_t(rec >> 32)) * scale;
+      if (!(x - lr > log2_thr - 0.01f)) continue;         // conf <= p_row: stale entries of the running-bound test go here
+      const float t2 = (x - lr) + (x - lse_c[size_t(n) * S + j]);
+      if (t2 > log2_thr) {
+        const u64 mine = pack_best(t2, j);
+        best = mine > best ? mine : best;
+        atomicMax(colbest + size_t(n) * S + j, pack_best(t2, i));
+      }
+    }
+  }
+  rowbest[r] = best;
+}
 
 }  // namespace
 
@@ -177,6 +210,13 @@ cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaSt
   const size_t rows = size_t(p.n) * p.L;
   cand_eval_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S,
                                                                 p.scale_log2, p.log2_thr, w.rowbest, w.colbest);
+  return cudaGetLastError();
+}
+
+cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st) {
+  const size_t rows = size_t(p.n) * p.L;
+  cand_eval_lists_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S,
+                                                                      p.scale_log2, p.log2_thr, w.rowbest, w.colbest);
   return cudaGetLastError();
 }
 

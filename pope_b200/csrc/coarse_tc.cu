@@ -1,9 +1,13 @@
 // coarse_tc.cu -- coarse matching on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), bf16 features, fp32 accumulate.
 //
 // Replaces src/matcher/utils/coarse_matching.py:106-119 and :175-189 of the reference (einsum -> /T -> dual softmax
-// -> threshold -> mutual max) without ever writing the L x S matrix.  Three sweeps over S = f0 f1^T (log2 units):
-//   sweep 1+2 (one launch): row log-sum-exp of S and of S^T (= column log-sum-exp of S), online softmax per row
-//   sweep 3               : recompute S, t2 = log2 conf = (x - lse_r[i]) + (x - lse_c[j]); cells above log2(thr) update
+// -> threshold -> mutual max) without ever writing the L x S matrix.  Sweeps over S = f0 f1^T (log2 units):
+//   sweep 1+2 (one launch): row log-sum-exp of S and of S^T (= column log-sum-exp of S), online softmax per row.
+//                           Two-sweep path (thr > 1/8): while sweeping the rows of S every epilogue thread also lists,
+//                           in a private slot array (no atomics), the cells that exceed thr x the RUNNING row sum --
+//                           a superset of the cells with p_row > thr, of which a row has fewer than 1/thr; a small
+//                           kernel evaluates the listed cells once both log-sum-exps are known.
+//   sweep 3 (thr <= 1/8)  : recompute S, t2 = log2 conf = (x - lse_r[i]) + (x - lse_c[j]); cells above log2(thr) update
 //                           the best-candidate record of their row and column (rare 64-bit atomicMax)
 //
 // Kernel anatomy (persistent, one CTA PAIR per two SMs, cta_group::2, 576 threads per CTA):
@@ -41,6 +45,7 @@ constexpr int kEpiWarps = 16;           // epilogue warps (multiple of 4: one pe
 constexpr int kColGroups = kEpiWarps / 4;            // threads per row
 constexpr int kChunks = (256 / 32) / kColGroups;     // 32-column chunks per thread and tile
 constexpr int kSpan = kChunks * 32;                  // columns per thread and tile
+static_assert(kColGroups == kListGroups, "one private candidate list per (row, column group) thread");
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t kTmemCols = 512;
@@ -171,10 +176,8 @@ struct SweepParams {
   const float* lse_c;
   u64* rowbest;
   u64* colbest;
-  const float* cbound;      // two-sweep path, sweep 2: per streamed row, raw-accumulator bound for p_row > thr
-  const float* cminb;       //   minimum of cbound over each aligned group of 32 streamed rows
-  int* cand_cnt;            //   per streamed row: cells with p_row > thr seen so far
-  u64* cand;                //   [.., kCandSlots] (raw accumulator bits << 32 | stationary row)
+  int* cand_cnt;            // two-sweep path: per row of S, one count byte per column quarter
+  u64* cand;                //   [n, L0, kListGroups, kCandSlots] (raw accumulator bits << 32 | column)
   int32_t* flags;
   unsigned long long* trace;   // developer diagnostics (POPE_TC_TRACE): clock stamps of CTA pair 0, or nullptr
   int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps
@@ -247,18 +250,30 @@ __device__ __forceinline__ float lse_update(const float (&v)[32], int vc, float 
   return cmax;      // raw-accumulator units
 }
 
-// two-sweep path: remember that streamed row `r` (global index over pairs) has p_row > thr at stationary row `row`
-__device__ __noinline__ void cand_emit(int* __restrict__ cand_cnt, u64* __restrict__ cand, int32_t* __restrict__ flags,
-                                       size_t r, float v, int row) {
-  const int slot = atomicAdd(cand_cnt + r, 1);
-  if (slot < kCandSlots) cand[r * kCandSlots + slot] = (u64(__float_as_uint(v)) << 32) | uint32_t(row);
-  else atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_CAND_OVERFLOW);
+// two-sweep path: append cell (value v, column col) to the calling thread's private list.  A full list is first
+// re-filtered against the current bound (the running row sum only grows, so entries below it are dead for good; fewer
+// than 1/thr < kCandSlots cells can stay above it).
+__device__ __noinline__ int list_push(u64* __restrict__ list, int cnt, float bound, float v, int col, int32_t* __restrict__ flags) {
+  if (cnt >= kCandSlots) {
+    int kept = 0;
+    for (int k = 0; k < kCandSlots; ++k) {
+      const u64 rec = list[k];
+      if (__uint_as_float(uint32_t(rec >> 32)) > bound) list[kept++] = rec;
+    }
+    cnt = kept;
+    if (cnt >= kCandSlots) {
+      atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_CAND_OVERFLOW);
+      return cnt;
+    }
+  }
+  list[cnt] = (u64(__float_as_uint(v)) << 32) | uint32_t(col);
+  return cnt + 1;
 }
 
 // MODE 0: row log-sum-exp of the stationary operand's rows.
 // MODE 1: candidate sweep of the three-sweep path (needs both log-sum-exps; direction 0 only).
-// MODE 2: MODE 0 + while streaming, every cell whose STREAMED-row softmax exceeds thr is appended to that row's
-//         candidate list (two-sweep path: run in direction 1 after a MODE 0 sweep in direction 0).
+// MODE 2: MODE 0 + in direction 0 (rows of S stationary) every thread lists the cells of its row that exceed thr x the
+//         running row sum in its private slots (two-sweep path; both directions run in one launch).
 // TRACE: developer diagnostics instantiation (clock stamps of CTA pair 0); the product launches use TRACE = false.
 template <int MODE, bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -401,7 +416,10 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       const float scale = P.scale_log2;
       const float* col_term = P.lse_c;      // MODE 1: per-column term lse_c, this thread's row term lse_r added per thread
       const float inv_s = 1.f / (2.f * scale);
-      const int nchunks = (LB + 31) / 32;   // MODE 2: 32-row groups of the streamed operand
+      const bool listing = (MODE == 2) && dir == 0 && row < LA;     // MODE 2: this thread lists candidates of its row
+      const float inv_scale = 1.f / scale;
+      u64* const mylist = P.cand + ((size_t(n) * LA + row) * kListGroups + colq) * kCandSlots;
+      int list_cnt = 0;
 
       float m_run = -INFINITY, s_run = 0.f;         // log-sum-exp state
       float lrp = INFINITY, lr = INFINITY;
@@ -429,13 +447,6 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             lc_next = (coln < LB) ? __ldg(col_term + size_t(n) * LB + coln) : INFINITY;
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        }
-        float minb[kChunks];                         // MODE 2: fetched before the wait so the latency is hidden
-#pragma unroll
-        for (int cc = 0; cc < kChunks; ++cc) {
-          minb[cc] = INFINITY;
-          const int c0 = (col0 >> 5) + colq * kChunks + cc;
-          if (MODE == 2 && c0 < nchunks) minb[cc] = __ldg(P.cminb + size_t(n) * nchunks + c0);
         }
         const bool etr = TRACE && P.trace && pair == 0 && rank == 0 && warp == 2 && lane == 0 && tile_ctr < kTraceTiles;
         unsigned long long* erec = P.trace + size_t(kTraceTiles + tile_ctr) * 8;
@@ -487,34 +498,16 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         } else {
           // ---- log-sum-exp sweeps: the accumulator stage is handed back to the MMA issuer as soon as this warp's
           //      last TMEM load has retired; the second chunk's arithmetic and every atomic run after the hand-back ----
-          float pend_v = 0.f;
-          int pend_col = -1;                         // MODE 2: one deferred candidate of chunk 0
-          auto scan = [&](const float (&v)[32], int cc, float cmax, bool defer) {
-            // MODE 2: does this 32x32 block hold a cell with p_row > thr?  group-level bound first (1 compare + vote),
-            // the per-element test only where it can succeed (~1 block in 4); bounds come from cand_bounds_kernel
-            const int chunk = colq * kChunks + cc;
-            const bool maybe = cmax > minb[cc];
-            if (__any_sync(kFullMask, maybe && row < LA) && !(P.debug & 2)) {
-              // bound rows are padded to a multiple of 32 with +inf, so every processed chunk is fully readable/aligned
-              const float4* lb = reinterpret_cast<const float4*>(P.cbound + (size_t(n) * nchunks << 5) + col0 + chunk * 32);
-              uint32_t mask = 0;
+          auto scan = [&](const float (&v)[32], int cc, int vc, float cmax) {
+            // MODE 2: cells above thr x (running row sum, this chunk included).  One MUFU.LG2 + a compare per chunk; the
+            // per-element scan runs only for the threads whose chunk maximum passes (the row's match, typically once).
+            const float b = (m_run + lg2_approx(s_run) + P.log2_thr) * inv_scale;
+            const float bound = isfinite(b) ? b - (1e-5f * fabsf(b) + 0.005f * inv_scale) : INFINITY;
+            if (cmax > bound && !(P.debug & 2)) {
+              const int colb = col0 + colq * kSpan + cc * 32;
 #pragma unroll
-              for (int j4 = 0; j4 < 32; j4 += 4) {
-                const float4 l4 = __ldg(lb + (j4 >> 2));
-                mask |= (v[j4 + 0] > l4.x ? 1u : 0u) << j4 | (v[j4 + 1] > l4.y ? 2u : 0u) << j4 |
-                        (v[j4 + 2] > l4.z ? 4u : 0u) << j4 | (v[j4 + 3] > l4.w ? 8u : 0u) << j4;
-              }
-              if (row >= LA) mask = 0;
-              if (mask) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if ((mask >> j) & 1u) {
-                    const int col = col0 + chunk * 32 + j;
-                    if (defer && pend_col < 0) { pend_v = v[j]; pend_col = col; }
-                    else cand_emit(P.cand_cnt, P.cand, P.flags, size_t(n) * LB + col, v[j], row);
-                  }
-                }
-              }
+              for (int j = 0; j < 32; ++j)
+                if (v[j] > bound && j < vc) list_cnt = list_push(mylist, list_cnt, bound, v[j], colb + j, P.flags);
             }
           };
           const bool skip = (P.debug & 1) != 0;
@@ -532,7 +525,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               const int vc = nvalid - cc * 32;
               if (vc > 0 && !skip) {
                 const float cmax = lse_update(v[cc], vc, scale, m_run, s_run);
-                if (MODE == 2) scan(v[cc], cc, cmax, false);
+                if (listing) scan(v[cc], cc, vc, cmax);
               }
             }
           } else {
@@ -542,7 +535,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             if (vc0 > 0 && !skip) {
               tmem_ld32(tbase, v);
               const float cmax = lse_update(v, vc0, scale, m_run, s_run);
-              if (MODE == 2) scan(v, 0, cmax, true);
+              if (listing) scan(v, 0, vc0, cmax);
             }
             if (vc1 > 0 && !skip) tmem_ld32(tbase + 32, v);
             tc_fence_before();
@@ -551,13 +544,13 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             if (etr) erec[2] = clock64();
             if (vc1 > 0 && !skip) {
               const float cmax = lse_update(v, vc1, scale, m_run, s_run);
-              if (MODE == 2) scan(v, 1, cmax, false);
+              if (listing) scan(v, 1, vc1, cmax);
             }
-            if (MODE == 2 && pend_col >= 0) cand_emit(P.cand_cnt, P.cand, P.flags, size_t(n) * LB + pend_col, pend_v, row);
             if (etr) erec[3] = clock64();
           }
         }
       }
+      if (listing) reinterpret_cast<uint8_t*>(P.cand_cnt)[(size_t(n) * LA + row) * kListGroups + colq] = uint8_t(list_cnt);
       if (kLse) {
         // the four column quarters of a row merge their (max, sum) through shared memory
         if (colq > 0) merge[(colq - 1) * 128 + row_in_cta] = make_float2(m_run, s_run);
@@ -655,26 +648,23 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   P.scale_log2 = p.scale_log2; P.log2_thr = p.log2_thr;
   P.lse_out0 = w.lse_r; P.lse_out1 = w.lse_c;
   P.lse_r = w.lse_r; P.lse_c = w.lse_c; P.rowbest = w.rowbest; P.colbest = w.colbest;
-  P.cbound = w.cbound; P.cminb = w.cminb; P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags;
+  P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags;
   const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows), u1 = p.n * ((p.S + kUnitRows - 1) / kUnitRows);
   const int max_pairs = sms / 2;
   // A cell with conf > thr has p_row > thr, and a row has fewer than 1/thr such cells: with thr > 1/kCandSlots the
   // column sweep can list them and the third (candidate) sweep is not needed.
   const bool two_sweeps = two_sweeps_possible(p) && !(P.debug & 8);
   if (two_sweeps) {
-    P.units_dir0 = u0; P.total_units = u0;                        // sweep 1: rows of S -> lse_r
-    P.trace = trace_mode == 0 ? g_trace : nullptr;
-    k0<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if ((e = cand_bounds_run(p, w, st)) != cudaSuccess) return e;
-    P.units_dir0 = 0; P.total_units = u1;                         // sweep 2: columns of S -> lse_c + candidate lists
+    // both log-sum-exp directions in one launch; the direction-0 units also fill the per-thread candidate lists
+    P.units_dir0 = u0; P.total_units = u0 + u1;
     P.trace = trace_mode == 2 ? g_trace : nullptr;
     k2<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return cand_eval_run(p, w, st);
+    return cand_eval_lists_run(p, w, st);
   }
   // three sweeps (small thresholds): both log-sum-exp directions in one launch, then the candidate sweep
   P.units_dir0 = u0; P.total_units = u0 + u1;
+  P.trace = trace_mode == 0 ? g_trace : nullptr;
   k0<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   P.total_units = u0;

@@ -42,15 +42,18 @@ __device__ __forceinline__ float lg2_approx(float x) {
 }
 
 // ---- coarse-match scratch layout -------------------------------------------------------------------------
-constexpr int kCandSlots = 8;   // per-row candidate slots of the two-sweep tcgen05 path (thr > 1/8 => at most 7 pass)
+constexpr int kCandSlots = 8;   // per-row candidate slots of the two-sweep paths (thr > 1/8 => at most 7 cells pass)
+// tcgen05 two-sweep path: every epilogue thread (row, quarter of the columns) keeps a PRIVATE list of kCandSlots cells,
+// so the sweep needs no atomics; the per-quarter counts are the four bytes of the row's cand_cnt word.
+constexpr int kListGroups = 4;
 
 struct CoarseScratch {
   float* lse_r;   // [n, L]  log2-domain log-sum-exp of every row of S
   float* lse_c;   // [n, S]  ... of every column
   u64* rowbest;   // [n, L]  best above-threshold candidate of the row   (pack_best(t2, j))
   u64* colbest;   // [n, S]  best above-threshold candidate of the column (pack_best(t2, i))
-  int* cand_cnt;  // [n, L]  two-sweep path: number of cells of the row with p_row > thr found by the column sweep
-  u64* cand;      // [n, L, kCandSlots]  (raw accumulator bits << 32 | column)
+  int* cand_cnt;  // [n, L]  two-sweep paths: number of listed cells of the row (tcgen05: one byte per column quarter)
+  u64* cand;      // [n, L, kListGroups, kCandSlots]  (raw accumulator bits << 32 | column); SIMT uses [n, L, kCandSlots]
   float* cbound;  // [n, 32*ceil(L/32)]  two-sweep path: raw-accumulator bound above which a cell of row i has p_row > thr
   float* cminb;   // [n, ceil(L/32)]  minimum of cbound over each group of 32 rows
   size_t zero_bytes;   // rowbest, colbest, cand_cnt are adjacent and cleared by one memset
@@ -67,7 +70,7 @@ inline CoarseScratch carve_coarse_scratch(void* base, int n, int L, int S) {
   w.zero_bytes = off;
   w.lse_r = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * L, 256);
   w.lse_c = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * S, 256);
-  w.cand = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L * kCandSlots, 256);
+  w.cand = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L * kListGroups * kCandSlots, 256);
   w.cbound = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32) * 32, 256);
   w.cminb = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32), 256);
   w.bytes = off;
@@ -94,6 +97,8 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
 // candidate test, and the evaluation of the listed candidates
 cudaError_t cand_bounds_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
 cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
+// evaluation of the per-thread (row, column quarter) lists written by the tcgen05 row sweep
+cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
 // a thr large enough that a row's cells with p_row > thr fit its kCandSlots candidate slots
 inline bool two_sweeps_possible(const CoarseProblem& p) { return exp2f(p.log2_thr) * float(kCandSlots) > 1.2f; }
 // coarse_finalize.cu -- mutual test, border removal, ordered compaction
