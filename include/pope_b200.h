@@ -57,6 +57,9 @@ typedef enum { POPE_COARSE_AUTO = 0, POPE_COARSE_SIMT = 1, POPE_COARSE_TCGEN05 =
 /* bits of counts[n_pairs + 1] written by pope_coarse_match */
 #define POPE_FLAG_NONFINITE_LSE 1u   /* a row/column log-sum-exp was inf/nan (inputs contain inf/nan) */
 #define POPE_FLAG_CAND_OVERFLOW 2u   /* a row had more above-threshold cells than 1/thr allows (inputs contain nan) */
+#define POPE_FLAG_ROBUST_PATH   4u   /* informational: the similarities left the range the single-sweep tcgen05 kernel
+                                        handles without per-row shifts (|S| log2(e) > ~90) or a candidate list filled up,
+                                        so the two-sweep online-softmax kernels recomputed the batch; results are valid */
 
 int pope_abi_version(void);
 const char* pope_status_string(int status);

@@ -15,6 +15,7 @@ POPE_F32, POPE_BF16 = 0, 1
 COARSE_AUTO, COARSE_SIMT, COARSE_TCGEN05 = 0, 1, 2
 FLAG_NONFINITE_LSE = 1
 FLAG_CAND_OVERFLOW = 2
+FLAG_ROBUST_PATH = 4
 
 _p, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 

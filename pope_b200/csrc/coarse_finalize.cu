@@ -167,11 +167,16 @@ __global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ 
 // tcgen05 two-sweep path: one thread per row i evaluates the cells its four epilogue threads listed during the row
 // sweep (a superset of the cells with p_row > thr: the test there ran against the RUNNING log-sum-exp, which only
 // grows).  Same arithmetic as cand_eval_kernel.
+// EXP: the lists hold 2^x (single-sweep kernel) instead of the raw accumulator.  want_robust: run only if
+// POPE_FLAG_ROBUST_PATH is set (1) / clear (0) in *flags; -1 = always.
+template <bool EXP>
 __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
                                                              const float* __restrict__ lse_r,
                                                              const float* __restrict__ lse_c, int n_pairs, int L, int S,
                                                              float scale, float log2_thr, u64* __restrict__ rowbest,
-                                                             u64* __restrict__ colbest) {
+                                                             u64* __restrict__ colbest, const int32_t* __restrict__ flags,
+                                                             int want_robust) {
+  if (want_robust >= 0 && int((uint32_t(*flags) & POPE_FLAG_ROBUST_PATH) != 0) != want_robust) return;
   const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= size_t(n_pairs) * L) return;
   const uint32_t c4 = uint32_t(cand_cnt[r]);
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restr
     for (int k = 0; k < c; ++k) {
       const u64 rec = cand[(r * kListGroups + q) * kCandSlots + k];
       const int j = int(uint32_t(rec));
-      const float x = __uint_as_float(uint32_t(rec >> 32)) * scale;
+      const float x = EXP ? log2f(__uint_as_float(uint32_t(rec >> 32))) : __uint_as_float(uint32_t(rec >> 32)) * scale;
       if (!(x - lr > log2_thr - 0.01f)) continue;         // conf <= p_row: stale entries of the running-bound test go here
       const float t2 = (x - lr) + (x - lse_c[size_t(n) * S + j]);
       if (t2 > log2_thr) {
@@ -196,6 +201,24 @@ __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restr
     }
   }
   rowbest[r] = best;
+}
+
+// single-sweep path: column sums of 2^x from the per-32-row partial sums written by the sweep -> column log-sum-exp
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ colpart, int ngroups, int S,
+                                                           float* __restrict__ lse_c, int32_t* __restrict__ flags) {
+  const int j = blockIdx.x * 256 + threadIdx.x, n = blockIdx.y;
+  if (j >= S) return;
+  const float* p = colpart + size_t(n) * ngroups * S + j;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int g = 0;
+  for (; g + 4 <= ngroups; g += 4) {
+    a0 += __ldcs(p + size_t(g) * S); a1 += __ldcs(p + size_t(g + 1) * S);
+    a2 += __ldcs(p + size_t(g + 2) * S); a3 += __ldcs(p + size_t(g + 3) * S);
+  }
+  for (; g < ngroups; ++g) a0 += __ldcs(p + size_t(g) * S);
+  const float tot = (a0 + a1) + (a2 + a3);
+  lse_c[size_t(n) * S + j] = log2f(tot);
+  if (!(tot > kSumLo && tot < kSumHi)) atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_ROBUST_PATH);
 }
 
 }  // namespace
@@ -213,10 +236,24 @@ cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaSt
   return cudaGetLastError();
 }
 
-cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st) {
+cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, int gate,
+                                cudaStream_t st) {
   const size_t rows = size_t(p.n) * p.L;
-  cand_eval_lists_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S,
-                                                                      p.scale_log2, p.log2_thr, w.rowbest, w.colbest);
+  cand_eval_lists_kernel<false><<<unsigned((rows + 255) / 256), 256, 0, st>>>(
+      w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S, p.scale_log2, p.log2_thr, w.rowbest, w.colbest, flags, gate ? 1 : -1);
+  return cudaGetLastError();
+}
+
+cudaError_t cand_eval_exp_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, cudaStream_t st) {
+  const size_t rows = size_t(p.n) * p.L;
+  cand_eval_lists_kernel<true><<<unsigned((rows + 255) / 256), 256, 0, st>>>(
+      w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S, p.scale_log2, p.log2_thr, w.rowbest, w.colbest, flags, 0);
+  return cudaGetLastError();
+}
+
+cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
+  dim3 grid((p.S + 255) / 256, p.n);
+  colsum_reduce_kernel<<<grid, 256, 0, st>>>(w.colpart, (p.L + 31) / 32, p.S, w.lse_c, flags);
   return cudaGetLastError();
 }
 

@@ -178,6 +178,8 @@ struct SweepParams {
   u64* colbest;
   int* cand_cnt;            // two-sweep path: per row of S, one count byte per column quarter
   u64* cand;                //   [n, L0, kListGroups, kCandSlots] (raw accumulator bits << 32 | column)
+  float* colpart;           // single-sweep path: [n, ceil(L0/32), L1] column sums of 2^x over each 32-row group
+  int gate;                 // != 0: the launch is a no-op unless POPE_FLAG_ROBUST_PATH is set in *flags
   int32_t* flags;
   unsigned long long* trace;   // developer diagnostics (POPE_TC_TRACE): clock stamps of CTA pair 0, or nullptr
   int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps
@@ -270,10 +272,79 @@ __device__ __noinline__ int list_push(u64* __restrict__ list, int cnt, float bou
   return cnt + 1;
 }
 
+// ---- single-sweep path (MODE 3) ----------------------------------------------------------------------------------------
+// Two tcgen05.ld.16x256b.x4 (lanes [0,16) and [16,32) of the warp's quadrant, 32 columns):
+//   v[16h + 4k + 2r + c] = D[lane/4 + 8(2h + r)][8k + 2(lane%4) + c]      (checked on the device by tools/micro/tmem_layout.cu)
+// so a thread holds 4 rows x 8 columns of the 32x32 block: row sums stay per thread, and a column sum needs 3 adds in
+// the thread plus a 7-shuffle transposed reduction over the 8 lanes that share lane%4.
+__device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr), "r"(taddr + (16u << 16)) : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// v <- 2^(v * scale) in place (0 for masked rows / columns), row sums accumulated, per-thread column sums returned
+template <bool FULL>
+__device__ __forceinline__ void ss_chunk(float (&v)[32], float scale, float (&rowacc)[4], float (&cp)[8], uint32_t rowmask,
+                                         int vc, int p) {
+#pragma unroll
+  for (int idx = 0; idx < 32; ++idx) {
+    const int h = idx >> 4, i = idx & 15, k = i >> 2, r = (i >> 1) & 1, c = i & 1, rho = 2 * h + r, c8 = 2 * k + c;
+    float e = ex2_approx(v[idx] * scale);
+    if (!FULL) {
+      const int col = 8 * k + 2 * p + c;
+      if (!((rowmask >> rho) & 1u) || col >= vc) e = 0.f;
+    }
+    v[idx] = e;
+    rowacc[rho] += e;
+    cp[c8] = (rho == 0) ? e : cp[c8] + e;
+  }
+}
+
+// transposed reduction of the 8 per-thread column sums over the 8 lanes with the same lane%4: lane l ends up with the
+// sum of column c8 = l / 4 (chunk column 8(c8/2) + 2(l%4) + c8%2) over the warp's 32 rows; fixed order -> deterministic
+__device__ __forceinline__ float ss_col_reduce(const float (&cp)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float q4[4], q2[2];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const float send = b4 ? cp[m] : cp[m + 4], keep = b4 ? cp[m + 4] : cp[m];
+    q4[m] = keep + __shfl_xor_sync(kFullMask, send, 16);
+  }
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const float send = b3 ? q4[m] : q4[m + 2], keep = b3 ? q4[m + 2] : q4[m];
+    q2[m] = keep + __shfl_xor_sync(kFullMask, send, 8);
+  }
+  const float send = b2 ? q2[0] : q2[1], keep = b2 ? q2[1] : q2[0];
+  return keep + __shfl_xor_sync(kFullMask, send, 4);
+}
+
+// append (2^x, column) to the (row, column group) list; the slot counter lives in shared memory for the unit
+__device__ __noinline__ void ss_push(int* cnt, u64* __restrict__ list, float e, int col, int32_t* __restrict__ flags) {
+  const int slot = atomicAdd(cnt, 1);
+  if (slot < kCandSlots) list[slot] = (u64(__float_as_uint(e)) << 32) | uint32_t(col);
+  else atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_ROBUST_PATH);
+}
+
 // MODE 0: row log-sum-exp of the stationary operand's rows.
 // MODE 1: candidate sweep of the three-sweep path (needs both log-sum-exps; direction 0 only).
 // MODE 2: MODE 0 + in direction 0 (rows of S stationary) every thread lists the cells of its row that exceed thr x the
 //         running row sum in its private slots (two-sweep path; both directions run in one launch).
+// MODE 3: single sweep over the rows of S (direction 0 only): unshifted 2^x, row sums per thread, column sums through a
+//         shuffle reduction and per-32-row partial sums in global memory, candidate lists as in MODE 2.  Valid while the
+//         sums stay in fp32 range; otherwise POPE_FLAG_ROBUST_PATH is raised and a gated MODE 2 launch redoes the batch.
 // TRACE: developer diagnostics instantiation (clock stamps of CTA pair 0); the product launches use TRACE = false.
 template <int MODE, bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -287,6 +358,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   const uint32_t bar_acc_full = bar_b_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 16;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
 
+  if (P.gate && !(uint32_t(*reinterpret_cast<const volatile int32_t*>(P.flags)) & POPE_FLAG_ROBUST_PATH)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -393,6 +465,109 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         }
         if (!(P.debug & 4)) umma_commit_2sm(bar_a_empty);   // stationary blocks may be overwritten
       }
+    }
+  } else if (MODE == 3) {
+    // =============================== single-sweep epilogue (16 warps: 4 lane quadrants x 4 groups of 64 columns) =====
+    const int g = lane >> 2, p = lane & 3;
+    const int cg = (warp - 2) >> 2, quad = warp & 3;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    int* scnt = reinterpret_cast<int*>(smem + kSmemLc);              // [128 rows][4 column groups] list fill counts
+    float* mergef = reinterpret_cast<float*>(smem + kSmemMerge);     // [3][128] row sums of column groups 1..3
+    const int rin = quad * 32 + g + 8 * p;                           // the row of the CTA this lane writes results for
+    scnt[(quad * 32 + lane) * kListGroups + cg] = 0;                 // entries (row, cg) are private to warp (quad(row), cg)
+    __syncwarp();
+    const float scale = P.scale_log2;
+    const float thrm = exp2f(P.log2_thr) * 0.99f;
+    const int LA = P.L0, LB = P.L1;
+    const int ntiles = (LB + kTileCols - 1) / kTileCols, ngroups = (LA + 31) / 32;
+    const int ccol = 8 * (g >> 1) + 2 * p + (g & 1);                 // chunk column whose sum ss_col_reduce leaves in this lane
+    uint32_t tile_ctr = 0;
+    for (int u = pair; u < P.total_units; u += npairs) {
+      int dir, n, rb;
+      decode(u, dir, n, rb);
+      const int rowbase = rb * kUnitRows + int(rank) * kBoxRows + quad * 32;
+      const int rows_valid = min(max(LA - rowbase, 0), 32);
+      uint32_t rowmask = 0;
+#pragma unroll
+      for (int rho = 0; rho < 4; ++rho) rowmask |= (g + 8 * rho < rows_valid) ? (1u << rho) : 0u;
+      float rowacc[4] = {0.f, 0.f, 0.f, 0.f};
+      float* const cpart = P.colpart + (size_t(n) * ngroups + (rowbase >> 5)) * LB;
+      u64* const lists = P.cand + (size_t(n) * LA + rowbase) * (kListGroups * kCandSlots) + cg * kCandSlots;
+
+      for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
+        const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
+        const int col0 = ct * kTileCols;
+        const int nvalid = min(LB - col0, kTileCols) - cg * kSpan;
+        const bool active = rows_valid > 0 && nvalid > 0 && !(P.debug & 1);
+        mbar_wait(bar_acc_full + 8 * s, acc_phase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + lane_addr + s * kTileCols + cg * kSpan;
+        float v[32];
+        auto process = [&](int cc) {
+          const int vc = nvalid - cc * 32;
+          const float b0 = rowacc[0], b1 = rowacc[1], b2 = rowacc[2], b3 = rowacc[3];
+          float cp[8];
+          if (rows_valid == 32 && vc >= 32) ss_chunk<true>(v, scale, rowacc, cp, rowmask, vc, p);
+          else ss_chunk<false>(v, scale, rowacc, cp, rowmask, vc, p);
+          const float cs = ss_col_reduce(cp, lane);
+          const int colb = col0 + cg * kSpan + cc * 32;
+          if (ccol < vc) cpart[colb + ccol] = cs;
+          // a cell can only have p_row > thr if it exceeds thr x (running row sum); first a test that needs no
+          // communication (this chunk's contribution to the thread's own partial sum), then the sharper one
+          const bool pass = (rowacc[0] - b0 > thrm * rowacc[0]) | (rowacc[1] - b1 > thrm * rowacc[1]) |
+                            (rowacc[2] - b2 > thrm * rowacc[2]) | (rowacc[3] - b3 > thrm * rowacc[3]);
+          if (__any_sync(kFullMask, pass) && !(P.debug & 2)) {
+            float bound[4];
+#pragma unroll
+            for (int rho = 0; rho < 4; ++rho) {
+              float rs = rowacc[rho];
+              rs += __shfl_xor_sync(kFullMask, rs, 1);
+              rs += __shfl_xor_sync(kFullMask, rs, 2);
+              bound[rho] = thrm * rs;
+            }
+#pragma unroll
+            for (int idx = 0; idx < 32; ++idx) {
+              const int h = idx >> 4, i = idx & 15, k = i >> 2, r = (i >> 1) & 1, c = i & 1, rho = 2 * h + r;
+              if (v[idx] > bound[rho]) {
+                const int rq = g + 8 * rho;
+                ss_push(scnt + (quad * 32 + rq) * kListGroups + cg, lists + size_t(rq) * (kListGroups * kCandSlots), v[idx],
+                        colb + 8 * k + 2 * p + c, P.flags);
+              }
+            }
+          }
+        };
+        if (active) {
+          tmem_ld_frag(tbase, v);
+          process(0);
+        }
+        if (active && nvalid > 32) tmem_ld_frag(tbase + 32, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
+        if (active && nvalid > 32) process(1);
+      }
+
+      // unit end: row sums over the 4 lanes of a row, then over the 4 column groups through shared memory
+#pragma unroll
+      for (int rho = 0; rho < 4; ++rho) {
+        rowacc[rho] += __shfl_xor_sync(kFullMask, rowacc[rho], 1);
+        rowacc[rho] += __shfl_xor_sync(kFullMask, rowacc[rho], 2);
+      }
+      const float mine = p == 0 ? rowacc[0] : p == 1 ? rowacc[1] : p == 2 ? rowacc[2] : rowacc[3];
+      if (cg > 0) mergef[(cg - 1) * 128 + rin] = mine;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      const int row = rb * kUnitRows + int(rank) * kBoxRows + rin;
+      if (row < LA) {
+        if (cg == 0) {
+          const float tot = ((mine + mergef[rin]) + mergef[128 + rin]) + mergef[256 + rin];
+          P.lse_out0[size_t(n) * LA + row] = log2f(tot);
+          if (!(tot > kSumLo && tot < kSumHi)) atomicOr(reinterpret_cast<unsigned*>(P.flags), POPE_FLAG_ROBUST_PATH);
+        }
+        reinterpret_cast<uint8_t*>(P.cand_cnt)[(size_t(n) * LA + row) * kListGroups + cg] =
+            uint8_t(min(scnt[rin * kListGroups + cg], 255));
+      }
+      scnt[rin * kListGroups + cg] = 0;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
   } else {
     // =============================== epilogue (16 warps; four threads per row, 64 columns of the tile each) =========
@@ -629,6 +804,8 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   // per-device attribute, cheap: set on every call so that any device of a multi-GPU process is covered
   auto k0 = sweep_tc_kernel<0, false>, k1 = sweep_tc_kernel<1, false>, k2 = sweep_tc_kernel<2, false>;
+  auto k3 = sweep_tc_kernel<3, false>;
+  if ((e = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   const char* trace_env = getenv("POPE_TC_TRACE");         // developer diagnostics: "0" / "2" = trace that sweep mode
   const int trace_mode = trace_env ? atoi(trace_env) : -1;
   if (trace_mode == 0) k0 = sweep_tc_kernel<0, true>;
@@ -648,19 +825,30 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   P.scale_log2 = p.scale_log2; P.log2_thr = p.log2_thr;
   P.lse_out0 = w.lse_r; P.lse_out1 = w.lse_c;
   P.lse_r = w.lse_r; P.lse_c = w.lse_c; P.rowbest = w.rowbest; P.colbest = w.colbest;
-  P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags;
+  P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags; P.colpart = w.colpart;
   const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows), u1 = p.n * ((p.S + kUnitRows - 1) / kUnitRows);
   const int max_pairs = sms / 2;
   // A cell with conf > thr has p_row > thr, and a row has fewer than 1/thr such cells: with thr > 1/kCandSlots the
   // column sweep can list them and the third (candidate) sweep is not needed.
   const bool two_sweeps = two_sweeps_possible(p) && !(P.debug & 8);
   if (two_sweeps) {
-    // both log-sum-exp directions in one launch; the direction-0 units also fill the per-thread candidate lists
+    if (!(P.debug & 16)) {
+      // single sweep over the rows of S: row sums, column partial sums and candidate lists in one pass; raises
+      // POPE_FLAG_ROBUST_PATH when the unshifted exponentials leave the safe range (debug bit4 skips it)
+      P.units_dir0 = u0; P.total_units = u0;
+      k3<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      if ((e = colsum_reduce_run(p, w, flags, st)) != cudaSuccess) return e;
+      if ((e = cand_eval_exp_run(p, w, flags, st)) != cudaSuccess) return e;
+      P.gate = 1;
+    }
+    // robust two-sweep path (online softmax per row, both directions in one launch; the direction-0 units also fill the
+    // per-thread candidate lists); after the single sweep it only runs if the flag was raised
     P.units_dir0 = u0; P.total_units = u0 + u1;
     P.trace = trace_mode == 2 ? g_trace : nullptr;
     k2<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return cand_eval_lists_run(p, w, st);
+    return cand_eval_lists_run(p, w, flags, P.gate, st);
   }
   // three sweeps (small thresholds): both log-sum-exp directions in one launch, then the candidate sweep
   P.units_dir0 = u0; P.total_units = u0 + u1;

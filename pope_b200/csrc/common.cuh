@@ -46,6 +46,9 @@ constexpr int kCandSlots = 8;   // per-row candidate slots of the two-sweep path
 // tcgen05 two-sweep path: every epilogue thread (row, quarter of the columns) keeps a PRIVATE list of kCandSlots cells,
 // so the sweep needs no atomics; the per-quarter counts are the four bytes of the row's cand_cnt word.
 constexpr int kListGroups = 4;
+// single-sweep path: row / column sums of 2^x must stay inside [2^-90, 2^110] for the unshifted exponentials to be exact
+// enough (terms lost to underflow < 2^-36 of the sum, no overflow); otherwise POPE_FLAG_ROBUST_PATH is raised
+constexpr float kSumLo = 8.0779357e-28f, kSumHi = 1.2980742e33f;
 
 struct CoarseScratch {
   float* lse_r;   // [n, L]  log2-domain log-sum-exp of every row of S
@@ -56,6 +59,7 @@ struct CoarseScratch {
   u64* cand;      // [n, L, kListGroups, kCandSlots]  (raw accumulator bits << 32 | column); SIMT uses [n, L, kCandSlots]
   float* cbound;  // [n, 32*ceil(L/32)]  two-sweep path: raw-accumulator bound above which a cell of row i has p_row > thr
   float* cminb;   // [n, ceil(L/32)]  minimum of cbound over each group of 32 rows
+  float* colpart; // [n, ceil(L/32), S]  single-sweep tcgen05 path: column sums of 2^x over each group of 32 rows
   size_t zero_bytes;   // rowbest, colbest, cand_cnt are adjacent and cleared by one memset
   size_t bytes;
 };
@@ -73,6 +77,7 @@ inline CoarseScratch carve_coarse_scratch(void* base, int n, int L, int S) {
   w.cand = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L * kListGroups * kCandSlots, 256);
   w.cbound = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32) * 32, 256);
   w.cminb = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32), 256);
+  w.colpart = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32) * S, 256);
   w.bytes = off;
   return w;
 }
@@ -98,7 +103,12 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
 cudaError_t cand_bounds_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
 cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
 // evaluation of the per-thread (row, column quarter) lists written by the tcgen05 row sweep
-cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
+// (gate != 0: only if POPE_FLAG_ROBUST_PATH is set in *flags)
+cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, int gate, cudaStream_t st);
+// single-sweep tcgen05 path: column log-sum-exp from the per-32-row partial sums; evaluation of its lists (which hold
+// 2^x instead of the raw accumulator); both set / honour POPE_FLAG_ROBUST_PATH
+cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st);
+cudaError_t cand_eval_exp_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, cudaStream_t st);
 // a thr large enough that a row's cells with p_row > thr fit its kCandSlots candidate slots
 inline bool two_sweeps_possible(const CoarseProblem& p) { return exp2f(p.log2_thr) * float(kCandSlots) > 1.2f; }
 // coarse_finalize.cu -- mutual test, border removal, ordered compaction

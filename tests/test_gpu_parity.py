@@ -32,8 +32,10 @@ def _need_tc(impl, C=256, L=4800, S=4800):
 
 def _run_coarse(f0, f1, hw0_c, hw1_c, impl, dtype, **kw):
     res = ops.coarse_match(f0.to(DEV, dtype), f1.to(DEV, dtype), hw0_c, hw1_c, 8.0, impl=impl, **kw)
-    assert res.flags() == 0
+    # POPE_FLAG_ROBUST_PATH is informational (the single-sweep kernel handed the batch to the online-softmax kernels)
+    assert res.flags() & ~_lib.FLAG_ROBUST_PATH == 0
     out = {k: v.cpu() for k, v in res.sliced().items()}
+    out["_flags"] = res.flags()
     counts = res["counts"][: f0.shape[0]].cpu()
     assert int(counts.sum()) == out["b_ids"].numel()
     assert torch.equal(torch.bincount(out["b_ids"], minlength=f0.shape[0]).to(torch.int32), counts)
@@ -104,6 +106,28 @@ def test_coarse_hard_set_bf16(impl):
     same, near, bad = compare_match_lists(out, want, mg)
     assert not bad, bad[:5]
     assert same > 100
+    if impl == "tcgen05":
+        # |S| log2(e) reaches the hundreds: the unshifted single sweep must have detected it and handed over
+        assert out["_flags"] & _lib.FLAG_ROBUST_PATH
+
+
+def test_coarse_single_sweep_vs_robust_path():
+    """tcgen05: the single-sweep kernel (unshifted 2^x, shuffle-reduced column sums) and the two-sweep online-softmax
+    kernels it falls back to must produce the same match lists on in-range data (ragged L != S, 3 pairs)."""
+    L, S = 50 * 70, 44 * 60
+    _need_tc("tcgen05", 256, L, S)
+    f0, f1 = synth.coarse_features(47, 3, L, S, 256, dtype=torch.bfloat16)
+    fast = _run_coarse(f0, f1, (50, 70), (44, 60), IMPLS["tcgen05"], torch.bfloat16)
+    assert fast["_flags"] == 0
+    os.environ["POPE_TC_DEBUG"] = "16"          # developer knob: skip the single sweep
+    try:
+        slow = _run_coarse(f0, f1, (50, 70), (44, 60), IMPLS["tcgen05"], torch.bfloat16)
+    finally:
+        del os.environ["POPE_TC_DEBUG"]
+    assert fast["b_ids"].numel() > 3000
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(fast[k], slow[k]), k
+    assert torch.allclose(fast["mconf"], slow["mconf"], rtol=2e-5, atol=0)
 
 
 @pytest.mark.parametrize("impl", list(IMPLS))
