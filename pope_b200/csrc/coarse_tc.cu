@@ -294,22 +294,53 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// v <- 2^(v * scale) in place (0 for masked rows / columns), row sums accumulated, per-thread column sums returned
+// packed fp32x2 arithmetic (sm_100: one issue slot for two lanes of a 64-bit register pair)
+__device__ __forceinline__ u64 pack2(float a, float b) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// v <- 2^(v * scale) in place (0 for masked rows / columns); the (even, odd) column pairs of a row are adjacent
+// registers, so scaling, row sums (rowacc2[rho] = {even-column sum, odd-column sum}) and the per-thread column sums
+// (cp2[k] = {column 8k+2p, column 8k+2p+1} over the thread's four rows) run on packed fp32x2 instructions
 template <bool FULL>
-__device__ __forceinline__ void ss_chunk(float (&v)[32], float scale, float (&rowacc)[4], float (&cp)[8], uint32_t rowmask,
+__device__ __forceinline__ void ss_chunk(float (&v)[32], u64 scale2, u64 (&rowacc2)[4], u64 (&cp2)[4], uint32_t rowmask,
                                          int vc, int p) {
 #pragma unroll
-  for (int idx = 0; idx < 32; ++idx) {
-    const int h = idx >> 4, i = idx & 15, k = i >> 2, r = (i >> 1) & 1, c = i & 1, rho = 2 * h + r, c8 = 2 * k + c;
-    float e = ex2_approx(v[idx] * scale);
-    if (!FULL) {
-      const int col = 8 * k + 2 * p + c;
-      if (!((rowmask >> rho) & 1u) || col >= vc) e = 0.f;
-    }
-    v[idx] = e;
-    rowacc[rho] += e;
-    cp[c8] = (rho == 0) ? e : cp[c8] + e;
-  }
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int idx = 16 * h + 4 * k + 2 * r, rho = 2 * h + r;
+        float a, b;
+        unpack2(mul2(pack2(v[idx], v[idx + 1]), scale2), a, b);
+        a = ex2_approx(a);
+        b = ex2_approx(b);
+        if (!FULL) {
+          const int col = 8 * k + 2 * p;
+          const bool rowok = (rowmask >> rho) & 1u;
+          if (!rowok || col >= vc) a = 0.f;
+          if (!rowok || col + 1 >= vc) b = 0.f;
+        }
+        v[idx] = a;
+        v[idx + 1] = b;
+        const u64 e2 = pack2(a, b);
+        rowacc2[rho] = add2(rowacc2[rho], e2);
+        cp2[k] = (rho == 0) ? e2 : add2(cp2[k], e2);
+      }
 }
 
 // transposed reduction of the 8 per-thread column sums over the 8 lanes with the same lane%4: lane l ends up with the
@@ -476,7 +507,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     const int rin = quad * 32 + g + 8 * p;                           // the row of the CTA this lane writes results for
     scnt[(quad * 32 + lane) * kListGroups + cg] = 0;                 // entries (row, cg) are private to warp (quad(row), cg)
     __syncwarp();
-    const float scale = P.scale_log2;
+    const u64 scale2 = pack2(P.scale_log2, P.scale_log2);
     const float thrm = exp2f(P.log2_thr) * 0.99f;
     const int LA = P.L0, LB = P.L1;
     const int ntiles = (LB + kTileCols - 1) / kTileCols, ngroups = (LA + 31) / 32;
@@ -490,7 +521,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       uint32_t rowmask = 0;
 #pragma unroll
       for (int rho = 0; rho < 4; ++rho) rowmask |= (g + 8 * rho < rows_valid) ? (1u << rho) : 0u;
-      float rowacc[4] = {0.f, 0.f, 0.f, 0.f};
+      u64 rowacc2[4] = {0ull, 0ull, 0ull, 0ull};                     // per row: {sum over even columns, sum over odd columns}
+      float rsum[4] = {0.f, 0.f, 0.f, 0.f};                          // the thread's row sums as of the previous chunk
       float* const cpart = P.colpart + (size_t(n) * ngroups + (rowbase >> 5)) * LB;
       u64* const lists = P.cand + (size_t(n) * LA + rowbase) * (kListGroups * kCandSlots) + cg * kCandSlots;
 
@@ -505,33 +537,56 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         float v[32];
         auto process = [&](int cc) {
           const int vc = nvalid - cc * 32;
-          const float b0 = rowacc[0], b1 = rowacc[1], b2 = rowacc[2], b3 = rowacc[3];
+          u64 cp2[4];
+          if (rows_valid == 32 && vc >= 32) ss_chunk<true>(v, scale2, rowacc2, cp2, rowmask, vc, p);
+          else ss_chunk<false>(v, scale2, rowacc2, cp2, rowmask, vc, p);
           float cp[8];
-          if (rows_valid == 32 && vc >= 32) ss_chunk<true>(v, scale, rowacc, cp, rowmask, vc, p);
-          else ss_chunk<false>(v, scale, rowacc, cp, rowmask, vc, p);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) unpack2(cp2[k], cp[2 * k], cp[2 * k + 1]);
           const float cs = ss_col_reduce(cp, lane);
           const int colb = col0 + cg * kSpan + cc * 32;
           if (ccol < vc) cpart[colb + ccol] = cs;
-          // a cell can only have p_row > thr if it exceeds thr x (running row sum); first a test that needs no
-          // communication (this chunk's contribution to the thread's own partial sum), then the sharper one
-          const bool pass = (rowacc[0] - b0 > thrm * rowacc[0]) | (rowacc[1] - b1 > thrm * rowacc[1]) |
-                            (rowacc[2] - b2 > thrm * rowacc[2]) | (rowacc[3] - b3 > thrm * rowacc[3]);
+          // A cell can only have p_row > thr if it exceeds thr x (running row sum).  Level 1, no communication: this
+          // chunk's contribution d[rho] to the thread's own row sum against that sum (true for the first chunks of a
+          // unit by construction).  Level 2: the same against the row sum over the 4 lanes that share the row.  Level 3
+          // (a real candidate, or the first chunk of a unit): the row's 8 cells one by one.
+          float d[4], now[4];
+          bool pass = false;
+#pragma unroll
+          for (int rho = 0; rho < 4; ++rho) {
+            float x, y;
+            unpack2(rowacc2[rho], x, y);
+            now[rho] = x + y;
+            d[rho] = now[rho] - rsum[rho];
+            rsum[rho] = now[rho];
+            pass |= d[rho] > thrm * now[rho];
+          }
           if (__any_sync(kFullMask, pass) && !(P.debug & 2)) {
             float bound[4];
+            bool hit = false;
 #pragma unroll
             for (int rho = 0; rho < 4; ++rho) {
-              float rs = rowacc[rho];
+              float rs = now[rho];
               rs += __shfl_xor_sync(kFullMask, rs, 1);
               rs += __shfl_xor_sync(kFullMask, rs, 2);
               bound[rho] = thrm * rs;
+              hit |= d[rho] > bound[rho];
             }
+            if (hit) {
 #pragma unroll
-            for (int idx = 0; idx < 32; ++idx) {
-              const int h = idx >> 4, i = idx & 15, k = i >> 2, r = (i >> 1) & 1, c = i & 1, rho = 2 * h + r;
-              if (v[idx] > bound[rho]) {
-                const int rq = g + 8 * rho;
-                ss_push(scnt + (quad * 32 + rq) * kListGroups + cg, lists + size_t(rq) * (kListGroups * kCandSlots), v[idx],
-                        colb + 8 * k + 2 * p + c, P.flags);
+              for (int rho = 0; rho < 4; ++rho) {
+                if (d[rho] > bound[rho]) {
+                  const int rq = g + 8 * rho;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                      const int idx = 16 * (rho >> 1) + 4 * k + 2 * (rho & 1) + c;
+                      if (v[idx] > bound[rho])
+                        ss_push(scnt + (quad * 32 + rq) * kListGroups + cg, lists + size_t(rq) * (kListGroups * kCandSlots),
+                                v[idx], colb + 8 * k + 2 * p + c, P.flags);
+                    }
+                }
               }
             }
           }
@@ -548,8 +603,12 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       }
 
       // unit end: row sums over the 4 lanes of a row, then over the 4 column groups through shared memory
+      float rowacc[4];
 #pragma unroll
       for (int rho = 0; rho < 4; ++rho) {
+        float x, y;
+        unpack2(rowacc2[rho], x, y);
+        rowacc[rho] = x + y;
         rowacc[rho] += __shfl_xor_sync(kFullMask, rowacc[rho], 1);
         rowacc[rho] += __shfl_xor_sync(kFullMask, rowacc[rho], 2);
       }
