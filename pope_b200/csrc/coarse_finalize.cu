@@ -47,12 +47,19 @@ __device__ __forceinline__ int block_sum(int v, int* smem) {
   return t;
 }
 
-__global__ void __launch_bounds__(FT) count_kernel(const u64* __restrict__ rowbest, const u64* __restrict__ colbest,
-                                                  const float* __restrict__ lse_r, const float* __restrict__ lse_c,
-                                                  int L, int S, Grid2 g0, Grid2 g1, int32_t* __restrict__ counts,
-                                                  int n_pairs) {
+// One CTA per pair: count the pair's matches, publish the count, wait for the counts of all earlier pairs (CTAs are
+// dispatched in blockIdx order, so an earlier pair's CTA is always running or done), then emit in (pair, i) order.
+// ready[n] must be 0 on entry for every pair; the kernel leaves it set (the caller clears it with the flag words).
+__global__ void __launch_bounds__(FT) count_emit_kernel(const u64* __restrict__ rowbest, const u64* __restrict__ colbest,
+                                                       const float* __restrict__ lse_r, const float* __restrict__ lse_c,
+                                                       int L, int S, Grid2 g0, Grid2 g1, float pixel_scale,
+                                                       int32_t* __restrict__ counts, int n_pairs, int* __restrict__ ready,
+                                                       int64_t* __restrict__ b_ids, int64_t* __restrict__ i_ids,
+                                                       int64_t* __restrict__ j_ids, float* __restrict__ mconf,
+                                                       float* __restrict__ mk0, float* __restrict__ mk1) {
   __shared__ int smem[32];
-  const int n = blockIdx.x;
+  __shared__ int warp_off[FT / 32];
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   rowbest += size_t(n) * L; colbest += size_t(n) * S;
   int c = 0, bad = 0;
   for (int i = threadIdx.x; i < L; i += FT) {
@@ -66,24 +73,22 @@ __global__ void __launch_bounds__(FT) count_kernel(const u64* __restrict__ rowbe
   if (threadIdx.x == 0) {
     counts[n] = c;
     if (bad) atomicOr(reinterpret_cast<unsigned*>(counts + n_pairs + 1), POPE_FLAG_NONFINITE_LSE);
+    __threadfence();
+    atomicExch(ready + n, 1);
   }
-}
-
-__global__ void __launch_bounds__(FT) emit_kernel(const u64* __restrict__ rowbest, const u64* __restrict__ colbest, int L,
-                                                 int S, Grid2 g0, Grid2 g1, float pixel_scale,
-                                                 int32_t* __restrict__ counts, int n_pairs,
-                                                 int64_t* __restrict__ b_ids, int64_t* __restrict__ i_ids,
-                                                 int64_t* __restrict__ j_ids, float* __restrict__ mconf,
-                                                 float* __restrict__ mk0, float* __restrict__ mk1) {
-  __shared__ int smem[32];
-  __shared__ int warp_off[FT / 32];
-  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  rowbest += size_t(n) * L; colbest += size_t(n) * S;
   // exclusive prefix of the per-pair counts = where this pair's matches start
   int part = 0;
-  for (int p = threadIdx.x; p < n; p += FT) part += counts[p];
+  for (int p = threadIdx.x; p < n; p += FT) {
+    const long long t0 = clock64();
+    while (atomicAdd(ready + p, 0) == 0) {
+      __nanosleep(64);
+      if (clock64() - t0 > 4000000000ll) __trap();   // never hang the GPU on a scheduling assumption
+    }
+    __threadfence();
+    part += *reinterpret_cast<volatile int32_t*>(counts + p);
+  }
   int base = block_sum(part, smem);
-  if (n == n_pairs - 1 && threadIdx.x == 0) counts[n_pairs] = base + counts[n];
+  if (n == n_pairs - 1 && threadIdx.x == 0) counts[n_pairs] = base + c;
   for (int i0 = 0; i0 < L; i0 += FT) {
     const int i = i0 + threadIdx.x;
     int j = 0; float t2 = 0.f;
@@ -167,36 +172,38 @@ __global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ 
 // tcgen05 two-sweep path: one thread per row i evaluates the cells its four epilogue threads listed during the row
 // sweep (a superset of the cells with p_row > thr: the test there ran against the RUNNING log-sum-exp, which only
 // grows).  Same arithmetic as cand_eval_kernel.
-// EXP: the lists hold 2^x (single-sweep kernel) instead of the raw accumulator.  want_robust: run only if
-// POPE_FLAG_ROBUST_PATH is set (1) / clear (0) in *flags; -1 = always.
-template <bool EXP>
+// mode 0: lists of raw accumulators (two-sweep kernels).  mode 1: single-sweep launch sequence -- the lists hold 2^x
+// unless POPE_FLAG_ROBUST_PATH is set, in which case the gated two-sweep launch has rewritten them with raw accumulators.
+// Every row's rowbest is written (0 = no candidate), so the caller need not clear it.
 __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
                                                              const float* __restrict__ lse_r,
                                                              const float* __restrict__ lse_c, int n_pairs, int L, int S,
                                                              float scale, float log2_thr, u64* __restrict__ rowbest,
                                                              u64* __restrict__ colbest, const int32_t* __restrict__ flags,
-                                                             int want_robust) {
-  if (want_robust >= 0 && int((uint32_t(*flags) & POPE_FLAG_ROBUST_PATH) != 0) != want_robust) return;
+                                                             int mode) {
+  const bool exp_lists = mode == 1 && !(uint32_t(*flags) & POPE_FLAG_ROBUST_PATH);
   const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= size_t(n_pairs) * L) return;
   const uint32_t c4 = uint32_t(cand_cnt[r]);
-  if (c4 == 0) return;
-  const int n = int(r / L), i = int(r - size_t(n) * L);
-  const float lr = lse_r[r];
   u64 best = 0;
+  if (c4 != 0) {
+    const int n = int(r / L), i = int(r - size_t(n) * L);
+    const float lr = lse_r[r];
 #pragma unroll
-  for (int q = 0; q < kListGroups; ++q) {
-    const int c = min(int((c4 >> (8 * q)) & 0xffu), kCandSlots);
-    for (int k = 0; k < c; ++k) {
-      const u64 rec = cand[(r * kListGroups + q) * kCandSlots + k];
-      const int j = int(uint32_t(rec));
-      const float x = EXP ? log2f(__uint_as_float(uint32_t(rec >> 32))) : __uint_as_float(uint32_t(rec >> 32)) * scale;
-      if (!(x - lr > log2_thr - 0.01f)) continue;         // conf <= p_row: stale entries of the running-bound test go here
-      const float t2 = (x - lr) + (x - lse_c[size_t(n) * S + j]);
-      if (t2 > log2_thr) {
-        const u64 mine = pack_best(t2, j);
-        best = mine > best ? mine : best;
-        atomicMax(colbest + size_t(n) * S + j, pack_best(t2, i));
+    for (int q = 0; q < kListGroups; ++q) {
+      const int c = min(int((c4 >> (8 * q)) & 0xffu), kCandSlots);
+      for (int k = 0; k < c; ++k) {
+        const u64 rec = cand[(r * kListGroups + q) * kCandSlots + k];
+        const int j = int(uint32_t(rec));
+        const float val = __uint_as_float(uint32_t(rec >> 32));
+        const float x = exp_lists ? log2f(val) : val * scale;
+        if (!(x - lr > log2_thr - 0.01f)) continue;         // conf <= p_row: stale entries of the running-bound test go here
+        const float t2 = (x - lr) + (x - lse_c[size_t(n) * S + j]);
+        if (t2 > log2_thr) {
+          const u64 mine = pack_best(t2, j);
+          best = mine > best ? mine : best;
+          atomicMax(colbest + size_t(n) * S + j, pack_best(t2, i));
+        }
       }
     }
   }
@@ -204,10 +211,14 @@ __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restr
 }
 
 // single-sweep path: column sums of 2^x from the per-32-row partial sums written by the sweep -> column log-sum-exp
+// (also clears the column's best-candidate record: the single-sweep launch sequence needs no memset of the scratch)
 __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ colpart, int ngroups, int S,
-                                                           float* __restrict__ lse_c, int32_t* __restrict__ flags) {
+                                                           float* __restrict__ lse_c, u64* __restrict__ colbest,
+                                                           int* __restrict__ ready, int32_t* __restrict__ flags) {
   const int j = blockIdx.x * 256 + threadIdx.x, n = blockIdx.y;
   if (j >= S) return;
+  colbest[size_t(n) * S + j] = 0ull;
+  if (j == 0) ready[n] = 0;
   const float* p = colpart + size_t(n) * ngroups * S + j;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   int g = 0;
@@ -236,24 +247,17 @@ cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaSt
   return cudaGetLastError();
 }
 
-cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, int gate,
+cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, int mode,
                                 cudaStream_t st) {
   const size_t rows = size_t(p.n) * p.L;
-  cand_eval_lists_kernel<false><<<unsigned((rows + 255) / 256), 256, 0, st>>>(
-      w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S, p.scale_log2, p.log2_thr, w.rowbest, w.colbest, flags, gate ? 1 : -1);
-  return cudaGetLastError();
-}
-
-cudaError_t cand_eval_exp_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, cudaStream_t st) {
-  const size_t rows = size_t(p.n) * p.L;
-  cand_eval_lists_kernel<true><<<unsigned((rows + 255) / 256), 256, 0, st>>>(
-      w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S, p.scale_log2, p.log2_thr, w.rowbest, w.colbest, flags, 0);
+  cand_eval_lists_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S,
+                                                                      p.scale_log2, p.log2_thr, w.rowbest, w.colbest, flags, mode);
   return cudaGetLastError();
 }
 
 cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
   dim3 grid((p.S + 255) / 256, p.n);
-  colsum_reduce_kernel<<<grid, 256, 0, st>>>(w.colpart, (p.L + 31) / 32, p.S, w.lse_c, flags);
+  colsum_reduce_kernel<<<grid, 256, 0, st>>>(w.colpart, (p.L + 31) / 32, p.S, w.lse_c, w.colbest, w.ready, flags);
   return cudaGetLastError();
 }
 
@@ -261,9 +265,8 @@ cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, 
                                 int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts,
                                 cudaStream_t st) {
   Grid2 g0{p.h0c, p.w0c, p.border}, g1{p.h1c, p.w1c, p.border};
-  count_kernel<<<p.n, FT, 0, st>>>(w.rowbest, w.colbest, w.lse_r, w.lse_c, p.L, p.S, g0, g1, counts, p.n);
-  emit_kernel<<<p.n, FT, 0, st>>>(w.rowbest, w.colbest, p.L, p.S, g0, g1, p.pixel_scale, counts, p.n, b_ids, i_ids,
-                                  j_ids, mconf, mk0, mk1);
+  count_emit_kernel<<<p.n, FT, 0, st>>>(w.rowbest, w.colbest, w.lse_r, w.lse_c, p.L, p.S, g0, g1, p.pixel_scale, counts, p.n,
+                                        w.ready, b_ids, i_ids, j_ids, mconf, mk0, mk1);
   return cudaGetLastError();
 }
 

@@ -91,8 +91,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();     // ~2 s at 2 GHz
+    if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000ll) __trap();     // ~2 s at 2 GHz
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -850,6 +851,13 @@ unsigned long long* trace_get() { return g_trace; }
 }  // namespace
 unsigned long long* trace_buffer() { return trace_get(); }
 
+static int debug_knob() {
+  const char* dbg = getenv("POPE_TC_DEBUG");
+  return dbg ? atoi(dbg) : 0;
+}
+
+bool coarse_tc_needs_clear(const CoarseProblem& p) { return !(two_sweeps_possible(p) && !(debug_knob() & (8 | 16))); }
+
 bool coarse_tc_supported(const CoarseProblem& p) {
   return p.dtype == POPE_BF16 && p.C % kBoxK == 0 && p.C >= kBoxK && p.C <= kBoxK * kMaxKChunks;
 }
@@ -873,7 +881,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   SweepParams P{};
-  if (const char* dbg = getenv("POPE_TC_DEBUG")) P.debug = atoi(dbg);
+  P.debug = debug_knob();
   if (trace_mode >= 0 && !g_trace) {
     if ((e = cudaMalloc(&g_trace, sizeof(unsigned long long) * 8 * 2 * kTraceTiles)) != cudaSuccess) return e;
     if ((e = cudaMemset(g_trace, 0, sizeof(unsigned long long) * 8 * 2 * kTraceTiles)) != cudaSuccess) return e;
@@ -898,7 +906,6 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
       k3<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       if ((e = colsum_reduce_run(p, w, flags, st)) != cudaSuccess) return e;
-      if ((e = cand_eval_exp_run(p, w, flags, st)) != cudaSuccess) return e;
       P.gate = 1;
     }
     // robust two-sweep path (online softmax per row, both directions in one launch; the direction-0 units also fill the

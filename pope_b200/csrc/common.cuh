@@ -60,7 +60,8 @@ struct CoarseScratch {
   float* cbound;  // [n, 32*ceil(L/32)]  two-sweep path: raw-accumulator bound above which a cell of row i has p_row > thr
   float* cminb;   // [n, ceil(L/32)]  minimum of cbound over each group of 32 rows
   float* colpart; // [n, ceil(L/32), S]  single-sweep tcgen05 path: column sums of 2^x over each group of 32 rows
-  size_t zero_bytes;   // rowbest, colbest, cand_cnt are adjacent and cleared by one memset
+  int* ready;     // [n]  count_emit_kernel: "this pair's count is published" (cleared before every call)
+  size_t zero_bytes;   // rowbest, colbest, cand_cnt, ready are adjacent and cleared by one memset
   size_t bytes;
 };
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -71,6 +72,7 @@ inline CoarseScratch carve_coarse_scratch(void* base, int n, int L, int S) {
   w.rowbest = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L, 256);
   w.colbest = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * S, 256);
   w.cand_cnt = reinterpret_cast<int*>(p + off); off += align_up(sizeof(int) * size_t(n) * L, 256);
+  w.ready = reinterpret_cast<int*>(p + off); off += align_up(sizeof(int) * size_t(n), 256);
   w.zero_bytes = off;
   w.lse_r = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * L, 256);
   w.lse_c = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * S, 256);
@@ -103,12 +105,13 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
 cudaError_t cand_bounds_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
 cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
 // evaluation of the per-thread (row, column quarter) lists written by the tcgen05 row sweep
-// (gate != 0: only if POPE_FLAG_ROBUST_PATH is set in *flags)
-cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, int gate, cudaStream_t st);
+// (mode 1: after the single-sweep launch sequence -- the list format follows POPE_FLAG_ROBUST_PATH in *flags)
+cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, int mode, cudaStream_t st);
 // single-sweep tcgen05 path: column log-sum-exp from the per-32-row partial sums; evaluation of its lists (which hold
 // 2^x instead of the raw accumulator); both set / honour POPE_FLAG_ROBUST_PATH
 cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st);
-cudaError_t cand_eval_exp_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, cudaStream_t st);
+// does coarse_tc_run need rowbest / colbest / cand_cnt cleared beforehand?  (not on the single-sweep launch sequence)
+bool coarse_tc_needs_clear(const CoarseProblem& p);
 // a thr large enough that a row's cells with p_row > thr fit its kCandSlots candidate slots
 inline bool two_sweeps_possible(const CoarseProblem& p) { return exp2f(p.log2_thr) * float(kCandSlots) > 1.2f; }
 // coarse_finalize.cu -- mutual test, border removal, ordered compaction
