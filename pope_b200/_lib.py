@@ -43,10 +43,10 @@ SIGNATURES = {
                                    _i, _i, _p, _p, _p, _p, _p, _p, _p]),
 }
 
-# kernels launched by one hot-path step (bench.py `gpu_launches`).  tcgen05 (thr > 0.15): row sweep, candidate bounds,
-# column sweep, candidate evaluation, count, emit, fused fine match.  SIMT: 2 log-sum-exp sweeps, candidate sweep, count,
-# emit, fused fine match (both families use the two-sweep scheme for thr > 0.15).
-KERNELS_PER_STEP = {"tcgen05": 7, "simt": 7}
+# kernels launched by one hot-path step (bench.py `gpu_launches`).  tcgen05 (thr > 0.15): single sweep, column-sum
+# reduction, gated two-sweep launch (a no-op unless the fallback flag is raised), list evaluation, count+emit, fused fine
+# match.  SIMT: row sweep, candidate bounds, column sweep, candidate evaluation, count+emit, fused fine match.
+KERNELS_PER_STEP = {"tcgen05": 6, "simt": 6}
 
 _lib: Optional[C.CDLL] = None
 

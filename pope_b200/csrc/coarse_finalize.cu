@@ -211,25 +211,44 @@ __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restr
 }
 
 // single-sweep path: column sums of 2^x from the per-32-row partial sums written by the sweep -> column log-sum-exp
-// (also clears the column's best-candidate record: the single-sweep launch sequence needs no memset of the scratch)
-__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ colpart, int ngroups, int S,
+// (also clears the column's best-candidate record and the pair's "count published" word: the single-sweep launch
+// sequence needs no memset of the scratch).  HBM-bound: n * ceil(L/32) * S * 4 bytes are read once; a thread owns VEC
+// adjacent columns and keeps 4 x VEC loads in flight; the summation order over the groups is fixed.
+template <int VEC>
+__global__ void __launch_bounds__(128) colsum_reduce_kernel(const float* __restrict__ colpart, int ngroups, int S,
                                                            float* __restrict__ lse_c, u64* __restrict__ colbest,
                                                            int* __restrict__ ready, int32_t* __restrict__ flags) {
-  const int j = blockIdx.x * 256 + threadIdx.x, n = blockIdx.y;
+  const int j = (blockIdx.x * 128 + threadIdx.x) * VEC, n = blockIdx.y;
   if (j >= S) return;
-  colbest[size_t(n) * S + j] = 0ull;
   if (j == 0) ready[n] = 0;
   const float* p = colpart + size_t(n) * ngroups * S + j;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float acc[4][VEC];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[u][v] = 0.f;
+  auto load_add = [&](int g, int u) {
+    if (VEC == 4) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(p + size_t(g) * S));
+      acc[u][0] += t.x; acc[u][1 % VEC] += t.y; acc[u][2 % VEC] += t.z; acc[u][3 % VEC] += t.w;
+    } else {
+      acc[u][0] += __ldcs(p + size_t(g) * S);
+    }
+  };
   int g = 0;
   for (; g + 4 <= ngroups; g += 4) {
-    a0 += __ldcs(p + size_t(g) * S); a1 += __ldcs(p + size_t(g + 1) * S);
-    a2 += __ldcs(p + size_t(g + 2) * S); a3 += __ldcs(p + size_t(g + 3) * S);
+    load_add(g, 0); load_add(g + 1, 1); load_add(g + 2, 2); load_add(g + 3, 3);
   }
-  for (; g < ngroups; ++g) a0 += __ldcs(p + size_t(g) * S);
-  const float tot = (a0 + a1) + (a2 + a3);
-  lse_c[size_t(n) * S + j] = log2f(tot);
-  if (!(tot > kSumLo && tot < kSumHi)) atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_ROBUST_PATH);
+  for (; g < ngroups; ++g) load_add(g, 0);
+  bool bad = false;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const float tot = (acc[0][v] + acc[1][v]) + (acc[2][v] + acc[3][v]);
+    lse_c[size_t(n) * S + j + v] = log2f(tot);
+    colbest[size_t(n) * S + j + v] = 0ull;
+    bad |= !(tot > kSumLo && tot < kSumHi);
+  }
+  if (bad) atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_ROBUST_PATH);
 }
 
 }  // namespace
@@ -256,8 +275,14 @@ cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, 
 }
 
 cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
-  dim3 grid((p.S + 255) / 256, p.n);
-  colsum_reduce_kernel<<<grid, 256, 0, st>>>(w.colpart, (p.L + 31) / 32, p.S, w.lse_c, w.colbest, w.ready, flags);
+  const int ngroups = (p.L + 31) / 32;
+  if (p.S % 4 == 0) {   // rows of the partial-sum array are then 16-byte aligned (the array itself is 256-byte aligned)
+    dim3 grid((p.S / 4 + 127) / 128, p.n);
+    colsum_reduce_kernel<4><<<grid, 128, 0, st>>>(w.colpart, ngroups, p.S, w.lse_c, w.colbest, w.ready, flags);
+  } else {
+    dim3 grid((p.S + 127) / 128, p.n);
+    colsum_reduce_kernel<1><<<grid, 128, 0, st>>>(w.colpart, ngroups, p.S, w.lse_c, w.colbest, w.ready, flags);
+  }
   return cudaGetLastError();
 }
 
