@@ -338,12 +338,13 @@ def main():
         return
 
     hbm, tf_burst, tf_sus, peak_src = measured_peaks()
-    # DRAM traffic per launch from the committed ncu --set full capture of this workload (profiles/r1_ncu_final_step.csv:
-    # dram__bytes_read.sum + dram__bytes_write.sum; coarse = row sweep + bounds + column sweep + cand_eval + count + emit).
-    # Two sweeps each stream the 315 MB of coarse features once, hence ~2.2x the algorithmic bytes.
+    # DRAM traffic per launch from the committed ncu --set full capture of this workload
+    # (profiles/r1_ncu_single_sweep_step.csv: dram__bytes_read.sum + dram__bytes_write.sum; coarse = single sweep +
+    # column-sum reduction + gated launch + list evaluation + count/emit).  The sweep streams the 315 MB of coarse
+    # features once and writes 170 MB of per-32-row column partial sums that the reduction reads back.
     std_workload = n == 64 and dtype == torch.bfloat16
-    coarse_traffic = 692.5e6 if std_workload else None
-    fine_traffic = 850.5e6 if std_workload else None
+    coarse_traffic = 721.9e6 if std_workload else None
+    fine_traffic = 850.3e6 if std_workload else None
     flops = n * 2.0 * L * L * C_COARSE
     ach = flops / (coarse_ms / 1e3) / 1e12
     fine_bytes = M * ((1 + 25) * C_FINE * esize + 3 * 8 + 8 + 12 + 8)     # 26 feature rows + ids + coords in/out
@@ -360,7 +361,7 @@ def main():
                    "matches_per_step": M, "flags": flags, "gather": "one NCCL all-gather of the job's live match records after the K steps (inside the timed region)" if world > 1 else "none"},
         "clocks": clocks,
         "stage_ms": {"coarse": coarse_ms, "fine_gather_match_fused": fine_ms},
-        "roofline": {"kernel": "coarse stage (tcgen05 row sweep + column sweep with candidate lists + compaction)" if tc else
+        "roofline": {"kernel": "coarse stage (tcgen05 single sweep: row sums + shuffle-reduced column sums + candidate lists; column-sum reduction, list evaluation, compaction)" if tc else
                                "coarse stage (fp32-FMA sweeps + compaction)", "bound": "tensor",
                      "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": coarse_traffic,
                      "peak_source": f"{peak_src} bf16_tflops_sustained", "algorithmic_flops_per_launch": flops},
