@@ -186,6 +186,40 @@ int pope_match_pairs_host(const void* feat_c0, const void* feat_c1, const void* 
  * Copies them to `out` (host); returns the number of u64 written, 0 when tracing is off.  tools/trace_sweep.py. */
 int pope_debug_trace_read(unsigned long long* out, int max_u64);
 
+/* ---- fine-level transformer and FinePreprocess Linears (bf16) ---------------------------------
+ * Replace src/matcher/loftr_module/transformer.py:34-58,95-104 + linear_attention.py:21-47 (LocalFeatureTransformer with
+ * d_model 128, 8 heads, 'linear' attention) and fine_preprocess.py:50-57 (down_proj / merge_feat) of the reference.
+ *
+ * Packed weights of ONE LoFTREncoderLayer, POPE_FINE_TF_LAYER_BYTES bytes, matrices bf16 row-major [out, in] exactly like
+ * nn.Linear.weight, LayerNorm parameters fp32:
+ *   +0       q_proj.weight | k_proj.weight | v_proj.weight   [384, 128]
+ *   +98304   merge.weight                                    [128, 128]
+ *   +131072  mlp.0.weight                                    [256, 256]
+ *   +262144  mlp.2.weight                                    [128, 256]
+ *   +327680  norm1.weight, norm1.bias, norm2.weight, norm2.bias   4 x [128] fp32
+ * Packed FinePreprocess weights, POPE_FINE_PRE_BYTES bytes:
+ *   +0       down_proj.weight [128, 256] bf16     +65536  merge_feat.weight [128, 256] bf16
+ *   +131072  down_proj.bias [128] fp32            +131584 merge_feat.bias [128] fp32                                   */
+#define POPE_FINE_TF_LAYER_BYTES 329728
+#define POPE_FINE_PRE_BYTES 132096
+
+/* Bytes of device scratch for m_windows windows of window_tokens tokens (7 activation planes of [m*tokens, 128] bf16). */
+size_t pope_fine_tf_workspace_bytes(int64_t m_windows, int window_tokens);
+
+/* feat0, feat1: [m_windows, window_tokens, 128] bf16, updated IN PLACE by n_layers encoder layers;
+ * layer_kinds[l] = 0 ('self': each side attends to itself) or 1 ('cross': feat0 attends to feat1, then feat1 to the new
+ * feat0), weights = n_layers consecutive packed layers.  Never synchronises; m_windows == 0 is a no-op. */
+int pope_fine_transformer(void* feat0, void* feat1, int64_t m_windows, int window_tokens, const void* weights,
+                          int n_layers, const int* layer_kinds, void* workspace, size_t workspace_bytes, void* stream);
+
+/* FinePreprocess' coarse-context mixing, IN PLACE on the gathered windows win0/win1 [m, window_tokens, 128] bf16:
+ *   c = down_proj(cat(feat_c0[b_ids, i_ids], feat_c1[b_ids, j_ids]));  win = merge_feat(cat(win, repeat(c)))
+ * feat_c0 [N, L, 256], feat_c1 [N, S, 256] bf16; ids are device int64 arrays of length m_windows. */
+int pope_fine_merge_coarse(void* win0, void* win1, int64_t m_windows, int window_tokens, const void* feat_c0,
+                           const void* feat_c1, int L, int S, int C, const int64_t* b_ids, const int64_t* i_ids,
+                           const int64_t* j_ids, const void* weights, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

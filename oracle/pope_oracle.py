@@ -157,6 +157,63 @@ def fine_match(win0: torch.Tensor, win1: torch.Tensor, mkpts0_c: torch.Tensor, m
     }
 
 
+def linear_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """LinearAttention.forward without masks (src/matcher/loftr_module/linear_attention.py:21-47):
+    q [N,L,H,D], k/v [N,S,H,D] -> [N,L,H,D]."""
+    Q = F.elu(q) + 1
+    K = F.elu(k) + 1
+    s = v.size(1)
+    KV = torch.einsum("nshd,nshv->nhdv", K, v / s)
+    Z = 1 / (torch.einsum("nlhd,nhd->nlh", Q, K.sum(dim=1)) + eps)
+    return torch.einsum("nlhd,nhdv,nlh->nlhv", Q, KV, Z) * s
+
+
+def encoder_layer(x: torch.Tensor, source: torch.Tensor, w: Dict[str, torch.Tensor], nhead: int = 8) -> torch.Tensor:
+    """LoFTREncoderLayer.forward (src/matcher/loftr_module/transformer.py:34-58).  `w` holds the layer's state dict
+    (q_proj.weight, k_proj.weight, v_proj.weight, merge.weight, mlp.0.weight, mlp.2.weight, norm1/2.weight/bias)."""
+    n, _, c = x.shape
+    d = c // nhead
+    q = F.linear(x, w["q_proj.weight"]).view(n, -1, nhead, d)
+    k = F.linear(source, w["k_proj.weight"]).view(n, -1, nhead, d)
+    v = F.linear(source, w["v_proj.weight"]).view(n, -1, nhead, d)
+    msg = linear_attention(q, k, v).reshape(n, -1, c)
+    msg = F.layer_norm(F.linear(msg, w["merge.weight"]), (c,), w["norm1.weight"], w["norm1.bias"])
+    msg = F.linear(torch.relu(F.linear(torch.cat([x, msg], dim=2), w["mlp.0.weight"])), w["mlp.2.weight"])
+    msg = F.layer_norm(msg, (c,), w["norm2.weight"], w["norm2.bias"])
+    return x + msg
+
+
+def fine_transformer(feat0: torch.Tensor, feat1: torch.Tensor, layers: Sequence[Dict[str, torch.Tensor]],
+                     layer_names: Sequence[str], nhead: int = 8) -> Tuple[torch.Tensor, torch.Tensor]:
+    """LocalFeatureTransformer.forward without masks (src/matcher/loftr_module/transformer.py:95-106):
+    'self' updates each side from itself, 'cross' updates feat0 from feat1 and then feat1 from the NEW feat0."""
+    feat0, feat1 = feat0.float(), feat1.float()
+    for w, name in zip(layers, layer_names):
+        if name == "self":
+            feat0 = encoder_layer(feat0, feat0, w, nhead)
+            feat1 = encoder_layer(feat1, feat1, w, nhead)
+        elif name == "cross":
+            feat0 = encoder_layer(feat0, feat1, w, nhead)
+            feat1 = encoder_layer(feat1, feat0, w, nhead)
+        else:
+            raise KeyError(name)
+    return feat0, feat1
+
+
+def fine_merge_coarse(win0: torch.Tensor, win1: torch.Tensor, feat_c0: torch.Tensor, feat_c1: torch.Tensor,
+                      b_ids: torch.Tensor, i_ids: torch.Tensor, j_ids: torch.Tensor, w: Dict[str, torch.Tensor]
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The coarse-context branch of FinePreprocess.forward (src/matcher/loftr_module/fine_preprocess.py:50-57);
+    `w`: down_proj.weight/bias, merge_feat.weight/bias."""
+    m, ww, _ = win0.shape
+    c_win = F.linear(torch.cat([feat_c0[b_ids, i_ids], feat_c1[b_ids, j_ids]], 0).float(), w["down_proj.weight"],
+                     w["down_proj.bias"])
+    both = torch.cat([win0, win1], 0).float()
+    merged = F.linear(torch.cat([both, c_win[:, None, :].expand(-1, ww, -1)], -1), w["merge_feat.weight"],
+                      w["merge_feat.bias"])
+    return merged[:m], merged[m:]
+
+
 def cosine_scores(q: torch.Tensor, refs: torch.Tensor) -> torch.Tensor:
     """score[r] = F.cosine_similarity(q, refs[r:r+1], dim=1, eps=1e-8), one crop at a time, exactly as the
     retrieval loop does (eval_linemod_json.py:94; token from dinov2_utils.py:106-111)."""

@@ -16,6 +16,8 @@ COARSE_AUTO, COARSE_SIMT, COARSE_TCGEN05 = 0, 1, 2
 FLAG_NONFINITE_LSE = 1
 FLAG_CAND_OVERFLOW = 2
 FLAG_ROBUST_PATH = 4
+FINE_TF_LAYER_BYTES = 329728      # include/pope_b200.h: packed weights of one LoFTREncoderLayer (d_model 128)
+FINE_PRE_BYTES = 132096           # ... of FinePreprocess' down_proj + merge_feat
 
 _p, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
@@ -32,6 +34,9 @@ SIGNATURES = {
     "pope_fine_match": (_i, [_p, _p, _i, _i64, _p, _i, _i, _p, _f, _p, _p, _p]),
     "pope_fine_match_maps": (_i, [_p, _p, _i, _i, _i, _i, _i, C.POINTER(_i64), _i, _i, C.POINTER(_i64),
                                   _i, _i, _i, _i, _p, _p, _p, _i64, _p, _p, _p, _f, _p, _p, _p]),
+    "pope_fine_tf_workspace_bytes": (_sz, [_i64, _i]),
+    "pope_fine_transformer": (_i, [_p, _p, _i64, _i, _p, _i, C.POINTER(_i), _p, _sz, _p]),
+    "pope_fine_merge_coarse": (_i, [_p, _p, _i64, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "pope_match_order_by_ref": (_i, [_p, _i, _i, _p, _p, _p]),
     "pope_cosine_topk": (_i, [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "pope_debug_trace_read": (_i, [_p, _i]),

@@ -1,0 +1,539 @@
+// fine_tf.cu -- the fine-level LoFTR transformer and the FinePreprocess Linears on sm_100a.
+//
+// Replaces, for bf16 windows, the op sequence of the reference's
+//   src/matcher/loftr_module/transformer.py:34-58      (LoFTREncoderLayer.forward: q/k/v projections, linear attention,
+//                                                       merge, LayerNorm, 2-layer MLP on cat(x, message), LayerNorm, residual)
+//   src/matcher/loftr_module/linear_attention.py:21-47 (elu(x)+1 feature map, KV = K^T V / S, Z = 1/(Q . sum K + eps))
+//   src/matcher/loftr_module/transformer.py:95-104     ('self' / 'cross' layer schedule)
+//   src/matcher/loftr_module/fine_preprocess.py:50-57  (down_proj of the matched coarse features, merge_feat on
+//                                                       cat(window, coarse))
+// Every Linear is one launch of linear_tc_kernel: a persistent, weight-stationary tcgen05 GEMM (the whole weight matrix
+// stays in shared memory, 128-token tiles of the activations stream through a TMA ring, accumulators in TMEM) whose
+// epilogue applies what follows the Linear in the reference (feature map, 1/S scale, ReLU, LayerNorm, residual, bias,
+// per-window vector) before the row is written back as bf16.  The attention itself (8 heads x 16 x 16 per 25-token
+// window) is a warp-per-window fp32 kernel.  Activations are bf16 in HBM, all arithmetic accumulates in fp32.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace pope {
+namespace {
+
+using namespace tc1;
+
+constexpr int kD = 128;                  // fine d_model
+constexpr int kHeads = 8, kHeadDim = 16;
+constexpr int kTile = 128;               // token rows per tile (MMA M)
+constexpr int kBoxK = 64;                // bf16 elements per 128-byte swizzle row
+constexpr int kBoxBytes = kTile * kBoxK * 2;          // 16384
+constexpr int kMaxWBoxes = 8;            // N/128 * K/64 <= 8 (256 x 256)
+constexpr int kStages = 5;               // activation ring depth
+constexpr int kSlots = 4;                // TMEM accumulator slots of 128 columns
+constexpr int kLinThreads = 192;         // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue (one per TMEM lane quadrant)
+constexpr int kSmemW = 0;
+constexpr int kSmemX = kSmemW + kMaxWBoxes * kBoxBytes;
+constexpr int kSmemBar = kSmemX + kStages * kBoxBytes;
+constexpr int kNumBars = 1 + 2 * kStages + 2 * kSlots;
+constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
+constexpr int kSmemBytes = kSmemTmemPtr + 16;
+constexpr int kSmemAlloc = kSmemBytes + 1024;         // slack for manual 1024-B alignment; > 113 KB -> one CTA per SM,
+                                                      // so the CTA may take all 512 TMEM columns
+
+enum EpiMode : int { EPI_COPY = 0, EPI_ELU1 = 1, EPI_SCALE = 2, EPI_RELU = 3, EPI_LN = 4, EPI_LN_RES = 5, EPI_ADDVEC = 6 };
+
+struct LinParams {
+  int T;                       // token rows
+  int kchunks, kchunks0;       // K/64; the first kchunks0 chunks come from source 0, the rest from source 1 (torch.cat)
+  int nblk;                    // N/128
+  void* out[3];                // per 128-column block of the output
+  int out_stride;              // row stride of the output, in elements
+  int out_f32;                 // rows are written as fp32 instead of bf16
+  int mode[3];
+  float scale;                 // EPI_SCALE
+  const float* bias;           // [N] or nullptr, added before the mode is applied
+  const float* gamma;          // EPI_LN / EPI_LN_RES: [128]
+  const float* beta;
+  const __nv_bfloat16* resid;  // EPI_LN_RES: [T, 128]
+  const float* rowvec;         // EPI_ADDVEC: [T / rows_per_vec, 128]
+  int rows_per_vec;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kLinThreads, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
+                 const __grid_constant__ CUtensorMap mapW, const LinParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kSmemBar;
+  const uint32_t bar_w_full = bar0;
+  const uint32_t bar_x_full = bar0 + 8, bar_x_empty = bar_x_full + 8 * kStages;
+  const uint32_t bar_acc_full = bar_x_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 8 * kSlots;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (P.T + kTile - 1) / kTile;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapX0); prefetch_tmap(&mapX1); prefetch_tmap(&mapW);
+    mbar_init(bar_w_full, 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemTmemPtr), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      mbar_expect_tx(bar_w_full, uint32_t(P.nblk * P.kchunks * kBoxBytes));
+      for (int j = 0; j < P.nblk; ++j)
+        for (int kc = 0; kc < P.kchunks; ++kc)
+          tma_load_2d(sbase + kSmemW + (j * P.kchunks + kc) * kBoxBytes, &mapW, bar_w_full, kc * kBoxK, j * kTile);
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+        for (int kc = 0; kc < P.kchunks; ++kc) {
+          mbar_wait(bar_x_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_x_full + 8 * stage, kBoxBytes);
+          const bool second = kc >= P.kchunks0;
+          tma_load_2d(sbase + kSmemX + stage * kBoxBytes, second ? &mapX1 : &mapX0, bar_x_full + 8 * stage,
+                      (second ? kc - P.kchunks0 : kc) * kBoxK, t * kTile);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(kTile, 128);
+      mbar_wait(bar_w_full, 0);
+      tc_fence_after();
+      uint32_t stage = 0, phase = 0, item = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int j = 0; j < P.nblk; ++j) {                      // the tile's accumulator slots must have been drained
+          const uint32_t it = item + j;
+          mbar_wait(bar_acc_empty + 8 * (it & (kSlots - 1)), ((it / kSlots) & 1) ^ 1);
+        }
+        tc_fence_after();
+        for (int kc = 0; kc < P.kchunks; ++kc) {
+          mbar_wait(bar_x_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = sbase + kSmemX + stage * kBoxBytes;
+          for (int j = 0; j < P.nblk; ++j) {
+            const uint32_t d = tmem_base + ((item + j) & (kSlots - 1)) * 128;
+            const uint32_t b_addr = sbase + kSmemW + (j * P.kchunks + kc) * kBoxBytes;
+#pragma unroll
+            for (int ks = 0; ks < kBoxK / 16; ++ks)
+              umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), idesc, (kc | ks) ? 1u : 0u);
+          }
+          umma_commit(bar_x_empty + 8 * stage);                 // ring slot free once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        for (int j = 0; j < P.nblk; ++j) umma_commit(bar_acc_full + 8 * ((item + j) & (kSlots - 1)));
+        item += P.nblk;
+      }
+    }
+  } else {
+    // =============================== epilogue: thread = token row, 128 channels in registers =========================
+    const int quad = warp & 3;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    uint32_t item = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int row = t * kTile + quad * 32 + lane;
+      for (int j = 0; j < P.nblk; ++j, ++item) {
+        const uint32_t slot = item & (kSlots - 1);
+        mbar_wait(bar_acc_full + 8 * slot, (item / kSlots) & 1);
+        tc_fence_after();
+        float v[kD];
+#pragma unroll
+        for (int c = 0; c < kD; c += 32) tmem_ld32(tmem_base + lane_addr + slot * 128 + c, v + c);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
+        if (row >= P.T) continue;
+        const int mode = P.mode[j];
+        if (P.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(P.bias + j * kD);
+#pragma unroll
+          for (int c = 0; c < kD; c += 4) {
+            const float4 b = __ldg(b4 + (c >> 2));
+            v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
+          }
+        }
+        if (mode == EPI_ELU1) {
+#pragma unroll
+          for (int c = 0; c < kD; ++c) v[c] = v[c] > 0.f ? v[c] + 1.f : __expf(v[c]);
+        } else if (mode == EPI_SCALE) {
+#pragma unroll
+          for (int c = 0; c < kD; ++c) v[c] *= P.scale;
+        } else if (mode == EPI_RELU) {
+#pragma unroll
+          for (int c = 0; c < kD; ++c) v[c] = fmaxf(v[c], 0.f);
+        } else if (mode == EPI_LN || mode == EPI_LN_RES) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+          for (int c = 0; c < kD; c += 4) { s0 += v[c]; s1 += v[c + 1]; s2 += v[c + 2]; s3 += v[c + 3]; }
+          const float mean = ((s0 + s1) + (s2 + s3)) * (1.f / kD);
+          s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+          for (int c = 0; c < kD; c += 4) {
+            const float d0 = v[c] - mean, d1 = v[c + 1] - mean, d2 = v[c + 2] - mean, d3 = v[c + 3] - mean;
+            s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+          }
+          const float rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.f / kD) + 1e-5f);      // nn.LayerNorm: biased variance
+          const float4* g4 = reinterpret_cast<const float4*>(P.gamma);
+          const float4* b4 = reinterpret_cast<const float4*>(P.beta);
+#pragma unroll
+          for (int c = 0; c < kD; c += 4) {
+            const float4 g = __ldg(g4 + (c >> 2)), b = __ldg(b4 + (c >> 2));
+            v[c] = fmaf((v[c] - mean) * rstd, g.x, b.x); v[c + 1] = fmaf((v[c + 1] - mean) * rstd, g.y, b.y);
+            v[c + 2] = fmaf((v[c + 2] - mean) * rstd, g.z, b.z); v[c + 3] = fmaf((v[c + 3] - mean) * rstd, g.w, b.w);
+          }
+          if (mode == EPI_LN_RES) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(P.resid + size_t(row) * kD);
+#pragma unroll
+            for (int c = 0; c < kD; c += 8) {
+              const uint4 r = r4[c >> 3];
+              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[c + 2 * e] += __uint_as_float(w[e] << 16);
+                v[c + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+              }
+            }
+          }
+        } else if (mode == EPI_ADDVEC) {
+          const float4* a4 = reinterpret_cast<const float4*>(P.rowvec + size_t(row / P.rows_per_vec) * kD);
+#pragma unroll
+          for (int c = 0; c < kD; c += 4) {
+            const float4 a = __ldg(a4 + (c >> 2));
+            v[c] += a.x; v[c + 1] += a.y; v[c + 2] += a.z; v[c + 3] += a.w;
+          }
+        }
+        if (P.out_f32) {
+          float4* o = reinterpret_cast<float4*>(static_cast<float*>(P.out[j]) + size_t(row) * P.out_stride);
+#pragma unroll
+          for (int c = 0; c < kD; c += 4) o[c >> 2] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(P.out[j]) + size_t(row) * P.out_stride);
+#pragma unroll
+          for (int c = 0; c < kD; c += 8)
+            o[c >> 3] = make_uint4(pack_bf16(v[c], v[c + 1]), pack_bf16(v[c + 2], v[c + 3]), pack_bf16(v[c + 4], v[c + 5]),
+                                   pack_bf16(v[c + 6], v[c + 7]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- linear attention, one warp per 25-token window ------------------------------------------------------------------
+// q, k already hold elu(.)+1 and v holds values / S (fused into the projection's epilogue).  Per head h (16 dims):
+//   KV[d][e] = sum_s k[s][d] v[s][e],  ksum[d] = sum_s k[s][d],  out[l][e] = S * (q[l] . KV[:, e]) / (q[l] . ksum + eps)
+// Phase 1: lane (h, r) accumulates KV rows d = 4r..4r+3 (64 values) over the window; the 256 values of a head go through
+// shared memory so that in phase 2 lane (h, r) owns output columns e = 4r..4r+3 for every token (no shuffles).
+constexpr int kAttnWarps = 4;
+
+__global__ void __launch_bounds__(kAttnWarps * 32)
+fine_attn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                 __nv_bfloat16* __restrict__ out, int64_t m, int S, float eps) {
+  __shared__ float kv_s[kAttnWarps][kHeads][kHeadDim][kHeadDim + 1];
+  __shared__ float ks_s[kAttnWarps][kHeads][kHeadDim];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = lane >> 2, r = lane & 3;
+  const int64_t w = int64_t(blockIdx.x) * kAttnWarps + warp;
+  if (w >= m) return;
+  const size_t base = size_t(w) * S * kD;
+  float kv[4][kHeadDim], ks[4];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    ks[d] = 0.f;
+#pragma unroll
+    for (int e = 0; e < kHeadDim; ++e) kv[d][e] = 0.f;
+  }
+  for (int s = 0; s < S; ++s) {
+    const uint2 kk = *reinterpret_cast<const uint2*>(k + base + size_t(s) * kD + h * kHeadDim + 4 * r);
+    const uint4* vp = reinterpret_cast<const uint4*>(v + base + size_t(s) * kD + h * kHeadDim);
+    const uint4 v0 = vp[0], v1 = vp[1];
+    const float kd[4] = {__uint_as_float(kk.x << 16), __uint_as_float(kk.x & 0xffff0000u), __uint_as_float(kk.y << 16),
+                         __uint_as_float(kk.y & 0xffff0000u)};
+    const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float ve[kHeadDim];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ve[2 * e] = __uint_as_float(vw[e] << 16); ve[2 * e + 1] = __uint_as_float(vw[e] & 0xffff0000u); }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      ks[d] += kd[d];
+#pragma unroll
+      for (int e = 0; e < kHeadDim; ++e) kv[d][e] = fmaf(kd[d], ve[e], kv[d][e]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    ks_s[warp][h][4 * r + d] = ks[d];
+#pragma unroll
+    for (int e = 0; e < kHeadDim; ++e) kv_s[warp][h][4 * r + d][e] = kv[d][e];
+  }
+  __syncwarp();
+  float kvc[kHeadDim][4], ksum[kHeadDim];       // KV[:, 4r..4r+3] and sum_s k of this head
+#pragma unroll
+  for (int d = 0; d < kHeadDim; ++d) {
+    ksum[d] = ks_s[warp][h][d];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) kvc[d][e] = kv_s[warp][h][d][4 * r + e];
+  }
+  const float fs = float(S);
+  for (int l = 0; l < S; ++l) {
+    const uint4* qp = reinterpret_cast<const uint4*>(q + base + size_t(l) * kD + h * kHeadDim);
+    const uint4 q0 = qp[0], q1 = qp[1];
+    const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    float z = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float qa = __uint_as_float(qw[e] << 16), qb = __uint_as_float(qw[e] & 0xffff0000u);
+      z = fmaf(qa, ksum[2 * e], z);
+      z = fmaf(qb, ksum[2 * e + 1], z);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[c] = fmaf(qa, kvc[2 * e][c], fmaf(qb, kvc[2 * e + 1][c], o[c]));
+    }
+    const float zi = fs / (z + eps);
+    *reinterpret_cast<uint2*>(out + base + size_t(l) * kD + h * kHeadDim + 4 * r) =
+        make_uint2(pack_bf16(o[0] * zi, o[1] * zi), pack_bf16(o[2] * zi, o[3] * zi));
+  }
+}
+
+// rows [0, m): f0[b, i, :], rows [m, 2m): f1[b, j, :]   (fine_preprocess.py:50-51, the cat along dim 0)
+__global__ void __launch_bounds__(256) gather_coarse_rows_kernel(const __nv_bfloat16* __restrict__ f0,
+                                                                const __nv_bfloat16* __restrict__ f1,
+                                                                const int64_t* __restrict__ b_ids,
+                                                                const int64_t* __restrict__ i_ids,
+                                                                const int64_t* __restrict__ j_ids, int64_t m, int L, int S,
+                                                                int C, __nv_bfloat16* __restrict__ out) {
+  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= 2 * m) return;
+  const int lane = threadIdx.x & 31;
+  const bool second = row >= m;
+  const int64_t mm = second ? row - m : row;
+  const __nv_bfloat16* src = second ? f1 + (size_t(b_ids[mm]) * S + size_t(j_ids[mm])) * C
+                                    : f0 + (size_t(b_ids[mm]) * L + size_t(i_ids[mm])) * C;
+  for (int c = lane * 8; c < C; c += 256)
+    *reinterpret_cast<uint4*>(out + size_t(row) * C + c) = *reinterpret_cast<const uint4*>(src + c);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// [rows, cols] bf16 with a row pitch of `pitch` elements, box = 64 columns x 128 rows, 128-byte swizzle, zero fill
+bool make_map2d(CUtensorMap* m, const void* base, int64_t rows, int cols, int64_t pitch) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(pitch) * 2};
+  cuuint32_t box[2] = {kBoxK, kTile};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Src { const void* ptr; int cols; int64_t pitch; };   // one K-part of the activations
+
+// Y[T, N] = epilogue(cat(X0, X1)[T, K] . W[N, K]^T)
+cudaError_t linear_run(int64_t T, Src x0, Src x1, const void* W, int N, int K, int64_t w_pitch, LinParams P, cudaStream_t st) {
+  if (T <= 0) return cudaSuccess;
+  if (T > 0x7fffffff - kTile || N % 128 || K % kBoxK || (N / 128) * (K / kBoxK) > kMaxWBoxes || N / 128 > 3)
+    return cudaErrorInvalidValue;
+  CUtensorMap m0, m1, mw;
+  if (!make_map2d(&m0, x0.ptr, T, x0.cols, x0.pitch)) return cudaErrorInvalidValue;
+  if (!make_map2d(&m1, x1.ptr ? x1.ptr : x0.ptr, T, x1.ptr ? x1.cols : x0.cols, x1.ptr ? x1.pitch : x0.pitch))
+    return cudaErrorInvalidValue;
+  if (!make_map2d(&mw, W, N, K, w_pitch)) return cudaErrorInvalidValue;
+  P.T = int(T);
+  P.kchunks = K / kBoxK;
+  P.kchunks0 = x0.cols / kBoxK;
+  P.nblk = N / 128;
+  int dev = 0, sms = 0;
+  cudaError_t e;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
+  const int ntiles = int((T + kTile - 1) / kTile);
+  linear_tc_kernel<<<min(ntiles, sms), kLinThreads, kSmemAlloc, st>>>(m0, m1, mw, P);
+  return cudaGetLastError();
+}
+
+// packed weights of one LoFTREncoderLayer (byte offsets; matrices bf16 row-major [out, in] like nn.Linear.weight)
+constexpr size_t kOffQkv = 0;                                  // [384, 128]  q_proj, k_proj, v_proj stacked
+constexpr size_t kOffMerge = kOffQkv + 384 * 128 * 2;          // [128, 128]
+constexpr size_t kOffMlp1 = kOffMerge + 128 * 128 * 2;         // [256, 256]
+constexpr size_t kOffMlp2 = kOffMlp1 + 256 * 256 * 2;          // [128, 256]
+constexpr size_t kOffLn = kOffMlp2 + 128 * 256 * 2;            // fp32: norm1.weight, norm1.bias, norm2.weight, norm2.bias
+constexpr size_t kLayerBytes = kOffLn + 4 * 128 * 4;
+static_assert(kLayerBytes == POPE_FINE_TF_LAYER_BYTES, "include/pope_b200.h documents this layout");
+// FinePreprocess Linears
+constexpr size_t kOffDown = 0;                                 // down_proj.weight [128, 256]
+constexpr size_t kOffMergeFeat = kOffDown + 128 * 256 * 2;     // merge_feat.weight [128, 256]
+constexpr size_t kOffPreBias = kOffMergeFeat + 128 * 256 * 2;  // fp32: down_proj.bias [128], merge_feat.bias [128]
+constexpr size_t kPreBytes = kOffPreBias + 2 * 128 * 4;
+static_assert(kPreBytes == POPE_FINE_PRE_BYTES, "include/pope_b200.h documents this layout");
+
+struct TfScratch { __nv_bfloat16 *q, *k, *v, *msg, *m1, *h; size_t bytes; };
+TfScratch carve_tf(void* base, int64_t m, int S) {
+  TfScratch w;
+  char* p = static_cast<char*>(base);
+  const size_t unit = align_up(size_t(m) * S * kD * 2, 256);
+  size_t off = 0;
+  w.q = reinterpret_cast<__nv_bfloat16*>(p + off); off += unit;
+  w.k = reinterpret_cast<__nv_bfloat16*>(p + off); off += unit;
+  w.v = reinterpret_cast<__nv_bfloat16*>(p + off); off += unit;
+  w.msg = reinterpret_cast<__nv_bfloat16*>(p + off); off += unit;
+  w.m1 = reinterpret_cast<__nv_bfloat16*>(p + off); off += unit;
+  w.h = reinterpret_cast<__nv_bfloat16*>(p + off); off += 2 * unit;
+  w.bytes = off;
+  return w;
+}
+
+// x <- x + norm2(mlp(cat(x, norm1(merge(attention(q(x), k(src), v(src)))))))      (transformer.py:34-58), in place on x
+cudaError_t encoder_layer(__nv_bfloat16* x, const __nv_bfloat16* src, int64_t m, int S, const char* wl, const TfScratch& w,
+                          cudaStream_t st) {
+  const int64_t T = m * S;
+  const float* ln = reinterpret_cast<const float*>(wl + kOffLn);
+  cudaError_t e;
+  LinParams P{};
+  P.out_stride = kD;
+  if (x == src) {                       // self: one pass over x produces q, k, v
+    P.out[0] = w.q; P.out[1] = w.k; P.out[2] = w.v;
+    P.mode[0] = EPI_ELU1; P.mode[1] = EPI_ELU1; P.mode[2] = EPI_SCALE; P.scale = 1.f / float(S);
+    if ((e = linear_run(T, {x, kD, kD}, {nullptr, 0, 0}, wl + kOffQkv, 384, kD, kD, P, st)) != cudaSuccess) return e;
+  } else {
+    P.out[0] = w.q; P.mode[0] = EPI_ELU1;
+    if ((e = linear_run(T, {x, kD, kD}, {nullptr, 0, 0}, wl + kOffQkv, 128, kD, kD, P, st)) != cudaSuccess) return e;
+    P.out[0] = w.k; P.out[1] = w.v; P.mode[0] = EPI_ELU1; P.mode[1] = EPI_SCALE; P.scale = 1.f / float(S);
+    if ((e = linear_run(T, {src, kD, kD}, {nullptr, 0, 0}, wl + kOffQkv + 128 * 128 * 2, 256, kD, kD, P, st)) != cudaSuccess) return e;
+  }
+  fine_attn_kernel<<<unsigned((m + kAttnWarps - 1) / kAttnWarps), kAttnWarps * 32, 0, st>>>(w.q, w.k, w.v, w.msg, m, S, 1e-6f);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  P = LinParams{};
+  P.out_stride = kD; P.out[0] = w.m1; P.mode[0] = EPI_LN; P.gamma = ln; P.beta = ln + 128;
+  if ((e = linear_run(T, {w.msg, kD, kD}, {nullptr, 0, 0}, wl + kOffMerge, 128, kD, kD, P, st)) != cudaSuccess) return e;
+  P = LinParams{};
+  P.out_stride = 2 * kD; P.out[0] = w.h; P.out[1] = w.h + kD; P.mode[0] = EPI_RELU; P.mode[1] = EPI_RELU;
+  if ((e = linear_run(T, {x, kD, kD}, {w.m1, kD, kD}, wl + kOffMlp1, 256, 256, 256, P, st)) != cudaSuccess) return e;
+  P = LinParams{};
+  P.out_stride = kD; P.out[0] = x; P.mode[0] = EPI_LN_RES; P.gamma = ln + 256; P.beta = ln + 384; P.resid = x;
+  return linear_run(T, {w.h, 2 * kD, 2 * kD}, {nullptr, 0, 0}, wl + kOffMlp2, 128, 256, 256, P, st);
+}
+
+}  // namespace
+}  // namespace pope
+
+using namespace pope;
+
+extern "C" size_t pope_fine_tf_workspace_bytes(int64_t m_windows, int window_tokens) {
+  if (m_windows <= 0 || window_tokens <= 0) return 0;
+  // the FinePreprocess Linears reuse the same scratch: gathered coarse rows [2m, 256] bf16, projected [2m, 128] bf16,
+  // per-window vectors [2m, 128] fp32 -- far smaller than the transformer's 7 activation planes
+  return carve_tf(nullptr, m_windows, window_tokens).bytes;
+}
+
+extern "C" int pope_fine_transformer(void* feat0, void* feat1, int64_t m_windows, int window_tokens, const void* weights,
+                                     int n_layers, const int* layer_kinds, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  if (!feat0 || !feat1 || !weights || !layer_kinds || !workspace) return POPE_ERR_INVALID_ARG;
+  if (m_windows < 0 || window_tokens <= 0 || n_layers < 0) return POPE_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(feat0) | reinterpret_cast<uintptr_t>(feat1) | reinterpret_cast<uintptr_t>(weights) |
+       reinterpret_cast<uintptr_t>(workspace)) & 15u)
+    return POPE_ERR_ALIGNMENT;
+  if (m_windows == 0) return POPE_OK;
+  const TfScratch w = carve_tf(workspace, m_windows, window_tokens);
+  if (workspace_bytes < w.bytes) return POPE_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* x0 = static_cast<__nv_bfloat16*>(feat0);
+  __nv_bfloat16* x1 = static_cast<__nv_bfloat16*>(feat1);
+  for (int l = 0; l < n_layers; ++l) {
+    const char* wl = static_cast<const char*>(weights) + size_t(l) * kLayerBytes;
+    cudaError_t e;
+    if (layer_kinds[l] == 0) {            // 'self'  (transformer.py:96-98)
+      if ((e = encoder_layer(x0, x0, m_windows, window_tokens, wl, w, st)) != cudaSuccess) return int(e);
+      if ((e = encoder_layer(x1, x1, m_windows, window_tokens, wl, w, st)) != cudaSuccess) return int(e);
+    } else if (layer_kinds[l] == 1) {     // 'cross' (:99-101): feat1 attends to the UPDATED feat0
+      if ((e = encoder_layer(x0, x1, m_windows, window_tokens, wl, w, st)) != cudaSuccess) return int(e);
+      if ((e = encoder_layer(x1, x0, m_windows, window_tokens, wl, w, st)) != cudaSuccess) return int(e);
+    } else {
+      return POPE_ERR_INVALID_ARG;
+    }
+  }
+  return POPE_OK;
+}
+
+extern "C" int pope_fine_merge_coarse(void* win0, void* win1, int64_t m_windows, int window_tokens, const void* feat_c0,
+                                      const void* feat_c1, int L, int S, int C, const int64_t* b_ids, const int64_t* i_ids,
+                                      const int64_t* j_ids, const void* weights, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  if (!win0 || !win1 || !feat_c0 || !feat_c1 || !b_ids || !i_ids || !j_ids || !weights || !workspace)
+    return POPE_ERR_INVALID_ARG;
+  if (m_windows < 0 || window_tokens <= 0 || L <= 0 || S <= 0) return POPE_ERR_INVALID_ARG;
+  if (C != 256) return POPE_ERR_SHAPE;
+  if (m_windows == 0) return POPE_OK;
+  const size_t need = size_t(2 * m_windows) * (256 * 2 + 128 * 2 + 128 * 4) + 768;
+  if (workspace_bytes < need) return POPE_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t m = m_windows;
+  char* p = static_cast<char*>(workspace);
+  __nv_bfloat16* cg = reinterpret_cast<__nv_bfloat16*>(p);
+  __nv_bfloat16* cd = reinterpret_cast<__nv_bfloat16*>(p + align_up(size_t(2 * m) * 256 * 2, 256));
+  float* cvec = reinterpret_cast<float*>(reinterpret_cast<char*>(cd) + align_up(size_t(2 * m) * 128 * 2, 256));
+  const char* wp = static_cast<const char*>(weights);
+  const float* bias = reinterpret_cast<const float*>(wp + kOffPreBias);
+  gather_coarse_rows_kernel<<<unsigned((2 * m + 7) / 8), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(feat_c0), static_cast<const __nv_bfloat16*>(feat_c1), b_ids, i_ids, j_ids, m, L, S, C, cg);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return int(e);
+  // feat_c_win = down_proj(cat(c0, c1))                                                  (fine_preprocess.py:50-51)
+  LinParams P{};
+  P.out_stride = kD; P.out[0] = cd; P.mode[0] = EPI_COPY; P.bias = bias;
+  if ((e = linear_run(2 * m, {cg, 256, 256}, {nullptr, 0, 0}, wp + kOffDown, 128, 256, 256, P, st)) != cudaSuccess) return int(e);
+  // merge_feat(cat(win, repeat(c))) = win . Wa^T + (c . Wb^T + bias): the second term once per window       (:52-55)
+  P = LinParams{};
+  P.out_stride = kD; P.out[0] = cvec; P.out_f32 = 1; P.mode[0] = EPI_COPY; P.bias = bias + 128;
+  if ((e = linear_run(2 * m, {cd, kD, kD}, {nullptr, 0, 0}, wp + kOffMergeFeat + 128 * 2, 128, 128, 256, P, st)) != cudaSuccess)
+    return int(e);
+  for (int side = 0; side < 2; ++side) {
+    void* win = side ? win1 : win0;
+    P = LinParams{};
+    P.out_stride = kD; P.out[0] = win; P.mode[0] = EPI_ADDVEC; P.rowvec = cvec + size_t(side) * m * kD;
+    P.rows_per_vec = window_tokens;
+    if ((e = linear_run(m * window_tokens, {win, kD, kD}, {nullptr, 0, 0}, wp + kOffMergeFeat, 128, 128, 256, P, st)) != cudaSuccess)
+      return int(e);
+  }
+  return POPE_OK;
+}

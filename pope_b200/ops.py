@@ -116,6 +116,92 @@ def fine_match(win0: torch.Tensor, win1: torch.Tensor, mkpts1_c: torch.Tensor, c
     return expec, mk1f
 
 
+def pack_fine_layer(sd: Dict[str, torch.Tensor], device) -> torch.Tensor:
+    """One LoFTREncoderLayer state dict (d_model 128) -> the packed byte layout of include/pope_b200.h."""
+    mats = [sd["q_proj.weight"], sd["k_proj.weight"], sd["v_proj.weight"], sd["merge.weight"], sd["mlp.0.weight"],
+            sd["mlp.2.weight"]]
+    shapes = [(128, 128)] * 4 + [(256, 256), (128, 256)]
+    for t, shp in zip(mats, shapes):
+        if tuple(t.shape) != shp:
+            raise _lib.PopeError(f"fine transformer weight of shape {tuple(t.shape)}, expected {shp} (d_model 128, 8 heads)")
+    w = torch.cat([t.detach().to(device=device, dtype=torch.bfloat16).reshape(-1) for t in mats]).view(torch.uint8)
+    ln = torch.cat([sd[k].detach().to(device=device, dtype=torch.float32).reshape(-1)
+                    for k in ("norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")]).view(torch.uint8)
+    out = torch.cat([w, ln])
+    assert out.numel() == _lib.FINE_TF_LAYER_BYTES
+    return out
+
+
+def pack_fine_pre(sd: Dict[str, torch.Tensor], device) -> torch.Tensor:
+    """FinePreprocess state dict (down_proj, merge_feat) -> the packed byte layout of include/pope_b200.h."""
+    w = torch.cat([sd[k].detach().to(device=device, dtype=torch.bfloat16).reshape(-1)
+                   for k in ("down_proj.weight", "merge_feat.weight")]).view(torch.uint8)
+    b = torch.cat([sd[k].detach().to(device=device, dtype=torch.float32).reshape(-1)
+                   for k in ("down_proj.bias", "merge_feat.bias")]).view(torch.uint8)
+    out = torch.cat([w, b])
+    assert out.numel() == _lib.FINE_PRE_BYTES
+    return out
+
+
+def fine_tf_workspace(m: int, ww: int, dev, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    need = lib().pope_fine_tf_workspace_bytes(int(m), int(ww))
+    if workspace is None or workspace.numel() < need or workspace.device != dev:
+        workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
+    return workspace
+
+
+def fine_transformer(feat0: torch.Tensor, feat1: torch.Tensor, packed_layers: torch.Tensor, layer_names,
+                     workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """LocalFeatureTransformer.forward on bf16 windows [M, WW, 128], IN PLACE (returns the same tensors).
+    `packed_layers`: concatenation of pack_fine_layer() of every layer, `layer_names`: 'self' / 'cross'."""
+    dev = require_cuda(feat0, feat1, packed_layers)
+    if feat0.dtype != torch.bfloat16 or feat1.dtype != torch.bfloat16:
+        raise _lib.PopeError("the CUDA fine transformer takes bfloat16 windows")
+    if feat0.shape != feat1.shape or feat0.dim() != 3 or feat0.shape[2] != 128:
+        raise _lib.PopeError("feat0 / feat1 must both be [M, WW, 128]")
+    if not (feat0.is_contiguous() and feat1.is_contiguous()):
+        raise _lib.PopeError("the CUDA fine transformer updates its inputs in place: pass contiguous tensors")
+    kinds = []
+    for name in layer_names:
+        if name not in ("self", "cross"):
+            raise KeyError(name)
+        kinds.append(0 if name == "self" else 1)
+    if packed_layers.numel() != len(kinds) * _lib.FINE_TF_LAYER_BYTES:
+        raise _lib.PopeError("packed_layers does not hold one packed layer per layer name")
+    M, WW, _ = feat0.shape
+    if M == 0:
+        return feat0, feat1
+    workspace = fine_tf_workspace(M, WW, dev, workspace)
+    arr = (_lib.C.c_int * max(len(kinds), 1))(*kinds)
+    with torch.cuda.device(dev):
+        st = lib().pope_fine_transformer(ptr(feat0), ptr(feat1), M, WW, ptr(packed_layers), len(kinds), arr,
+                                         ptr(workspace), workspace.numel(), stream_ptr(dev))
+    check(st, "pope_fine_transformer")
+    return feat0, feat1
+
+
+def fine_merge_coarse(win0: torch.Tensor, win1: torch.Tensor, feat_c0: torch.Tensor, feat_c1: torch.Tensor, b_ids, i_ids,
+                      j_ids, packed_pre: torch.Tensor, workspace: Optional[torch.Tensor] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """FinePreprocess' down_proj / merge_feat on bf16 windows [M, WW, 128], IN PLACE (returns the same tensors)."""
+    dev = require_cuda(win0, win1, feat_c0, feat_c1, b_ids, i_ids, j_ids, packed_pre)
+    for t in (win0, win1, feat_c0, feat_c1):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous():
+            raise _lib.PopeError("fine_merge_coarse takes contiguous bfloat16 tensors")
+    M, WW, _ = win0.shape
+    if M == 0:
+        return win0, win1
+    n, L, C_ = feat_c0.shape
+    S = feat_c1.shape[1]
+    workspace = fine_tf_workspace(M, WW, dev, workspace)
+    with torch.cuda.device(dev):
+        st = lib().pope_fine_merge_coarse(ptr(win0), ptr(win1), M, WW, ptr(feat_c0), ptr(feat_c1), L, S, C_,
+                                          ptr(b_ids.contiguous()), ptr(i_ids.contiguous()), ptr(j_ids.contiguous()),
+                                          ptr(packed_pre), ptr(workspace), workspace.numel(), stream_ptr(dev))
+    check(st, "pope_fine_merge_coarse")
+    return win0, win1
+
+
 def match_order_by_ref(counts: torch.Tensor, n_pairs: int, S: int, j_ids: torch.Tensor) -> torch.Tensor:
     """order[k] = index of the k-th match in (pair, reference cell) order; see pope_match_order_by_ref."""
     dev = require_cuda(counts, j_ids)
