@@ -29,17 +29,20 @@ constexpr int kTile = 128;               // token rows per tile (MMA M)
 constexpr int kBoxK = 64;                // bf16 elements per 128-byte swizzle row
 constexpr int kBoxBytes = kTile * kBoxK * 2;          // 16384
 constexpr int kMaxWBoxes = 8;            // N/128 * K/64 <= 8 (256 x 256)
-constexpr int kStages = 5;               // activation ring depth
+constexpr int kMaxStages = 8;            // activation ring depth (as many as fit beside the weights)
 constexpr int kSlots = 4;                // TMEM accumulator slots of 128 columns
-constexpr int kLinThreads = 192;         // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue (one per TMEM lane quadrant)
-constexpr int kSmemW = 0;
-constexpr int kSmemX = kSmemW + kMaxWBoxes * kBoxBytes;
-constexpr int kSmemBar = kSmemX + kStages * kBoxBytes;
-constexpr int kNumBars = 1 + 2 * kStages + 2 * kSlots;
+constexpr int kEpiWarps = 8;             // two sets of four (one warp per TMEM lane quadrant); sets alternate items
+constexpr int kLinThreads = 64 + kEpiWarps * 32;      // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
+constexpr int kStageOutBytes = 32 * 128;              // per epilogue warp: 32 rows x 64 bf16 columns, 128B-swizzled
+constexpr int kSmemBudget = 227 * 1024 - 1024;        // dynamic shared memory we ask for (1 KB alignment slack inside)
+// layout: [staging: 8 x 4 KB][barriers][weights: nbox x 16 KB][ring: stages x 16 KB]
+constexpr int kSmemOut = 0;
+constexpr int kSmemBar = kSmemOut + kEpiWarps * kStageOutBytes;
+constexpr int kNumBars = 1 + 2 * kMaxStages + 2 * kSlots + kEpiWarps;
 constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
-constexpr int kSmemBytes = kSmemTmemPtr + 16;
-constexpr int kSmemAlloc = kSmemBytes + 1024;         // slack for manual 1024-B alignment; > 113 KB -> one CTA per SM,
-                                                      // so the CTA may take all 512 TMEM columns
+constexpr int kSmemW = 34 * 1024;                     // first 1024-aligned offset past the barriers
+static_assert(kSmemTmemPtr + 16 <= kSmemW, "barrier block overlaps the weights");
+constexpr int kSmemAlloc = kSmemBudget;               // > 113 KB -> one CTA per SM, so the CTA may take all 512 TMEM columns
 
 enum EpiMode : int { EPI_COPY = 0, EPI_ELU1 = 1, EPI_SCALE = 2, EPI_RELU = 3, EPI_LN = 4, EPI_LN_RES = 5, EPI_ADDVEC = 6 };
 
@@ -47,15 +50,13 @@ struct LinParams {
   int T;                       // token rows
   int kchunks, kchunks0;       // K/64; the first kchunks0 chunks come from source 0, the rest from source 1 (torch.cat)
   int nblk;                    // N/128
-  void* out[3];                // per 128-column block of the output
-  int out_stride;              // row stride of the output, in elements
-  int out_f32;                 // rows are written as fp32 instead of bf16
+  int stages;                  // ring depth that fits beside the weights
+  float* out_f32;              // if set: the (single) output block is written as fp32 rows [T, 128] with plain stores
   int mode[3];
   float scale;                 // EPI_SCALE
   const float* bias;           // [N] or nullptr, added before the mode is applied
   const float* gamma;          // EPI_LN / EPI_LN_RES: [128]
   const float* beta;
-  const __nv_bfloat16* resid;  // EPI_LN_RES: [T, 128]
   const float* rowvec;         // EPI_ADDVEC: [T / rows_per_vec, 128]
   int rows_per_vec;
 };
@@ -65,25 +66,33 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// mapO[j]: output block j as a [T, 128] bf16 tensor (box 64 x 32 rows); mapR: residual [T, 128] (EPI_LN_RES)
 __global__ void __launch_bounds__(kLinThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
-                 const __grid_constant__ CUtensorMap mapW, const LinParams P) {
+                 const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO0,
+                 const __grid_constant__ CUtensorMap mapO1, const __grid_constant__ CUtensorMap mapO2,
+                 const __grid_constant__ CUtensorMap mapR, const LinParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + kSmemBar;
   const uint32_t bar_w_full = bar0;
-  const uint32_t bar_x_full = bar0 + 8, bar_x_empty = bar_x_full + 8 * kStages;
-  const uint32_t bar_acc_full = bar_x_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 8 * kSlots;
+  const uint32_t bar_x_full = bar0 + 8, bar_x_empty = bar_x_full + 8 * kMaxStages;
+  const uint32_t bar_acc_full = bar_x_empty + 8 * kMaxStages, bar_acc_empty = bar_acc_full + 8 * kSlots;
+  const uint32_t bar_res = bar_acc_empty + 8 * kSlots;           // one per epilogue warp (residual tile landed)
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (P.T + kTile - 1) / kTile;
+  const uint32_t smem_x = sbase + kSmemW + P.nblk * P.kchunks * kBoxBytes;
+  const int stages = P.stages;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapX0); prefetch_tmap(&mapX1); prefetch_tmap(&mapW);
+    prefetch_tmap(&mapO0); prefetch_tmap(&mapO1); prefetch_tmap(&mapO2); prefetch_tmap(&mapR);
     mbar_init(bar_w_full, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
     for (int s = 0; s < kSlots; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 4); }
+    for (int s = 0; s < kEpiWarps; ++s) mbar_init(bar_res + 8 * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -102,15 +111,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
       for (int j = 0; j < P.nblk; ++j)
         for (int kc = 0; kc < P.kchunks; ++kc)
           tma_load_2d(sbase + kSmemW + (j * P.kchunks + kc) * kBoxBytes, &mapW, bar_w_full, kc * kBoxK, j * kTile);
-      uint32_t stage = 0, phase = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
         for (int kc = 0; kc < P.kchunks; ++kc) {
           mbar_wait(bar_x_empty + 8 * stage, phase ^ 1);
           mbar_expect_tx(bar_x_full + 8 * stage, kBoxBytes);
           const bool second = kc >= P.kchunks0;
-          tma_load_2d(sbase + kSmemX + stage * kBoxBytes, second ? &mapX1 : &mapX0, bar_x_full + 8 * stage,
+          tma_load_2d(smem_x + stage * kBoxBytes, second ? &mapX1 : &mapX0, bar_x_full + 8 * stage,
                       (second ? kc - P.kchunks0 : kc) * kBoxK, t * kTile);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
     }
   } else if (warp == 1) {
@@ -119,7 +129,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
       constexpr uint32_t idesc = idesc_bf16(kTile, 128);
       mbar_wait(bar_w_full, 0);
       tc_fence_after();
-      uint32_t stage = 0, phase = 0, item = 0;
+      int stage = 0;
+      uint32_t phase = 0, item = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         for (int j = 0; j < P.nblk; ++j) {                      // the tile's accumulator slots must have been drained
           const uint32_t it = item + j;
@@ -129,7 +140,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
         for (int kc = 0; kc < P.kchunks; ++kc) {
           mbar_wait(bar_x_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t a_addr = sbase + kSmemX + stage * kBoxBytes;
+          const uint32_t a_addr = smem_x + stage * kBoxBytes;
           for (int j = 0; j < P.nblk; ++j) {
             const uint32_t d = tmem_base + ((item + j) & (kSlots - 1)) * 128;
             const uint32_t b_addr = sbase + kSmemW + (j * P.kchunks + kc) * kBoxBytes;
@@ -138,7 +149,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
               umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), idesc, (kc | ks) ? 1u : 0u);
           }
           umma_commit(bar_x_empty + 8 * stage);                 // ring slot free once these MMAs have read it
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         for (int j = 0; j < P.nblk; ++j) umma_commit(bar_acc_full + 8 * ((item + j) & (kSlots - 1)));
         item += P.nblk;
@@ -146,13 +157,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
     }
   } else {
     // =============================== epilogue: thread = token row, 128 channels in registers =========================
-    const int quad = warp & 3;
+    // Rows leave through a 128B-swizzled shared-memory box and a TMA store (a thread-per-row store to global memory
+    // touches 32 different lines per instruction and was measured LSU-bound); the residual rows arrive the same way.
+    const int ew = warp - 2, set = ew >> 2, quad = warp & 3;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    const uint32_t stage_buf = sbase + kSmemOut + ew * kStageOutBytes;
+    const uint32_t my_row = stage_buf + lane * 128;
+    const uint32_t sw = uint32_t(lane & 7);
+    const uint32_t bar_my_res = bar_res + 8 * ew;
+    uint32_t res_phase = 0;
     uint32_t item = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int row = t * kTile + quad * 32 + lane;
+      const int row0 = t * kTile + quad * 32, row = row0 + lane;
       for (int j = 0; j < P.nblk; ++j, ++item) {
+        if ((item & 1u) != uint32_t(set)) continue;
         const uint32_t slot = item & (kSlots - 1);
+        const int mode = P.mode[j];
         mbar_wait(bar_acc_full + 8 * slot, (item / kSlots) & 1);
         tc_fence_after();
         float v[kD];
@@ -161,8 +181,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
-        if (row >= P.T) continue;
-        const int mode = P.mode[j];
         if (P.bias) {
           const float4* b4 = reinterpret_cast<const float4*>(P.bias + j * kD);
 #pragma unroll
@@ -173,7 +191,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
         }
         if (mode == EPI_ELU1) {
 #pragma unroll
-          for (int c = 0; c < kD; ++c) v[c] = v[c] > 0.f ? v[c] + 1.f : __expf(v[c]);
+          for (int c = 0; c < kD; ++c) v[c] = v[c] > 0.f ? v[c] + 1.f : ex2_approx(v[c] * kLog2e);
         } else if (mode == EPI_SCALE) {
 #pragma unroll
           for (int c = 0; c < kD; ++c) v[c] *= P.scale;
@@ -201,39 +219,73 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
             v[c + 2] = fmaf((v[c + 2] - mean) * rstd, g.z, b.z); v[c + 3] = fmaf((v[c + 3] - mean) * rstd, g.w, b.w);
           }
           if (mode == EPI_LN_RES) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(P.resid + size_t(row) * kD);
+            // + x: the warp's 32 residual rows come through the staging box, one 64-column half at a time
 #pragma unroll
-            for (int c = 0; c < kD; c += 8) {
-              const uint4 r = r4[c >> 3];
-              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[c + 2 * e] += __uint_as_float(w[e] << 16);
-                v[c + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+            for (int half = 0; half < 2; ++half) {
+              if (lane == 0) {
+                tma_store_wait_read();                          // the box may still be the source of an earlier store
+                mbar_expect_tx(bar_my_res, kStageOutBytes);
+                tma_load_2d(stage_buf, &mapR, bar_my_res, half * 64, row0);
               }
+              __syncwarp();
+              mbar_wait(bar_my_res, res_phase);
+              res_phase ^= 1;
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8) {
+                uint4 r;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                             : "r"(my_row + ((uint32_t(c8) ^ sw) << 4)));
+                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[half * 64 + c8 * 8 + 2 * e] += __uint_as_float(w[e] << 16);
+                  v[half * 64 + c8 * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                }
+              }
+              __syncwarp();                                     // everyone has read the box before it is refilled
             }
           }
         } else if (mode == EPI_ADDVEC) {
-          const float4* a4 = reinterpret_cast<const float4*>(P.rowvec + size_t(row / P.rows_per_vec) * kD);
+          if (row < P.T) {
+            const float4* a4 = reinterpret_cast<const float4*>(P.rowvec + size_t(row / P.rows_per_vec) * kD);
 #pragma unroll
-          for (int c = 0; c < kD; c += 4) {
-            const float4 a = __ldg(a4 + (c >> 2));
-            v[c] += a.x; v[c + 1] += a.y; v[c + 2] += a.z; v[c + 3] += a.w;
+            for (int c = 0; c < kD; c += 4) {
+              const float4 a = __ldg(a4 + (c >> 2));
+              v[c] += a.x; v[c + 1] += a.y; v[c + 2] += a.z; v[c + 3] += a.w;
+            }
           }
         }
         if (P.out_f32) {
-          float4* o = reinterpret_cast<float4*>(static_cast<float*>(P.out[j]) + size_t(row) * P.out_stride);
+          if (row < P.T) {
+            float4* o = reinterpret_cast<float4*>(P.out_f32 + size_t(row) * kD);
 #pragma unroll
-          for (int c = 0; c < kD; c += 4) o[c >> 2] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            for (int c = 0; c < kD; c += 4) o[c >> 2] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          }
         } else {
-          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(P.out[j]) + size_t(row) * P.out_stride);
+          const CUtensorMap* mo = j == 0 ? &mapO0 : (j == 1 ? &mapO1 : &mapO2);
 #pragma unroll
-          for (int c = 0; c < kD; c += 8)
-            o[c >> 3] = make_uint4(pack_bf16(v[c], v[c + 1]), pack_bf16(v[c + 2], v[c + 3]), pack_bf16(v[c + 4], v[c + 5]),
-                                   pack_bf16(v[c + 6], v[c + 7]));
+          for (int half = 0; half < 2; ++half) {
+            if (lane == 0) tma_store_wait_read();               // the previous store out of this box has read it
+            __syncwarp();
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const int c = half * 64 + c8 * 8;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(my_row + ((uint32_t(c8) ^ sw) << 4)), "r"(pack_bf16(v[c], v[c + 1])),
+                             "r"(pack_bf16(v[c + 2], v[c + 3])), "r"(pack_bf16(v[c + 4], v[c + 5])),
+                             "r"(pack_bf16(v[c + 6], v[c + 7])) : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(mo, stage_buf, half * 64, row0);     // rows past T are clipped by the tensor map
+              tma_store_commit();
+            }
+          }
         }
       }
     }
+    if (lane == 0) tma_store_wait_all();                        // global writes complete before the CTA exits
   }
 
   tc_fence_before();
@@ -352,13 +404,13 @@ EncodeTiledFn encode_fn() {
   }();
   return fn;
 }
-// [rows, cols] bf16 with a row pitch of `pitch` elements, box = 64 columns x 128 rows, 128-byte swizzle, zero fill
-bool make_map2d(CUtensorMap* m, const void* base, int64_t rows, int cols, int64_t pitch) {
+// [rows, cols] bf16 with a row pitch of `pitch` elements, box = 64 columns x box_rows rows, 128-byte swizzle, zero fill
+bool make_map2d(CUtensorMap* m, const void* base, int64_t rows, int cols, int64_t pitch, int box_rows = kTile) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return false;
   cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
   cuuint64_t strides[1] = {cuuint64_t(pitch) * 2};
-  cuuint32_t box[2] = {kBoxK, kTile};
+  cuuint32_t box[2] = {kBoxK, cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -366,28 +418,39 @@ bool make_map2d(CUtensorMap* m, const void* base, int64_t rows, int cols, int64_
 }
 
 struct Src { const void* ptr; int cols; int64_t pitch; };   // one K-part of the activations
+struct Dst { void* ptr; int64_t pitch; };                   // one 128-column block of the output (bf16, row pitch in elements)
 
-// Y[T, N] = epilogue(cat(X0, X1)[T, K] . W[N, K]^T)
-cudaError_t linear_run(int64_t T, Src x0, Src x1, const void* W, int N, int K, int64_t w_pitch, LinParams P, cudaStream_t st) {
+// Y[T, N] = epilogue(cat(X0, X1)[T, K] . W[N, K]^T);  out[j] receives output columns [128 j, 128 j + 128)
+cudaError_t linear_run(int64_t T, Src x0, Src x1, const void* W, int N, int K, int64_t w_pitch, const Dst (&out)[3],
+                       const __nv_bfloat16* resid, LinParams P, cudaStream_t st) {
   if (T <= 0) return cudaSuccess;
   if (T > 0x7fffffff - kTile || N % 128 || K % kBoxK || (N / 128) * (K / kBoxK) > kMaxWBoxes || N / 128 > 3)
     return cudaErrorInvalidValue;
-  CUtensorMap m0, m1, mw;
+  CUtensorMap m0, m1, mw, mo[3], mr;
   if (!make_map2d(&m0, x0.ptr, T, x0.cols, x0.pitch)) return cudaErrorInvalidValue;
   if (!make_map2d(&m1, x1.ptr ? x1.ptr : x0.ptr, T, x1.ptr ? x1.cols : x0.cols, x1.ptr ? x1.pitch : x0.pitch))
     return cudaErrorInvalidValue;
   if (!make_map2d(&mw, W, N, K, w_pitch)) return cudaErrorInvalidValue;
+  const void* any_out = P.out_f32 ? x0.ptr : out[0].ptr;       // unused maps still have to be valid descriptors
+  for (int j = 0; j < 3; ++j) {
+    const bool used = !P.out_f32 && j < N / 128;
+    if (used && !out[j].ptr) return cudaErrorInvalidValue;
+    if (!make_map2d(&mo[j], used ? out[j].ptr : any_out, T, kD, used ? out[j].pitch : kD, 32)) return cudaErrorInvalidValue;
+  }
+  if (!make_map2d(&mr, resid ? static_cast<const void*>(resid) : any_out, T, kD, kD, 32)) return cudaErrorInvalidValue;
   P.T = int(T);
   P.kchunks = K / kBoxK;
   P.kchunks0 = x0.cols / kBoxK;
   P.nblk = N / 128;
+  P.stages = min(kMaxStages, (kSmemBudget - 1024 - kSmemW - P.nblk * P.kchunks * kBoxBytes) / kBoxBytes);
+  if (P.stages < 2) return cudaErrorInvalidValue;
   int dev = 0, sms = 0;
   cudaError_t e;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   const int ntiles = int((T + kTile - 1) / kTile);
-  linear_tc_kernel<<<min(ntiles, sms), kLinThreads, kSmemAlloc, st>>>(m0, m1, mw, P);
+  linear_tc_kernel<<<min(ntiles, sms), kLinThreads, kSmemAlloc, st>>>(m0, m1, mw, mo[0], mo[1], mo[2], mr, P);
   return cudaGetLastError();
 }
 
@@ -427,30 +490,36 @@ cudaError_t encoder_layer(__nv_bfloat16* x, const __nv_bfloat16* src, int64_t m,
                           cudaStream_t st) {
   const int64_t T = m * S;
   const float* ln = reinterpret_cast<const float*>(wl + kOffLn);
+  const Src none{nullptr, 0, 0};
   cudaError_t e;
   LinParams P{};
-  P.out_stride = kD;
   if (x == src) {                       // self: one pass over x produces q, k, v
-    P.out[0] = w.q; P.out[1] = w.k; P.out[2] = w.v;
     P.mode[0] = EPI_ELU1; P.mode[1] = EPI_ELU1; P.mode[2] = EPI_SCALE; P.scale = 1.f / float(S);
-    if ((e = linear_run(T, {x, kD, kD}, {nullptr, 0, 0}, wl + kOffQkv, 384, kD, kD, P, st)) != cudaSuccess) return e;
+    const Dst o[3] = {{w.q, kD}, {w.k, kD}, {w.v, kD}};
+    if ((e = linear_run(T, {x, kD, kD}, none, wl + kOffQkv, 384, kD, kD, o, nullptr, P, st)) != cudaSuccess) return e;
   } else {
-    P.out[0] = w.q; P.mode[0] = EPI_ELU1;
-    if ((e = linear_run(T, {x, kD, kD}, {nullptr, 0, 0}, wl + kOffQkv, 128, kD, kD, P, st)) != cudaSuccess) return e;
-    P.out[0] = w.k; P.out[1] = w.v; P.mode[0] = EPI_ELU1; P.mode[1] = EPI_SCALE; P.scale = 1.f / float(S);
-    if ((e = linear_run(T, {src, kD, kD}, {nullptr, 0, 0}, wl + kOffQkv + 128 * 128 * 2, 256, kD, kD, P, st)) != cudaSuccess) return e;
+    P.mode[0] = EPI_ELU1;
+    const Dst oq[3] = {{w.q, kD}, {nullptr, 0}, {nullptr, 0}};
+    if ((e = linear_run(T, {x, kD, kD}, none, wl + kOffQkv, 128, kD, kD, oq, nullptr, P, st)) != cudaSuccess) return e;
+    P.mode[0] = EPI_ELU1; P.mode[1] = EPI_SCALE; P.scale = 1.f / float(S);
+    const Dst okv[3] = {{w.k, kD}, {w.v, kD}, {nullptr, 0}};
+    if ((e = linear_run(T, {src, kD, kD}, none, wl + kOffQkv + 128 * 128 * 2, 256, kD, kD, okv, nullptr, P, st)) != cudaSuccess)
+      return e;
   }
   fine_attn_kernel<<<unsigned((m + kAttnWarps - 1) / kAttnWarps), kAttnWarps * 32, 0, st>>>(w.q, w.k, w.v, w.msg, m, S, 1e-6f);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   P = LinParams{};
-  P.out_stride = kD; P.out[0] = w.m1; P.mode[0] = EPI_LN; P.gamma = ln; P.beta = ln + 128;
-  if ((e = linear_run(T, {w.msg, kD, kD}, {nullptr, 0, 0}, wl + kOffMerge, 128, kD, kD, P, st)) != cudaSuccess) return e;
+  P.mode[0] = EPI_LN; P.gamma = ln; P.beta = ln + 128;
+  const Dst om[3] = {{w.m1, kD}, {nullptr, 0}, {nullptr, 0}};
+  if ((e = linear_run(T, {w.msg, kD, kD}, none, wl + kOffMerge, 128, kD, kD, om, nullptr, P, st)) != cudaSuccess) return e;
   P = LinParams{};
-  P.out_stride = 2 * kD; P.out[0] = w.h; P.out[1] = w.h + kD; P.mode[0] = EPI_RELU; P.mode[1] = EPI_RELU;
-  if ((e = linear_run(T, {x, kD, kD}, {w.m1, kD, kD}, wl + kOffMlp1, 256, 256, 256, P, st)) != cudaSuccess) return e;
+  P.mode[0] = EPI_RELU; P.mode[1] = EPI_RELU;
+  const Dst oh[3] = {{w.h, 2 * kD}, {w.h + kD, 2 * kD}, {nullptr, 0}};
+  if ((e = linear_run(T, {x, kD, kD}, {w.m1, kD, kD}, wl + kOffMlp1, 256, 256, 256, oh, nullptr, P, st)) != cudaSuccess) return e;
   P = LinParams{};
-  P.out_stride = kD; P.out[0] = x; P.mode[0] = EPI_LN_RES; P.gamma = ln + 256; P.beta = ln + 384; P.resid = x;
-  return linear_run(T, {w.h, 2 * kD, 2 * kD}, {nullptr, 0, 0}, wl + kOffMlp2, 128, 256, 256, P, st);
+  P.mode[0] = EPI_LN_RES; P.gamma = ln + 256; P.beta = ln + 384;
+  const Dst ox[3] = {{x, kD}, {nullptr, 0}, {nullptr, 0}};
+  return linear_run(T, {w.h, 2 * kD, 2 * kD}, none, wl + kOffMlp2, 128, 256, 256, ox, x, P, st);
 }
 
 }  // namespace
@@ -519,20 +588,23 @@ extern "C" int pope_fine_merge_coarse(void* win0, void* win1, int64_t m_windows,
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return int(e);
   // feat_c_win = down_proj(cat(c0, c1))                                                  (fine_preprocess.py:50-51)
+  const Src none{nullptr, 0, 0};
   LinParams P{};
-  P.out_stride = kD; P.out[0] = cd; P.mode[0] = EPI_COPY; P.bias = bias;
-  if ((e = linear_run(2 * m, {cg, 256, 256}, {nullptr, 0, 0}, wp + kOffDown, 128, 256, 256, P, st)) != cudaSuccess) return int(e);
+  P.mode[0] = EPI_COPY; P.bias = bias;
+  const Dst od[3] = {{cd, kD}, {nullptr, 0}, {nullptr, 0}};
+  if ((e = linear_run(2 * m, {cg, 256, 256}, none, wp + kOffDown, 128, 256, 256, od, nullptr, P, st)) != cudaSuccess) return int(e);
   // merge_feat(cat(win, repeat(c))) = win . Wa^T + (c . Wb^T + bias): the second term once per window       (:52-55)
   P = LinParams{};
-  P.out_stride = kD; P.out[0] = cvec; P.out_f32 = 1; P.mode[0] = EPI_COPY; P.bias = bias + 128;
-  if ((e = linear_run(2 * m, {cd, kD, kD}, {nullptr, 0, 0}, wp + kOffMergeFeat + 128 * 2, 128, 128, 256, P, st)) != cudaSuccess)
+  P.out_f32 = cvec; P.mode[0] = EPI_COPY; P.bias = bias + 128;
+  const Dst onone[3] = {{nullptr, 0}, {nullptr, 0}, {nullptr, 0}};
+  if ((e = linear_run(2 * m, {cd, kD, kD}, none, wp + kOffMergeFeat + 128 * 2, 128, 128, 256, onone, nullptr, P, st)) != cudaSuccess)
     return int(e);
   for (int side = 0; side < 2; ++side) {
     void* win = side ? win1 : win0;
     P = LinParams{};
-    P.out_stride = kD; P.out[0] = win; P.mode[0] = EPI_ADDVEC; P.rowvec = cvec + size_t(side) * m * kD;
-    P.rows_per_vec = window_tokens;
-    if ((e = linear_run(m * window_tokens, {win, kD, kD}, {nullptr, 0, 0}, wp + kOffMergeFeat, 128, 128, 256, P, st)) != cudaSuccess)
+    P.mode[0] = EPI_ADDVEC; P.rowvec = cvec + size_t(side) * m * kD; P.rows_per_vec = window_tokens;
+    const Dst ow[3] = {{win, kD}, {nullptr, 0}, {nullptr, 0}};
+    if ((e = linear_run(m * window_tokens, {win, kD, kD}, none, wp + kOffMergeFeat, 128, 128, 256, ow, nullptr, P, st)) != cudaSuccess)
       return int(e);
   }
   return POPE_OK;
