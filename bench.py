@@ -142,44 +142,53 @@ def cpu_reference_pairs_per_sec(n_sample: int, repeats: int = 1):
 
 
 def in_matcher_figure(n_pairs: int, dev):
-    """Steps 3-5 of Matcher.forward (src/matcher/matcher.py:71-79) with the drop-in modules: CUDA coarse match -> CUDA
-    window gather -> torch Linears -> torch fine transformer -> CUDA fine match, fp32 features like the reference."""
+    """Steps 3-5 of Matcher.forward (src/matcher/matcher.py:71-79) with the drop-in modules, i.e. WITH the FinePreprocess
+    Linears and the fine transformer between coarse and fine matching (SURVEY 8(d) 'in-Matcher' figure), two ways:
+      fp32      : CUDA coarse (fp32-FMA path) -> CUDA gather -> torch Linears -> torch fine transformer -> CUDA fine match
+      bf16_cuda : Matcher(config, fine_cuda_bf16=True) on bf16 features: tcgen05 coarse -> bf16 gather -> CUDA Linears ->
+                  CUDA fine transformer (csrc/fine_tf.cu) -> CUDA fine match"""
     import pope_b200
     from pope_b200 import synth
-    torch.manual_seed(0)
-    m = pope_b200.Matcher(pope_b200.make_default_cfg()).eval().to(dev)
-    f0, f1 = synth.coarse_features(99, n_pairs, L, L, C_COARSE)
-    g = torch.Generator(device=dev).manual_seed(98)
     hf, wf = HC * FINE_STRIDE, WC * FINE_STRIDE
-    ff0 = torch.randn(n_pairs, hf, wf, C_FINE, device=dev, generator=g).permute(0, 3, 1, 2)
-    ff1 = torch.randn(n_pairs, hf, wf, C_FINE, device=dev, generator=g).permute(0, 3, 1, 2)
-    f0, f1 = f0.to(dev), f1.to(dev)
     shapes = {"hw0_i": torch.Size([H, W_IMG]), "hw1_i": torch.Size([H, W_IMG]), "hw0_c": torch.Size([HC, WC]),
               "hw1_c": torch.Size([HC, WC]), "hw0_f": torch.Size([hf, wf]), "hw1_f": torch.Size([hf, wf]), "bs": n_pairs}
+    out = {}
+    for name, dtype, reps in (("fp32", torch.float32, 2), ("bf16_cuda", torch.bfloat16, 5)):
+        torch.manual_seed(0)
+        m = pope_b200.Matcher(pope_b200.make_default_cfg(), fine_cuda_bf16=(dtype == torch.bfloat16)).eval().to(dev)
+        f0, f1 = synth.coarse_features(99, n_pairs, L, L, C_COARSE, dtype=dtype)
+        g = torch.Generator(device=dev).manual_seed(98)
+        ff0 = torch.randn(n_pairs, hf, wf, C_FINE, device=dev, generator=g).to(dtype).permute(0, 3, 1, 2)
+        ff1 = torch.randn(n_pairs, hf, wf, C_FINE, device=dev, generator=g).to(dtype).permute(0, 3, 1, 2)
+        f0, f1 = f0.to(dev), f1.to(dev)
 
-    def run():
-        data = dict(shapes)
-        with torch.no_grad():
-            m.coarse_matching(f0, f1, data)
-            w0, w1 = m.fine_preprocess(ff0, ff1, f0, f1, data)
-            if w0.size(0):
-                w0, w1 = m.loftr_fine(w0, w1)
-            m.fine_matching(w0, w1, data)
-        return data
+        def run():
+            data = dict(shapes)
+            with torch.no_grad():
+                m.coarse_matching(f0, f1, data)
+                w0, w1 = m.fine_preprocess(ff0, ff1, f0, f1, data)
+                if w0.size(0):
+                    w0, w1 = m.loftr_fine(w0, w1)
+                m.fine_matching(w0, w1, data)
+            return data
 
-    for _ in range(2):
-        data = run()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        data = run()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / 3
-    return {"value": n_pairs / (ms / 1e3), "unit": UNIT, "pairs": n_pairs, "ms": ms, "matches": int(data["mconf"].numel()),
-            "dtype": "f32", "note": "CUDA coarse (fp32-FMA path) + CUDA gather + torch Linears + torch fine transformer + CUDA "
-                                    "fine match; the fine transformer (SURVEY 8(f) next row 1) dominates"}
+        for _ in range(2):
+            data = run()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            data = run()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"value": n_pairs / (ms / 1e3), "unit": UNIT, "pairs": n_pairs, "ms": ms,
+                     "matches": int(data["mconf"].numel())}
+        del m, f0, f1, ff0, ff1, data
+        torch.cuda.empty_cache()
+    out["note"] = ("steps 3-5 of Matcher.forward incl. FinePreprocess Linears + fine transformer; the module flow has one host "
+                   "sync per call (the match count), like the reference's torch.where")
+    return out
 
 
 def run_reference(args):

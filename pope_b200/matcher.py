@@ -14,13 +14,16 @@ import torch
 import torch.nn as nn
 
 from .coarse_matching import CoarseMatching
-from .feature_net import LocalFeatureTransformer, PositionEncodingSine, build_backbone
+from .feature_net import FineTransformerB200, LocalFeatureTransformer, PositionEncodingSine, build_backbone
 from .fine_matching import FineMatching
 from .fine_preprocess import FinePreprocess
 
 
 class Matcher(nn.Module):
-    def __init__(self, config: dict):
+    def __init__(self, config: dict, fine_cuda_bf16: bool = False):
+        """`fine_cuda_bf16` (not in the reference): run the fine level -- window gather, FinePreprocess Linears, fine
+        transformer, fine matching -- in bfloat16 inside libpope_b200.so instead of fp32 torch modules between the CUDA
+        stages.  Parameters and state-dict keys are unchanged either way."""
         super().__init__()
         self.config = config
         self.backbone = build_backbone(config)
@@ -29,8 +32,16 @@ class Matcher(nn.Module):
         self.loftr_coarse = LocalFeatureTransformer(config["coarse"])
         self.coarse_matching = CoarseMatching(config["match_coarse"])
         self.fine_preprocess = FinePreprocess(config)
-        self.loftr_fine = LocalFeatureTransformer(config["fine"])
+        self.loftr_fine = FineTransformerB200(config["fine"])
         self.fine_matching = FineMatching()
+        self.set_fine_cuda_bf16(fine_cuda_bf16)
+
+    def set_fine_cuda_bf16(self, on: bool) -> None:
+        if on and not self.loftr_fine.cuda_supported():
+            raise NotImplementedError("the CUDA fine transformer covers d_model 128 / 8 heads / linear attention")
+        self.fine_cuda_bf16 = bool(on)
+        self.fine_preprocess.cuda_bf16 = bool(on)
+        self.loftr_fine.inplace = bool(on)
 
     def forward(self, data: dict, only_att_fea: bool = False):
         img0, img1 = data["image0"], data["image1"]

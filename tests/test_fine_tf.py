@@ -180,3 +180,44 @@ def test_cuda_fine_merge_coarse_vs_reference_fixture():
     for got, want in ((d0.cpu(), want0), (d1.cpu(), want1)):
         rms, mx = _rel_err(got, want)
         assert rms < 4e-3 and mx < 2e-2, (rms, mx)        # one bf16 rounding of c and one of the output
+
+
+@pytest.mark.gpu
+def test_matcher_bf16_fine_path_vs_fp32_module_flow():
+    """Steps 3-5 of Matcher.forward with `fine_cuda_bf16=True` (bf16 window gather -> CUDA Linears -> CUDA fine transformer
+    -> CUDA fine match) against the same modules in fp32 on the CPU (oracle for the hot-path stages, the weight-sharing
+    torch modules for the Linears / transformer).  Match indices are identical (the coarse stage is untouched); the
+    refined coordinates carry the bf16 fine level: |delta| is a small fraction of the +-4 px refinement range."""
+    import copy
+    import pope_b200
+    from pope_b200 import synth
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m_cpu = pope_b200.Matcher(pope_b200.make_default_cfg()).eval()
+    m_gpu = copy.deepcopy(m_cpu).to(dev)
+    m_gpu.set_fine_cuda_bf16(True)
+    h, w, n = 20, 24, 2
+    f0, f1 = synth.coarse_features(61, n, h * w, h * w, 256, sigma=0.85)
+    ff0, ff1 = synth.fine_feature_maps(62, n, h * 4, w * 4, 128, channels_last=False)
+    data = {"hw0_i": torch.Size([h * 8, w * 8]), "hw1_i": torch.Size([h * 8, w * 8]), "hw0_c": torch.Size([h, w]),
+            "hw1_c": torch.Size([h, w]), "hw0_f": torch.Size([h * 4, w * 4]), "hw1_f": torch.Size([h * 4, w * 4]), "bs": n}
+    with torch.no_grad():
+        m_gpu.coarse_matching(f0.to(dev), f1.to(dev), data)
+        w0, w1 = m_gpu.fine_preprocess(ff0.to(dev), ff1.to(dev), f0.to(dev), f1.to(dev), data)
+        assert w0.dtype == torch.bfloat16
+        w0, w1 = m_gpu.loftr_fine(w0, w1)
+        m_gpu.fine_matching(w0, w1, data)
+        want = O.coarse_match(f0, f1, data["hw0_i"], (h, w), (h, w))
+        c0, c1 = O.fine_windows(ff0, want["b_ids"], want["i_ids"]), O.fine_windows(ff1, want["b_ids"], want["j_ids"])
+        cw = m_cpu.fine_preprocess.down_proj(torch.cat([f0[want["b_ids"], want["i_ids"]], f1[want["b_ids"], want["j_ids"]]], 0))
+        mg = m_cpu.fine_preprocess.merge_feat(torch.cat([torch.cat([c0, c1], 0), cw[:, None].expand(-1, 25, -1)], -1))
+        c0, c1 = m_cpu.loftr_fine(*mg.chunk(2, 0))
+        wf = O.fine_match(c0, c1, want["mkpts0_c"], want["mkpts1_c"], 2.0)
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(data[k].cpu(), want[k])
+    assert data["mkpts1_f"].dtype == torch.float32 and data["expec_f"].shape == (want["b_ids"].numel(), 3)
+    d = (data["mkpts1_f"].cpu() - wf["mkpts1_f"]).abs()
+    assert want["b_ids"].numel() > 200
+    assert float(d.mean()) < 0.03 and float(d.max()) < 0.3, (float(d.mean()), float(d.max()))     # pixels, range +-4
+    # the state dict is the reference's whether or not the CUDA fine level is on
+    assert list(m_gpu.state_dict().keys()) == list(m_cpu.state_dict().keys())
