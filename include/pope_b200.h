@@ -186,6 +186,15 @@ int pope_match_pairs_host(const void* feat_c0, const void* feat_c1, const void* 
  * Copies them to `out` (host); returns the number of u64 written, 0 when tracing is off.  tools/trace_sweep.py. */
 int pope_debug_trace_read(unsigned long long* out, int max_u64);
 
+/* Match-list consumer of the eval loop (eval_linemod_json.py:118-119 `np.where(confidences > 0.9)` per crop and :146
+ * `np.argmax(matching_score)` per query; SURVEY.md 8(f) rank 3, selection part), without copying the lists to the host:
+ *   scores[p] = #{matches of pair p with mconf > thr};  best[g] = first arg-max of scores over the `group` consecutive
+ *   pairs [g*group, (g+1)*group) (one query image against its retrieved crops).
+ * mconf / counts: as written by pope_coarse_match (counts int32[n_pairs+2]).  scores int32[n_pairs],
+ * best int32[ceil(n_pairs / group)], both on the device. */
+int pope_match_scores(const float* mconf, const int32_t* counts, int n_pairs, int group, float thr, int32_t* scores,
+                      int32_t* best, void* stream);
+
 /* ---- fine-level transformer and FinePreprocess Linears (bf16) ---------------------------------
  * Replace src/matcher/loftr_module/transformer.py:34-58,95-104 + linear_attention.py:21-47 (LocalFeatureTransformer with
  * d_model 128, 8 heads, 'linear' attention) and fine_preprocess.py:50-57 (down_proj / merge_feat) of the reference.

@@ -22,6 +22,7 @@ from __future__ import annotations
 import math
 from typing import Dict, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -234,6 +235,14 @@ def running_topk(scores: Sequence[float], k: int = 3) -> Tuple[list, list]:
             slot_s[lo] = sc
             slot_i[lo] = r
     return slot_s, slot_i
+
+
+def match_scores(mconf_per_pair: Sequence[torch.Tensor], group: int = 3, thr: float = 0.9) -> Tuple[list, list]:
+    """eval_linemod_json.py:118-119 (`np.where(confidences > 0.9)[0].shape[0]` per crop) and :146 (`np.argmax` of the
+    scores of one query's crops).  Returns (scores per pair, first arg-max per group of `group` consecutive pairs)."""
+    scores = [int((np.asarray(c) > thr).sum()) for c in mconf_per_pair]
+    best = [int(np.argmax(scores[g:g + group])) for g in range(0, len(scores), group)]
+    return scores, best
 
 
 def match_pairs(feat_c0, feat_c1, feat_f0, feat_f1, hw0_i, hw0_c, hw1_c, thr=THR, border_rm=BORDER_RM,

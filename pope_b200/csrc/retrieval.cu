@@ -51,10 +51,55 @@ __global__ void running_topk_kernel(const float* __restrict__ scores, int R, int
   }
 }
 
+// Match-list consumer of the eval loop (eval_linemod_json.py:118-119, :146): for every pair the number of matches with
+// mconf > thr ("matching_score"), and for every group of `group` consecutive pairs (one query against its retrieved
+// crops) the first arg-max of those scores (np.argmax).  One CTA per group; the pair's matches are the contiguous range
+// [prefix(counts), +counts[n]) of the (pair, i)-sorted list written by pope_coarse_match.
+__global__ void __launch_bounds__(256) match_score_kernel(const float* __restrict__ mconf, const int32_t* __restrict__ counts,
+                                                         int n_pairs, int group, float thr, int32_t* __restrict__ scores,
+                                                         int32_t* __restrict__ best) {
+  __shared__ int red[8];
+  const int g = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p0 = g * group, p1 = min(p0 + group, n_pairs);
+  auto block_sum = [&](int v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    int t = lane < 8 ? red[lane] : 0;
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) t += __shfl_xor_sync(kFullMask, t, o);
+    return __shfl_sync(kFullMask, t, 0);
+  };
+  int part = 0;
+  for (int p = threadIdx.x; p < p0; p += blockDim.x) part += counts[p];
+  int64_t off = block_sum(part);
+  int best_score = -1, best_idx = 0;
+  for (int p = p0; p < p1; ++p) {
+    const int c = counts[p];
+    int hits = 0;
+    for (int k = threadIdx.x; k < c; k += blockDim.x) hits += mconf[off + k] > thr ? 1 : 0;
+    hits = block_sum(hits);
+    off += c;
+    if (threadIdx.x == 0) scores[p] = hits;
+    if (hits > best_score) { best_score = hits; best_idx = p - p0; }      // strict: the first maximum wins
+  }
+  if (threadIdx.x == 0) best[g] = best_idx;
+}
+
 }  // namespace
 }  // namespace pope
 
 using namespace pope;
+
+extern "C" int pope_match_scores(const float* mconf, const int32_t* counts, int n_pairs, int group, float thr,
+                                 int32_t* scores, int32_t* best, void* stream) {
+  if (!mconf || !counts || !scores || !best || n_pairs <= 0 || group <= 0) return POPE_ERR_INVALID_ARG;
+  const int groups = (n_pairs + group - 1) / group;
+  match_score_kernel<<<groups, 256, 0, static_cast<cudaStream_t>(stream)>>>(mconf, counts, n_pairs, group, thr, scores, best);
+  return int(cudaGetLastError());
+}
 
 extern "C" int pope_cosine_topk(const void* q, const void* refs, int dtype, int R, int D, int k, float eps,
                                 float* scores, float* slot_scores, int32_t* slot_idx, void* stream) {

@@ -236,6 +236,20 @@ def fine_match_maps(feat_f0: torch.Tensor, feat_f1: torch.Tensor, b_ids, i_ids, 
     return expec, mk1f
 
 
+def match_scores(mconf: torch.Tensor, counts: torch.Tensor, n_pairs: int, group: int = 3, thr: float = 0.9
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(scores [n_pairs] int32, best [ceil(n_pairs/group)] int32): per-pair count of mconf > thr and, per group of
+    consecutive pairs, the first arg-max -- the `matching_score` / `np.argmax` of eval_linemod_json.py:118-119,146."""
+    dev = require_cuda(mconf, counts)
+    scores = torch.empty(n_pairs, dtype=torch.int32, device=dev)
+    best = torch.empty((n_pairs + group - 1) // group, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().pope_match_scores(ptr(mconf), ptr(counts), int(n_pairs), int(group), float(thr), ptr(scores), ptr(best),
+                                     stream_ptr(dev))
+    check(st, "pope_match_scores")
+    return scores, best
+
+
 def cosine_topk(q: torch.Tensor, refs: torch.Tensor, k: int = 3, eps: float = 1e-8):
     """q [1,D] or [D], refs [R,D] -> (scores [R], slot_scores [k], slot_idx [k] int32; -1 = empty slot)."""
     dev = require_cuda(q, refs)

@@ -426,3 +426,21 @@ def test_host_pipeline_equals_device_path():
         assert torch.equal(cat["mconf"], res["mconf"][:m].cpu())
         assert torch.equal(cat["mkpts0_f"], res["mkpts0_f"][:m].cpu())
         assert torch.equal(cat["mkpts1_f"], res["mkpts1_f"][:m].cpu())
+
+
+def test_match_scores_vs_oracle():
+    """Per-pair count of mconf > 0.9 and the per-query arg-max (eval_linemod_json.py:118-119,146) on the device list."""
+    n, h, w = 7, 20, 24
+    f0, f1 = synth.coarse_features(71, n, h * w, h * w, 256, sigma=0.95)
+    res = ops.coarse_match(f0.to(DEV), f1.to(DEV), (h, w), (h, w), 8.0)
+    scores, best = ops.match_scores(res["mconf"], res["counts"], n, group=3, thr=0.9)
+    out = res.sliced()
+    per_pair = [out["mconf"][out["b_ids"] == p].cpu().numpy() for p in range(n)]
+    want_s, want_b = O.match_scores(per_pair, group=3, thr=0.9)
+    assert scores.tolist() == want_s and best.tolist() == want_b
+    assert sum(want_s) > 0
+    # ties: equal scores -> the first crop wins, like np.argmax
+    conf = torch.tensor([0.95, 0.95, 0.5, 0.95, 0.95, 0.1], device=DEV)
+    cnt = torch.tensor([2, 1, 2, 1, 6, 0], dtype=torch.int32, device=DEV)      # pairs 0..3 (+ total, flags)
+    s2, b2 = ops.match_scores(conf, cnt, 4, group=4, thr=0.9)
+    assert s2.tolist() == [2, 0, 2, 0] and b2.tolist() == [0]
