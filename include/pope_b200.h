@@ -195,6 +195,13 @@ int pope_debug_trace_read(unsigned long long* out, int max_u64);
 int pope_match_scores(const float* mconf, const int32_t* counts, int n_pairs, int group, float thr, int32_t* scores,
                       int32_t* best, void* stream);
 
+/* Packs the live matches of one batch into 32-byte records (int32[8]: global pair index = b + pair_offset, i, j, mconf,
+ * x0, y0, x1, y1; floats as bit patterns): the unit of the single cross-GPU gather of match lists.
+ * m_dev: device pointer to the live match count (counts + n_pairs of pope_coarse_match); records: int32[capacity * 8]. */
+int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids, const float* mconf,
+                      const float* mkpts0_f, const float* mkpts1_f, const int32_t* m_dev, int64_t capacity,
+                      int pair_offset, int32_t* records, void* stream);
+
 /* ---- fine-level transformer and FinePreprocess Linears (bf16) ---------------------------------
  * Replace src/matcher/loftr_module/transformer.py:34-58,95-104 + linear_attention.py:21-47 (LocalFeatureTransformer with
  * d_model 128, 8 heads, 'linear' attention) and fine_preprocess.py:50-57 (down_proj / merge_feat) of the reference.

@@ -38,6 +38,7 @@ SIGNATURES = {
     "pope_fine_transformer": (_i, [_p, _p, _i64, _i, _p, _i, C.POINTER(_i), _p, _sz, _p]),
     "pope_fine_merge_coarse": (_i, [_p, _p, _i64, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "pope_match_order_by_ref": (_i, [_p, _i, _i, _p, _p, _p]),
+    "pope_pack_records": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _p, _p]),
     "pope_match_scores": (_i, [_p, _p, _i, _i, _f, _p, _p, _p]),
     "pope_cosine_topk": (_i, [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "pope_debug_trace_read": (_i, [_p, _i]),

@@ -88,10 +88,42 @@ __global__ void __launch_bounds__(256) match_score_kernel(const float* __restric
   if (threadIdx.x == 0) best[g] = best_idx;
 }
 
+// One 32-byte record per live match: (global pair index, i, j, mconf, x0, y0, x1, y1), floats as bit patterns -- the
+// unit of the job-level gather of match lists.  The live count is read on the device.
+__global__ void __launch_bounds__(256) pack_records_kernel(const int64_t* __restrict__ b_ids, const int64_t* __restrict__ i_ids,
+                                                          const int64_t* __restrict__ j_ids, const float* __restrict__ mconf,
+                                                          const float2* __restrict__ mk0, const float2* __restrict__ mk1,
+                                                          const int32_t* __restrict__ m_dev, int64_t capacity,
+                                                          int pair_offset, int4* __restrict__ rec) {
+  const int64_t m = min(int64_t(*m_dev), capacity);
+  for (int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < m; k += int64_t(gridDim.x) * blockDim.x) {
+    const float2 a = mk0[k], b = mk1[k];
+    rec[2 * k] = make_int4(int(b_ids[k]) + pair_offset, int(i_ids[k]), int(j_ids[k]), __float_as_int(mconf[k]));
+    rec[2 * k + 1] = make_int4(__float_as_int(a.x), __float_as_int(a.y), __float_as_int(b.x), __float_as_int(b.y));
+  }
+}
+
 }  // namespace
 }  // namespace pope
 
 using namespace pope;
+
+extern "C" int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids, const float* mconf,
+                                 const float* mkpts0_f, const float* mkpts1_f, const int32_t* m_dev, int64_t capacity,
+                                 int pair_offset, int32_t* records, void* stream) {
+  if (!b_ids || !i_ids || !j_ids || !mconf || !mkpts0_f || !mkpts1_f || !m_dev || !records || capacity < 0)
+    return POPE_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(mkpts0_f) | reinterpret_cast<uintptr_t>(mkpts1_f)) & 7u ||
+      reinterpret_cast<uintptr_t>(records) & 15u)
+    return POPE_ERR_ALIGNMENT;
+  if (capacity == 0) return POPE_OK;
+  const int64_t want = (capacity + 255) / 256;
+  const unsigned blocks = unsigned(want < 148 * 8 ? want : 148 * 8);
+  pack_records_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      b_ids, i_ids, j_ids, mconf, reinterpret_cast<const float2*>(mkpts0_f), reinterpret_cast<const float2*>(mkpts1_f), m_dev,
+      capacity, pair_offset, reinterpret_cast<int4*>(records));
+  return int(cudaGetLastError());
+}
 
 extern "C" int pope_match_scores(const float* mconf, const int32_t* counts, int n_pairs, int group, float thr,
                                  int32_t* scores, int32_t* best, void* stream) {

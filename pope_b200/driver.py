@@ -155,11 +155,25 @@ def gather_matches(local: Dict[str, torch.Tensor], n_pairs: int, rank: int, worl
 
 def pack_records(res, pair_offset: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Capacity-sized result -> packed int32 records [cap, 8] = (b_global, i, j, mconf, x0, y0, x1, y1; floats as bit
-    patterns); rows past the live count are garbage.  No host sync."""
-    rec = torch.cat([(res["b_ids"] + pair_offset).to(torch.int32)[:, None], res["i_ids"].to(torch.int32)[:, None],
-                     res["j_ids"].to(torch.int32)[:, None], res["mconf"].view(torch.int32)[:, None],
-                     res["mkpts0_f"].view(torch.int32), res["mkpts1_f"].view(torch.int32)], 1, out=out)
-    return rec
+    patterns); rows past the live count are not written.  One kernel (`pope_pack_records`), no host sync."""
+    cap = res["i_ids"].shape[0]
+    dev = res["i_ids"].device
+    if dev.type != "cuda":
+        # host-side bookkeeping of already-computed results (the world_size-2 gloo tests of the sharding logic); the
+        # records themselves are produced on the GPU in every real run
+        return torch.cat([(res["b_ids"] + pair_offset).to(torch.int32)[:, None], res["i_ids"].to(torch.int32)[:, None],
+                          res["j_ids"].to(torch.int32)[:, None], res["mconf"].view(torch.int32)[:, None],
+                          res["mkpts0_f"].view(torch.int32), res["mkpts1_f"].view(torch.int32)], 1, out=out)
+    if out is None:
+        out = torch.empty(cap, 8, dtype=torch.int32, device=dev)
+    n = res["n_pairs"]
+    with torch.cuda.device(dev):
+        st = _lib.lib().pope_pack_records(res["b_ids"].data_ptr(), res["i_ids"].data_ptr(), res["j_ids"].data_ptr(),
+                                          res["mconf"].data_ptr(), res["mkpts0_f"].contiguous().data_ptr(),
+                                          res["mkpts1_f"].contiguous().data_ptr(), res["counts"][n:n + 1].data_ptr(), cap,
+                                          int(pair_offset), out.data_ptr(), _lib.stream_ptr(dev))
+    _lib.check(st, "pope_pack_records")
+    return out
 
 
 class JobGather:

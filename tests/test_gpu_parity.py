@@ -444,3 +444,18 @@ def test_match_scores_vs_oracle():
     cnt = torch.tensor([2, 1, 2, 1, 6, 0], dtype=torch.int32, device=DEV)      # pairs 0..3 (+ total, flags)
     s2, b2 = ops.match_scores(conf, cnt, 4, group=4, thr=0.9)
     assert s2.tolist() == [2, 0, 2, 0] and b2.tolist() == [0]
+
+
+def test_pack_records_kernel_equals_torch_packing():
+    """pope_pack_records (one kernel, live count read on the device) against the torch cat it replaced."""
+    from pope_b200 import driver
+    n, h, w = 3, 20, 24
+    f0, f1 = synth.coarse_features(72, n, h * w, h * w, 256, sigma=0.9)
+    ff0, ff1 = synth.fine_feature_maps(73, n, h * 4, w * 4, 128, channels_last=True)
+    res = ops.match_pairs_device(f0.to(DEV), f1.to(DEV), ff0.to(DEV), ff1.to(DEV), (h * 8, w * 8), (h, w), (h, w))
+    m = res.total()
+    rec = driver.pack_records(res, 40)
+    want = torch.cat([(res["b_ids"] + 40).to(torch.int32)[:, None], res["i_ids"].to(torch.int32)[:, None],
+                      res["j_ids"].to(torch.int32)[:, None], res["mconf"].view(torch.int32)[:, None],
+                      res["mkpts0_f"].view(torch.int32), res["mkpts1_f"].view(torch.int32)], 1)
+    assert m > 100 and rec.shape == want.shape and torch.equal(rec[:m], want[:m])
