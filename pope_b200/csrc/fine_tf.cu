@@ -296,6 +296,254 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
   }
 }
 
+// ---- fused MLP: x <- x + LayerNorm2(W2 . relu(W1 . cat(x, m1)))   (transformer.py:52-58) ---------------------------------
+// One CTA PAIR per 256 token rows (cta_group::2, 128 rows per CTA).  Both weight matrices stay resident, split across the
+// pair along their output dimension (W1: 2 x 128 of 256 rows, W2: 2 x 64 of 128 rows), which is what makes them fit:
+//   MMA 1   D1[256 x 256] = cat(x, m1) . W1^T     (x / m1 tiles stream through a TMA ring; K = 256)
+//   epi 1   relu(D1) -> bf16 -> the hidden tile h, written straight into shared memory in the K-major 128B-swizzled
+//           operand layout (never to HBM: saves 4 of the 8 activation planes the two separate launches move)
+//   MMA 2   D2[256 x 128] = h . W2^T
+//   epi 2   LayerNorm2, + x (residual rows by TMA), bf16, TMA store in place
+// warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer (leader CTA), warps 2-9: epilogue in two sets of four lane
+// quadrants; a tile is owned by set (tile & 1), so epilogue 2 of tile t overlaps epilogue 1 of tile t+1 (D1, h and D2
+// are single-buffered; the barriers below order their reuse).
+namespace fm {
+constexpr int kFmThreads = 320;
+constexpr int kFmStages = 2;
+constexpr int kW2BoxBytes = 64 * kBoxK * 2;                     // 64 rows (N/2 per CTA) x 64 k = 8 KB
+constexpr int kFmOut = 0;                                      // 8 x 4 KB staging boxes
+constexpr int kFmBar = 8 * kStageOutBytes;                     // 32 KB
+constexpr int kFmW1 = 33 * 1024;                               // 4 k-chunks x 16 KB
+constexpr int kFmW2 = kFmW1 + 4 * kBoxBytes;                 // 4 k-chunks x 8 KB
+constexpr int kFmH = kFmW2 + 4 * kW2BoxBytes;                // 4 k-chunks x 16 KB
+constexpr int kFmX = kFmH + 4 * kBoxBytes;                   // kFmStages x 16 KB
+constexpr int kFmEnd = kFmX + kFmStages * kBoxBytes;
+constexpr int kFmTmemPtr = kFmBar + 64 * 8;
+static_assert(kFmTmemPtr + 16 <= kFmW1 && kFmEnd + 1024 <= 227 * 1024, "fused-MLP shared memory layout");
+constexpr int kFmAlloc = kFmEnd + 1024;
+}  // namespace fm
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(fm::kFmThreads, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM1,
+                 const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
+                 const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapR, int T,
+                 const float* __restrict__ gamma, const float* __restrict__ beta) {
+  using namespace fm;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kFmBar;
+  const uint32_t bar_w_full = bar0;
+  const uint32_t bar_x_full = bar0 + 8, bar_x_empty = bar_x_full + 8 * kFmStages;
+  // d1_full / d2_full exist once per epilogue set (even / odd tiles): a parity wait must see every phase of its barrier
+  const uint32_t bar_d1_full = bar_x_empty + 8 * kFmStages, bar_h_full = bar_d1_full + 16;
+  const uint32_t bar_d2_full = bar_h_full + 8, bar_d2_empty = bar_d2_full + 16;
+  const uint32_t bar_res = bar_d2_empty + 8;                     // 8: one per epilogue warp
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kFmTmemPtr);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc2::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int ntiles = (T + 2 * kTile - 1) / (2 * kTile);          // 256-row tiles
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapX); prefetch_tmap(&mapM1); prefetch_tmap(&mapW1); prefetch_tmap(&mapW2);
+    prefetch_tmap(&mapO); prefetch_tmap(&mapR);
+    mbar_init(bar_w_full, 1);
+    for (int s = 0; s < kFmStages; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
+    mbar_init(bar_d1_full, 1); mbar_init(bar_d1_full + 8, 1);
+    mbar_init(bar_h_full, 8);                                    // the owning set (4 warps) of each CTA; leader's copy is used
+    mbar_init(bar_d2_full, 1); mbar_init(bar_d2_full + 8, 1);
+    mbar_init(bar_d2_empty, 8);                                  // likewise
+    for (int s = 0; s < 8; ++s) mbar_init(bar_res + 8 * s, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kFmTmemPtr), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc2::cluster_sync_all();                                       // peer barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + 256;
+
+  if (warp == 0) {
+    // =============================== TMA producer (both CTAs) ===============================
+    if (lane == 0) {
+      if (rank == 0) mbar_expect_tx(bar_w_full, 2 * (4 * kBoxBytes + 4 * kW2BoxBytes));
+      for (int kc = 0; kc < 4; ++kc) {
+        tc2::tma_load_2d_2sm(sbase + kFmW1 + kc * kBoxBytes, &mapW1, bar_w_full, kc * kBoxK, int(rank) * 128);
+        tc2::tma_load_2d_2sm(sbase + kFmW2 + kc * kW2BoxBytes, &mapW2, bar_w_full, kc * kBoxK, int(rank) * 64);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        const int row0 = t * 2 * kTile + int(rank) * kTile;
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(bar_x_empty + 8 * stage, phase ^ 1);
+          if (rank == 0) mbar_expect_tx(bar_x_full + 8 * stage, 2 * kBoxBytes);
+          tc2::tma_load_2d_2sm(sbase + kFmX + stage * kBoxBytes, kc < 2 ? &mapX : &mapM1, bar_x_full + 8 * stage,
+                               (kc & 1) * kBoxK, row0);
+          if (++stage == kFmStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA) ===============================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc1 = tc2::idesc_bf16_m256(256), idesc2 = tc2::idesc_bf16_m256(128);
+      mbar_wait(bar_w_full, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (int t = pair; t < ntiles; t += npairs, ++it) {
+        // D1 is free: the epilogue warps finished reading the previous tile's D1 before they signalled h_full, which
+        // this thread waited for below
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(bar_x_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = sbase + kFmX + stage * kBoxBytes, b_addr = sbase + kFmW1 + kc * kBoxBytes;
+#pragma unroll
+          for (int ks = 0; ks < kBoxK / 16; ++ks)
+            tc2::umma_bf16(tmem_d1, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), idesc1, (kc | ks) ? 1u : 0u);
+          tc2::umma_commit(bar_x_empty + 8 * stage);
+          if (++stage == kFmStages) { stage = 0; phase ^= 1; }
+        }
+        tc2::umma_commit(bar_d1_full + 8 * (it & 1));
+        mbar_wait(bar_h_full, it & 1);                           // both CTAs' hidden tiles are in shared memory
+        mbar_wait(bar_d2_empty, (it & 1) ^ 1);                   // the previous tile's D2 has been read
+        tc_fence_after();
+        for (int kc = 0; kc < 4; ++kc) {
+          const uint32_t a_addr = sbase + kFmH + kc * kBoxBytes, b_addr = sbase + kFmW2 + kc * kW2BoxBytes;
+#pragma unroll
+          for (int ks = 0; ks < kBoxK / 16; ++ks)
+            tc2::umma_bf16(tmem_d2, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), idesc2, (kc | ks) ? 1u : 0u);
+        }
+        tc2::umma_commit(bar_d2_full + 8 * (it & 1));
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int ew = warp - 2, set = ew >> 2, quad = warp & 3;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    const int rin = quad * 32 + lane;                            // row of this CTA's 128-row tile
+    const uint32_t sw = uint32_t(lane & 7);
+    const uint32_t stage_buf = sbase + kFmOut + ew * kStageOutBytes;
+    const uint32_t my_row = stage_buf + lane * 128;
+    const uint32_t bar_my_res = bar_res + 8 * ew;
+    uint32_t res_phase = 0, it = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++it) {
+      if ((it & 1u) != uint32_t(set)) continue;                  // the other set owns this tile
+      const int row0 = t * 2 * kTile + int(rank) * kTile + quad * 32;
+      // ---- epilogue 1: relu(D1) -> h (4 k-chunks of 64 hidden columns) ---------------------------------------------
+      mbar_wait(bar_d1_full + 8 * (it & 1), (it >> 1) & 1);
+      if (it > 0) mbar_wait(bar_d2_full + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);   // MMA 2 of the previous tile no longer reads h
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        float v[64];
+        tmem_ld32(tmem_d1 + lane_addr + chunk * 64, v);
+        tmem_ld32(tmem_d1 + lane_addr + chunk * 64 + 32, v + 32);
+        const uint32_t hrow = sbase + kFmH + chunk * kBoxBytes + uint32_t(rin) * 128;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const int c = c8 * 8;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(hrow + ((uint32_t(c8) ^ sw) << 4)), "r"(pack_bf16(fmaxf(v[c], 0.f), fmaxf(v[c + 1], 0.f))),
+                         "r"(pack_bf16(fmaxf(v[c + 2], 0.f), fmaxf(v[c + 3], 0.f))),
+                         "r"(pack_bf16(fmaxf(v[c + 4], 0.f), fmaxf(v[c + 5], 0.f))),
+                         "r"(pack_bf16(fmaxf(v[c + 6], 0.f), fmaxf(v[c + 7], 0.f))) : "memory");
+        }
+      }
+      fence_proxy_async();                                       // the MMA reads h through the async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc2::mbar_arrive_leader_release(bar_h_full);
+      // ---- epilogue 2: LayerNorm2(D2) + x -> out ------------------------------------------------------------
+      mbar_wait(bar_d2_full + 8 * (it & 1), (it >> 1) & 1);
+      tc_fence_after();
+      float v[kD];
+#pragma unroll
+      for (int c = 0; c < kD; c += 32) tmem_ld32(tmem_d2 + lane_addr + c, v + c);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc2::mbar_arrive_leader(bar_d2_empty);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kD; c += 4) { s0 += v[c]; s1 += v[c + 1]; s2 += v[c + 2]; s3 += v[c + 3]; }
+      const float mean = ((s0 + s1) + (s2 + s3)) * (1.f / kD);
+      s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kD; c += 4) {
+        const float d0 = v[c] - mean, d1 = v[c + 1] - mean, d2 = v[c + 2] - mean, d3 = v[c + 3] - mean;
+        s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+      }
+      const float rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.f / kD) + 1e-5f);
+      const float4* g4 = reinterpret_cast<const float4*>(gamma);
+      const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+      for (int c = 0; c < kD; c += 4) {
+        const float4 g = __ldg(g4 + (c >> 2)), b = __ldg(b4 + (c >> 2));
+        v[c] = fmaf((v[c] - mean) * rstd, g.x, b.x); v[c + 1] = fmaf((v[c + 1] - mean) * rstd, g.y, b.y);
+        v[c + 2] = fmaf((v[c + 2] - mean) * rstd, g.z, b.z); v[c + 3] = fmaf((v[c + 3] - mean) * rstd, g.w, b.w);
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {                     // + x: residual rows through the staging box
+        if (lane == 0) {
+          tma_store_wait_read();
+          mbar_expect_tx(bar_my_res, kStageOutBytes);
+          tma_load_2d(stage_buf, &mapR, bar_my_res, half * 64, row0);
+        }
+        __syncwarp();
+        mbar_wait(bar_my_res, res_phase);
+        res_phase ^= 1;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint4 r;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                       : "r"(my_row + ((uint32_t(c8) ^ sw) << 4)));
+          const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[half * 64 + c8 * 8 + 2 * e] += __uint_as_float(w[e] << 16);
+            v[half * 64 + c8 * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const int c = half * 64 + c8 * 8;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(my_row + ((uint32_t(c8) ^ sw) << 4)), "r"(pack_bf16(v[c], v[c + 1])),
+                         "r"(pack_bf16(v[c + 2], v[c + 3])), "r"(pack_bf16(v[c + 4], v[c + 5])),
+                         "r"(pack_bf16(v[c + 6], v[c + 7])) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&mapO, stage_buf, half * 64, row0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc2::cluster_sync_all();                                       // the peer may still be signalling / reading this CTA
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- linear attention, one warp per 25-token window ------------------------------------------------------------------
 // q, k already hold elu(.)+1 and v holds values / S (fused into the projection's epilogue).  Per head h (16 dims):
 //   KV[d][e] = sum_s k[s][d] v[s][e],  ksum[d] = sum_s k[s][d],  out[l][e] = S * (q[l] . KV[:, e]) / (q[l] . ksum + eps)
@@ -601,6 +849,26 @@ cudaError_t linear_run(int64_t T, Src x0, Src x1, const void* W, int N, int K, i
   return cudaGetLastError();
 }
 
+// x <- x + LayerNorm(W2 . relu(W1 . cat(x, m1))) in place, one launch
+cudaError_t mlp_fused_run(__nv_bfloat16* x, const __nv_bfloat16* m1, int64_t T, const void* W1, const void* W2, const float* gamma,
+                          const float* beta, cudaStream_t st) {
+  if (T <= 0) return cudaSuccess;
+  if (T > 0x7fffffff - 2 * kTile) return cudaErrorInvalidValue;
+  CUtensorMap mx, mm, mw1, mw2, mo, mr;
+  if (!make_map2d(&mx, x, T, kD, kD) || !make_map2d(&mm, m1, T, kD, kD) || !make_map2d(&mw1, W1, 256, 256, 256) ||
+      !make_map2d(&mw2, W2, 128, 256, 256, 64) || !make_map2d(&mo, x, T, kD, kD, 32) || !make_map2d(&mr, x, T, kD, kD, 32))
+    return cudaErrorInvalidValue;
+  int dev = 0, sms = 0;
+  cudaError_t e;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fm::kFmAlloc)) != cudaSuccess)
+    return e;
+  const int ntiles = int((T + 2 * kTile - 1) / (2 * kTile));
+  mlp_fused_kernel<<<2 * min(ntiles, sms / 2), fm::kFmThreads, fm::kFmAlloc, st>>>(mx, mm, mw1, mw2, mo, mr, int(T), gamma, beta);
+  return cudaGetLastError();
+}
+
 // packed weights of one LoFTREncoderLayer (byte offsets; matrices bf16 row-major [out, in] like nn.Linear.weight)
 constexpr size_t kOffQkv = 0;                                  // [384, 128]  q_proj, k_proj, v_proj stacked
 constexpr size_t kOffMerge = kOffQkv + 384 * 128 * 2;          // [128, 128]
@@ -677,6 +945,8 @@ cudaError_t encoder_layer(__nv_bfloat16* x, const __nv_bfloat16* src, int64_t m,
   P.mode[0] = EPI_LN; P.gamma = ln; P.beta = ln + 128;
   const Dst om[3] = {{w.m1, kD}, {nullptr, 0}, {nullptr, 0}};
   if ((e = linear_run(T, {w.msg, kD, kD}, none, wl + kOffMerge, 128, kD, kD, om, nullptr, P, st)) != cudaSuccess) return e;
+  static const bool unfused_mlp = getenv("POPE_MLP_UNFUSED") != nullptr;     // developer knob: the two separate launches
+  if (!unfused_mlp) return mlp_fused_run(x, w.m1, T, wl + kOffMlp1, wl + kOffMlp2, ln + 256, ln + 384, st);
   P = LinParams{};
   P.mode[0] = EPI_RELU; P.mode[1] = EPI_RELU;
   const Dst oh[3] = {{w.h, 2 * kD}, {w.h + kD, 2 * kD}, {nullptr, 0}};

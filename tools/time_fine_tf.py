@@ -32,8 +32,9 @@ print(f"CUDA bf16 fine transformer: {t_cuda:.3f} ms for M={M} windows ({M * 25 *
 Ms = min(M, 20000)
 with torch.no_grad():
     x0, x1 = w0[:Ms].float(), w1[:Ms].float()
+    from pope_b200.feature_net import LocalFeatureTransformer
     t32 = timed(lambda: m.loftr_fine(x0, x1), 2)
     mb = pope_b200.Matcher(pope_b200.make_default_cfg()).eval().to(dev).to(torch.bfloat16)
     y0, y1 = w0[:Ms], w1[:Ms]
-    t16 = timed(lambda: mb.loftr_fine(y0, y1), 2)
+    t16 = timed(lambda: LocalFeatureTransformer.forward(mb.loftr_fine, y0, y1), 2)      # the stock PyTorch layers
 print(f"torch fp32 modules: {t32 * M / Ms:.1f} ms (scaled from {Ms} windows), torch bf16 modules: {t16 * M / Ms:.1f} ms")
