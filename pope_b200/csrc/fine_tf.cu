@@ -176,8 +176,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
         mbar_wait(bar_acc_full + 8 * slot, (item / kSlots) & 1);
         tc_fence_after();
         float v[kD];
-#pragma unroll
-        for (int c = 0; c < kD; c += 32) tmem_ld32(tmem_base + lane_addr + slot * 128 + c, v + c);
+        tmem_ld128(tmem_base + lane_addr + slot * 128, v);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
@@ -441,19 +440,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       if (it > 0) mbar_wait(bar_d2_full + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);   // MMA 2 of the previous tile no longer reads h
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        float v[64];
-        tmem_ld32(tmem_d1 + lane_addr + chunk * 64, v);
-        tmem_ld32(tmem_d1 + lane_addr + chunk * 64 + 32, v + 32);
-        const uint32_t hrow = sbase + kFmH + chunk * kBoxBytes + uint32_t(rin) * 128;
+      for (int hb = 0; hb < 2; ++hb) {                           // 128 hidden columns per pass: one TMEM round trip
+        float v[kD];
+        tmem_ld128(tmem_d1 + lane_addr + hb * 128, v);
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          const int c = c8 * 8;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                       ::"r"(hrow + ((uint32_t(c8) ^ sw) << 4)), "r"(pack_bf16(fmaxf(v[c], 0.f), fmaxf(v[c + 1], 0.f))),
-                         "r"(pack_bf16(fmaxf(v[c + 2], 0.f), fmaxf(v[c + 3], 0.f))),
-                         "r"(pack_bf16(fmaxf(v[c + 4], 0.f), fmaxf(v[c + 5], 0.f))),
-                         "r"(pack_bf16(fmaxf(v[c + 6], 0.f), fmaxf(v[c + 7], 0.f))) : "memory");
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t hrow = sbase + kFmH + (2 * hb + half) * kBoxBytes + uint32_t(rin) * 128;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const int c = half * 64 + c8 * 8;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(hrow + ((uint32_t(c8) ^ sw) << 4)), "r"(pack_bf16(fmaxf(v[c], 0.f), fmaxf(v[c + 1], 0.f))),
+                           "r"(pack_bf16(fmaxf(v[c + 2], 0.f), fmaxf(v[c + 3], 0.f))),
+                           "r"(pack_bf16(fmaxf(v[c + 4], 0.f), fmaxf(v[c + 5], 0.f))),
+                           "r"(pack_bf16(fmaxf(v[c + 6], 0.f), fmaxf(v[c + 7], 0.f))) : "memory");
+          }
         }
       }
       fence_proxy_async();                                       // the MMA reads h through the async proxy
@@ -464,8 +465,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       mbar_wait(bar_d2_full + 8 * (it & 1), (it >> 1) & 1);
       tc_fence_after();
       float v[kD];
-#pragma unroll
-      for (int c = 0; c < kD; c += 32) tmem_ld32(tmem_d2 + lane_addr + c, v + c);
+      tmem_ld128(tmem_d2 + lane_addr, v);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tc2::mbar_arrive_leader(bar_d2_empty);
