@@ -303,16 +303,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constan
 //           operand layout (never to HBM: saves 4 of the 8 activation planes the two separate launches move)
 //   MMA 2   D2[256 x 128] = h . W2^T
 //   epi 2   LayerNorm2, + x (residual rows by TMA), bf16, TMA store in place
-// warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer (leader CTA), warps 2-9: epilogue in two sets of four lane
-// quadrants; a tile is owned by set (tile & 1), so epilogue 2 of tile t overlaps epilogue 1 of tile t+1 (D1, h and D2
-// are single-buffered; the barriers below order their reuse).
+// warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer (leader CTA), warps 2-5: epilogue 2 of every tile, warps 6-9:
+// epilogue 1 of every tile (four lane quadrants each), so epilogue 2 of tile t overlaps epilogue 1 of tile t+1.
+// TMEM holds two 256-column buffers: buffer (tile & 1) receives D1 of its tile and, once epilogue 1 has drained it, D2
+// of the same tile, so MMA 1 of tile t+1 runs while tile t is in epilogue 1; h is single-buffered).
 namespace fm {
 constexpr int kFmThreads = 320;
-constexpr int kFmStages = 2;
+constexpr int kFmStages = 3;
 constexpr int kW2BoxBytes = 64 * kBoxK * 2;                     // 64 rows (N/2 per CTA) x 64 k = 8 KB
-constexpr int kFmOut = 0;                                      // 8 x 4 KB staging boxes
-constexpr int kFmBar = 8 * kStageOutBytes;                     // 32 KB
-constexpr int kFmW1 = 33 * 1024;                               // 4 k-chunks x 16 KB
+constexpr int kFmOut = 0;                                      // 4 x 4 KB staging boxes (epilogue-2 warps)
+constexpr int kFmBar = 4 * kStageOutBytes;                     // 16 KB
+constexpr int kFmW1 = 17 * 1024;                               // 4 k-chunks x 16 KB
 constexpr int kFmW2 = kFmW1 + 4 * kBoxBytes;                 // 4 k-chunks x 8 KB
 constexpr int kFmH = kFmW2 + 4 * kW2BoxBytes;                // 4 k-chunks x 16 KB
 constexpr int kFmX = kFmH + 4 * kBoxBytes;                   // kFmStages x 16 KB
@@ -336,8 +337,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
   const uint32_t bar_x_full = bar0 + 8, bar_x_empty = bar_x_full + 8 * kFmStages;
   // d1_full / d2_full exist once per epilogue set (even / odd tiles): a parity wait must see every phase of its barrier
   const uint32_t bar_d1_full = bar_x_empty + 8 * kFmStages, bar_h_full = bar_d1_full + 16;
-  const uint32_t bar_d2_full = bar_h_full + 8, bar_d2_empty = bar_d2_full + 16;
-  const uint32_t bar_res = bar_d2_empty + 8;                     // 8: one per epilogue warp
+  const uint32_t bar_d2_full = bar_h_full + 8, bar_d2_empty = bar_d2_full + 16;      // d2_empty: one per TMEM buffer
+  const uint32_t bar_res = bar_d2_empty + 16;                    // 8: one per epilogue warp
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kFmTmemPtr);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc2::cluster_ctarank();
@@ -350,9 +351,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     mbar_init(bar_w_full, 1);
     for (int s = 0; s < kFmStages; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
     mbar_init(bar_d1_full, 1); mbar_init(bar_d1_full + 8, 1);
-    mbar_init(bar_h_full, 8);                                    // the owning set (4 warps) of each CTA; leader's copy is used
+    mbar_init(bar_h_full, 8);                                    // the 4 epilogue-1 warps of each CTA; leader's copy is used
     mbar_init(bar_d2_full, 1); mbar_init(bar_d2_full + 8, 1);
-    mbar_init(bar_d2_empty, 8);                                  // likewise
+    mbar_init(bar_d2_empty, 8); mbar_init(bar_d2_empty + 8, 8);  // likewise
     for (int s = 0; s < 8; ++s) mbar_init(bar_res + 8 * s, 1);
     fence_barrier_init();
   }
@@ -365,7 +366,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
   tc2::cluster_sync_all();                                       // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + 256;
 
   if (warp == 0) {
     // =============================== TMA producer (both CTAs) ===============================
@@ -395,31 +395,51 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       mbar_wait(bar_w_full, 0);
       tc_fence_after();
       int stage = 0;
-      uint32_t phase = 0, it = 0;
-      for (int t = pair; t < ntiles; t += npairs, ++it) {
-        // D1 is free: the epilogue warps finished reading the previous tile's D1 before they signalled h_full, which
-        // this thread waited for below
-        for (int kc = 0; kc < 4; ++kc) {
-          mbar_wait(bar_x_full + 8 * stage, phase);
+      uint32_t phase = 0;
+      const uint32_t n_it = pair < ntiles ? uint32_t((ntiles - 1 - pair) / npairs + 1) : 0u;
+      // Two instruction streams share the tensor pipe: MMA 1 of tile it1 (D1 -> TMEM buffer it1 & 1, free once epilogue 2
+      // of tile it1 - 2 has read its D2; one 64-wide k-chunk per ring stage) and MMA 2 of tile it2 <= it1 (needs the
+      // hidden tile).  The issuer polls: MMA 2 goes first whenever its operands are ready (it unblocks epilogue 2 and
+      // the reuse of h), otherwise the next chunk of MMA 1 whose ring stage has landed, at most one tile ahead.
+      uint32_t it1 = 0, it2 = 0;
+      int kc1 = 0;
+      const long long t0 = clock64();
+      uint32_t spins = 0;
+      while (it2 < n_it) {
+        bool progressed = false;
+        if (it2 < it1 && mbar_try_wait(bar_h_full, it2 & 1)) {
           tc_fence_after();
-          const uint32_t a_addr = sbase + kFmX + stage * kBoxBytes, b_addr = sbase + kFmW1 + kc * kBoxBytes;
+          const uint32_t d = tmem_base + (it2 & 1) * 256;
+          for (int kc = 0; kc < 4; ++kc) {
+            const uint32_t a_addr = sbase + kFmH + kc * kBoxBytes, b_addr = sbase + kFmW2 + kc * kW2BoxBytes;
+#pragma unroll
+            for (int ks = 0; ks < kBoxK / 16; ++ks)
+              tc2::umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), idesc2, (kc | ks) ? 1u : 0u);
+          }
+          tc2::umma_commit(bar_d2_full + 8 * (it2 & 1));
+          ++it2;
+          progressed = true;
+        }
+        if (it1 < n_it && it1 <= it2 + 1 &&
+            (kc1 > 0 || mbar_try_wait(bar_d2_empty + 8 * (it1 & 1), ((it1 >> 1) & 1) ^ 1)) &&
+            mbar_try_wait(bar_x_full + 8 * stage, phase)) {
+          tc_fence_after();
+          const uint32_t d = tmem_base + (it1 & 1) * 256;
+          const uint32_t a_addr = sbase + kFmX + stage * kBoxBytes, b_addr = sbase + kFmW1 + kc1 * kBoxBytes;
 #pragma unroll
           for (int ks = 0; ks < kBoxK / 16; ++ks)
-            tc2::umma_bf16(tmem_d1, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), idesc1, (kc | ks) ? 1u : 0u);
+            tc2::umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), idesc1, (kc1 | ks) ? 1u : 0u);
           tc2::umma_commit(bar_x_empty + 8 * stage);
           if (++stage == kFmStages) { stage = 0; phase ^= 1; }
+          if (++kc1 == 4) {
+            tc2::umma_commit(bar_d1_full + 8 * (it1 & 1));
+            kc1 = 0;
+            ++it1;
+          }
+          progressed = true;
         }
-        tc2::umma_commit(bar_d1_full + 8 * (it & 1));
-        mbar_wait(bar_h_full, it & 1);                           // both CTAs' hidden tiles are in shared memory
-        mbar_wait(bar_d2_empty, (it & 1) ^ 1);                   // the previous tile's D2 has been read
-        tc_fence_after();
-        for (int kc = 0; kc < 4; ++kc) {
-          const uint32_t a_addr = sbase + kFmH + kc * kBoxBytes, b_addr = sbase + kFmW2 + kc * kW2BoxBytes;
-#pragma unroll
-          for (int ks = 0; ks < kBoxK / 16; ++ks)
-            tc2::umma_bf16(tmem_d2, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), idesc2, (kc | ks) ? 1u : 0u);
-        }
-        tc2::umma_commit(bar_d2_full + 8 * (it & 1));
+        if (progressed) spins = 0;
+        else if ((++spins & 1023u) == 0 && clock64() - t0 > 8000000000ll) __trap();     // never hang the GPU
       }
     }
   } else {
@@ -428,21 +448,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     const int rin = quad * 32 + lane;                            // row of this CTA's 128-row tile
     const uint32_t sw = uint32_t(lane & 7);
-    const uint32_t stage_buf = sbase + kFmOut + ew * kStageOutBytes;
+    const uint32_t stage_buf = sbase + kFmOut + quad * kStageOutBytes;        // epilogue-2 warps only
     const uint32_t my_row = stage_buf + lane * 128;
-    const uint32_t bar_my_res = bar_res + 8 * ew;
+    const uint32_t bar_my_res = bar_res + 8 * quad;
     uint32_t res_phase = 0, it = 0;
     for (int t = pair; t < ntiles; t += npairs, ++it) {
-      if ((it & 1u) != uint32_t(set)) continue;                  // the other set owns this tile
       const int row0 = t * 2 * kTile + int(rank) * kTile + quad * 32;
-      // ---- epilogue 1: relu(D1) -> h (4 k-chunks of 64 hidden columns) ---------------------------------------------
+      if (set == 1) {
+      // ---- epilogue 1 (warps 6-9): relu(D1) -> h (4 k-chunks of 64 hidden columns) -----------------------------------
       mbar_wait(bar_d1_full + 8 * (it & 1), (it >> 1) & 1);
       if (it > 0) mbar_wait(bar_d2_full + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);   // MMA 2 of the previous tile no longer reads h
       tc_fence_after();
 #pragma unroll 1
       for (int hb = 0; hb < 2; ++hb) {                           // 128 hidden columns per pass: one TMEM round trip
         float v[kD];
-        tmem_ld128(tmem_d1 + lane_addr + hb * 128, v);
+        tmem_ld128(tmem_base + (it & 1) * 256 + lane_addr + hb * 128, v);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const uint32_t hrow = sbase + kFmH + (2 * hb + half) * kBoxBytes + uint32_t(rin) * 128;
@@ -461,14 +481,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tc2::mbar_arrive_leader_release(bar_h_full);
-      // ---- epilogue 2: LayerNorm2(D2) + x -> out ------------------------------------------------------------
+      continue;
+      }
+      // ---- epilogue 2 (warps 2-5): LayerNorm2(D2) + x -> out ------------------------------------------------------------
       mbar_wait(bar_d2_full + 8 * (it & 1), (it >> 1) & 1);
       tc_fence_after();
       float v[kD];
-      tmem_ld128(tmem_d2 + lane_addr, v);
+      tmem_ld128(tmem_base + (it & 1) * 256 + lane_addr, v);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc2::mbar_arrive_leader(bar_d2_empty);
+      if (lane == 0) tc2::mbar_arrive_leader(bar_d2_empty + 8 * (it & 1));
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
       for (int c = 0; c < kD; c += 4) { s0 += v[c]; s1 += v[c + 1]; s2 += v[c + 2]; s3 += v[c + 3]; }
