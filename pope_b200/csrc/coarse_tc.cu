@@ -391,7 +391,10 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
 
   if (P.gate && !(uint32_t(*reinterpret_cast<const volatile int32_t*>(P.flags)) & POPE_FLAG_ROBUST_PATH)) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (volatile read: the compiler otherwise re-derives lane bits from SR_TID.X inside the epilogue loops, ~6 S2R per chunk)
+  uint32_t lane_u;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_u));
+  const int warp = threadIdx.x >> 5, lane = int(lane_u);
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
