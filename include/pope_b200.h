@@ -140,7 +140,7 @@ int pope_match_order_by_ref(const int32_t* counts, int n_pairs, int S, const int
 /* Retrieval: cosine similarity (x.y / (max(|x|,eps) * max(|y|,eps))) of one query token against R reference
  * tokens, followed by the eval loop's slot-replacement top-k (slots start at 0; a score greater than any slot
  * overwrites the first arg-min slot), evaluated in reference order so slot order matches the loop.
- *   q [D], refs [R, D] contiguous.  Outputs scores float[R], slot_scores float[k], slot_idx int32[k] (-1 = empty). */
+ *   q [D], refs [R, D] contiguous, k <= 16.  Outputs scores float[R], slot_scores float[k], slot_idx int32[k] (-1 = empty). */
 int pope_cosine_topk(const void* q, const void* refs, int dtype, int R, int D, int k, float eps,
                      float* scores, float* slot_scores, int32_t* slot_idx, void* stream);
 

@@ -924,7 +924,7 @@ TfScratch carve_tf(void* base, int64_t m, int S) {
 
 cudaError_t attention_run(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int64_t m,
                           int S, cudaStream_t st) {
-  static const bool force_simt = getenv("POPE_ATTN_SIMT") != nullptr;      // developer knob: the fp32 SIMT kernel
+  const bool force_simt = getenv("POPE_ATTN_SIMT") != nullptr;             // developer knob: the fp32 SIMT kernel
   if (S > kTileRows || force_simt) {
     fine_attn_kernel<<<unsigned((m + kAttnWarps - 1) / kAttnWarps), kAttnWarps * 32, 0, st>>>(q, k, v, out, m, S, 1e-6f);
     return cudaGetLastError();
@@ -967,7 +967,7 @@ cudaError_t encoder_layer(__nv_bfloat16* x, const __nv_bfloat16* src, int64_t m,
   P.mode[0] = EPI_LN; P.gamma = ln; P.beta = ln + 128;
   const Dst om[3] = {{w.m1, kD}, {nullptr, 0}, {nullptr, 0}};
   if ((e = linear_run(T, {w.msg, kD, kD}, none, wl + kOffMerge, 128, kD, kD, om, nullptr, P, st)) != cudaSuccess) return e;
-  static const bool unfused_mlp = getenv("POPE_MLP_UNFUSED") != nullptr;     // developer knob: the two separate launches
+  const bool unfused_mlp = getenv("POPE_MLP_UNFUSED") != nullptr;            // developer knob: the two separate launches
   if (!unfused_mlp) return mlp_fused_run(x, w.m1, T, wl + kOffMlp1, wl + kOffMlp2, ln + 256, ln + 384, st);
   P = LinParams{};
   P.mode[0] = EPI_RELU; P.mode[1] = EPI_RELU;

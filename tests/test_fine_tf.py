@@ -221,3 +221,34 @@ def test_matcher_bf16_fine_path_vs_fp32_module_flow():
     assert float(d.mean()) < 0.03 and float(d.max()) < 0.3, (float(d.mean()), float(d.max()))     # pixels, range +-4
     # the state dict is the reference's whether or not the CUDA fine level is on
     assert list(m_gpu.state_dict().keys()) == list(m_cpu.state_dict().keys())
+
+
+@pytest.mark.gpu
+def test_cuda_fine_transformer_alternative_kernels_agree():
+    """The developer knobs select the kernels the default path replaced (fp32 SIMT attention instead of mma.sync, two
+    Linear launches instead of the fused CTA-pair MLP); all of them implement the same layer, so their outputs agree to
+    bf16 rounding noise and each stays within the tolerance against the oracle."""
+    from pope_b200 import ops
+    dev = torch.device("cuda:0")
+    g, meta, layers, _ = _load()
+    f0, f1 = _inputs(321, 300)
+    packed = _cuda_layers(layers, dev)
+    want0, want1 = O.fine_transformer(f0, f1, layers, meta["layer_names"])
+    outs = {}
+    for knob in (None, "POPE_ATTN_SIMT", "POPE_MLP_UNFUSED"):
+        if knob:
+            os.environ[knob] = "1"
+        try:
+            d0, d1 = f0.to(dev, torch.bfloat16), f1.to(dev, torch.bfloat16)
+            ops.fine_transformer(d0, d1, packed, meta["layer_names"])
+            torch.cuda.synchronize()
+        finally:
+            if knob:
+                del os.environ[knob]
+        outs[knob] = (d0.float().cpu(), d1.float().cpu())
+        for got, want in zip(outs[knob], (want0, want1)):
+            rms, mx = _rel_err(got, want)
+            assert rms < 1.5e-2 and mx < 8e-2, (knob, rms, mx)
+    for knob in ("POPE_ATTN_SIMT", "POPE_MLP_UNFUSED"):
+        for a, b in zip(outs[None], outs[knob]):
+            assert _rel_err(a, b)[0] < 1e-2, knob

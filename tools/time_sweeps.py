@@ -1,19 +1,26 @@
-"""Times the coarse stage (64 pairs, 480x640, bf16) with CUDA events; used with POPE_TC_DEBUG experiments."""
+"""Times the coarse stage with CUDA events; used with POPE_TC_DEBUG experiments.
+    python tools/time_sweeps.py                 64 pairs at 480x640 (60x80 tokens), bf16
+    python tools/time_sweeps.py highres [n]     n (default 4) pairs at 960x1280 (120x160 = 19 200 tokens, BASELINE configs[3])"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pope_b200 import _lib, ops, synth
-n = 64
+hi = len(sys.argv) > 1 and sys.argv[1] == "highres"
+n = (int(sys.argv[2]) if len(sys.argv) > 2 else 4) if hi else 64
+hc, wc = (120, 160) if hi else (60, 80)
+L = hc * wc
 dev = torch.device("cuda:0")
-f0, f1 = synth.coarse_features(1234, n, 4800, 4800, 256, dtype=torch.bfloat16)
+f0, f1 = synth.coarse_features(1234, n, L, L, 256, dtype=torch.bfloat16)
 d0, d1 = f0.to(dev), f1.to(dev)
-ws = torch.empty(_lib.lib().pope_coarse_workspace_bytes(n, 4800, 4800), dtype=torch.uint8, device=dev)
+ws = torch.empty(_lib.lib().pope_coarse_workspace_bytes(n, L, L), dtype=torch.uint8, device=dev)
 for _ in range(3):
-    r = ops.coarse_match(d0, d1, (60, 80), (60, 80), 8.0, workspace=ws)
+    r = ops.coarse_match(d0, d1, (hc, wc), (hc, wc), 8.0, workspace=ws)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(10):
-    r = ops.coarse_match(d0, d1, (60, 80), (60, 80), 8.0, workspace=ws)
+    r = ops.coarse_match(d0, d1, (hc, wc), (hc, wc), 8.0, workspace=ws)
 e1.record(); torch.cuda.synchronize()
-print("POPE_TC_DEBUG=%s coarse %.3f ms/step  M=%d" % (os.environ.get("POPE_TC_DEBUG", "0"), e0.elapsed_time(e1) / 10, r.total()))
+ms = e0.elapsed_time(e1) / 10
+print("POPE_TC_DEBUG=%s coarse %.3f ms/step  n=%d L=S=%d  M=%d flags=%d  %.0f TFLOP/s algorithmic (2 L S C per pair)" % (
+    os.environ.get("POPE_TC_DEBUG", "0"), ms, n, L, r.total(), r.flags(), n * 2.0 * L * L * 256 / (ms * 1e-3) / 1e12))
