@@ -46,7 +46,8 @@ typedef enum {
   POPE_ERR_WORKSPACE = -3,     /* workspace smaller than pope_coarse_workspace_bytes() */
   POPE_ERR_SHAPE = -4,         /* shape not supported by the requested implementation */
   POPE_ERR_ALIGNMENT = -5,     /* pointer / stride not aligned as documented */
-  POPE_ERR_CAPACITY = -6       /* output capacity smaller than n_pairs * min(L, S) */
+  POPE_ERR_CAPACITY = -6,      /* output capacity smaller than n_pairs * min(L, S) */
+  POPE_ERR_IO = -7             /* a file could not be created / written (points_io) */
 } pope_status_t;
 
 typedef enum { POPE_F32 = 0, POPE_BF16 = 1 } pope_dtype_t;
@@ -201,6 +202,20 @@ int pope_match_scores(const float* mconf, const int32_t* counts, int n_pairs, in
 int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids, const float* mconf,
                       const float* mkpts0_f, const float* mkpts1_f, const int32_t* m_dev, int64_t capacity,
                       int pair_offset, int32_t* records, void* stream);
+
+/* ---- on-disk match format (host code) ------------------------------------------------------------
+ * numpy.savetxt(path, a) as the reference uses it (linemod.py:168-171: '%.18e', one space between columns, '\n' after
+ * every row; a 1-D array = one value per line = cols 1): byte-identical output, read back by pose/dataset.py with
+ * numpy.loadtxt.  data: host memory, row-major [rows, cols]. */
+int pope_savetxt_f32(const char* path, const float* data, int64_t rows, int cols);
+int pope_savetxt_f64(const char* path, const double* data, int64_t rows, int cols);
+/* All pairs of a batch at once, from the host pipeline's per-pair slots (pope_pipeline_run / pope_match_pairs_host:
+ * mkpts0_f, mkpts1_f float32[n_pairs, capacity, 2], counts int32[n_pairs]): for every pair with at least min_matches
+ * matches (the reference skips pairs with fewer than 5, linemod.py:143-146) writes <dir>/mkpts0/<names[p]>.txt and
+ * <dir>/mkpts1/<names[p]>.txt on n_threads host threads (<= 0: all cores).  *written = number of pairs written. */
+int pope_write_match_files(const char* dir, const char* const* names, int n_pairs, const float* mkpts0,
+                           const float* mkpts1, const int32_t* counts, int64_t capacity, int min_matches, int n_threads,
+                           int32_t* written);
 
 /* ---- fine-level transformer and FinePreprocess Linears (bf16) ---------------------------------
  * Replace src/matcher/loftr_module/transformer.py:34-58,95-104 + linear_attention.py:21-47 (LocalFeatureTransformer with

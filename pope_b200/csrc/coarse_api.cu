@@ -16,6 +16,7 @@ extern "C" const char* pope_status_string(int status) {
     case POPE_ERR_SHAPE: return "shape not supported by the requested implementation";
     case POPE_ERR_ALIGNMENT: return "pointer or stride not sufficiently aligned";
     case POPE_ERR_CAPACITY: return "output capacity too small";
+    case POPE_ERR_IO: return "file could not be created or written";
     default: return status > 0 ? cudaGetErrorString(static_cast<cudaError_t>(status)) : "unknown status";
   }
 }

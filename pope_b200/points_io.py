@@ -1,0 +1,55 @@
+"""On-disk match format of the reference, written by libpope_b200.so.
+
+The reference stores every pair's matches with `np.savetxt` (linemod.py:147-171: `data/<set>-points/<object>/{pre_bbox,
+mkpts0,mkpts1,pre_K}/<pair>.txt`) and `pose/dataset.py` reads them back with `np.loadtxt`.  `savetxt` here produces
+byte-identical files; `write_match_files` writes the mkpts0 / mkpts1 files of a whole batch from the host pipeline's
+output slots on a pool of native threads (no per-pair Python loop, no per-value Python string formatting)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import PopeError, check, lib
+
+
+def savetxt(path: str, a) -> None:
+    """np.savetxt(path, a) for a float32 / float64 array of 1 or 2 dimensions (default format, delimiter, newline)."""
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    if a.ndim == 0 or a.ndim > 2:
+        raise PopeError("savetxt takes 1-D or 2-D arrays (like numpy.savetxt)")
+    rows, cols = (a.shape[0], 1) if a.ndim == 1 else a.shape
+    if cols == 0:
+        raise PopeError("savetxt: arrays without columns are not supported")
+    if a.dtype == np.float32:
+        a = np.ascontiguousarray(a)
+        st = lib().pope_savetxt_f32(os.fsencode(path), a.ctypes.data, rows, cols)
+    else:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        st = lib().pope_savetxt_f64(os.fsencode(path), a.ctypes.data, rows, cols)
+    check(st, "pope_savetxt")
+
+
+def write_match_files(out_dir: str, names: Sequence[str], out: Dict[str, torch.Tensor], min_matches: int = 5,
+                      threads: int = 0) -> int:
+    """Writes <out_dir>/mkpts0/<name>.txt and <out_dir>/mkpts1/<name>.txt for every pair of a host-pipeline result
+    (`Pipeline.run` / `match_pairs_host`: mkpts0_f, mkpts1_f [n, cap, 2] float32, counts [n] int32) that has at least
+    `min_matches` matches (linemod.py:143-146 skips the others).  Returns the number of pairs written."""
+    k0, k1, cnt = out["mkpts0_f"], out["mkpts1_f"], out["counts"]
+    n, cap = k0.shape[0], k0.shape[1]
+    if len(names) != n:
+        raise PopeError("one file name per pair is required")
+    for t in (k0, k1, cnt):
+        if t.device.type != "cpu" or not t.is_contiguous():
+            raise PopeError("write_match_files takes the contiguous host tensors of the pipeline")
+    if k0.dtype != torch.float32 or k1.dtype != torch.float32 or cnt.dtype != torch.int32:
+        raise PopeError("mkpts*_f must be float32 and counts int32")
+    arr = (C.c_char_p * max(n, 1))(*[os.fsencode(s) for s in names])
+    written = C.c_int32(0)
+    st = lib().pope_write_match_files(os.fsencode(out_dir), arr, n, k0.data_ptr(), k1.data_ptr(), cnt.data_ptr(), cap,
+                                      int(min_matches), int(threads), C.byref(written))
+    check(st, "pope_write_match_files")
+    return int(written.value)

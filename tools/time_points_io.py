@@ -1,0 +1,32 @@
+"""Throughput of the native on-disk match writer against a numpy.savetxt loop on the bench workload's shape
+(n pairs x ~2 544 matches, mkpts0 + mkpts1; default n = 512).  Host only."""
+import os, shutil, sys, tempfile, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from pope_b200 import points_io
+
+rng = np.random.default_rng(0)
+n, cap = (int(sys.argv[1]) if len(sys.argv) > 1 else 512), 4800
+counts = torch.from_numpy(rng.integers(2300, 2800, n).astype(np.int32))
+out = {"mkpts0_f": torch.from_numpy(rng.uniform(0, 640, (n, cap, 2)).astype(np.float32)),
+       "mkpts1_f": torch.from_numpy(rng.uniform(0, 640, (n, cap, 2)).astype(np.float32)), "counts": counts}
+names = [f"{p:04d}" for p in range(n)]
+d = tempfile.mkdtemp()
+for thr in (1, 0):
+    t0 = time.perf_counter()
+    w = points_io.write_match_files(d + f"/b{thr}", names, out, threads=thr)
+    dt = time.perf_counter() - t0
+    print(f"native writer, threads={'all' if thr == 0 else thr}: {1e3 * dt:.1f} ms for {w} pairs ({int(counts.sum())} matches, "
+          f"{n / dt:.0f} pairs/s)")
+os.makedirs(d + "/np/mkpts0"); os.makedirs(d + "/np/mkpts1")
+t0 = time.perf_counter()
+n_np = min(n, 64)
+for p in range(n_np):
+    np.savetxt(d + f"/np/mkpts0/{names[p]}.txt", out["mkpts0_f"][p, :counts[p]].numpy())
+    np.savetxt(d + f"/np/mkpts1/{names[p]}.txt", out["mkpts1_f"][p, :counts[p]].numpy())
+dt = time.perf_counter() - t0
+same = all(open(d + f"/np/{s}/{names[p]}.txt", "rb").read() == open(d + f"/b0/{s}/{names[p]}.txt", "rb").read()
+           for p in range(n_np) for s in ("mkpts0", "mkpts1"))
+print(f"numpy.savetxt loop over {n_np} pairs: {1e3 * dt:.1f} ms ({n_np / dt:.0f} pairs/s); files byte-identical: {same}; host cores: {os.cpu_count()}")
+shutil.rmtree(d)
