@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <charconv>
@@ -77,8 +78,9 @@ extern "C" int pope_write_match_files(const char* dir, const char* const* names,
   if (!dir || !names || !mkpts0 || !mkpts1 || !counts || n_pairs < 0 || capacity < 0) return POPE_ERR_INVALID_ARG;
   const std::string root(dir);
   if (!make_dir(root) || !make_dir(root + "/mkpts0") || !make_dir(root + "/mkpts1")) return POPE_ERR_IO;
-  if (n_threads <= 0) n_threads = int(std::thread::hardware_concurrency());
+  if (n_threads <= 0) n_threads = int(sysconf(_SC_NPROCESSORS_ONLN));
   if (n_threads <= 0) n_threads = 1;
+  if (n_threads > 64) n_threads = 64;
   if (n_threads > n_pairs) n_threads = n_pairs > 0 ? n_pairs : 1;
   std::atomic<int> next(0), status(POPE_OK), done(0);
   auto work = [&]() {

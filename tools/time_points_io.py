@@ -12,11 +12,14 @@ counts = torch.from_numpy(rng.integers(2300, 2800, n).astype(np.int32))
 out = {"mkpts0_f": torch.from_numpy(rng.uniform(0, 640, (n, cap, 2)).astype(np.float32)),
        "mkpts1_f": torch.from_numpy(rng.uniform(0, 640, (n, cap, 2)).astype(np.float32)), "counts": counts}
 names = [f"{p:04d}" for p in range(n)]
-d = tempfile.mkdtemp()
+d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)      # RAM-backed: formatting, not the disk
 for thr in (1, 0):
-    t0 = time.perf_counter()
-    w = points_io.write_match_files(d + f"/b{thr}", names, out, threads=thr)
-    dt = time.perf_counter() - t0
+    dt = 1e9
+    for rep in range(3):                                                           # best of 3
+        shutil.rmtree(d + f"/b{thr}", ignore_errors=True)
+        t0 = time.perf_counter()
+        w = points_io.write_match_files(d + f"/b{thr}", names, out, threads=thr)
+        dt = min(dt, time.perf_counter() - t0)
     print(f"native writer, threads={'all' if thr == 0 else thr}: {1e3 * dt:.1f} ms for {w} pairs ({int(counts.sum())} matches, "
           f"{n / dt:.0f} pairs/s)")
 os.makedirs(d + "/np/mkpts0"); os.makedirs(d + "/np/mkpts1")
