@@ -243,6 +243,9 @@ size_t pope_fine_tf_workspace_bytes(int64_t m_windows, int window_tokens);
 int pope_fine_transformer(void* feat0, void* feat1, int64_t m_windows, int window_tokens, const void* weights,
                           int n_layers, const int* layer_kinds, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Bytes of device scratch pope_fine_merge_coarse needs (gathered + projected coarse rows, per-window vectors). */
+size_t pope_fine_merge_workspace_bytes(int64_t m_windows);
+
 /* FinePreprocess' coarse-context mixing, IN PLACE on the gathered windows win0/win1 [m, window_tokens, 128] bf16:
  *   c = down_proj(cat(feat_c0[b_ids, i_ids], feat_c1[b_ids, j_ids]));  win = merge_feat(cat(win, repeat(c)))
  * feat_c0 [N, L, 256], feat_c1 [N, S, 256] bf16; ids are device int64 arrays of length m_windows. */

@@ -986,8 +986,6 @@ using namespace pope;
 
 extern "C" size_t pope_fine_tf_workspace_bytes(int64_t m_windows, int window_tokens) {
   if (m_windows <= 0 || window_tokens <= 0) return 0;
-  // the FinePreprocess Linears reuse the same scratch: gathered coarse rows [2m, 256] bf16, projected [2m, 128] bf16,
-  // per-window vectors [2m, 128] fp32 -- far smaller than the transformer's 7 activation planes
   return carve_tf(nullptr, m_windows, window_tokens).bytes;
 }
 
@@ -1021,6 +1019,15 @@ extern "C" int pope_fine_transformer(void* feat0, void* feat1, int64_t m_windows
   return POPE_OK;
 }
 
+static size_t merge_scratch_bytes(int64_t m) {
+  // gathered coarse rows [2m, 256] bf16, projected rows [2m, 128] bf16, per-window vectors [2m, 128] fp32
+  return align_up(size_t(2 * m) * 256 * 2, 256) + align_up(size_t(2 * m) * 128 * 2, 256) + align_up(size_t(2 * m) * 128 * 4, 256);
+}
+
+extern "C" size_t pope_fine_merge_workspace_bytes(int64_t m_windows) {
+  return m_windows > 0 ? merge_scratch_bytes(m_windows) : 0;
+}
+
 extern "C" int pope_fine_merge_coarse(void* win0, void* win1, int64_t m_windows, int window_tokens, const void* feat_c0,
                                       const void* feat_c1, int L, int S, int C, const int64_t* b_ids, const int64_t* i_ids,
                                       const int64_t* j_ids, const void* weights, void* workspace, size_t workspace_bytes,
@@ -1030,8 +1037,7 @@ extern "C" int pope_fine_merge_coarse(void* win0, void* win1, int64_t m_windows,
   if (m_windows < 0 || window_tokens <= 0 || L <= 0 || S <= 0) return POPE_ERR_INVALID_ARG;
   if (C != 256) return POPE_ERR_SHAPE;
   if (m_windows == 0) return POPE_OK;
-  const size_t need = size_t(2 * m_windows) * (256 * 2 + 128 * 2 + 128 * 4) + 768;
-  if (workspace_bytes < need) return POPE_ERR_WORKSPACE;
+  if (workspace_bytes < merge_scratch_bytes(m_windows)) return POPE_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t m = m_windows;
   char* p = static_cast<char*>(workspace);

@@ -193,7 +193,9 @@ def fine_merge_coarse(win0: torch.Tensor, win1: torch.Tensor, feat_c0: torch.Ten
         return win0, win1
     n, L, C_ = feat_c0.shape
     S = feat_c1.shape[1]
-    workspace = fine_tf_workspace(M, WW, dev, workspace)
+    need = lib().pope_fine_merge_workspace_bytes(int(M))
+    if workspace is None or workspace.numel() < need or workspace.device != dev:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         st = lib().pope_fine_merge_coarse(ptr(win0), ptr(win1), M, WW, ptr(feat_c0), ptr(feat_c1), L, S, C_,
                                           ptr(b_ids.contiguous()), ptr(i_ids.contiguous()), ptr(j_ids.contiguous()),
