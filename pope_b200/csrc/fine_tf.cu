@@ -672,6 +672,103 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// Phases 1 and 2 + store for ONE window whose q / k / v tiles ([32 x 128] bf16, XOR-swizzled rows of 256 B, rows S..31 zero in
+// k and v) are in shared memory at sq / sk / sv.  The k tile is reused as the output staging area and its tail is cleared
+// again afterwards.  `out`: the window's [S, 128] rows in global memory.
+__device__ __forceinline__ void attn_window_core(uint32_t sq, uint32_t sk, uint32_t sv, int S, float eps,
+                                                 __nv_bfloat16* __restrict__ out, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int nchunk = S * (kD * 2 / 16);                     // 16-byte chunks of one [S, 128] tile
+  const float fs = float(S);
+  const uint32_t ones = (g == 0) ? 0x3f803f80u : 0u;        // A fragment of the "row 0 = all ones" matrix
+  const int lrow = lane & 7, lmat = lane >> 3;              // ldmatrix: this lane addresses row lrow of matrix lmat
+  const size_t base = 0;
+  // ---- phase 1: per head KV^T (16 x 16) and ksum (16) in fp32 accumulators ---------------------------------------
+  float kvt[kHeads][2][4];        // [head][key-dim tile][fragment]: rows = value dim (g, g+8), cols = key dim 2t, 2t+1
+  float ksum[kHeads][4];          // ksum[16h + {2t, 2t+1, 2t+8, 2t+9}] (valid in lanes with g == 0, broadcast below)
+#pragma unroll
+  for (int h = 0; h < kHeads; ++h) {
+    float one_acc[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { kvt[h][n][e] = 0.f; one_acc[n][e] = 0.f; }
+#pragma unroll
+    for (int s0 = 0; s0 < kTileRows; s0 += 16) {
+      uint32_t a[4], b[4];
+      {   // A = V_h^T: matrices (tokens s0.., chunk 2h), (s0.., 2h+1), (s0+8.., 2h), (s0+8.., 2h+1), transposed
+        const int row = s0 + ((lmat >> 1) << 3) + lrow, chunk = 2 * h + (lmat & 1);
+        ldsm_x4_trans(sv + uint32_t(row) * 256u + (uint32_t(chunk ^ (row & 7)) << 4), a);
+      }
+      {   // B = K_h: matrices (s0.., 2h), (s0+8.., 2h), (s0.., 2h+1), (s0+8.., 2h+1), transposed
+        const int row = s0 + ((lmat & 1) << 3) + lrow, chunk = 2 * h + (lmat >> 1);
+        ldsm_x4_trans(sk + uint32_t(row) * 256u + (uint32_t(chunk ^ (row & 7)) << 4), b);
+      }
+      mma_bf16(kvt[h][0], a[0], a[1], a[2], a[3], b[0], b[1]);
+      mma_bf16(kvt[h][1], a[0], a[1], a[2], a[3], b[2], b[3]);
+      mma_bf16(one_acc[0], ones, 0u, ones, 0u, b[0], b[1]);
+      mma_bf16(one_acc[1], ones, 0u, ones, 0u, b[2], b[3]);
+    }
+    // row 0 of the ones-product lives in lanes g == 0: lane t holds key dims 2t, 2t+1 (tile 0) and 2t+8, 2t+9 (tile 1)
+    ksum[h][0] = __shfl_sync(kFullMask, one_acc[0][0], t);
+    ksum[h][1] = __shfl_sync(kFullMask, one_acc[0][1], t);
+    ksum[h][2] = __shfl_sync(kFullMask, one_acc[1][0], t);
+    ksum[h][3] = __shfl_sync(kFullMask, one_acc[1][1], t);
+  }
+  __syncwarp();                   // every lane is done reading the k tile: it becomes the output staging area
+
+  // ---- phase 2: out_h = (Q_h KV_h) * S / (Q_h . ksum + eps) ------------------------------------------------------
+#pragma unroll
+  for (int h = 0; h < kHeads; ++h) {
+    // B fragments of KV_h from the accumulators of KV_h^T: value-dim tile 0 <- rows g (c0, c1), tile 1 <- rows g+8
+    const uint32_t b00 = pack_bf16(kvt[h][0][0], kvt[h][0][1]), b01 = pack_bf16(kvt[h][1][0], kvt[h][1][1]);
+    const uint32_t b10 = pack_bf16(kvt[h][0][2], kvt[h][0][3]), b11 = pack_bf16(kvt[h][1][2], kvt[h][1][3]);
+#pragma unroll
+    for (int m0 = 0; m0 < kTileRows; m0 += 16) {
+      if (m0 >= S) break;
+      uint32_t a[4];
+      {   // A = Q_h: matrices (tokens m0.., chunk 2h), (m0+8.., 2h), (m0.., 2h+1), (m0+8.., 2h+1)
+        const int row = m0 + ((lmat & 1) << 3) + lrow, chunk = 2 * h + (lmat >> 1);
+        ldsm_x4(sq + uint32_t(row) * 256u + (uint32_t(chunk ^ (row & 7)) << 4), a);
+      }
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16(o0, a[0], a[1], a[2], a[3], b00, b01);
+      mma_bf16(o1, a[0], a[1], a[2], a[3], b10, b11);
+      float z0 = bf_lo(a[0]) * ksum[h][0] + bf_hi(a[0]) * ksum[h][1] + bf_lo(a[2]) * ksum[h][2] + bf_hi(a[2]) * ksum[h][3];
+      float z1 = bf_lo(a[1]) * ksum[h][0] + bf_hi(a[1]) * ksum[h][1] + bf_lo(a[3]) * ksum[h][2] + bf_hi(a[3]) * ksum[h][3];
+      z0 += __shfl_xor_sync(kFullMask, z0, 1); z0 += __shfl_xor_sync(kFullMask, z0, 2);
+      z1 += __shfl_xor_sync(kFullMask, z1, 1); z1 += __shfl_xor_sync(kFullMask, z1, 2);
+      const float zi0 = fs / (z0 + eps), zi1 = fs / (z1 + eps);
+      const uint32_t r0 = sk + uint32_t(m0 + g) * kOutPitch + uint32_t(16 * h + 2 * t) * 2;
+      const uint32_t r1 = r0 + 8 * kOutPitch;
+      if (m0 + g < S) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(r0), "r"(pack_bf16(o0[0] * zi0, o0[1] * zi0)) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(r0 + 16), "r"(pack_bf16(o1[0] * zi0, o1[1] * zi0)) : "memory");
+      }
+      if (m0 + g + 8 < S) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(r1), "r"(pack_bf16(o0[2] * zi1, o0[3] * zi1)) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(r1 + 16), "r"(pack_bf16(o1[2] * zi1, o1[3] * zi1)) : "memory");
+      }
+    }
+  }
+  __syncwarp();
+  // ---- store: 16 bytes per lane, consecutive lanes -> consecutive addresses -------------------------------------------
+  for (int i = lane; i < nchunk; i += 32) {
+    const int r = i >> 4, c = i & 15;
+    uint4 val;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                 : "r"(sk + uint32_t(r) * kOutPitch + uint32_t(c) * 16));
+    *reinterpret_cast<uint4*>(out + base + size_t(i) * 8) = val;
+  }
+  __syncwarp();
+  // the staging area overwrote rows of the k tile beyond what the next load rewrites (pitch 272 vs 256): clear the tail
+  for (int i = lane; i < (kTileRows - S) * 16 + 16; i += 32) {
+    const uint32_t off = uint32_t(kTileBytes) - 16u * uint32_t(i + 1);
+    if (off >= uint32_t(S) * 256u) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sk + off), "r"(0u) : "memory");
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kMmaWarps * 32)
 fine_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                      const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int64_t m, int S, float eps) {
@@ -684,9 +781,6 @@ fine_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sq + i * 16), "r"(0u) : "memory");
   __syncwarp();
   const int nchunk = S * (kD * 2 / 16);                     // 16-byte chunks of one [S, 128] tile
-  const float fs = float(S);
-  const uint32_t ones = (g == 0) ? 0x3f803f80u : 0u;        // A fragment of the "row 0 = all ones" matrix
-  const int lrow = lane & 7, lmat = lane >> 3;              // ldmatrix: this lane addresses row lrow of matrix lmat
 
   for (int64_t w = int64_t(blockIdx.x) * kMmaWarps + warp; w < m; w += int64_t(gridDim.x) * kMmaWarps) {
     const size_t base = size_t(w) * S * kD;
@@ -701,90 +795,7 @@ fine_attn_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 
-    // ---- phase 1: per head KV^T (16 x 16) and ksum (16) in fp32 accumulators ---------------------------------------
-    float kvt[kHeads][2][4];        // [head][key-dim tile][fragment]: rows = value dim (g, g+8), cols = key dim 2t, 2t+1
-    float ksum[kHeads][4];          // ksum[16h + {2t, 2t+1, 2t+8, 2t+9}] (valid in lanes with g == 0, broadcast below)
-#pragma unroll
-    for (int h = 0; h < kHeads; ++h) {
-      float one_acc[2][4];
-#pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { kvt[h][n][e] = 0.f; one_acc[n][e] = 0.f; }
-#pragma unroll
-      for (int s0 = 0; s0 < kTileRows; s0 += 16) {
-        uint32_t a[4], b[4];
-        {   // A = V_h^T: matrices (tokens s0.., chunk 2h), (s0.., 2h+1), (s0+8.., 2h), (s0+8.., 2h+1), transposed
-          const int row = s0 + ((lmat >> 1) << 3) + lrow, chunk = 2 * h + (lmat & 1);
-          ldsm_x4_trans(sv + uint32_t(row) * 256u + (uint32_t(chunk ^ (row & 7)) << 4), a);
-        }
-        {   // B = K_h: matrices (s0.., 2h), (s0+8.., 2h), (s0.., 2h+1), (s0+8.., 2h+1), transposed
-          const int row = s0 + ((lmat & 1) << 3) + lrow, chunk = 2 * h + (lmat >> 1);
-          ldsm_x4_trans(sk + uint32_t(row) * 256u + (uint32_t(chunk ^ (row & 7)) << 4), b);
-        }
-        mma_bf16(kvt[h][0], a[0], a[1], a[2], a[3], b[0], b[1]);
-        mma_bf16(kvt[h][1], a[0], a[1], a[2], a[3], b[2], b[3]);
-        mma_bf16(one_acc[0], ones, 0u, ones, 0u, b[0], b[1]);
-        mma_bf16(one_acc[1], ones, 0u, ones, 0u, b[2], b[3]);
-      }
-      // row 0 of the ones-product lives in lanes g == 0: lane t holds key dims 2t, 2t+1 (tile 0) and 2t+8, 2t+9 (tile 1)
-      ksum[h][0] = __shfl_sync(kFullMask, one_acc[0][0], t);
-      ksum[h][1] = __shfl_sync(kFullMask, one_acc[0][1], t);
-      ksum[h][2] = __shfl_sync(kFullMask, one_acc[1][0], t);
-      ksum[h][3] = __shfl_sync(kFullMask, one_acc[1][1], t);
-    }
-    __syncwarp();                   // every lane is done reading the k tile: it becomes the output staging area
-
-    // ---- phase 2: out_h = (Q_h KV_h) * S / (Q_h . ksum + eps) ------------------------------------------------------
-#pragma unroll
-    for (int h = 0; h < kHeads; ++h) {
-      // B fragments of KV_h from the accumulators of KV_h^T: value-dim tile 0 <- rows g (c0, c1), tile 1 <- rows g+8
-      const uint32_t b00 = pack_bf16(kvt[h][0][0], kvt[h][0][1]), b01 = pack_bf16(kvt[h][1][0], kvt[h][1][1]);
-      const uint32_t b10 = pack_bf16(kvt[h][0][2], kvt[h][0][3]), b11 = pack_bf16(kvt[h][1][2], kvt[h][1][3]);
-#pragma unroll
-      for (int m0 = 0; m0 < kTileRows; m0 += 16) {
-        if (m0 >= S) break;
-        uint32_t a[4];
-        {   // A = Q_h: matrices (tokens m0.., chunk 2h), (m0+8.., 2h), (m0.., 2h+1), (m0+8.., 2h+1)
-          const int row = m0 + ((lmat & 1) << 3) + lrow, chunk = 2 * h + (lmat >> 1);
-          ldsm_x4(sq + uint32_t(row) * 256u + (uint32_t(chunk ^ (row & 7)) << 4), a);
-        }
-        float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_bf16(o0, a[0], a[1], a[2], a[3], b00, b01);
-        mma_bf16(o1, a[0], a[1], a[2], a[3], b10, b11);
-        float z0 = bf_lo(a[0]) * ksum[h][0] + bf_hi(a[0]) * ksum[h][1] + bf_lo(a[2]) * ksum[h][2] + bf_hi(a[2]) * ksum[h][3];
-        float z1 = bf_lo(a[1]) * ksum[h][0] + bf_hi(a[1]) * ksum[h][1] + bf_lo(a[3]) * ksum[h][2] + bf_hi(a[3]) * ksum[h][3];
-        z0 += __shfl_xor_sync(kFullMask, z0, 1); z0 += __shfl_xor_sync(kFullMask, z0, 2);
-        z1 += __shfl_xor_sync(kFullMask, z1, 1); z1 += __shfl_xor_sync(kFullMask, z1, 2);
-        const float zi0 = fs / (z0 + eps), zi1 = fs / (z1 + eps);
-        const uint32_t r0 = sk + uint32_t(m0 + g) * kOutPitch + uint32_t(16 * h + 2 * t) * 2;
-        const uint32_t r1 = r0 + 8 * kOutPitch;
-        if (m0 + g < S) {
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(r0), "r"(pack_bf16(o0[0] * zi0, o0[1] * zi0)) : "memory");
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(r0 + 16), "r"(pack_bf16(o1[0] * zi0, o1[1] * zi0)) : "memory");
-        }
-        if (m0 + g + 8 < S) {
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(r1), "r"(pack_bf16(o0[2] * zi1, o0[3] * zi1)) : "memory");
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(r1 + 16), "r"(pack_bf16(o1[2] * zi1, o1[3] * zi1)) : "memory");
-        }
-      }
-    }
-    __syncwarp();
-    // ---- store: 16 bytes per lane, consecutive lanes -> consecutive addresses -------------------------------------------
-    for (int i = lane; i < nchunk; i += 32) {
-      const int r = i >> 4, c = i & 15;
-      uint4 val;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                   : "r"(sk + uint32_t(r) * kOutPitch + uint32_t(c) * 16));
-      *reinterpret_cast<uint4*>(out + base + size_t(i) * 8) = val;
-    }
-    __syncwarp();
-    // the staging area overwrote rows of the k tile beyond what the next load rewrites (pitch 272 vs 256): clear the tail
-    for (int i = lane; i < (kTileRows - S) * 16 + 16; i += 32) {
-      const uint32_t off = uint32_t(kTileBytes) - 16u * uint32_t(i + 1);
-      if (off >= uint32_t(S) * 256u) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sk + off), "r"(0u) : "memory");
-    }
-    __syncwarp();
+    attn_window_core(sq, sk, sv, S, eps, out + base, lane);
   }
 }
 
