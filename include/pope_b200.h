@@ -52,7 +52,8 @@ typedef enum {
 
 typedef enum { POPE_F32 = 0, POPE_BF16 = 1 } pope_dtype_t;
 
-/* which coarse kernel family runs: AUTO picks TCGEN05 for bf16 with C % 64 == 0 && C <= 256, else SIMT */
+/* which coarse kernel family runs: AUTO picks TCGEN05 for bf16 (and, given the _ex workspace, fp32) features with
+ * C % 64 == 0 && C <= 256, else SIMT (fp32 FMA) */
 typedef enum { POPE_COARSE_AUTO = 0, POPE_COARSE_SIMT = 1, POPE_COARSE_TCGEN05 = 2 } pope_coarse_impl_t;
 
 /* bits of counts[n_pairs + 1] written by pope_coarse_match */
@@ -70,6 +71,11 @@ int pope_coarse_auto_impl(int dtype, int L, int S, int C);
 
 /* Bytes of device scratch pope_coarse_match needs for this problem (row/col log-sum-exp + best-candidate keys). */
 size_t pope_coarse_workspace_bytes(int n_pairs, int L, int S);
+/* The same plus, for POPE_F32 features with C % 64 == 0 && C <= 256, room for the three bf16 planes of every feature
+ * value that the tensor-core path for fp32 inputs works on (fp32 accuracy: a = a1 + a2 + a3, six products).  With a
+ * workspace of this size POPE_COARSE_AUTO / POPE_COARSE_TCGEN05 run fp32 features on the tensor cores (thr > 1/8);
+ * with the smaller one fp32 features run the fp32-FMA kernels. */
+size_t pope_coarse_workspace_bytes_ex(int n_pairs, int L, int S, int C, int dtype);
 
 /* Coarse matching for n_pairs independent image pairs.
  *   feat_c0 [n_pairs, L, C], feat_c1 [n_pairs, S, C]  contiguous, 16-byte aligned, L = h0c*w0c, S = h1c*w1c.

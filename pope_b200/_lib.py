@@ -27,6 +27,7 @@ SIGNATURES = {
     "pope_status_string": (C.c_char_p, [_i]),
     "pope_coarse_auto_impl": (_i, [_i, _i, _i, _i]),
     "pope_coarse_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pope_coarse_workspace_bytes_ex": (_sz, [_i, _i, _i, _i, _i]),
     "pope_coarse_match": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _i, _i, _p, _sz,
                                _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "pope_fine_gather": (_i, [_p, _p, _i, _i, _i, _i, _i, C.POINTER(_i64), _i, _i, C.POINTER(_i64),

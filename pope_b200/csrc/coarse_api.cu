@@ -24,12 +24,20 @@ extern "C" const char* pope_status_string(int status) {
 extern "C" int pope_coarse_auto_impl(int dtype, int L, int S, int C) {
   CoarseProblem p{};
   p.dtype = dtype; p.L = L; p.S = S; p.C = C; p.n = 1;
-  return coarse_tc_supported(p) ? POPE_COARSE_TCGEN05 : POPE_COARSE_SIMT;
+  p.log2_thr = -2.3219281f;      // thr = 0.2: fp32 features take the split tensor-core path at the default threshold
+  return (coarse_tc_supported(p) || coarse_tc_split_supported(p)) ? POPE_COARSE_TCGEN05 : POPE_COARSE_SIMT;
 }
 
 extern "C" size_t pope_coarse_workspace_bytes(int n_pairs, int L, int S) {
   if (n_pairs <= 0 || L <= 0 || S <= 0) return 0;
   return carve_coarse_scratch(nullptr, n_pairs, L, S).bytes;
+}
+
+extern "C" size_t pope_coarse_workspace_bytes_ex(int n_pairs, int L, int S, int C, int dtype) {
+  if (n_pairs <= 0 || L <= 0 || S <= 0 || C <= 0) return 0;
+  size_t bytes = align_up(carve_coarse_scratch(nullptr, n_pairs, L, S).bytes, 256);
+  if (dtype == POPE_F32 && C % 64 == 0 && C <= 256) bytes += coarse_tc_split_bytes(n_pairs, L, S, C);
+  return bytes;
 }
 
 extern "C" int pope_coarse_match(const void* feat_c0, const void* feat_c1, int dtype, int n_pairs, int L, int S, int C,
@@ -60,20 +68,34 @@ extern "C" int pope_coarse_match(const void* feat_c0, const void* feat_c1, int d
   p.log2_thr = static_cast<float>(log2(double(thr)));   // `conf > thr` is evaluated on fp32 values: thr arrives as float
   p.border = border_rm; p.pixel_scale = pixel_scale;
 
-  bool use_tc;
+  // fp32 features: the tensor-core path splits every value into three bf16 terms (fp32 accuracy) and needs the larger
+  // workspace of pope_coarse_workspace_bytes_ex; with the plain workspace (or thr <= 1/8) fp32 runs the fp32-FMA kernels
+  const size_t std_bytes = align_up(w.bytes, 256);
+  const bool split_ok = coarse_tc_split_supported(p) && workspace_bytes >= std_bytes + coarse_tc_split_bytes(n_pairs, L, S, C);
+  bool use_tc, use_split = false;
   if (impl == POPE_COARSE_SIMT) use_tc = false;
-  else if (impl == POPE_COARSE_TCGEN05) { if (!coarse_tc_supported(p)) return POPE_ERR_SHAPE; use_tc = true; }
-  else if (impl == POPE_COARSE_AUTO) use_tc = coarse_tc_supported(p);
+  else if (impl == POPE_COARSE_TCGEN05) {
+    if (coarse_tc_supported(p)) use_tc = true;
+    else if (coarse_tc_split_supported(p)) { if (!split_ok) return POPE_ERR_WORKSPACE; use_tc = false; use_split = true; }
+    else return POPE_ERR_SHAPE;
+  }
+  else if (impl == POPE_COARSE_AUTO) { use_tc = coarse_tc_supported(p); use_split = !use_tc && split_ok; }
   else return POPE_ERR_INVALID_ARG;
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   // clear the best-candidate records, candidate counters and "count published" words (adjacent; the single-sweep
   // tcgen05 sequence clears / writes them all itself) and the total/flag words
-  if (!use_tc || coarse_tc_needs_clear(p))
+  if (!use_split && (!use_tc || coarse_tc_needs_clear(p)))
     if ((e = cudaMemsetAsync(w.rowbest, 0, w.zero_bytes, st)) != cudaSuccess) return int(e);
   if ((e = cudaMemsetAsync(counts + n_pairs, 0, 2 * sizeof(int32_t), st)) != cudaSuccess) return int(e);
-  e = use_tc ? coarse_tc_run(p, w, counts + n_pairs + 1, st) : coarse_simt_run(p, w, counts + n_pairs + 1, st);
+  if (use_split) {
+    // single sweep on the split planes, then the fp32-FMA kernels as a gated fallback (no-ops unless the flag was raised)
+    e = coarse_tc_split_run(p, w, static_cast<char*>(workspace) + std_bytes, counts + n_pairs + 1, st);
+    if (e == cudaSuccess) e = coarse_simt_run(p, w, counts + n_pairs + 1, st, true);
+  } else {
+    e = use_tc ? coarse_tc_run(p, w, counts + n_pairs + 1, st) : coarse_simt_run(p, w, counts + n_pairs + 1, st);
+  }
   if (e != cudaSuccess) return int(e);
   e = coarse_finalize_run(p, w, b_ids, i_ids, j_ids, mconf, mkpts0_c, mkpts1_c, counts, st);
   return int(e);

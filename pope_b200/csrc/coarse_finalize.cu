@@ -122,9 +122,20 @@ __global__ void __launch_bounds__(FT) count_emit_kernel(const u64* __restrict__ 
 // Two-sweep path, between the sweeps: cell (i, j) can only have conf > thr if p_row(i, j) > thr, i.e. if its raw
 // accumulator exceeds (lse_r[i] + log2 thr) / scale.  One warp per aligned group of 32 rows writes that bound (margin on
 // the safe side, +inf for non-finite lse) and the group's minimum.
+__device__ __forceinline__ bool gate_closed(const int32_t* gate) {
+  return gate && !(uint32_t(*gate) & POPE_FLAG_ROBUST_PATH);
+}
+
+__global__ void __launch_bounds__(256) gated_clear_kernel(uint4* __restrict__ ptr, size_t n16, const int32_t* __restrict__ gate) {
+  if (gate_closed(gate)) return;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += size_t(gridDim.x) * blockDim.x)
+    ptr[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void __launch_bounds__(256) cand_bounds_kernel(const float* __restrict__ lse_r, int n_pairs, int L, float scale,
                                                          float log2_thr, float* __restrict__ cbound,
-                                                         float* __restrict__ cminb) {
+                                                         float* __restrict__ cminb, const int32_t* __restrict__ gate) {
+  if (gate_closed(gate)) return;
   const int lane = threadIdx.x & 31;
   const int nchunks = (L + 31) / 32;
   const size_t g = size_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -147,7 +158,9 @@ __global__ void __launch_bounds__(256) cand_bounds_kernel(const float* __restric
 __global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
                                                        const float* __restrict__ lse_r, const float* __restrict__ lse_c,
                                                        int n_pairs, int L, int S, float scale, float log2_thr,
-                                                       u64* __restrict__ rowbest, u64* __restrict__ colbest) {
+                                                       u64* __restrict__ rowbest, u64* __restrict__ colbest,
+                                                       const int32_t* __restrict__ gate) {
+  if (gate_closed(gate)) return;
   const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= size_t(n_pairs) * L) return;
   const int n = int(r / L), i = int(r - size_t(n) * L);
@@ -181,7 +194,8 @@ __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restr
                                                              float scale, float log2_thr, u64* __restrict__ rowbest,
                                                              u64* __restrict__ colbest, const int32_t* __restrict__ flags,
                                                              int mode) {
-  const bool exp_lists = mode == 1 && !(uint32_t(*flags) & POPE_FLAG_ROBUST_PATH);
+  if (mode == 2 && (uint32_t(*flags) & POPE_FLAG_ROBUST_PATH)) return;
+  const bool exp_lists = mode == 2 || (mode == 1 && !(uint32_t(*flags) & POPE_FLAG_ROBUST_PATH));
   const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= size_t(n_pairs) * L) return;
   const uint32_t c4 = uint32_t(cand_cnt[r]);
@@ -253,16 +267,22 @@ __global__ void __launch_bounds__(128) colsum_reduce_kernel(const float* __restr
 
 }  // namespace
 
-cudaError_t cand_bounds_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st) {
+cudaError_t cand_bounds_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st, const int32_t* gate) {
   const size_t groups = size_t(p.n) * ((p.L + 31) / 32);
-  cand_bounds_kernel<<<unsigned((groups + 7) / 8), 256, 0, st>>>(w.lse_r, p.n, p.L, p.scale_log2, p.log2_thr, w.cbound, w.cminb);
+  cand_bounds_kernel<<<unsigned((groups + 7) / 8), 256, 0, st>>>(w.lse_r, p.n, p.L, p.scale_log2, p.log2_thr, w.cbound, w.cminb,
+                                                                gate);
   return cudaGetLastError();
 }
 
-cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st) {
+cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st, const int32_t* gate) {
   const size_t rows = size_t(p.n) * p.L;
   cand_eval_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(w.cand_cnt, w.cand, w.lse_r, w.lse_c, p.n, p.L, p.S,
-                                                                p.scale_log2, p.log2_thr, w.rowbest, w.colbest);
+                                                                p.scale_log2, p.log2_thr, w.rowbest, w.colbest, gate);
+  return cudaGetLastError();
+}
+
+cudaError_t gated_clear_run(void* ptr, size_t bytes, const int32_t* gate, cudaStream_t st) {
+  gated_clear_kernel<<<148 * 2, 256, 0, st>>>(static_cast<uint4*>(ptr), bytes / 16, gate);
   return cudaGetLastError();
 }
 

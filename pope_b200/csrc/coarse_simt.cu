@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(NT) rowlse_simt_kernel(const T* __restrict__ A
                                                         int LA, int LB, int C, float scale_log2,
                                                         float* __restrict__ lse_out, const float* __restrict__ cbound,
                                                         int* __restrict__ cand_cnt, u64* __restrict__ cand,
-                                                        int32_t* __restrict__ flags) {
+                                                        int32_t* __restrict__ flags, const int32_t* __restrict__ gate) {
+  if (gate && !(uint32_t(*gate) & POPE_FLAG_ROBUST_PATH)) return;      // fallback launch of the fp32 tensor-core path
   __shared__ __align__(16) float As[BK][BM + LDS_PAD];
   __shared__ __align__(16) float Bs[BK][BN + LDS_PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -195,20 +196,28 @@ __global__ void __launch_bounds__(NT) candidates_simt_kernel(const T* __restrict
 }
 
 template <typename T>
-cudaError_t run_typed(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
+cudaError_t run_typed(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st, bool gated) {
   const T* f0 = static_cast<const T*>(p.f0);
   const T* f1 = static_cast<const T*>(p.f1);
+  const int32_t* gate = gated ? flags : nullptr;
   dim3 gr((p.L + BM - 1) / BM, p.n), gc((p.S + BM - 1) / BM, p.n);
-  rowlse_simt_kernel<T, false><<<gr, NT, 0, st>>>(f0, f1, p.L, p.S, p.C, p.scale_log2, w.lse_r, nullptr, nullptr, nullptr, nullptr);
+  cudaError_t e;
+  if (gated) {
+    if (!two_sweeps_possible(p)) return cudaErrorInvalidValue;     // the gated form exists for the two-sweep scheme only
+    if ((e = gated_clear_run(w.rowbest, w.zero_bytes, gate, st)) != cudaSuccess) return e;
+  }
+  rowlse_simt_kernel<T, false><<<gr, NT, 0, st>>>(f0, f1, p.L, p.S, p.C, p.scale_log2, w.lse_r, nullptr, nullptr, nullptr, nullptr,
+                                                  gate);
   if (two_sweeps_possible(p)) {
     // same two-sweep scheme as the tcgen05 path: the column sweep lists the cells with p_row > thr
-    cudaError_t e;
-    if ((e = cand_bounds_run(p, w, st)) != cudaSuccess) return e;
-    rowlse_simt_kernel<T, true><<<gc, NT, 0, st>>>(f1, f0, p.S, p.L, p.C, p.scale_log2, w.lse_c, w.cbound, w.cand_cnt, w.cand, flags);
+    if ((e = cand_bounds_run(p, w, st, gate)) != cudaSuccess) return e;
+    rowlse_simt_kernel<T, true><<<gc, NT, 0, st>>>(f1, f0, p.S, p.L, p.C, p.scale_log2, w.lse_c, w.cbound, w.cand_cnt, w.cand, flags,
+                                                   gate);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return cand_eval_run(p, w, st);
+    return cand_eval_run(p, w, st, gate);
   }
-  rowlse_simt_kernel<T, false><<<gc, NT, 0, st>>>(f1, f0, p.S, p.L, p.C, p.scale_log2, w.lse_c, nullptr, nullptr, nullptr, nullptr);
+  rowlse_simt_kernel<T, false><<<gc, NT, 0, st>>>(f1, f0, p.S, p.L, p.C, p.scale_log2, w.lse_c, nullptr, nullptr, nullptr, nullptr,
+                                                  nullptr);
   candidates_simt_kernel<T><<<gr, NT, 0, st>>>(f0, f1, p.L, p.S, p.C, p.scale_log2, p.log2_thr, w.lse_r, w.lse_c,
                                                 w.rowbest, w.colbest);
   return cudaGetLastError();
@@ -216,8 +225,8 @@ cudaError_t run_typed(const CoarseProblem& p, const CoarseScratch& w, int32_t* f
 
 }  // namespace
 
-cudaError_t coarse_simt_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
-  return p.dtype == POPE_BF16 ? run_typed<__nv_bfloat16>(p, w, flags, st) : run_typed<float>(p, w, flags, st);
+cudaError_t coarse_simt_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st, bool gated) {
+  return p.dtype == POPE_BF16 ? run_typed<__nv_bfloat16>(p, w, flags, st, gated) : run_typed<float>(p, w, flags, st, gated);
 }
 
 }  // namespace pope

@@ -57,14 +57,11 @@ constexpr uint32_t kPeerMask = 0xFEFFFFFFu;          // clears the CTA-rank bit 
 
 // dynamic shared memory layout (base aligned to 1024 B for the 128B swizzle); identical in both CTAs of a pair
 constexpr int kSmemA = 0;                                            // 4 k-chunks x 16 KB
-constexpr int kSmemB = kSmemA + kMaxKChunks * kBoxBytes;             // kStages x 16 KB
-constexpr int kSmemLc = kSmemB + kStages * kBoxBytes;                // sweep 3: 2 stages x 256 x {bound, exact} floats
-constexpr int kSmemMerge = kSmemLc + 2 * 2 * kTileCols * 4;          // sweep 1+2: 3 x 128 x (max, sum)
-constexpr int kSmemBar = kSmemMerge + 3 * 128 * 8;                   // barriers
-constexpr int kNumBars = 2 + 2 * kStages + 4;
-constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
-constexpr int kSmemBytes = kSmemTmemPtr + 16;
-constexpr int kSmemAlloc = kSmemBytes + 1024;                        // slack for manual 1024-B alignment
+// then (offsets computed inside the kernel, they depend on MODE): the stationary block(s), the ring of kStages (MODE 4: 5)
+// 16 KB boxes, 4 KB of staged per-column terms / list counters, 3 KB of row-sum merge space, the barriers, the TMEM pointer
+constexpr int kSmemAlloc = 2 * kMaxKChunks * kBoxBytes + 5 * kBoxBytes + 2 * 2 * kTileCols * 4 + 3 * 128 * 8 + 256 + 16 + 1024;
+static_assert(kSmemAlloc >= kMaxKChunks * kBoxBytes + kStages * kBoxBytes + 2 * 2 * kTileCols * 4 + 3 * 128 * 8 + 256 + 16 + 1024 &&
+              kSmemAlloc <= 227 * 1024, "shared-memory allocation");
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -377,10 +374,28 @@ __device__ __noinline__ void ss_push(int* cnt, u64* __restrict__ list, float e, 
 // MODE 3: single sweep over the rows of S (direction 0 only): unshifted 2^x, row sums per thread, column sums through a
 //         shuffle reduction and per-32-row partial sums in global memory, candidate lists as in MODE 2.  Valid while the
 //         sums stay in fp32 range; otherwise POPE_FLAG_ROBUST_PATH is raised and a gated MODE 2 launch redoes the batch.
+// MODE 4: MODE 3 for FP32 features at fp32 accuracy on the bf16 tensor cores.  Every feature value is split into three bf16
+//         terms a = a1 + a2 + a3 (24 mantissa bits, split3_kernel) and the contraction is the six significant products
+//         a1b1 + a2b1 + a3b1 + a1b2 + a2b2 + a1b3 (the dropped ones are below 2^-24 of |a||b|) accumulated in fp32 in
+//         TMEM -- 6x the MMAs of MODE 3, which hides the epilogue completely.  The a1 and a2 blocks of the unit stay
+//         resident (128 KB), a3 and the b planes stream through a 5-stage ring.  maps: map0..2 = planes of f0,
+//         map3..5 = planes of f1.
 // TRACE: developer diagnostics instantiation (clock stamps of CTA pair 0); the product launches use TRACE = false.
 template <int MODE, bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const SweepParams P) {
+sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
+                const __grid_constant__ CUtensorMap map4, const __grid_constant__ CUtensorMap map5, const SweepParams P) {
+  // shared-memory layout: MODE 4 keeps two stationary blocks (a1, a2) and a shorter ring
+  constexpr int kAChunks = (MODE == 4) ? 2 * kMaxKChunks : kMaxKChunks;
+  constexpr int kRing = (MODE == 4) ? 5 : kStages;
+  constexpr int kSmemB = kSmemA + kAChunks * kBoxBytes;
+  constexpr int kSmemLc = kSmemB + kRing * kBoxBytes;
+  constexpr int kSmemMerge = kSmemLc + 2 * 2 * kTileCols * 4;
+  constexpr int kSmemBar = kSmemMerge + 3 * 128 * 8;
+  constexpr int kSmemTmemPtr = kSmemBar + (2 + 2 * kRing + 4) * 8;
+  static_assert(kSmemTmemPtr + 16 + 1024 <= kSmemAlloc, "shared-memory layout exceeds the allocation");
+  constexpr int kStages = kRing;                    // shadows the file-level ring depth inside the kernel
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -441,23 +456,35 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         decode(u, dir, n, rb);
         const CUtensorMap* mapA = dir ? &map1 : &map0;
         const CUtensorMap* mapB = dir ? &map0 : &map1;
+        const int arow = rb * kUnitRows + int(rank) * kBoxRows;
+        auto ring_load = [&](const CUtensorMap* mp, int kc, int row) {
+          mbar_wait(bar_b_empty + 8 * b_stage, b_phase ^ 1);
+          if (rank == 0) mbar_expect_tx(bar_b_full + 8 * b_stage, 2 * kBoxBytes);
+          tma_load_3d_2sm(sbase + kSmemB + b_stage * kBoxBytes, mp, bar_b_full + 8 * b_stage, kc * kBoxK, row, n);
+          if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
+        };
         if (!(P.debug & 4) || u == pair) {            // debug bit2: timing experiment, the stationary block is loaded once
           mbar_wait(bar_a_empty, a_phase ^ 1);
-          if (rank == 0) mbar_expect_tx(bar_a_full, 2 * kchunks * kBoxBytes);
-          for (int kc = 0; kc < kchunks; ++kc)
-            tma_load_3d_2sm(sbase + kSmemA + kc * kBoxBytes, mapA, bar_a_full, kc * kBoxK,
-                            rb * kUnitRows + int(rank) * kBoxRows, n);
+          if (rank == 0) mbar_expect_tx(bar_a_full, (MODE == 4 ? 4 : 2) * kchunks * kBoxBytes);
+          for (int kc = 0; kc < kchunks; ++kc) {
+            tma_load_3d_2sm(sbase + kSmemA + kc * kBoxBytes, mapA, bar_a_full, kc * kBoxK, arow, n);
+            if (MODE == 4)      // a2 block behind the a1 block
+              tma_load_3d_2sm(sbase + kSmemA + (kMaxKChunks + kc) * kBoxBytes, &map1, bar_a_full, kc * kBoxK, arow, n);
+          }
           a_phase ^= 1;
         }
         const int ntiles = ((dir ? P.L0 : P.L1) + kTileCols - 1) / kTileCols;
-        for (int ct = 0; ct < ntiles; ++ct)
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(bar_b_empty + 8 * b_stage, b_phase ^ 1);
-            if (rank == 0) mbar_expect_tx(bar_b_full + 8 * b_stage, 2 * kBoxBytes);
-            tma_load_3d_2sm(sbase + kSmemB + b_stage * kBoxBytes, mapB, bar_b_full + 8 * b_stage, kc * kBoxK,
-                            ct * kTileCols + int(rank) * kBoxRows, n);
-            if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
+        for (int ct = 0; ct < ntiles; ++ct) {
+          const int brow = ct * kTileCols + int(rank) * kBoxRows;
+          if (MODE == 4) {
+            // ring order = the issuer's order: (a3[c], b1[c]) for every k-chunk, then the b2 chunks, then the b3 chunks
+            for (int kc = 0; kc < kchunks; ++kc) { ring_load(&map2, kc, arow); ring_load(&map3, kc, brow); }
+            for (int kc = 0; kc < kchunks; ++kc) ring_load(&map4, kc, brow);
+            for (int kc = 0; kc < kchunks; ++kc) ring_load(&map5, kc, brow);
+          } else {
+            for (int kc = 0; kc < kchunks; ++kc) ring_load(mapB, kc, brow);
           }
+        }
       }
     }
   } else if (warp == 1) {
@@ -482,6 +509,52 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           if (tr) rec[1] = clock64();
           tc_fence_after();
           const uint32_t d = tmem_base + s * kTileCols;
+          if (MODE == 4) {
+            // six products per k-chunk: (a1 + a2 + a3) b1, (a1 + a2) b2, a1 b3; a1 / a2 resident, a3 and b* from the ring
+            uint32_t first = 0;
+            auto mma4 = [&](uint32_t a_addr, uint32_t b_addr) {
+#pragma unroll
+              for (int ks = 0; ks < kBoxK / 16; ++ks) {
+                umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), first);
+                first = 1u;
+              }
+            };
+            auto ring_wait = [&]() {
+              mbar_wait(bar_b_full + 8 * b_stage, b_phase);
+              tc_fence_after();
+              const uint32_t addr = sbase + kSmemB + b_stage * kBoxBytes;
+              return addr;
+            };
+            auto ring_done = [&]() {
+              umma_commit_2sm(bar_b_empty + 8 * b_stage);
+              if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
+            };
+            for (int kc = 0; kc < kchunks; ++kc) {
+              const uint32_t a3 = ring_wait();
+              const uint32_t a3_stage = b_stage;
+              uint32_t nxt = b_stage + 1 == kStages ? 0 : b_stage + 1;
+              mbar_wait(bar_b_full + 8 * nxt, nxt == 0 ? b_phase ^ 1 : b_phase);
+              tc_fence_after();
+              const uint32_t b1 = sbase + kSmemB + nxt * kBoxBytes;
+              mma4(sbase + kSmemA + kc * kBoxBytes, b1);
+              mma4(sbase + kSmemA + (kMaxKChunks + kc) * kBoxBytes, b1);
+              mma4(a3, b1);
+              (void)a3_stage;
+              ring_done();                                         // a3[kc]
+              ring_done();                                         // b1[kc]
+            }
+            for (int kc = 0; kc < kchunks; ++kc) {
+              const uint32_t b2 = ring_wait();
+              mma4(sbase + kSmemA + kc * kBoxBytes, b2);
+              mma4(sbase + kSmemA + (kMaxKChunks + kc) * kBoxBytes, b2);
+              ring_done();
+            }
+            for (int kc = 0; kc < kchunks; ++kc) {
+              const uint32_t b3 = ring_wait();
+              mma4(sbase + kSmemA + kc * kBoxBytes, b3);
+              ring_done();
+            }
+          } else
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(bar_b_full + 8 * b_stage, b_phase);
             if (tr && kc == 0) rec[2] = clock64();
@@ -501,7 +574,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         if (!(P.debug & 4)) umma_commit_2sm(bar_a_empty);   // stationary blocks may be overwritten
       }
     }
-  } else if (MODE == 3) {
+  } else if (MODE == 3 || MODE == 4) {
     // =============================== single-sweep epilogue (16 warps: 4 lane quadrants x 4 groups of 64 columns) =====
     const int g = lane >> 2, p = lane & 3;
     const int cg = (warp - 2) >> 2, quad = warp & 3;
@@ -818,6 +891,28 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   }
 }
 
+// fp32 -> three bf16 planes with a = a1 + a2 + a3 (each residual is exact in fp32): 8 + 8 + 8 mantissa bits
+__global__ void __launch_bounds__(256) split3_kernel(const float4* __restrict__ in, uint2* __restrict__ p1, uint2* __restrict__ p2,
+                                                    uint2* __restrict__ p3, size_t n4) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
+    const float4 a = __ldcs(in + i);
+    const float v[4] = {a.x, a.y, a.z, a.w};
+    uint32_t h1[4], h2[4], h3[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat16 b1 = __float2bfloat16_rn(v[e]);
+      const float r1 = v[e] - __bfloat162float(b1);
+      const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(b2);
+      const __nv_bfloat16 b3 = __float2bfloat16_rn(r2);
+      h1[e] = __bfloat16_as_ushort(b1); h2[e] = __bfloat16_as_ushort(b2); h3[e] = __bfloat16_as_ushort(b3);
+    }
+    p1[i] = make_uint2(h1[0] | (h1[1] << 16), h1[2] | (h1[3] << 16));
+    p2[i] = make_uint2(h2[0] | (h2[1] << 16), h2[2] | (h2[3] << 16));
+    p3[i] = make_uint2(h3[0] | (h3[1] << 16), h3[2] | (h3[3] << 16));
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -865,6 +960,51 @@ bool coarse_tc_supported(const CoarseProblem& p) {
   return p.dtype == POPE_BF16 && p.C % kBoxK == 0 && p.C >= kBoxK && p.C <= kBoxK * kMaxKChunks;
 }
 
+// fp32 features on the tensor cores through the three-way bf16 split (single-sweep path only: thr > 1/8)
+bool coarse_tc_split_supported(const CoarseProblem& p) {
+  return p.dtype == POPE_F32 && p.C % kBoxK == 0 && p.C >= kBoxK && p.C <= kBoxK * kMaxKChunks && two_sweeps_possible(p) &&
+         !(debug_knob() & (8 | 16));
+}
+
+size_t coarse_tc_split_bytes(int n, int L, int S, int C) { return 3 * 2 * (size_t(n) * L * C + size_t(n) * S * C) + 6 * 256; }
+
+// planes: 3 x [n, L, C] then 3 x [n, S, C] bf16 in `planes` (coarse_tc_split_bytes).  Single sweep; if the sums leave the safe
+// range the flag is raised and the caller's gated fp32-FMA launches redo the batch.
+cudaError_t coarse_tc_split_run(const CoarseProblem& p, const CoarseScratch& w, void* planes, int32_t* flags, cudaStream_t st) {
+  const size_t e0 = size_t(p.n) * p.L * p.C, e1 = size_t(p.n) * p.S * p.C;
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  char* base = static_cast<char*>(planes);
+  __nv_bfloat16* pl[6];
+  size_t off = 0;
+  for (int k = 0; k < 6; ++k) { pl[k] = reinterpret_cast<__nv_bfloat16*>(base + off); off += up((k < 3 ? e0 : e1) * 2); }
+  cudaError_t e;
+  split3_kernel<<<148 * 8, 256, 0, st>>>(static_cast<const float4*>(p.f0), reinterpret_cast<uint2*>(pl[0]),
+                                         reinterpret_cast<uint2*>(pl[1]), reinterpret_cast<uint2*>(pl[2]), e0 / 4);
+  split3_kernel<<<148 * 8, 256, 0, st>>>(static_cast<const float4*>(p.f1), reinterpret_cast<uint2*>(pl[3]),
+                                         reinterpret_cast<uint2*>(pl[4]), reinterpret_cast<uint2*>(pl[5]), e1 / 4);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  CUtensorMap m[6];
+  for (int k = 0; k < 6; ++k)
+    if (!make_map(&m[k], pl[k], p.n, k < 3 ? p.L : p.S, p.C)) return cudaErrorInvalidValue;
+  int dev = 0, sms = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  auto k4 = sweep_tc_kernel<4, false>;
+  if ((e = cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
+  SweepParams P{};
+  P.debug = debug_knob();
+  P.n = p.n; P.L0 = p.L; P.L1 = p.S; P.kchunks = p.C / kBoxK;
+  P.scale_log2 = p.scale_log2; P.log2_thr = p.log2_thr;
+  P.lse_out0 = w.lse_r; P.lse_out1 = w.lse_c; P.lse_r = w.lse_r; P.lse_c = w.lse_c; P.rowbest = w.rowbest; P.colbest = w.colbest;
+  P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags; P.colpart = w.colpart;
+  const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows);
+  P.units_dir0 = u0; P.total_units = u0;
+  k4<<<2 * min(u0, sms / 2), kThreads, kSmemAlloc, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = colsum_reduce_run(p, w, flags, st)) != cudaSuccess) return e;
+  return cand_eval_lists_run(p, w, flags, 2, st);       // mode 2: 2^x lists; a no-op once the fallback flag is up
+}
+
 cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
   CUtensorMap map0, map1;
   if (!make_map(&map0, p.f0, p.n, p.L, p.C) || !make_map(&map1, p.f1, p.n, p.S, p.C)) return cudaErrorInvalidValue;
@@ -906,7 +1046,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
       // single sweep over the rows of S: row sums, column partial sums and candidate lists in one pass; raises
       // POPE_FLAG_ROBUST_PATH when the unshifted exponentials leave the safe range (debug bit4 skips it)
       P.units_dir0 = u0; P.total_units = u0;
-      k3<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+      k3<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, map0, map1, map0, map1, P);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       if ((e = colsum_reduce_run(p, w, flags, st)) != cudaSuccess) return e;
       P.gate = 1;
@@ -915,17 +1055,17 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
     // per-thread candidate lists); after the single sweep it only runs if the flag was raised
     P.units_dir0 = u0; P.total_units = u0 + u1;
     P.trace = trace_mode == 2 ? g_trace : nullptr;
-    k2<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+    k2<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, map0, map1, map0, map1, P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return cand_eval_lists_run(p, w, flags, P.gate, st);
   }
   // three sweeps (small thresholds): both log-sum-exp directions in one launch, then the candidate sweep
   P.units_dir0 = u0; P.total_units = u0 + u1;
   P.trace = trace_mode == 0 ? g_trace : nullptr;
-  k0<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+  k0<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, map0, map1, map0, map1, P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   P.total_units = u0;
-  k1<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, P);
+  k1<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, map0, map1, map0, map1, P);
   return cudaGetLastError();
 }
 

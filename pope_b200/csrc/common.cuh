@@ -95,17 +95,26 @@ struct CoarseProblem {
   float pixel_scale;
 };
 
-// coarse_simt.cu -- fp32-FMA kernels (fp32 or bf16 inputs): the fp32 product path and the cross-check for tcgen05
-cudaError_t coarse_simt_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st);
+// coarse_simt.cu -- fp32-FMA kernels (fp32 or bf16 inputs): the fp32 product path and the cross-check for tcgen05.
+// gated: every launch is a no-op unless POPE_FLAG_ROBUST_PATH is set in *flags (the fallback of the fp32 tensor-core path);
+// the gated sequence starts by clearing the best-candidate records and counters itself.
+cudaError_t coarse_simt_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st, bool gated = false);
 // coarse_tc.cu -- tcgen05/TMEM/TMA kernels (bf16 inputs, C in {64,128,192,256})
 bool coarse_tc_supported(const CoarseProblem& p);
+// fp32 features through the three-way bf16 split (fp32 accuracy on the bf16 tensor cores); planes: extra scratch
+bool coarse_tc_split_supported(const CoarseProblem& p);
+size_t coarse_tc_split_bytes(int n, int L, int S, int C);
+cudaError_t coarse_tc_split_run(const CoarseProblem& p, const CoarseScratch& w, void* planes, int32_t* flags, cudaStream_t st);
 cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st);
 // coarse_finalize.cu -- two-sweep helpers (shared by both kernel families): per-row bounds for the column sweep's
 // candidate test, and the evaluation of the listed candidates
-cudaError_t cand_bounds_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
-cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st);
+cudaError_t cand_bounds_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st, const int32_t* gate = nullptr);
+cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaStream_t st, const int32_t* gate = nullptr);
+// zero `bytes` (multiple of 16) at ptr if POPE_FLAG_ROBUST_PATH is set in *gate
+cudaError_t gated_clear_run(void* ptr, size_t bytes, const int32_t* gate, cudaStream_t st);
 // evaluation of the per-thread (row, column quarter) lists written by the tcgen05 row sweep
-// (mode 1: after the single-sweep launch sequence -- the list format follows POPE_FLAG_ROBUST_PATH in *flags)
+// (mode 1: after the single-sweep launch sequence -- the list format follows POPE_FLAG_ROBUST_PATH in *flags;
+//  mode 2: 2^x lists, and nothing at all if the flag is set: the fp32 fallback evaluates its own lists)
 cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, int mode, cudaStream_t st);
 // single-sweep tcgen05 path: column log-sum-exp from the per-32-row partial sums; evaluation of its lists (which hold
 // 2^x instead of the raw accumulator); both set / honour POPE_FLAG_ROBUST_PATH

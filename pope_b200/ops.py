@@ -52,7 +52,9 @@ def coarse_match(feat_c0: torch.Tensor, feat_c1: torch.Tensor, hw0_c: Sequence[i
     if feat_c1.shape[0] != n or feat_c1.shape[2] != Cc:
         raise _lib.PopeError(f"shape mismatch {tuple(feat_c0.shape)} vs {tuple(feat_c1.shape)}")
     h = lib()
-    need = h.pope_coarse_workspace_bytes(n, L, S)
+    # fp32 features: the larger workspace enables the tensor-core path (three-way bf16 split) unless SIMT is requested
+    need = (h.pope_coarse_workspace_bytes(n, L, S) if impl == _lib.COARSE_SIMT
+            else h.pope_coarse_workspace_bytes_ex(n, L, S, feat_c0.shape[2], dtype_code(feat_c0)))
     if workspace is None or workspace.numel() < need or workspace.device != dev:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
     cap = n * min(L, S)

@@ -22,7 +22,9 @@ def _load(golden_dir, name):
 
 
 def _tc_ok(C, dtype, L=4800, S=4800):
-    return dtype == torch.bfloat16 and _lib.tcgen05_available(L, S, C)
+    """bf16 features run the tcgen05 kernels directly; fp32 features run them through the three-way bf16 split
+    (same shapes; ops.coarse_match allocates the larger workspace that path needs)."""
+    return dtype in (torch.bfloat16, torch.float32) and _lib.tcgen05_available(L, S, C)
 
 
 def _need_tc(impl, C=256, L=4800, S=4800):
@@ -52,7 +54,7 @@ def test_coarse_golden(golden_dir, name, impl):
     for dtype in dtypes:
         if impl == "tcgen05" and not _tc_ok(case["C"], dtype, case["hw0_c"][0] * case["hw0_c"][1],
                                             case["hw1_c"][0] * case["hw1_c"][1]):
-            pytest.skip("tcgen05 path takes bf16 features with C in {64,128,192,256}")
+            pytest.skip("tcgen05 path takes features with C in {64,128,192,256}")
         out = _run_coarse(f0, f1, case["hw0_c"], case["hw1_c"], IMPLS[impl], dtype)
         want = {k: torch.from_numpy(g[k]) for k in ("b_ids", "i_ids", "j_ids", "mconf", "mkpts0_c", "mkpts1_c")}
         same, near, bad = compare_match_lists(out, want, g)
@@ -80,8 +82,6 @@ def test_coarse_golden(golden_dir, name, impl):
 def test_coarse_full_size_vs_oracle(impl, dtype):
     """BASELINE configs[1] shape (480x640 -> 60x80 tokens, d=256), 3 pairs, against the oracle on the same
     (bf16-rounded) values."""
-    if impl == "tcgen05" and dtype != torch.bfloat16:
-        pytest.skip("tcgen05 path is bf16-only")
     _need_tc(impl)
     f0, f1 = synth.coarse_features(41, 3, 4800, 4800, 256, dtype=dtype)
     want, mg = oracle_with_margins(f0.float(), f1.float(), (480, 640), (60, 80), (60, 80))
@@ -109,6 +109,27 @@ def test_coarse_hard_set_bf16(impl):
     if impl == "tcgen05":
         # |S| log2(e) reaches the hundreds: the unshifted single sweep must have detected it and handed over
         assert out["_flags"] & _lib.FLAG_ROBUST_PATH
+
+
+def test_coarse_fp32_on_tensor_cores_vs_fp32_fma():
+    """fp32 features through the tcgen05 split path (a = a1 + a2 + a3 in bf16, six products, fp32 accumulation) against
+    the fp32-FMA kernels on the same inputs: identical match lists, confidences to a few fp32 ulps of the logits; on
+    out-of-range data (rows x50) the split path must hand over to the fp32-FMA kernels (flag) and then be bit-identical."""
+    L, S = 50 * 70, 44 * 60
+    _need_tc("tcgen05", 256, L, S)
+    f0, f1 = synth.coarse_features(48, 3, L, S, 256)
+    tc = _run_coarse(f0, f1, (50, 70), (44, 60), IMPLS["tcgen05"], torch.float32)
+    fma = _run_coarse(f0, f1, (50, 70), (44, 60), IMPLS["simt"], torch.float32)
+    assert tc["_flags"] == 0 and tc["b_ids"].numel() > 3000
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(tc[k], fma[k]), k
+    assert torch.allclose(tc["mconf"], fma["mconf"], rtol=3e-5, atol=0)
+    h0, h1 = synth.hard_coarse_features(49, 2, 40 * 48, 36 * 56, 256, sigma=0.9)
+    tc = _run_coarse(h0, h1, (40, 48), (36, 56), IMPLS["tcgen05"], torch.float32)
+    fma = _run_coarse(h0, h1, (40, 48), (36, 56), IMPLS["simt"], torch.float32)
+    assert tc["_flags"] & _lib.FLAG_ROBUST_PATH
+    for k in ("b_ids", "i_ids", "j_ids", "mconf"):
+        assert torch.equal(tc[k], fma[k]), k
 
 
 def test_coarse_single_sweep_vs_robust_path():
