@@ -357,7 +357,7 @@ def main():
     flops = n * 2.0 * L * L * C_COARSE
     ach = flops / (coarse_ms / 1e3) / 1e12
     fine_bytes = M * ((1 + 25) * C_FINE * esize + 3 * 8 + 8 + 12 + 8)     # 26 feature rows + ids + coords in/out
-    tc = impl == _lib.COARSE_TCGEN05 or (impl == _lib.COARSE_AUTO and dtype == torch.bfloat16 and _lib.tcgen05_available())
+    tc = impl == _lib.COARSE_TCGEN05 or (impl == _lib.COARSE_AUTO and _lib.tcgen05_available())   # fp32: split path
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -365,7 +365,7 @@ def main():
         "config": {"workload": "batch of 64 pairs at 480x640, coarse+fine matching (BASELINE configs[1])" if n == 64 else
                    f"batch of {n} pairs at 480x640, coarse+fine matching",
                    "pairs_per_gpu_per_step": n, "coarse_tokens": [HC, WC], "d_coarse": C_COARSE, "d_fine": C_FINE,
-                   "window": WIN, "coarse_impl": "tcgen05" if tc else "simt-fp32fma", "fine_map_layout": "channels_last",
+                   "window": WIN, "coarse_impl": ("tcgen05" if dtype == torch.bfloat16 else "tcgen05 on a three-way bf16 split of the fp32 features") if tc else "simt-fp32fma", "fine_map_layout": "channels_last",
                    "l2_policy": "inputs_exceed_l2 (2.8 GB of features per step vs 126 MB L2)",
                    "matches_per_step": M, "flags": flags, "gather": "one NCCL all-gather of the job's live match records after the K steps (inside the timed region)" if world > 1 else "none"},
         "clocks": clocks,

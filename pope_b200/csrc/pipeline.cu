@@ -104,7 +104,9 @@ extern "C" int pope_pipeline_create(pope_pipeline_t** out, int device, int dtype
   pl->L = h0c * w0c; pl->S = h1c * w1c; pl->cap = pl->L < pl->S ? pl->L : pl->S;
   pl->esize = dtype == POPE_BF16 ? 2 : 4; pl->impl = impl; pl->border = border_rm;
   pl->pixel_scale = pixel_scale; pl->fine_scale = fine_scale; pl->temperature = temperature; pl->thr = thr;
-  pl->ws_bytes = pope_coarse_workspace_bytes(chunk_pairs, pl->L, pl->S);
+  // (for fp32 features the larger size lets the coarse stage run on the tensor cores, see pope_b200.h)
+  pl->ws_bytes = impl == POPE_COARSE_SIMT ? pope_coarse_workspace_bytes(chunk_pairs, pl->L, pl->S)
+                                          : pope_coarse_workspace_bytes_ex(chunk_pairs, pl->L, pl->S, C, dtype);
   {
     const size_t n = chunk_pairs, e = pl->esize, capt = n * pl->cap;
     const size_t f0px = size_t(h0c) * fine_stride * w0c * fine_stride, f1px = size_t(h1c) * fine_stride * w1c * fine_stride;
