@@ -204,10 +204,12 @@ int pope_match_scores(const float* mconf, const int32_t* counts, int n_pairs, in
 
 /* Packs the live matches of one batch into 32-byte records (int32[8]: global pair index = b + pair_offset, i, j, mconf,
  * x0, y0, x1, y1; floats as bit patterns): the unit of the single cross-GPU gather of match lists.
- * m_dev: device pointer to the live match count (counts + n_pairs of pope_coarse_match); records: int32[capacity * 8]. */
+ * m_dev: device pointer to the live match count (counts + n_pairs of pope_coarse_match); records: int32[capacity * 8].
+ * base_dev (may be NULL): device int64 holding the number of records already in `records`; the batch is appended behind
+ * them (the caller advances the counter), so a job's records stay contiguous without a compaction pass. */
 int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids, const float* mconf,
                       const float* mkpts0_f, const float* mkpts1_f, const int32_t* m_dev, int64_t capacity,
-                      int pair_offset, int32_t* records, void* stream);
+                      int pair_offset, int32_t* records, const int64_t* base_dev, void* stream);
 
 /* ---- on-disk match format (host code) ------------------------------------------------------------
  * numpy.savetxt(path, a) as the reference uses it (linemod.py:168-171: '%.18e', one space between columns, '\n' after

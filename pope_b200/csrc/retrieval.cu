@@ -157,8 +157,10 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const int64_t* __rest
                                                           const int64_t* __restrict__ j_ids, const float* __restrict__ mconf,
                                                           const float2* __restrict__ mk0, const float2* __restrict__ mk1,
                                                           const int32_t* __restrict__ m_dev, int64_t capacity,
-                                                          int pair_offset, int4* __restrict__ rec) {
+                                                          int pair_offset, int4* __restrict__ rec,
+                                                          const int64_t* __restrict__ base_dev) {
   const int64_t m = min(int64_t(*m_dev), capacity);
+  if (base_dev) rec += 2 * *base_dev;                       // append behind the records already in the buffer
   for (int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < m; k += int64_t(gridDim.x) * blockDim.x) {
     const float2 a = mk0[k], b = mk1[k];
     rec[2 * k] = make_int4(int(b_ids[k]) + pair_offset, int(i_ids[k]), int(j_ids[k]), __float_as_int(mconf[k]));
@@ -173,7 +175,7 @@ using namespace pope;
 
 extern "C" int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids, const float* mconf,
                                  const float* mkpts0_f, const float* mkpts1_f, const int32_t* m_dev, int64_t capacity,
-                                 int pair_offset, int32_t* records, void* stream) {
+                                 int pair_offset, int32_t* records, const int64_t* base_dev, void* stream) {
   if (!b_ids || !i_ids || !j_ids || !mconf || !mkpts0_f || !mkpts1_f || !m_dev || !records || capacity < 0)
     return POPE_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(mkpts0_f) | reinterpret_cast<uintptr_t>(mkpts1_f)) & 7u ||
@@ -184,7 +186,7 @@ extern "C" int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, con
   const unsigned blocks = unsigned(want < 148 * 8 ? want : 148 * 8);
   pack_records_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       b_ids, i_ids, j_ids, mconf, reinterpret_cast<const float2*>(mkpts0_f), reinterpret_cast<const float2*>(mkpts1_f), m_dev,
-      capacity, pair_offset, reinterpret_cast<int4*>(records));
+      capacity, pair_offset, reinterpret_cast<int4*>(records), base_dev);
   return int(cudaGetLastError());
 }
 

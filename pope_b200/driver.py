@@ -153,17 +153,24 @@ def gather_matches(local: Dict[str, torch.Tensor], n_pairs: int, rank: int, worl
             "mkpts0_f": fl[:, 1:3], "mkpts1_f": fl[:, 3:5], "per_rank_matches": totals}
 
 
-def pack_records(res, pair_offset: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def pack_records(res, pair_offset: int, out: Optional[torch.Tensor] = None, base: Optional[torch.Tensor] = None
+                 ) -> torch.Tensor:
     """Capacity-sized result -> packed int32 records [cap, 8] = (b_global, i, j, mconf, x0, y0, x1, y1; floats as bit
-    patterns); rows past the live count are not written.  One kernel (`pope_pack_records`), no host sync."""
+    patterns); rows past the live count are not written.  One kernel (`pope_pack_records`), no host sync.
+    `base` (device int64[1]): the batch is appended to `out` behind the `base` records already there."""
     cap = res["i_ids"].shape[0]
     dev = res["i_ids"].device
     if dev.type != "cuda":
         # host-side bookkeeping of already-computed results (the world_size-2 gloo tests of the sharding logic); the
         # records themselves are produced on the GPU in every real run
-        return torch.cat([(res["b_ids"] + pair_offset).to(torch.int32)[:, None], res["i_ids"].to(torch.int32)[:, None],
-                          res["j_ids"].to(torch.int32)[:, None], res["mconf"].view(torch.int32)[:, None],
-                          res["mkpts0_f"].view(torch.int32), res["mkpts1_f"].view(torch.int32)], 1, out=out)
+        rec = torch.cat([(res["b_ids"] + pair_offset).to(torch.int32)[:, None], res["i_ids"].to(torch.int32)[:, None],
+                         res["j_ids"].to(torch.int32)[:, None], res["mconf"].view(torch.int32)[:, None],
+                         res["mkpts0_f"].view(torch.int32), res["mkpts1_f"].view(torch.int32)], 1)
+        if out is None:
+            return rec
+        m, b = int(res["counts"][res["n_pairs"]]), (int(base) if base is not None else 0)
+        out[b:b + m] = rec[:m]
+        return out
     if out is None:
         out = torch.empty(cap, 8, dtype=torch.int32, device=dev)
     n = res["n_pairs"]
@@ -171,46 +178,52 @@ def pack_records(res, pair_offset: int, out: Optional[torch.Tensor] = None) -> t
         st = _lib.lib().pope_pack_records(res["b_ids"].data_ptr(), res["i_ids"].data_ptr(), res["j_ids"].data_ptr(),
                                           res["mconf"].data_ptr(), res["mkpts0_f"].contiguous().data_ptr(),
                                           res["mkpts1_f"].contiguous().data_ptr(), res["counts"][n:n + 1].data_ptr(), cap,
-                                          int(pair_offset), out.data_ptr(), _lib.stream_ptr(dev))
+                                          int(pair_offset), out.data_ptr(), None if base is None else base.data_ptr(),
+                                          _lib.stream_ptr(dev))
     _lib.check(st, "pope_pack_records")
     return out
 
 
 class JobGather:
-    """The single cross-GPU step of a sharded job: every rank appends the packed records of
-    each of its steps to a device buffer (no sync, no collective); `finish()` runs once at the end of the job -- one
-    host read of the per-step totals, one all-gather of the totals and one all-gather of the live records."""
+    """The single cross-GPU step of a sharded job: every rank appends the packed records of each
+    of its steps behind the previous ones in one device buffer (no sync, no collective, no compaction: the running count
+    stays on the device); `finish()` runs once at the end of the job -- one host read of the rank's total, one all-gather
+    of the totals and ONE collective on the records: a gather to rank 0 (default) or an all-gather (`to_all=True`)."""
 
     def __init__(self, steps: int, cap: int, device):
-        self.rec = torch.empty(steps, cap, 8, dtype=torch.int32, device=device)
-        self.tot = torch.zeros(steps, dtype=torch.int32, device=device)
-        self.k = 0
+        self.rec = torch.empty(steps * cap, 8, dtype=torch.int32, device=device)
+        self.total = torch.zeros(1, dtype=torch.int64, device=device)
 
     def add(self, res, pair_offset: int):
-        pack_records(res, pair_offset, out=self.rec[self.k])
         n = res["n_pairs"]
-        self.tot[self.k:self.k + 1].copy_(res["counts"][n:n + 1])
-        self.k += 1
+        pack_records(res, pair_offset, out=self.rec, base=self.total)
+        self.total += res["counts"][n:n + 1]
 
-    def finish(self, rank: int, world: int, group=None):
+    def finish(self, rank: int, world: int, group=None, to_all: bool = False):
+        """Returns (records [world, max_total, 8], totals): rank r's records are records[r, :totals[r]], sorted by (b, i)
+        within each step.  With the default gather only rank 0 receives the records (the others get None)."""
         import torch.distributed as dist
-        tot = self.tot[: self.k].tolist()                       # the job's one host read
-        live = torch.cat([self.rec[k, :m] for k, m in enumerate(tot)], 0) if sum(tot) else self.rec[0, :0]
-        mine = torch.tensor([live.shape[0]], dtype=torch.int64, device=live.device)
+        mine = int(self.total.item())                           # the job's one host read
         if world == 1:
-            self.k = 0
-            return live, [int(mine)]
-        sizes = torch.empty(world, dtype=torch.int64, device=live.device)
-        dist.all_gather_into_tensor(sizes, mine, group=group)
+            self.total.zero_()
+            return self.rec[:mine].unsqueeze(0), [mine]
+        sizes = torch.empty(world, dtype=torch.int64, device=self.rec.device)
+        dist.all_gather_into_tensor(sizes, self.total, group=group)
         sizes = sizes.tolist()
         mx = max(max(sizes), 1)
-        padded = torch.zeros(mx, 8, dtype=torch.int32, device=live.device)
-        padded[: live.shape[0]] = live
-        out = torch.empty(world * mx, 8, dtype=torch.int32, device=live.device)     # concatenation along dim 0
-        dist.all_gather_into_tensor(out, padded, group=group)
-        out = out.view(world, mx, 8)
-        self.k = 0
-        return out, sizes                                       # rank r's records: out[r, :sizes[r]], sorted by (b, i)
+        send = self.rec[:mx]                                    # rows past the rank's own total are never read
+        out = None
+        if to_all:
+            out = torch.empty(world * mx, 8, dtype=torch.int32, device=self.rec.device)
+            dist.all_gather_into_tensor(out, send, group=group)
+            out = out.view(world, mx, 8)
+        else:
+            parts = [torch.empty(mx, 8, dtype=torch.int32, device=self.rec.device) for _ in range(world)] if rank == 0 else None
+            dist.gather(send, parts, dst=0, group=group)
+            if rank == 0:
+                out = torch.stack(parts)
+        self.total.zero_()
+        return out, sizes
 
 
 def bind_host_to_gpu(device_index: int):
