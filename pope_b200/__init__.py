@@ -11,7 +11,8 @@ from .matcher import Matcher                               # noqa: F401
 from .coarse_matching import CoarseMatching                # noqa: F401
 from .fine_preprocess import FinePreprocess                # noqa: F401
 from .fine_matching import FineMatching                    # noqa: F401
-from .retrieval import retrieve_topk                       # noqa: F401
+from .retrieval import retrieve_topk, retrieve_topk_images  # noqa: F401
+from .dino_vit import DinoViT                              # noqa: F401
 
 __all__ = ["Matcher", "default_cfg", "make_default_cfg", "CoarseMatching", "FinePreprocess", "FineMatching",
-           "retrieve_topk"]
+           "retrieve_topk", "retrieve_topk_images", "DinoViT"]
