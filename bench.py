@@ -9,7 +9,10 @@ Workload (BASELINE.json configs[1]): a batch of 64 synthetic 480x640 pairs per G
 (pope_b200/synth.py).  A "step" is one pass of the hot path over that batch.
 
   value : pairs/s with the inputs already resident in HBM (CUDA events, max over ranks).  The batch's inputs
-          (2.8 GB) are far larger than the 126 MB L2, so every step streams them from HBM.
+          (2.8 GB) are far larger than the 126 MB L2, so every step streams them from HBM.  Consecutive steps alternate
+          between two CUDA streams (own scratch each), so the small latency-bound kernels that end a step (column-sum
+          reduction, list evaluation, compaction) overlap the next step's sweep; stage_ms / roofline come from a separate
+          pass on one stream, where events bracket the kernels and not the queue.
   e2e   : the same metric through the C-ABI host entry (pope_pipeline_run): pinned host buffers in, pinned host
           buffers out, host<->device copies inside the timed region.
   roofline : the coarse stage (dominant) against the measured bf16 tensor peak; algorithmic work 2*L*S*C per pair.
@@ -53,6 +56,9 @@ def parse():
     ap.add_argument("--in-matcher", type=int, default=0, metavar="PAIRS",
                     help="also time steps 3-5 of Matcher.forward on PAIRS pairs with the PyTorch FinePreprocess Linears and "
                          "fine transformer between the CUDA stages (fp32, SURVEY 8(d) 'in-Matcher' figure)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="device-resident steps alternate between this many CUDA streams (each with its own scratch), so "
+                         "that the small latency-bound kernels at the end of a step overlap the next step's sweep")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -244,9 +250,42 @@ def main():
     ff0 = torch.randn(n, hf, wf, C_FINE, device=dev, generator=g).to(dtype).permute(0, 3, 1, 2)   # channels-last
     ff1 = torch.randn(n, hf, wf, C_FINE, device=dev, generator=g).to(dtype).permute(0, 3, 1, 2)
     d_f0, d_f1 = f0.to(dev), f1.to(dev)
-    ws = torch.empty(_lib.lib().pope_coarse_workspace_bytes(n, L, L), dtype=torch.uint8, device=dev)
+    # N > 1: every step appends its packed match records to a device buffer; the job's ONE cross-GPU step (a single
+    # gather of the live records) runs at the end of the K timed steps, inside the timed region
+    job = driver.JobGather(max(args.steps, args.warmup, 3), n * L, dev) if world > 1 else None
+    n_streams = max(1, args.streams)
+    wss = [torch.empty(_lib.lib().pope_coarse_workspace_bytes_ex(n, L, L, C_COARSE, _lib.dtype_code(d_f0)), dtype=torch.uint8,
+                       device=dev) for _ in range(n_streams)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else [torch.cuda.current_stream(dev)]
+    step_no = [0]
+
+    last_add = [None]                      # event after the previous step's append to the job's record buffer
 
     def step_device(ev=None):
+        k = step_no[0] % n_streams
+        step_no[0] += 1
+        with torch.cuda.stream(streams[k]):
+            res = _step_on_stream(ev, wss[k])
+            if job is not None:            # appends happen in step order: chain them with events across the streams
+                if last_add[0] is not None:
+                    streams[k].wait_event(last_add[0])
+                job.add(res, rank * n)
+                last_add[0] = torch.cuda.Event()
+                last_add[0].record(streams[k])
+            return res
+
+    def join_streams():
+        """the default stream waits for everything queued on the step streams"""
+        if n_streams > 1:
+            for st in streams:
+                torch.cuda.current_stream(dev).wait_stream(st)
+
+    def fork_streams():
+        if n_streams > 1:
+            for st in streams:
+                st.wait_stream(torch.cuda.current_stream(dev))
+
+    def _step_on_stream(ev, ws):
         if ev: ev[0].record()
         res = ops.coarse_match(d_f0, d_f1, (HC, WC), (HC, WC), 8.0, impl=impl, workspace=ws)
         if ev: ev[1].record()
@@ -258,15 +297,12 @@ def main():
         res.update(mkpts1_f=mk1f, mkpts0_f=res["mkpts0_c"], expec_f=expec)
         return res
 
-    # N > 1: every step appends its packed match records to a device buffer; the job's ONE cross-GPU step (a single
-    # all-gather of the live records) runs at the end of the K timed steps, inside the timed region
-    job = driver.JobGather(max(args.steps, args.warmup, 3), n * L, dev) if world > 1 else None
 
     def gather_step(res):
-        if job is not None:
-            job.add(res, rank * n)
+        pass                               # (the append to the job's record buffer is part of step_device)
 
     def finish_job():
+        join_streams()
         if job is not None:
             job.finish(rank, world)
 
@@ -282,13 +318,13 @@ def main():
         gather_step(step_device())
     finish_job()
     barrier()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()
     t_beg.record()
+    fork_streams()
     for k in range(args.steps):
-        res = step_device(evs[k])
+        res = step_device()
         gather_step(res)
     finish_job()
     t_end.record()
@@ -301,8 +337,21 @@ def main():
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = world * n * args.steps / (total_ms / 1e3)
-    coarse_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    fine_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    # per-stage durations for the rooflines: a few extra steps on ONE stream (with several streams the stages of
+    # consecutive steps overlap, so events around them would time the queue, not the kernels); not part of `value`
+    n_streams_saved, n_streams = n_streams, 1
+    job_saved, job = job, None
+    k_stage = max(4, min(args.steps, 6))
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(k_stage)]
+    for k in range(k_stage):
+        res = step_device(evs[k])
+    torch.cuda.synchronize(dev)
+    n_streams, job = n_streams_saved, job_saved
+    if os.environ.get("POPE_BENCH_DEBUG"):
+        print("stage pass:", [(round(e[0].elapsed_time(e[1]), 3), round(e[1].elapsed_time(e[2]), 3)) for e in evs], file=sys.stderr)
+    # the first step of the pass starts on an idle stream: its first event also times the host's launch latency
+    coarse_ms = statistics.median(e[0].elapsed_time(e[1]) for e in evs[1:])
+    fine_ms = statistics.median(e[1].elapsed_time(e[2]) for e in evs[1:])
     M = res.total()
     flags = res.flags()
 
@@ -367,6 +416,7 @@ def main():
                    "pairs_per_gpu_per_step": n, "coarse_tokens": [HC, WC], "d_coarse": C_COARSE, "d_fine": C_FINE,
                    "window": WIN, "coarse_impl": ("tcgen05" if dtype == torch.bfloat16 else "tcgen05 on a three-way bf16 split of the fp32 features") if tc else "simt-fp32fma", "fine_map_layout": "channels_last",
                    "l2_policy": "inputs_exceed_l2 (2.8 GB of features per step vs 126 MB L2)",
+                   "streams": n_streams,
                    "matches_per_step": M, "flags": flags, "gather": "one NCCL all-gather of the job's live match records after the K steps (inside the timed region)" if world > 1 else "none"},
         "clocks": clocks,
         "stage_ms": {"coarse": coarse_ms, "fine_gather_match_fused": fine_ms},
