@@ -7,7 +7,9 @@ from pope_b200 import _lib, driver, ops, synth
 dev = torch.device("cuda:0")
 for (n, hw0, hw1, C, dtype, impl, thr) in [(2, (12, 16), (10, 9), 256, torch.bfloat16, _lib.COARSE_TCGEN05, 0.2),
                                            (1, (20, 24), (18, 28), 128, torch.bfloat16, _lib.COARSE_TCGEN05, 0.1),
-                                           (2, (12, 16), (10, 9), 64, torch.float32, _lib.COARSE_SIMT, 0.2)]:
+                                           (2, (12, 16), (10, 9), 64, torch.float32, _lib.COARSE_SIMT, 0.2),
+                                           (2, (13, 17), (10, 9), 192, torch.float32, _lib.COARSE_TCGEN05, 0.2),   # split path
+                                           (1, (37, 41), (33, 29), 256, torch.bfloat16, _lib.COARSE_TCGEN05, 0.3)]:
     L, S = hw0[0] * hw0[1], hw1[0] * hw1[1]
     f0, f1 = synth.coarse_features(5, n, L, S, C, sigma=0.8, dtype=dtype)
     ff0, _ = synth.fine_feature_maps(6, n, hw0[0] * 4, hw0[1] * 4, 128, dtype=dtype)
@@ -20,6 +22,22 @@ for (n, hw0, hw1, C, dtype, impl, thr) in [(2, (12, 16), (10, 9), 256, torch.bfl
     w0, w1 = ops.fine_gather(ff0.contiguous().to(dev), ff1.contiguous().to(dev), res["b_ids"][:m], res["i_ids"][:m],
                              res["j_ids"][:m], hw0[1], hw1[1], 4, 5)     # NCHW path
     order = ops.match_order_by_ref(res["counts"], n, S, res["j_ids"])
+# fine-level transformer + FinePreprocess Linears on a ragged window count, match-list consumer, record packing
+import pope_b200
+torch.manual_seed(1)
+mm = pope_b200.Matcher(pope_b200.make_default_cfg()).eval()
+packed = torch.cat([ops.pack_fine_layer(l.state_dict(), dev) for l in mm.loftr_fine.layers])
+for mw in (1, 37, 333):
+    a = torch.randn(mw, 25, 128, device=dev).to(torch.bfloat16)
+    b = torch.randn(mw, 25, 128, device=dev).to(torch.bfloat16)
+    ops.fine_transformer(a, b, packed, mm.loftr_fine.layer_names)
+    fc0 = torch.randn(2, 50, 256, device=dev).to(torch.bfloat16)
+    fc1 = torch.randn(2, 40, 256, device=dev).to(torch.bfloat16)
+    ids = [torch.randint(0, hi, (mw,), device=dev) for hi in (2, 50, 40)]
+    ops.fine_merge_coarse(a, b, fc0, fc1, *ids, ops.pack_fine_pre(mm.fine_preprocess.state_dict(), dev))
+    print("fine_tf windows", mw, "finite", bool(torch.isfinite(a.float()).all() and torch.isfinite(b.float()).all()))
+print("match_scores", [t.tolist() for t in ops.match_scores(res["mconf"], res["counts"], n, group=2)])
+print("pack_records", tuple(driver.pack_records(dict(res, mkpts0_f=res["mkpts0_c"], mkpts1_f=res["mkpts1_c"]), 3).shape))
 q, refs = synth.retrieval_tokens(3, 100, 384)
 print("topk", ops.cosine_topk(q.to(dev), refs.to(dev), 3)[2].tolist())
 f0, f1 = synth.coarse_features(8, 3, 192, 192, 256, sigma=0.8, dtype=torch.bfloat16)
