@@ -50,41 +50,50 @@ __device__ __forceinline__ int block_sum(int v, int* smem) {
 // One CTA per pair: count the pair's matches, publish the count, wait for the counts of all earlier pairs (CTAs are
 // dispatched in blockIdx order, so an earlier pair's CTA is always running or done), then emit in (pair, i) order.
 // ready[n] must be 0 on entry for every pair; the kernel leaves it set (the caller clears it with the flag words).
+// phase 0: count, look back, emit in one launch (all CTAs co-resident: n_pairs <= 2 x SMs).  Larger batches do not rely
+// on the dispatch order: phase 1 = count only, phase 2 = emit only, as two launches.
 __global__ void __launch_bounds__(FT) count_emit_kernel(const u64* __restrict__ rowbest, const u64* __restrict__ colbest,
                                                        const float* __restrict__ lse_r, const float* __restrict__ lse_c,
                                                        int L, int S, Grid2 g0, Grid2 g1, float pixel_scale,
                                                        int32_t* __restrict__ counts, int n_pairs, int* __restrict__ ready,
                                                        int64_t* __restrict__ b_ids, int64_t* __restrict__ i_ids,
                                                        int64_t* __restrict__ j_ids, float* __restrict__ mconf,
-                                                       float* __restrict__ mk0, float* __restrict__ mk1) {
+                                                       float* __restrict__ mk0, float* __restrict__ mk1, int phase) {
   __shared__ int smem[32];
   __shared__ int warp_off[FT / 32];
   const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   rowbest += size_t(n) * L; colbest += size_t(n) * S;
   int c = 0, bad = 0;
-  for (int i = threadIdx.x; i < L; i += FT) {
-    int j; float t2;
-    c += row_match(rowbest, colbest, L, S, i, g0, g1, j, t2) ? 1 : 0;
-    bad |= !isfinite(lse_r[size_t(n) * L + i]);
-  }
-  for (int j = threadIdx.x; j < S; j += FT) bad |= !isfinite(lse_c[size_t(n) * S + j]);
-  c = block_sum(c, smem);
-  bad = block_sum(bad, smem);
-  if (threadIdx.x == 0) {
-    counts[n] = c;
-    if (bad) atomicOr(reinterpret_cast<unsigned*>(counts + n_pairs + 1), POPE_FLAG_NONFINITE_LSE);
-    __threadfence();
-    atomicExch(ready + n, 1);
+  if (phase != 2) {
+    for (int i = threadIdx.x; i < L; i += FT) {
+      int j; float t2;
+      c += row_match(rowbest, colbest, L, S, i, g0, g1, j, t2) ? 1 : 0;
+      bad |= !isfinite(lse_r[size_t(n) * L + i]);
+    }
+    for (int j = threadIdx.x; j < S; j += FT) bad |= !isfinite(lse_c[size_t(n) * S + j]);
+    c = block_sum(c, smem);
+    bad = block_sum(bad, smem);
+    if (threadIdx.x == 0) {
+      counts[n] = c;
+      if (bad) atomicOr(reinterpret_cast<unsigned*>(counts + n_pairs + 1), POPE_FLAG_NONFINITE_LSE);
+      __threadfence();
+      atomicExch(ready + n, 1);
+    }
+    if (phase == 1) return;
+  } else {
+    c = counts[n];
   }
   // exclusive prefix of the per-pair counts = where this pair's matches start
   int part = 0;
   for (int p = threadIdx.x; p < n; p += FT) {
-    const long long t0 = clock64();
-    while (atomicAdd(ready + p, 0) == 0) {
-      __nanosleep(64);
-      if (clock64() - t0 > 4000000000ll) __trap();   // never hang the GPU on a scheduling assumption
+    if (phase == 0) {
+      const long long t0 = clock64();
+      while (atomicAdd(ready + p, 0) == 0) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000ll) __trap();   // never hang the GPU
+      }
+      __threadfence();
     }
-    __threadfence();
     part += *reinterpret_cast<volatile int32_t*>(counts + p);
   }
   int base = block_sum(part, smem);
@@ -310,8 +319,14 @@ cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, 
                                 int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts,
                                 cudaStream_t st) {
   Grid2 g0{p.h0c, p.w0c, p.border}, g1{p.h1c, p.w1c, p.border};
-  count_emit_kernel<<<p.n, FT, 0, st>>>(w.rowbest, w.colbest, w.lse_r, w.lse_c, p.L, p.S, g0, g1, p.pixel_scale, counts, p.n,
-                                        w.ready, b_ids, i_ids, j_ids, mconf, mk0, mk1);
+  int dev = 0, sms = 0;
+  cudaError_t e;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  const bool one_launch = p.n <= 2 * sms;            // two 1024-thread CTAs per SM: every CTA of the grid is resident
+  for (int phase = one_launch ? 0 : 1; phase <= (one_launch ? 0 : 2); ++phase)
+    count_emit_kernel<<<p.n, FT, 0, st>>>(w.rowbest, w.colbest, w.lse_r, w.lse_c, p.L, p.S, g0, g1, p.pixel_scale, counts, p.n,
+                                          w.ready, b_ids, i_ids, j_ids, mconf, mk0, mk1, phase);
   return cudaGetLastError();
 }
 

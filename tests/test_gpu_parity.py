@@ -480,3 +480,17 @@ def test_pack_records_kernel_equals_torch_packing():
                       res["j_ids"].to(torch.int32)[:, None], res["mconf"].view(torch.int32)[:, None],
                       res["mkpts0_f"].view(torch.int32), res["mkpts1_f"].view(torch.int32)], 1)
     assert m > 100 and rec.shape == want.shape and torch.equal(rec[:m], want[:m])
+
+
+def test_coarse_many_pairs_two_launch_compaction():
+    """More pairs than co-resident compaction CTAs (n > 2 x SMs): count and emit run as two launches; same lists as the
+    pairs processed in small batches."""
+    n, h, w = 320, 8, 10
+    f0, f1 = synth.coarse_features(81, n, h * w, h * w, 64, sigma=0.8, dtype=torch.bfloat16)
+    big = _run_coarse(f0.float(), f1.float(), (h, w), (h, w), IMPLS["tcgen05"], torch.bfloat16)
+    parts = [_run_coarse(f0[a:a + 64].float(), f1[a:a + 64].float(), (h, w), (h, w), IMPLS["tcgen05"], torch.bfloat16)
+             for a in range(0, n, 64)]
+    assert big["b_ids"].numel() > 1000
+    assert torch.equal(big["b_ids"], torch.cat([p["b_ids"] + 64 * k for k, p in enumerate(parts)]))
+    for key in ("i_ids", "j_ids", "mconf"):
+        assert torch.equal(big[key], torch.cat([p[key] for p in parts])), key
