@@ -398,7 +398,11 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   constexpr int kStages = kRing;                    // shadows the file-level ring depth inside the kernel
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t sbase = smem_u32(smem);
+  // (made opaque: otherwise the compiler re-derives the aligned shared-memory base -- S2UR SR_CgaCtaId and ~20 dependent
+  //  instructions -- for every tile in the epilogue instead of spending a register on it)
+  uint32_t sbase_pin = smem_u32(smem);
+  asm volatile("" : "+r"(sbase_pin));
+  const uint32_t sbase = sbase_pin;
   const uint32_t bar0 = sbase + kSmemBar;
   const uint32_t bar_a_full = bar0, bar_a_empty = bar0 + 8;
   const uint32_t bar_b_full = bar0 + 16, bar_b_empty = bar_b_full + 8 * kStages;
