@@ -35,7 +35,9 @@ def both():
     cur = torch.cuda.current_stream()
     sa.wait_stream(cur); sb.wait_stream(cur)
     with torch.cuda.stream(sb): coarse()
-    with torch.cuda.stream(sa): fine()
+    with torch.cuda.stream(sa):
+        torch.cuda._sleep(400000)        # ~0.2 ms: the sweep is resident on every SM when the fine kernel is launched
+        fine()
     cur.wait_stream(sa); cur.wait_stream(sb)
 
 print(f"coarse alone {timed(coarse):.3f} ms, fine alone {timed(fine):.3f} ms, both on two streams {timed(both):.3f} ms")
