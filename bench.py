@@ -428,7 +428,7 @@ def main():
                           "bound": "hbm", "achieved": fine_bytes / (fine_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
                           "frac": fine_bytes / (fine_ms / 1e3) / 1e9 / hbm, "traffic": fine_traffic,
                           "algorithmic_bytes_per_launch": fine_bytes},
-        "gpu_launches": args.steps * _lib.KERNELS_PER_STEP["tcgen05" if tc else "simt"],
+        "gpu_launches": args.steps * _lib.KERNELS_PER_STEP[("tcgen05" if dtype == torch.bfloat16 else "tcgen05_f32") if tc else "simt"],
     }
     if args.in_matcher > 0:
         line["in_matcher"] = in_matcher_figure(args.in_matcher, dev)

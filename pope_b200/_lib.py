@@ -58,7 +58,9 @@ SIGNATURES = {
 # kernels launched by one hot-path step (bench.py `gpu_launches`).  tcgen05 (thr > 0.15): single sweep, column-sum
 # reduction, gated two-sweep launch (a no-op unless the fallback flag is raised), list evaluation, count+emit, fused fine
 # match.  SIMT: row sweep, candidate bounds, column sweep, candidate evaluation, count+emit, fused fine match.
-KERNELS_PER_STEP = {"tcgen05": 6, "simt": 6}
+# fp32 on tcgen05: 2 split launches, sweep, column-sum reduction, list evaluation, 5 gated fp32-FMA fallback launches (no-ops
+# unless the fallback flag is raised), count+emit, fused fine match.
+KERNELS_PER_STEP = {"tcgen05": 6, "tcgen05_f32": 12, "simt": 6}
 
 _lib: Optional[C.CDLL] = None
 
