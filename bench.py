@@ -9,8 +9,8 @@ Workload (BASELINE.json configs[1]): a batch of 64 synthetic 480x640 pairs per G
 (pope_b200/synth.py).  A "step" is one pass of the hot path over that batch.
 
   value : pairs/s with the inputs already resident in HBM (CUDA events, max over ranks).  The batch's inputs
-          (2.8 GB) are far larger than the 126 MB L2, so every step streams them from HBM.  Consecutive steps alternate
-          between two CUDA streams (own scratch each), so the small latency-bound kernels that end a step (column-sum
+          (2.8 GB) are far larger than the 126 MB L2, so every step streams them from HBM.  Consecutive steps go through
+          pope_b200.driver.DeviceBatchRunner: they alternate between two CUDA streams (own scratch each), so the small latency-bound kernels that end a step (column-sum
           reduction, list evaluation, compaction) overlap the next step's sweep; stage_ms / roofline come from a separate
           pass on one stream, where events bracket the kernels and not the queue.
   e2e   : the same metric through the C-ABI host entry (pope_pipeline_run): pinned host buffers in, pinned host
@@ -260,30 +260,29 @@ def main():
     step_no = [0]
 
     last_add = [None]                      # event after the previous step's append to the job's record buffer
+    runner = driver.DeviceBatchRunner(dev, n_streams)      # the public form of "consecutive batches on alternating streams"
+
+    def add_to_job(res):                   # appends happen in step order: chain them with events across the streams
+        st = torch.cuda.current_stream(dev)
+        if last_add[0] is not None:
+            st.wait_event(last_add[0])
+        job.add(res, rank * n)
+        last_add[0] = torch.cuda.Event()
+        last_add[0].record(st)
 
     def step_device(ev=None):
-        k = step_no[0] % n_streams
-        step_no[0] += 1
-        with torch.cuda.stream(streams[k]):
-            res = _step_on_stream(ev, wss[k])
-            if job is not None:            # appends happen in step order: chain them with events across the streams
-                if last_add[0] is not None:
-                    streams[k].wait_event(last_add[0])
-                job.add(res, rank * n)
-                last_add[0] = torch.cuda.Event()
-                last_add[0].record(streams[k])
-            return res
+        if ev is not None:                 # stage-timing pass: one stream, events around the two stages
+            with torch.cuda.stream(streams[0]):
+                return _step_on_stream(ev, wss[0])
+        res, _ = runner.submit(d_f0, d_f1, ff0, ff1, (H, W_IMG), (HC, WC), (HC, WC), impl=impl,
+                               after=add_to_job if job is not None else None)
+        return res
 
     def join_streams():
-        """the default stream waits for everything queued on the step streams"""
-        if n_streams > 1:
-            for st in streams:
-                torch.cuda.current_stream(dev).wait_stream(st)
+        runner.join()
 
     def fork_streams():
-        if n_streams > 1:
-            for st in streams:
-                st.wait_stream(torch.cuda.current_stream(dev))
+        runner.fork()
 
     def _step_on_stream(ev, ws):
         if ev: ev[0].record()
@@ -339,14 +338,11 @@ def main():
     value = world * n * args.steps / (total_ms / 1e3)
     # per-stage durations for the rooflines: a few extra steps on ONE stream (with several streams the stages of
     # consecutive steps overlap, so events around them would time the queue, not the kernels); not part of `value`
-    n_streams_saved, n_streams = n_streams, 1
-    job_saved, job = job, None
     k_stage = max(4, min(args.steps, 6))
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(k_stage)]
     for k in range(k_stage):
         res = step_device(evs[k])
     torch.cuda.synchronize(dev)
-    n_streams, job = n_streams_saved, job_saved
     if os.environ.get("POPE_BENCH_DEBUG"):
         print("stage pass:", [(round(e[0].elapsed_time(e[1]), 3), round(e[1].elapsed_time(e[2]), 3)) for e in evs], file=sys.stderr)
     # the first step of the pass starts on an idle stream: its first event also times the host's launch latency

@@ -113,6 +113,52 @@ def flatten_slots(out: Dict[str, torch.Tensor], pair_offset: int = 0) -> Dict[st
             "mkpts0_f": out["mkpts0_f"][live], "mkpts1_f": out["mkpts1_f"][live], "counts": out["counts"]}
 
 
+# ---- batches of device-resident pairs -------------------------------------------------------------------------------
+
+class DeviceBatchRunner:
+    """Runs the hot path (`ops.match_pairs_device`) on a sequence of device-resident batches, consecutive batches on
+    alternating CUDA streams with their own coarse scratch.  A batch ends with a few latency-bound kernels (column-sum
+    reduction, list evaluation, compaction) that need a fraction of an SM each; on alternating streams they run beside
+    the next batch's sweep (B200, 64 pairs at 480x640: 0.97 -> 0.91 ms per batch).  No host synchronisation anywhere:
+    results are capacity-sized `CoarseResult`s whose match count stays on the device; call `join()` before reading them
+    on another stream."""
+
+    def __init__(self, device, n_streams: int = 2):
+        self.device = torch.device(device)
+        self.streams = ([torch.cuda.Stream(device=self.device) for _ in range(n_streams)] if n_streams > 1
+                        else [torch.cuda.current_stream(self.device)])
+        self.workspaces = [None] * len(self.streams)
+        self._k = 0
+
+    def fork(self) -> None:
+        """the runner's streams wait for everything queued so far on the current stream (inputs being produced there)"""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            if st != cur:
+                st.wait_stream(cur)
+
+    def join(self) -> None:
+        """the current stream waits for every batch submitted so far"""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            if st != cur:
+                cur.wait_stream(st)
+
+    def submit(self, feat_c0, feat_c1, feat_f0, feat_f1, hw0_i, hw0_c, hw1_c, after=None, **kw):
+        """Queues one batch; returns (result, stream it was queued on).  `after(result)` runs inside the batch's stream
+        context (e.g. to append the batch's records to a job buffer)."""
+        from . import ops
+        k = self._k % len(self.streams)
+        self._k += 1
+        with torch.cuda.stream(self.streams[k]):
+            res = ops.match_pairs_device(feat_c0, feat_c1, feat_f0, feat_f1, hw0_i, hw0_c, hw1_c,
+                                         workspace=self.workspaces[k], **kw)
+            self.workspaces[k] = res["workspace"]
+            if after is not None:
+                after(res)
+        return res, self.streams[k]
+
+
 # ---- multi-GPU sharding -----------------------------------------------------------------------------------------
 
 def shard_range(n_pairs: int, rank: int, world: int):

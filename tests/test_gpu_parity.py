@@ -494,3 +494,25 @@ def test_coarse_many_pairs_two_launch_compaction():
     assert torch.equal(big["b_ids"], torch.cat([p["b_ids"] + 64 * k for k, p in enumerate(parts)]))
     for key in ("i_ids", "j_ids", "mconf"):
         assert torch.equal(big[key], torch.cat([p[key] for p in parts])), key
+
+
+def test_device_batch_runner_equals_sequential_steps():
+    """driver.DeviceBatchRunner: batches on alternating streams give the results of one-at-a-time calls."""
+    from pope_b200 import driver
+    h, w = 20, 24
+    batches = []
+    for seed in (91, 92, 93):
+        f0, f1 = synth.coarse_features(seed, 2, h * w, h * w, 256, sigma=0.9, dtype=torch.bfloat16)
+        ff0, ff1 = synth.fine_feature_maps(seed + 10, 2, h * 4, w * 4, 128, dtype=torch.bfloat16)
+        batches.append([t.to(DEV) for t in (f0, f1, ff0, ff1)])
+    runner = driver.DeviceBatchRunner(DEV, 2)
+    runner.fork()
+    got = [runner.submit(*b, (h * 8, w * 8), (h, w), (h, w))[0] for b in batches]
+    runner.join()
+    torch.cuda.synchronize()
+    for b, res in zip(batches, got):
+        want = ops.match_pairs_device(*b, (h * 8, w * 8), (h, w), (h, w))
+        m = want.total()
+        assert res.total() == m and m > 100
+        for k in ("b_ids", "i_ids", "j_ids", "mconf", "mkpts1_f", "expec_f"):
+            assert torch.equal(res[k][:m], want[k][:m]), k
