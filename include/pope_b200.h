@@ -211,6 +211,26 @@ int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t*
                       const float* mkpts0_f, const float* mkpts1_f, const int32_t* m_dev, int64_t capacity,
                       int pair_offset, int32_t* records, const int64_t* base_dev, void* stream);
 
+/* ---- batched relative pose from the match lists --------------------------------------------------
+ * Replaces the per-pair `estimate_pose(kpts0, kpts1, K0, K1, thresh, conf)` of the reference (src/utils/metrics.py:69-94:
+ * cv2.findEssentialMat(..., threshold, prob=conf, method=cv2.RANSAC) followed by cv2.recoverPose) for a whole batch of match
+ * lists that are still on the device.  mkpts0 / mkpts1: float32 [capacity, 2] pixel coordinates, the matches of pair p at
+ * rows [sum(counts[:p]), sum(counts[:p+1])) (the layout pope_fine_match_maps leaves); counts: int32 [n_pairs] (device);
+ * K0 / K1: float64 [n_pairs, 9] intrinsics (device).  thresh is in pixels, conf the RANSAC confidence, max_iters
+ * (<= POPE_POSE_MAX_ITERS; OpenCV's default is 1000) the iteration bound; seed selects the minimal samples (counter-based
+ * hash, see csrc/pose_math.cuh).  Outputs (device): R float64 [n_pairs, 9], t float64 [n_pairs, 3] (unit norm), E float64
+ * [n_pairs, 9], inliers uint8 [capacity] (the mask recoverPose returns: RANSAC inliers that pass the cheirality test),
+ * n_inliers / status / iters int32 [n_pairs]; status 0 is the reference's `return None` (fewer than 5 matches, no model, or
+ * no point in front of both cameras), iters the number of minimal samples the equivalent sequential loop consumed.
+ * Results equal a sequential RANSAC over the same samples with OpenCV's adaptive iteration bound; they are deterministic in
+ * (inputs, seed).  All arithmetic is float64. */
+#define POPE_POSE_MAX_ITERS 1024
+size_t pope_pose_workspace_bytes(int n_pairs, int64_t capacity);
+int pope_estimate_pose_batch(const float* mkpts0, const float* mkpts1, const int32_t* counts, int n_pairs, int64_t capacity,
+                             const double* K0, const double* K1, double thresh, double conf, int max_iters, uint64_t seed,
+                             double* R, double* t, double* E, uint8_t* inliers, int32_t* n_inliers, int32_t* status,
+                             int32_t* iters, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- on-disk match format (host code) ------------------------------------------------------------
  * numpy.savetxt(path, a) as the reference uses it (linemod.py:168-171: '%.18e', one space between columns, '\n' after
  * every row; a 1-D array = one value per line = cols 1): byte-identical output, read back by pose/dataset.py with

@@ -45,6 +45,9 @@ SIGNATURES = {
     "pope_write_match_files": (_i, [C.c_char_p, C.POINTER(C.c_char_p), _i, _p, _p, _p, _i64, _i, _i, C.POINTER(C.c_int32)]),
     "pope_pack_records": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p]),
     "pope_match_scores": (_i, [_p, _p, _i, _i, _f, _p, _p, _p]),
+    "pope_pose_workspace_bytes": (_sz, [_i, _i64]),
+    "pope_estimate_pose_batch": (_i, [_p, _p, _p, _i, _i64, _p, _p, C.c_double, C.c_double, _i, C.c_uint64, _p, _p, _p, _p,
+                                      _p, _p, _p, _p, _sz, _p]),
     "pope_cosine_topk": (_i, [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "pope_debug_trace_read": (_i, [_p, _i]),
     "pope_pipeline_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i]),
