@@ -12,6 +12,8 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "pope_b200.h"
 #include "pose_math.cuh"
 
@@ -42,6 +44,8 @@ struct PoseWs {
     uint8_t* flags;       // [capacity]
     double* cand;         // [n, 21]: R1, R2, t of the best model
     int32_t* good;        // [n, 4]: cheirality votes of the four candidates
+    int32_t* work;        // [n * kMaxWave]: (pair, sample) items of the current wave that produced models
+    int32_t* work_n;      // [kWaves]: item count per wave
 };
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -65,6 +69,8 @@ size_t carve(PoseWs* w, void* base, int n, int64_t capacity) {
     tmp.flags = (uint8_t*)take((size_t)capacity);
     tmp.cand = (double*)take(sizeof(double) * 21 * n);
     tmp.good = (int32_t*)take(sizeof(int32_t) * 4 * n);
+    tmp.work = (int32_t*)take(sizeof(int32_t) * (size_t)kMaxWave * n);
+    tmp.work_n = (int32_t*)take(sizeof(int32_t) * kWaves);
     if (w) *w = tmp;
     return off;
 }
@@ -92,6 +98,7 @@ __global__ void pose_prepare_kernel(const int32_t* __restrict__ counts, const do
         __syncthreads();
     }
     if (threadIdx.x == 0) w.offsets[0] = 0;
+    if (threadIdx.x < kWaves) w.work_n[threadIdx.x] = 0;
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
         // thresh / np.mean([K0[0,0], K1[1,1], K0[0,0], K1[1,1]])   (metrics.py:77)
         const double f0 = K0[p * 9 + 0], f1 = K1[p * 9 + 4];
@@ -125,7 +132,7 @@ __global__ void pose_normalize_kernel(const float* __restrict__ mk0, const float
 }
 
 // One thread per (pair, sample of this wave): hashed minimal sample -> five-point solver -> up to ten models.
-__global__ void pose_solve_kernel(int n, int start, int wsize, uint64_t seed, PoseWs w) {
+__global__ void pose_solve_kernel(int n, int start, int wsize, int wave, uint64_t seed, PoseWs w) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n * wsize) return;
     const int p = gid / wsize, s = gid % wsize, h = start + s;
@@ -146,39 +153,44 @@ __global__ void pose_solve_kernel(int n, int start, int wsize, uint64_t seed, Po
         }
     }
     w.nmodels[(size_t)p * kMaxWave + s] = nm;
+    if (nm > 0) w.work[atomicAdd(&w.work_n[wave], 1)] = p * kMaxWave + s;
 }
 
-// One block per (sample, pair): inlier count of each of the sample's models over all matches of the pair.
-__global__ void __launch_bounds__(kScoreThreads) pose_score_kernel(PoseWs w) {
-    const int s = blockIdx.x, p = blockIdx.y;
-    const int nm = w.nmodels[(size_t)p * kMaxWave + s];
-    if (nm == 0) return;
+// Inlier count of each model over all matches of its pair: the blocks walk the wave's list of (pair, sample) items that
+// produced models (the list order is arbitrary, the results are stored per item).
+__global__ void __launch_bounds__(kScoreThreads) pose_score_kernel(int wave, PoseWs w) {
     __shared__ double sE[pm::kMaxModels][9];
     __shared__ int scnt[pm::kMaxModels];
-    const double* src = w.models + ((size_t)p * kMaxWave + s) * 90;
-    for (int i = threadIdx.x; i < nm * 9; i += kScoreThreads) sE[i / 9][i % 9] = src[i];
-    if (threadIdx.x < pm::kMaxModels) scnt[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t lo = w.offsets[p], hi = w.offsets[p + 1];
-    const double thr2 = w.thr2[p];
-    int cnt[pm::kMaxModels];
+    const int items = w.work_n[wave];
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int ps = w.work[item], p = ps / kMaxWave;
+        const int nm = w.nmodels[ps];
+        const double* src = w.models + (size_t)ps * 90;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nm * 9; i += kScoreThreads) sE[i / 9][i % 9] = src[i];
+        if (threadIdx.x < pm::kMaxModels) scnt[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t lo = w.offsets[p], hi = w.offsets[p + 1];
+        const double thr2 = w.thr2[p];
+        int cnt[pm::kMaxModels];
 #pragma unroll
-    for (int r = 0; r < pm::kMaxModels; ++r) cnt[r] = 0;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += kScoreThreads) {
-        const double4 q = reinterpret_cast<const double4*>(w.pts)[i];
+        for (int r = 0; r < pm::kMaxModels; ++r) cnt[r] = 0;
+        for (int64_t i = lo + threadIdx.x; i < hi; i += kScoreThreads) {
+            const double4 q = reinterpret_cast<const double4*>(w.pts)[i];
 #pragma unroll
-        for (int r = 0; r < pm::kMaxModels; ++r)
-            if (r < nm) cnt[r] += pm::sampson_inlier(sE[r], q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
-    }
-#pragma unroll
-    for (int r = 0; r < pm::kMaxModels; ++r) {
-        if (r < nm) {
-            const int tot = __reduce_add_sync(0xffffffffu, cnt[r]);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&scnt[r], tot);
+            for (int r = 0; r < pm::kMaxModels; ++r)
+                if (r < nm) cnt[r] += pm::sampson_inlier(sE[r], q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
         }
+#pragma unroll
+        for (int r = 0; r < pm::kMaxModels; ++r) {
+            if (r < nm) {
+                const int tot = __reduce_add_sync(0xffffffffu, cnt[r]);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&scnt[r], tot);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < nm) w.mcount[(size_t)ps * 10 + threadIdx.x] = scnt[threadIdx.x];
     }
-    __syncthreads();
-    if (threadIdx.x < nm) w.mcount[((size_t)p * kMaxWave + s) * 10 + threadIdx.x] = scnt[threadIdx.x];
 }
 
 // cv::RANSACUpdateNumIters of OpenCV 4.x (calib3d/src/ptsetreg.cpp), model size 5.
@@ -194,23 +206,32 @@ __device__ int update_num_iters(double p, double ep, int max_iters) {
     return (denom >= 0.0 || -num >= max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
 }
 
-// One thread per pair: consume this wave's scored models in sample order like the sequential loop would.
+// One warp per pair: consume this wave's scored models in sample order like the sequential loop would.  Each lane fetches
+// one sample's best model (the first one with the sample's largest count: within a sample only that one can end up as the
+// running best, and the iteration bound after the sample depends on it alone); the warp then walks the 32 samples in order.
 __global__ void pose_scan_kernel(int n, int start, int wsize, double conf, int last_wave, PoseWs w) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (p >= n) return;
     PairState st = w.state[p];
     if (st.done) return;
     const int m = (int)(w.offsets[p + 1] - w.offsets[p]);
-    for (int s = 0; s < wsize; ++s) {
-        const int h = start + s;
-        if (h >= st.niters) { st.done = 1; st.used = st.niters; break; }
-        const int nm = w.nmodels[(size_t)p * kMaxWave + s];
-        for (int r = 0; r < nm; ++r) {
-            const int cnt = w.mcount[((size_t)p * kMaxWave + s) * 10 + r];
+    for (int s0 = 0; s0 < wsize && !st.done; s0 += 32) {
+        const int s = s0 + lane;
+        int bc = 0, br = 0;
+        if (s < wsize) {
+            const int nm = w.nmodels[(size_t)p * kMaxWave + s];
+            for (int r = 0; r < nm; ++r) {
+                const int cnt = w.mcount[((size_t)p * kMaxWave + s) * 10 + r];
+                if (cnt > bc) { bc = cnt; br = r; }
+            }
+        }
+        for (int l = 0; l < 32 && s0 + l < wsize; ++l) {
+            if (start + s0 + l >= st.niters) { st.done = 1; st.used = st.niters; break; }
+            const int cnt = __shfl_sync(0xffffffffu, bc, l), r = __shfl_sync(0xffffffffu, br, l);
             if (cnt > max(st.best_cnt, 4)) {
                 st.best_cnt = cnt;
-                const double* src = w.models + (((size_t)p * kMaxWave + s) * 10 + r) * 9;
-                for (int e = 0; e < 9; ++e) w.best_e[p * 9 + e] = src[e];
+                const double* src = w.models + (((size_t)p * kMaxWave + s0 + l) * 10 + r) * 9;
+                if (lane < 9) w.best_e[p * 9 + lane] = src[lane];
                 st.niters = update_num_iters(conf, (double)(m - cnt) / (double)m, st.niters);
             }
         }
@@ -219,7 +240,8 @@ __global__ void pose_scan_kernel(int n, int start, int wsize, double conf, int l
         st.done = 1;
         st.used = min(st.niters, start + wsize);
     }
-    w.state[p] = st;
+    __syncwarp();
+    if (lane == 0) w.state[p] = st;
 }
 
 // One thread per pair: best model -> the two rotations and the translation direction; clears the votes.
@@ -333,9 +355,9 @@ extern "C" int pope_estimate_pose_batch(const float* mkpts0, const float* mkpts1
     for (int wv = 0; wv < kWaves && start < max_iters; ++wv) {
         const int ws = wave_size(wv);
         const bool last = (wv == kWaves - 1) || (start + ws >= max_iters);
-        pose_solve_kernel<<<(n_pairs * ws + 31) / 32, 32, 0, st>>>(n_pairs, start, ws, seed, w);
-        pose_score_kernel<<<dim3(ws, n_pairs), kScoreThreads, 0, st>>>(w);
-        pose_scan_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(n_pairs, start, ws, conf, last ? 1 : 0, w);
+        pose_solve_kernel<<<(n_pairs * ws + 31) / 32, 32, 0, st>>>(n_pairs, start, ws, wv, seed, w);
+        pose_score_kernel<<<(int)std::min<int64_t>((int64_t)n_pairs * ws, 148 * 16), kScoreThreads, 0, st>>>(wv, w);
+        pose_scan_kernel<<<(n_pairs + 3) / 4, 128, 0, st>>>(n_pairs, start, ws, conf, last ? 1 : 0, w);
         start += ws;
     }
     pose_decompose_kernel<<<(n_pairs + 63) / 64, 64, 0, st>>>(n_pairs, w);

@@ -123,30 +123,35 @@ PM_HD void conv_acc(double* out, const double* a, int da, const double* b, int d
 
 // Real roots of a degree-10 polynomial (ascending coefficients c[0..10], any scale): sign changes of p on a uniform grid of
 // [-1, 1] and of the reversed polynomial u^10 p(1/u) on the same grid (roots with |z| > 1), each bracket bisected kBisect
-// times.  Returns the number of roots (<= 10), in grid order.  Two roots inside one cell are not separated.
+// times.  Returns the number of roots (<= 10), in grid order.  Two roots inside one cell are not separated.  The brackets
+// are collected first and bisected afterwards so that the lanes of a warp bisect their k-th brackets in lockstep.
 PM_HD int real_roots10(const double* c, double* roots) {
     int n = 0;
+    int bracket[kMaxModels];
     double rev[11];
     for (int k = 0; k <= 10; ++k) rev[k] = c[10 - k];
     for (int part = 0; part < 2; ++part) {
         const double* p = part == 0 ? c : rev;
-        bool sg[kGridCells + 1];
+        bool slo = horner(p, 10, -1.0) > 0.0;
 #pragma unroll 8
-        for (int g = 0; g <= kGridCells; ++g) sg[g] = horner(p, 10, (double)g * (2.0 / kGridCells) - 1.0) > 0.0;
         for (int cell = 0; cell < kGridCells; ++cell) {
-            const bool slo = sg[cell];
-            if (sg[cell + 1] != slo && n < kMaxModels) {
-                double a = (double)cell * (2.0 / kGridCells) - 1.0, b = (double)(cell + 1) * (2.0 / kGridCells) - 1.0;
-                for (int it = 0; it < kBisect; ++it) {
-                    const double mid = 0.5 * (a + b);
-                    const bool sm = horner(p, 10, mid) > 0.0;
-                    if (sm == slo) a = mid; else b = mid;
-                }
-                const double r = 0.5 * (a + b);
-                if (part == 0) roots[n++] = r;
-                else if (r != 0.0) roots[n++] = 1.0 / r;
-            }
+            const bool shi = horner(p, 10, (double)(cell + 1) * (2.0 / kGridCells) - 1.0) > 0.0;
+            if (shi != slo && n < kMaxModels) bracket[n++] = part * kGridCells + cell;
+            slo = shi;
         }
+    }
+    for (int r = 0; r < n; ++r) {
+        const int part = bracket[r] / kGridCells, cell = bracket[r] % kGridCells;
+        const double* p = part == 0 ? c : rev;
+        double a = (double)cell * (2.0 / kGridCells) - 1.0, b = (double)(cell + 1) * (2.0 / kGridCells) - 1.0;
+        const bool slo = horner(p, 10, a) > 0.0;
+        for (int it = 0; it < kBisect; ++it) {
+            const double mid = 0.5 * (a + b);
+            const bool sm = horner(p, 10, mid) > 0.0;
+            if (sm == slo) a = mid; else b = mid;
+        }
+        const double z = 0.5 * (a + b);          // never exactly 0: the bracket is still 2^-46 wide
+        roots[r] = part == 0 ? z : 1.0 / z;
     }
     return n;
 }
@@ -360,7 +365,7 @@ PM_HD bool cheirality(const double* R, const double* t, double x0, double y0, do
     double S[4][4], V[4][4];
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j) S[i][j] = ((Am[0][i] * Am[0][j] + Am[1][i] * Am[1][j]) + Am[2][i] * Am[2][j]) + Am[3][i] * Am[3][j];
-    jacobi_eig<4, 6>(S, V);
+    jacobi_eig<4, 4>(S, V);   // four sweeps: the vote only needs the signs of the null vector
     int im = 0;
     for (int i = 1; i < 4; ++i) if (S[i][i] < S[im][im]) im = i;
     const double q0 = V[0][im], q1 = V[1][im], q2 = V[2][im], q3 = V[3][im];

@@ -221,3 +221,25 @@ def test_estimate_pose_drop_in_signature(gold):
     assert R.shape == (3, 3) and t.shape == (3,) and mask.shape == (m0,) and mask.dtype == bool
     assert rot_angle(R, gold["R_gt"][0]) < 1.0
     assert pose.estimate_pose(gold["mkpts0"][:4], gold["mkpts1"][:4], gold["K0"][0], gold["K1"][0], 0.5) is None
+
+
+@pytest.mark.gpu
+def test_pose_consumes_the_hot_path_output_without_leaving_the_device():
+    """match_pairs_device -> estimate_pose_batch on the capacity-sized device arrays (no host sync in between); the
+    oracle gets the same match lists."""
+    from pope_b200 import ops, pose, synth
+    dev = torch.device("cuda:0")
+    n, h, w = 3, 24, 32
+    f0, f1 = synth.coarse_features(11, n, h * w, h * w, 256, sigma=0.9, dtype=torch.bfloat16)
+    ff0, ff1 = synth.fine_feature_maps(12, n, h * 4, w * 4, 128, dtype=torch.bfloat16)
+    res = ops.match_pairs_device(f0.to(dev), f1.to(dev), ff0.to(dev), ff1.to(dev), (h * 8, w * 8), (h, w), (h, w))
+    K = torch.tensor([[300.0, 0, w * 4.0], [0, 300.0, h * 4.0], [0, 0, 1]], dtype=torch.float64).expand(n, 3, 3)
+    got = pose.estimate_pose_batch(res["mkpts0_f"], res["mkpts1_f"], res["counts"], K, K, 0.5, 0.99, max_iters=64)
+    counts = res["counts"][:n].cpu().numpy()
+    m = int(counts.sum())
+    assert m > 100
+    want = O.estimate_pose_batch(res["mkpts0_f"][:m].cpu().numpy(), res["mkpts1_f"][:m].cpu().numpy(), counts, K.numpy(),
+                                 K.numpy(), 0.5, 0.99, 64, seed=0)
+    for k in ("status", "iters", "n_inliers", "E", "R", "t"):
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    assert np.array_equal(got["inliers"][:m].cpu().numpy(), want["inliers"])

@@ -38,6 +38,18 @@ for mw in (1, 37, 333):
     print("fine_tf windows", mw, "finite", bool(torch.isfinite(a.float()).all() and torch.isfinite(b.float()).all()))
 print("match_scores", [t.tolist() for t in ops.match_scores(res["mconf"], res["counts"], n, group=2)])
 print("pack_records", tuple(driver.pack_records(dict(res, mkpts0_f=res["mkpts0_c"], mkpts1_f=res["mkpts1_c"]), 3).shape))
+# batched pose RANSAC on ragged match lists (one pair below five matches, one empty)
+import numpy as np
+from oracle.gen_golden_pose import scene
+from pope_b200 import pose
+rng = np.random.default_rng(0)
+sc = [scene(rng, mm_, 0.3, 0.1, 600.0, 650.0) for mm_ in (300, 3, 0, 77, 1000)]
+po = pose.estimate_pose_batch(torch.from_numpy(np.concatenate([s_[0] for s_ in sc])).to(dev),
+                              torch.from_numpy(np.concatenate([s_[1] for s_ in sc])).to(dev),
+                              torch.tensor([len(s_[0]) for s_ in sc], dtype=torch.int32, device=dev),
+                              torch.from_numpy(np.stack([s_[2] for s_ in sc])), torch.from_numpy(np.stack([s_[3] for s_ in sc])),
+                              0.5, 0.99999)
+print("pose status", po["status"].tolist(), "inliers", po["n_inliers"].tolist(), "iters", po["iters"].tolist())
 q, refs = synth.retrieval_tokens(3, 100, 384)
 print("topk", ops.cosine_topk(q.to(dev), refs.to(dev), 3)[2].tolist())
 f0, f1 = synth.coarse_features(8, 3, 192, 192, 256, sigma=0.8, dtype=torch.bfloat16)
