@@ -89,24 +89,30 @@ PM_HD void jacobi_eig(double (&A)[N][N], double (&V)[N][N]) {
 // Monomials of the ten cubic constraints in Nister's order:
 //  0:x^3 1:y^3 2:x^2y 3:xy^2 4:x^2z 5:x^2 6:y^2z 7:y^2 8:xyz 9:xy | 10:xz^2 11:xz 12:x 13:yz^2 14:yz 15:y 16:z^3 17:z^2 18:z 19:1
 // degree-1 polynomials are stored as [x, y, z, 1]; degree-2 as [x^2, y^2, xy, xz, x, yz, y, z^2, z, 1].
-#ifdef __CUDA_ARCH__
-#define PM_TABLE __device__ const
-#else
-#define PM_TABLE static const
-#endif
-PM_TABLE int8_t kMul11[4][4] = {{0, 2, 3, 4}, {2, 1, 5, 6}, {3, 5, 7, 8}, {4, 6, 8, 9}};
-PM_TABLE int8_t kMul21[10][4] = {{0, 2, 4, 5},   {3, 1, 6, 7},    {2, 3, 8, 9},    {4, 8, 10, 11},  {5, 9, 11, 12},
+// The tables are only ever indexed by fully unrolled loop counters, so every index below folds to a literal.
+PM_HD constexpr int mul11(int a, int b) {
+    constexpr int8_t t[4][4] = {{0, 2, 3, 4}, {2, 1, 5, 6}, {3, 5, 7, 8}, {4, 6, 8, 9}};
+    return t[a][b];
+}
+PM_HD constexpr int mul21(int a, int b) {
+    constexpr int8_t t[10][4] = {{0, 2, 4, 5},   {3, 1, 6, 7},    {2, 3, 8, 9},    {4, 8, 10, 11},  {5, 9, 11, 12},
                                  {8, 6, 13, 14}, {9, 7, 14, 15}, {10, 13, 16, 17}, {11, 14, 17, 18}, {12, 15, 18, 19}};
+    return t[a][b];
+}
 
 // r (degree 2) += sign * p * q, p and q of degree 1
 PM_HD void acc11(double* r, const double* p, const double* q, double sign) {
+#pragma unroll
     for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) r[kMul11[a][b]] = r[kMul11[a][b]] + sign * (p[a] * q[b]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) r[mul11(a, b)] = r[mul11(a, b)] + sign * (p[a] * q[b]);
 }
 // r (degree 3, 20 monomials) += p (degree 2) * q (degree 1)
 PM_HD void acc21(double* r, const double* p, const double* q) {
+#pragma unroll
     for (int a = 0; a < 10; ++a)
-        for (int b = 0; b < 4; ++b) r[kMul21[a][b]] = r[kMul21[a][b]] + p[a] * q[b];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) r[mul21(a, b)] = r[mul21(a, b)] + p[a] * q[b];
 }
 
 PM_HD double horner(const double* c, int deg, double z) {
