@@ -19,8 +19,9 @@
 
 namespace {
 
-constexpr int kWaves = 6;
-__host__ __device__ constexpr int wave_size(int w) { return w == 0 ? 32 : (32 << (w - 1)); }   // 32 32 64 128 256 512
+constexpr int kWaves = 5;
+// 64 64 128 256 512: the solve kernel is bound by the latency of one thread's solver, so a first wave of 64 costs what 32 would
+__host__ __device__ constexpr int wave_size(int w) { return w == 0 ? 64 : (64 << (w - 1)); }
 constexpr int kMaxWave = 512;
 constexpr int kScoreThreads = 128;
 constexpr int kFinalThreads = 256;
@@ -44,7 +45,7 @@ struct PoseWs {
     uint8_t* flags;       // [capacity]
     double* cand;         // [n, 21]: R1, R2, t of the best model
     int32_t* good;        // [n, 4]: cheirality votes of the four candidates
-    int32_t* work;        // [n * kMaxWave]: (pair, sample) items of the current wave that produced models
+    int32_t* work;        // [n * kMaxWave * 10]: (pair, sample, model) items of the current wave
     int32_t* work_n;      // [kWaves]: item count per wave
 };
 
@@ -69,7 +70,7 @@ size_t carve(PoseWs* w, void* base, int n, int64_t capacity) {
     tmp.flags = (uint8_t*)take((size_t)capacity);
     tmp.cand = (double*)take(sizeof(double) * 21 * n);
     tmp.good = (int32_t*)take(sizeof(int32_t) * 4 * n);
-    tmp.work = (int32_t*)take(sizeof(int32_t) * (size_t)kMaxWave * n);
+    tmp.work = (int32_t*)take(sizeof(int32_t) * 10 * (size_t)kMaxWave * n);
     tmp.work_n = (int32_t*)take(sizeof(int32_t) * kWaves);
     if (w) *w = tmp;
     return off;
@@ -153,43 +154,32 @@ __global__ void pose_solve_kernel(int n, int start, int wsize, int wave, uint64_
         }
     }
     w.nmodels[(size_t)p * kMaxWave + s] = nm;
-    if (nm > 0) w.work[atomicAdd(&w.work_n[wave], 1)] = p * kMaxWave + s;
+    if (nm > 0) {
+        const int at = atomicAdd(&w.work_n[wave], nm);
+        for (int r = 0; r < nm; ++r) w.work[at + r] = (p * kMaxWave + s) * 10 + r;
+    }
 }
 
-// Inlier count of each model over all matches of its pair: the blocks walk the wave's list of (pair, sample) items that
-// produced models (the list order is arbitrary, the results are stored per item).
+// Inlier count of each model over all matches of its pair: the warps walk the wave's list of (pair, sample, model) items
+// (the list order is arbitrary, the counts are stored per item), the lanes stride over the matches.
 __global__ void __launch_bounds__(kScoreThreads) pose_score_kernel(int wave, PoseWs w) {
-    __shared__ double sE[pm::kMaxModels][9];
-    __shared__ int scnt[pm::kMaxModels];
     const int items = w.work_n[wave];
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int ps = w.work[item], p = ps / kMaxWave;
-        const int nm = w.nmodels[ps];
-        const double* src = w.models + (size_t)ps * 90;
-        __syncthreads();
-        for (int i = threadIdx.x; i < nm * 9; i += kScoreThreads) sE[i / 9][i % 9] = src[i];
-        if (threadIdx.x < pm::kMaxModels) scnt[threadIdx.x] = 0;
-        __syncthreads();
+    const int lane = threadIdx.x & 31, warps = (gridDim.x * kScoreThreads) >> 5;
+    for (int item = (blockIdx.x * kScoreThreads + threadIdx.x) >> 5; item < items; item += warps) {
+        const int id = w.work[item], p = id / (kMaxWave * 10);
+        double E[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) E[e] = w.models[(size_t)id * 9 + e];
         const int64_t lo = w.offsets[p], hi = w.offsets[p + 1];
         const double thr2 = w.thr2[p];
-        int cnt[pm::kMaxModels];
-#pragma unroll
-        for (int r = 0; r < pm::kMaxModels; ++r) cnt[r] = 0;
-        for (int64_t i = lo + threadIdx.x; i < hi; i += kScoreThreads) {
+        int cnt = 0;
+#pragma unroll 2
+        for (int64_t i = lo + lane; i < hi; i += 32) {
             const double4 q = reinterpret_cast<const double4*>(w.pts)[i];
-#pragma unroll
-            for (int r = 0; r < pm::kMaxModels; ++r)
-                if (r < nm) cnt[r] += pm::sampson_inlier(sE[r], q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
+            cnt += pm::sampson_inlier(E, q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
         }
-#pragma unroll
-        for (int r = 0; r < pm::kMaxModels; ++r) {
-            if (r < nm) {
-                const int tot = __reduce_add_sync(0xffffffffu, cnt[r]);
-                if ((threadIdx.x & 31) == 0) atomicAdd(&scnt[r], tot);
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < nm) w.mcount[(size_t)ps * 10 + threadIdx.x] = scnt[threadIdx.x];
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) w.mcount[id] = cnt;
     }
 }
 
@@ -356,7 +346,7 @@ extern "C" int pope_estimate_pose_batch(const float* mkpts0, const float* mkpts1
         const int ws = wave_size(wv);
         const bool last = (wv == kWaves - 1) || (start + ws >= max_iters);
         pose_solve_kernel<<<(n_pairs * ws + 31) / 32, 32, 0, st>>>(n_pairs, start, ws, wv, seed, w);
-        pose_score_kernel<<<(int)std::min<int64_t>((int64_t)n_pairs * ws, 148 * 16), kScoreThreads, 0, st>>>(wv, w);
+        pose_score_kernel<<<(int)std::min<int64_t>(((int64_t)n_pairs * ws * 4 + 3) / 4, 148 * 16), kScoreThreads, 0, st>>>(wv, w);
         pose_scan_kernel<<<(n_pairs + 3) / 4, 128, 0, st>>>(n_pairs, start, ws, conf, last ? 1 : 0, w);
         start += ws;
     }

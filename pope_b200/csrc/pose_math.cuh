@@ -20,7 +20,18 @@
 #define PM_HDN inline
 #endif
 
+// developer diagnostics (tools/micro/pose_phases.cu): clock stamps after each phase of the solver
+#if defined(PM_TRACE) && defined(__CUDA_ARCH__)
+#define PM_STAMP(k) pm::pm_trace_clk[k] = clock64()
+#else
+#define PM_STAMP(k)
+#endif
+
 namespace pm {
+
+#if defined(PM_TRACE) && defined(__CUDACC__)
+__device__ long long pm_trace_clk[8];
+#endif
 
 constexpr int kMaxModels = 10;    // a tenth-degree polynomial has at most ten real roots
 constexpr int kGridCells = 128;   // sign-change cells on [-1, 1], for p(z) and for the reversed polynomial
@@ -139,25 +150,57 @@ PM_HD int real_roots10(const double* c, double* roots) {
     for (int part = 0; part < 2; ++part) {
         const double* p = part == 0 ? c : rev;
         bool slo = horner(p, 10, -1.0) > 0.0;
-#pragma unroll 8
-        for (int cell = 0; cell < kGridCells; ++cell) {
-            const bool shi = horner(p, 10, (double)(cell + 1) * (2.0 / kGridCells) - 1.0) > 0.0;
-            if (shi != slo && n < kMaxModels) bracket[n++] = part * kGridCells + cell;
-            slo = shi;
+        for (int cell = 0; cell < kGridCells; cell += 4) {          // four independent Horner chains at a time
+            double z[4], v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { z[u] = (double)(cell + u + 1) * (2.0 / kGridCells) - 1.0; v[u] = p[10]; }
+#pragma unroll
+            for (int k = 9; k >= 0; --k) {
+                const double ck = p[k];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = v[u] * z[u] + ck;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool shi = v[u] > 0.0;
+                if (shi != slo && n < kMaxModels) bracket[n++] = part * kGridCells + cell + u;
+                slo = shi;
+            }
         }
     }
-    for (int r = 0; r < n; ++r) {
-        const int part = bracket[r] / kGridCells, cell = bracket[r] % kGridCells;
-        const double* p = part == 0 ? c : rev;
-        double a = (double)cell * (2.0 / kGridCells) - 1.0, b = (double)(cell + 1) * (2.0 / kGridCells) - 1.0;
-        const bool slo = horner(p, 10, a) > 0.0;
-        for (int it = 0; it < kBisect; ++it) {
-            const double mid = 0.5 * (a + b);
-            const bool sm = horner(p, 10, mid) > 0.0;
-            if (sm == slo) a = mid; else b = mid;
+    for (int r = 0; r < n; r += 2) {                                 // two brackets at a time
+        const double* p[2];
+        double a[2], b[2];
+        bool slo[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int br = bracket[r + u < n ? r + u : r], cell = br % kGridCells;
+            p[u] = br / kGridCells == 0 ? c : rev;
+            a[u] = (double)cell * (2.0 / kGridCells) - 1.0;
+            b[u] = (double)(cell + 1) * (2.0 / kGridCells) - 1.0;
+            slo[u] = horner(p[u], 10, a[u]) > 0.0;
         }
-        const double z = 0.5 * (a + b);          // never exactly 0: the bracket is still 2^-46 wide
-        roots[r] = part == 0 ? z : 1.0 / z;
+        for (int it = 0; it < kBisect; ++it) {
+            double mid[2], v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { mid[u] = 0.5 * (a[u] + b[u]); v[u] = p[u][10]; }
+#pragma unroll
+            for (int k = 9; k >= 0; --k) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) v[u] = v[u] * mid[u] + p[u][k];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if ((v[u] > 0.0) == slo[u]) a[u] = mid[u]; else b[u] = mid[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (r + u < n) {
+                const double z = 0.5 * (a[u] + b[u]);          // never exactly 0: the bracket is still 2^-46 wide
+                roots[r + u] = bracket[r + u] / kGridCells == 0 ? z : 1.0 / z;
+            }
+        }
     }
     return n;
 }
@@ -166,6 +209,7 @@ PM_HD int real_roots10(const double* c, double* roots) {
 // satisfy [x1 y1 1] E [x0 y0 1]^T = 0.  Writes up to ten unit-Frobenius-norm essential matrices (row-major); returns
 // how many.
 PM_HDN int five_point(const double* x0, const double* y0, const double* x1, const double* y1, double (*models)[9]) {
+    PM_STAMP(0);
     // 1. null space of the 5 x 9 epipolar constraint matrix: orthonormalise the five rows (modified Gram-Schmidt, every
     //    projection done twice), then complete the basis four times with the unit vector e_j that has the largest residual
     double basis[9][9];
@@ -173,21 +217,28 @@ PM_HDN int five_point(const double* x0, const double* y0, const double* x1, cons
         const double row[9] = {x1[k] * x0[k], x1[k] * y0[k], x1[k], y1[k] * x0[k], y1[k] * y0[k], y1[k], x0[k], y0[k], 1.0};
         for (int i = 0; i < 9; ++i) basis[k][i] = row[i];
     }
+#pragma unroll
     for (int nb = 0; nb < 9; ++nb) {
         if (nb >= 5) {
             int best = 0;
             double best_res = -1.0;
+#pragma unroll
             for (int j = 0; j < 9; ++j) {
                 double res = 1.0;
+#pragma unroll
                 for (int k = 0; k < nb; ++k) res = res - basis[k][j] * basis[k][j];
                 if (res > best_res) { best_res = res; best = j; }
             }
             for (int i = 0; i < 9; ++i) basis[nb][i] = (i == best) ? 1.0 : 0.0;
         }
+#pragma unroll
         for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
             for (int k = 0; k < nb; ++k) {
                 double d = 0.0;
+#pragma unroll
                 for (int i = 0; i < 9; ++i) d = d + basis[k][i] * basis[nb][i];
+#pragma unroll
                 for (int i = 0; i < 9; ++i) basis[nb][i] = basis[nb][i] - d * basis[k][i];
             }
         double nrm = 0.0;
@@ -200,6 +251,7 @@ PM_HDN int five_point(const double* x0, const double* y0, const double* x1, cons
     for (int e = 0; e < 9; ++e)
         for (int s = 0; s < 4; ++s) Ec[e][s] = basis[5 + s][e];
 
+    PM_STAMP(1);
     // 2. the ten cubic constraints: 2 E E^T E - trace(E E^T) E = 0 (nine, halved) and det E = 0
     double A[10][20];
     for (int r = 0; r < 10; ++r)
@@ -233,23 +285,41 @@ PM_HDN int five_point(const double* x0, const double* y0, const double* x1, cons
         acc21(A[9], m2, Ec[2]);
     }
 
-    // 3. Gauss-Jordan on the first ten columns (partial pivoting over rows)
+    PM_STAMP(2);
+    // 3. Gauss-Jordan on the first ten columns (partial pivoting over rows).  Only rows 4..9 are read afterwards, so a
+    //    pivot step updates the rows below the pivot and, of the rows above it, only those from 4 on; the pivot row is scaled
+    //    by one reciprocal.  Fully unrolled: every index except the pivot row is a literal.
+#pragma unroll
     for (int c = 0; c < 10; ++c) {
         int piv = c;
+        double best = fabs(A[c][c]);
+#pragma unroll
+        for (int r = c + 1; r < 10; ++r) {
+            const double v = fabs(A[r][c]);
+            if (v > best) { best = v; piv = r; }
+        }
+#pragma unroll
         for (int r = c + 1; r < 10; ++r)
-            if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
-        if (piv != c)
-            for (int m = 0; m < 20; ++m) { const double tmp = A[c][m]; A[c][m] = A[piv][m]; A[piv][m] = tmp; }
+            if (r == piv) {
+#pragma unroll
+                for (int m = c; m < 20; ++m) { const double tmp = A[c][m]; A[c][m] = A[r][m]; A[r][m] = tmp; }
+            }
         const double d = A[c][c];
         if (!(fabs(d) > 0.0)) return 0;
-        for (int m = c; m < 20; ++m) A[c][m] = A[c][m] / d;
+        const double inv = 1.0 / d;
+#pragma unroll
+        for (int m = c + 1; m < 20; ++m) A[c][m] = A[c][m] * inv;
+#pragma unroll
         for (int r = 0; r < 10; ++r) {
-            if (r == c) continue;
-            const double f = A[r][c];
-            for (int m = c; m < 20; ++m) A[r][m] = A[r][m] - f * A[c][m];
+            if (r > c || (r >= 4 && r < c)) {
+                const double f = A[r][c];
+#pragma unroll
+                for (int m = c + 1; m < 20; ++m) A[r][m] = A[r][m] - f * A[c][m];
+            }
         }
     }
 
+    PM_STAMP(3);
     // 4. B(z) [x y 1]^T = 0 with rows <k> = <e> - z<f>, <l> = <g> - z<h>, <m> = <i> - z<j>
     double bx[3][4], by[3][4], b1[3][5];
     for (int r = 0; r < 3; ++r) {
@@ -274,9 +344,11 @@ PM_HDN int five_point(const double* x0, const double* y0, const double* x1, cons
     if (!(scale > 0.0) || !(scale < 1e300)) return 0;
     for (int k = 0; k < 11; ++k) poly[k] = poly[k] / scale;
 
+    PM_STAMP(4);
     // 5. real roots z -> (x, y) from the best-conditioned pair of rows of B(z) -> E
     double roots[kMaxModels];
     const int nroots = real_roots10(poly, roots);
+    PM_STAMP(5);
     int n = 0;
     for (int i = 0; i < nroots; ++i) {
         const double z = roots[i];
@@ -305,6 +377,7 @@ PM_HDN int five_point(const double* x0, const double* y0, const double* x1, cons
         for (int e = 0; e < 9; ++e) models[n][e] = E[e] / nrm;
         ++n;
     }
+    PM_STAMP(6);
     return n;
 }
 
