@@ -243,3 +243,73 @@ def test_pose_consumes_the_hot_path_output_without_leaving_the_device():
     for k in ("status", "iters", "n_inliers", "E", "R", "t"):
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
     assert np.array_equal(got["inliers"][:m].cpu().numpy(), want["inliers"])
+
+
+def _edge_batch():
+    """Ragged and degenerate match lists: tiny pairs, identical points, collinear points, pure noise, a pair at the maximum
+    list length of the path (4 800), plus unused capacity behind the last pair."""
+    from oracle.gen_golden_pose import scene
+    rng = np.random.default_rng(17)
+    parts = []
+    for m, outl in ((5, 0.0), (6, 0.0), (9, 0.3), (31, 0.2), (33, 0.5), (4800, 0.3)):
+        s = scene(rng, m, outl, 0.1, 600.0, 640.0)
+        parts.append((s[0], s[1], s[2], s[3]))
+    K = parts[0][2]
+    same = np.full((40, 2), 123.5, dtype=np.float32)
+    parts.append((same, same.copy(), K, K))                                         # all matches identical
+    line = np.stack([np.linspace(10, 500, 50), np.linspace(20, 400, 50)], 1).astype(np.float32)
+    parts.append((line, line[::-1].copy(), K, K))                                   # collinear in both images
+    parts.append((rng.uniform(0, 600, (200, 2)).astype(np.float32), rng.uniform(0, 600, (200, 2)).astype(np.float32), K, K))
+    parts.append((np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), K, K))
+    mk0 = np.concatenate([p[0] for p in parts] + [np.full((100, 2), 7.0, np.float32)])   # 100 rows of unused capacity
+    mk1 = np.concatenate([p[1] for p in parts] + [np.full((100, 2), 9.0, np.float32)])
+    counts = np.array([len(p[0]) for p in parts], dtype=np.int32)
+    return mk0, mk1, counts, np.stack([p[2] for p in parts]), np.stack([p[3] for p in parts])
+
+
+@pytest.mark.gpu
+def test_gpu_pose_edge_cases_against_oracle():
+    from pope_b200 import pose
+    mk0, mk1, counts, K0, K1 = _edge_batch()
+    dev = torch.device("cuda:0")
+    for conf, max_iters in ((0.99999, 200), (0.99, 1)):
+        got = pose.estimate_pose_batch(torch.from_numpy(mk0).to(dev), torch.from_numpy(mk1).to(dev),
+                                       torch.from_numpy(counts).to(dev), torch.from_numpy(K0), torch.from_numpy(K1), 0.5, conf,
+                                       max_iters, seed=5)
+        m = int(counts.sum())
+        want = O.estimate_pose_batch(mk0[:m], mk1[:m], counts, K0, K1, 0.5, conf, max_iters, seed=5)
+        for k in ("status", "iters", "n_inliers", "E", "R", "t"):
+            assert np.array_equal(got[k].cpu().numpy(), want[k], equal_nan=True), (k, conf)
+        assert np.array_equal(got["inliers"][:m].cpu().numpy(), want["inliers"])
+        assert not got["inliers"][m:].any()
+        assert got["status"][-1].item() == 0 and got["status"][5].item() == 1
+
+
+@pytest.mark.gpu
+def test_gpu_pose_many_small_pairs_and_nonfinite_input():
+    from oracle.gen_golden_pose import scene
+    from pope_b200 import pose
+    rng = np.random.default_rng(23)
+    sc = [scene(rng, int(rng.integers(0, 40)), 0.2, 0.1, 600.0, 640.0) for _ in range(700)]
+    mk0, mk1 = np.concatenate([s[0] for s in sc]), np.concatenate([s[1] for s in sc])
+    counts = np.array([len(s[0]) for s in sc], dtype=np.int32)
+    K0, K1 = np.stack([s[2] for s in sc]), np.stack([s[3] for s in sc])
+    dev = torch.device("cuda:0")
+    got = pose.estimate_pose_batch(torch.from_numpy(mk0).to(dev), torch.from_numpy(mk1).to(dev), torch.from_numpy(counts).to(dev),
+                                   torch.from_numpy(K0), torch.from_numpy(K1), 0.5, 0.99, 64, seed=1)
+    sel = list(range(0, 700, 23))                      # the oracle is slow: check a spread of pairs exactly
+    off = np.concatenate([[0], np.cumsum(counts)])
+    for p in sel:
+        w = O.estimate_pose(mk0[off[p]:off[p + 1]], mk1[off[p]:off[p + 1]], K0[p], K1[p], 0.5, 0.99, 64, 1, p)
+        assert got["status"][p].item() == w["status"] and got["iters"][p].item() == w["iters"]
+        assert np.array_equal(got["R"][p].cpu().numpy(), w["R"]) and np.array_equal(got["t"][p].cpu().numpy(), w["t"])
+        assert np.array_equal(got["inliers"][off[p]:off[p + 1]].cpu().numpy(), w["inliers"])
+    assert bool(((got["status"] == 1) == (got["n_inliers"] > 0)).all())
+    # non-finite coordinates must neither hang nor produce a pose for the poisoned pair
+    bad0 = mk0.copy()
+    p = int(np.argmax(counts))
+    bad0[off[p]:off[p + 1]] = np.nan
+    got = pose.estimate_pose_batch(torch.from_numpy(bad0).to(dev), torch.from_numpy(mk1).to(dev), torch.from_numpy(counts).to(dev),
+                                   torch.from_numpy(K0), torch.from_numpy(K1), 0.5, 0.99, 64, seed=1)
+    torch.cuda.synchronize()
+    assert got["status"][p].item() == 0 and got["n_inliers"][p].item() == 0
