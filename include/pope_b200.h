@@ -215,7 +215,8 @@ int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t*
  * Replaces the per-pair `estimate_pose(kpts0, kpts1, K0, K1, thresh, conf)` of the reference (src/utils/metrics.py:69-94:
  * cv2.findEssentialMat(..., threshold, prob=conf, method=cv2.RANSAC) followed by cv2.recoverPose) for a whole batch of match
  * lists that are still on the device.  mkpts0 / mkpts1: float32 [capacity, 2] pixel coordinates, the matches of pair p at
- * rows [sum(counts[:p]), sum(counts[:p+1])) (the layout pope_fine_match_maps leaves); counts: int32 [n_pairs] (device);
+ * rows [sum(counts[:p]), sum(counts[:p+1])) (the layout pope_fine_match_maps leaves; lists are clipped at `capacity`);
+ * counts: int32 [n_pairs] (device);
  * K0 / K1: float64 [n_pairs, 9] intrinsics (device).  thresh is in pixels, conf the RANSAC confidence, max_iters
  * (<= POPE_POSE_MAX_ITERS; OpenCV's default is 1000) the iteration bound; seed selects the minimal samples (counter-based
  * hash, see csrc/pose_math.cuh).  Outputs (device): R float64 [n_pairs, 9], t float64 [n_pairs, 3] (unit norm), E float64
@@ -223,7 +224,7 @@ int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t*
  * n_inliers / status / iters int32 [n_pairs]; status 0 is the reference's `return None` (fewer than 5 matches, no model, or
  * no point in front of both cameras), iters the number of minimal samples the equivalent sequential loop consumed.
  * Results equal a sequential RANSAC over the same samples with OpenCV's adaptive iteration bound; they are deterministic in
- * (inputs, seed).  All arithmetic is float64. */
+ * (inputs, seed).  All arithmetic is float64.  Workspace: about 0.37 MB per pair plus 33 bytes per row of capacity. */
 #define POPE_POSE_MAX_ITERS 1024
 size_t pope_pose_workspace_bytes(int n_pairs, int64_t capacity);
 int pope_estimate_pose_batch(const float* mkpts0, const float* mkpts1, const int32_t* counts, int n_pairs, int64_t capacity,

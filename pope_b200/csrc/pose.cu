@@ -78,14 +78,15 @@ size_t carve(PoseWs* w, void* base, int n, int64_t capacity) {
 
 // Prefix of the per-pair match counts, per-pair threshold and initial loop state.  One block.
 __global__ void pose_prepare_kernel(const int32_t* __restrict__ counts, const double* __restrict__ K0,
-                                    const double* __restrict__ K1, int n, double thresh, int max_iters, PoseWs w) {
+                                    const double* __restrict__ K1, int n, int64_t capacity, double thresh, int max_iters,
+                                    PoseWs w) {
     __shared__ int64_t carry;
     __shared__ int64_t part[1024];
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < n; base += blockDim.x) {
         const int p = base + threadIdx.x;
-        part[threadIdx.x] = p < n ? (int64_t)counts[p] : 0;
+        part[threadIdx.x] = p < n ? (int64_t)max(counts[p], 0) : 0;
         __syncthreads();
         for (int d = 1; d < (int)blockDim.x; d <<= 1) {          // inclusive Hillis-Steele scan
             const int64_t v = threadIdx.x >= (unsigned)d ? part[threadIdx.x - d] : 0;
@@ -93,13 +94,14 @@ __global__ void pose_prepare_kernel(const int32_t* __restrict__ counts, const do
             part[threadIdx.x] += v;
             __syncthreads();
         }
-        if (p < n) w.offsets[p + 1] = carry + part[threadIdx.x];
+        if (p < n) w.offsets[p + 1] = min(carry + part[threadIdx.x], capacity);   // lists never run past the arrays
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) carry += part[threadIdx.x];
         __syncthreads();
     }
     if (threadIdx.x == 0) w.offsets[0] = 0;
     if (threadIdx.x < kWaves) w.work_n[threadIdx.x] = 0;
+    __syncthreads();
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
         // thresh / np.mean([K0[0,0], K1[1,1], K0[0,0], K1[1,1]])   (metrics.py:77)
         const double f0 = K0[p * 9 + 0], f1 = K1[p * 9 + 4];
@@ -108,7 +110,7 @@ __global__ void pose_prepare_kernel(const int32_t* __restrict__ counts, const do
         PairState s;
         s.best_cnt = 0;
         s.niters = max_iters;
-        s.done = counts[p] < 5 ? 1 : 0;      // metrics.py:70-71
+        s.done = w.offsets[p + 1] - w.offsets[p] < 5 ? 1 : 0;      // metrics.py:70-71
         s.used = 0;
         w.state[p] = s;
     }
@@ -339,7 +341,7 @@ extern "C" int pope_estimate_pose_batch(const float* mkpts0, const float* mkpts1
     PoseWs w;
     if (!workspace || workspace_bytes < carve(&w, workspace, n_pairs, capacity)) return POPE_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    pose_prepare_kernel<<<1, 1024, 0, st>>>(counts, K0, K1, n_pairs, thresh, max_iters, w);
+    pose_prepare_kernel<<<1, 1024, 0, st>>>(counts, K0, K1, n_pairs, capacity, thresh, max_iters, w);
     pose_normalize_kernel<<<n_pairs, 256, 0, st>>>(mkpts0, mkpts1, K0, K1, w);
     int start = 0;
     for (int wv = 0; wv < kWaves && start < max_iters; ++wv) {

@@ -305,6 +305,12 @@ def test_gpu_pose_many_small_pairs_and_nonfinite_input():
         assert np.array_equal(got["R"][p].cpu().numpy(), w["R"]) and np.array_equal(got["t"][p].cpu().numpy(), w["t"])
         assert np.array_equal(got["inliers"][off[p]:off[p + 1]].cpu().numpy(), w["inliers"])
     assert bool(((got["status"] == 1) == (got["n_inliers"] > 0)).all())
+    # counts that promise more matches than the arrays hold are clipped to the capacity, not followed out of bounds
+    lying = counts.copy()
+    lying[-1] += 10_000
+    got2 = pose.estimate_pose_batch(torch.from_numpy(mk0).to(dev), torch.from_numpy(mk1).to(dev), torch.from_numpy(lying).to(dev),
+                                    torch.from_numpy(K0), torch.from_numpy(K1), 0.5, 0.99, 64, seed=1)
+    assert torch.equal(got2["R"][:-1], got["R"][:-1]) and torch.equal(got2["inliers"], got["inliers"])
     # non-finite coordinates must neither hang nor produce a pose for the poisoned pair
     bad0 = mk0.copy()
     p = int(np.argmax(counts))
