@@ -13,7 +13,8 @@ from .fine_preprocess import FinePreprocess                # noqa: F401
 from .fine_matching import FineMatching                    # noqa: F401
 from .retrieval import retrieve_topk, retrieve_topk_images  # noqa: F401
 from .dino_vit import DinoViT                              # noqa: F401
-from .pose import estimate_pose, estimate_pose_batch       # noqa: F401
+from .pose import compute_pose_errors, estimate_pose, estimate_pose_batch, relative_pose_error_batch  # noqa: F401
 
 __all__ = ["Matcher", "default_cfg", "make_default_cfg", "CoarseMatching", "FinePreprocess", "FineMatching",
-           "retrieve_topk", "retrieve_topk_images", "DinoViT", "estimate_pose", "estimate_pose_batch"]
+           "retrieve_topk", "retrieve_topk_images", "DinoViT", "estimate_pose", "estimate_pose_batch", "compute_pose_errors",
+           "relative_pose_error_batch"]

@@ -73,3 +73,42 @@ def estimate_pose(kpts0: np.ndarray, kpts1: np.ndarray, K0: np.ndarray, K1: np.n
     if int(out["status"][0].item()) == 0:
         return None
     return out["R"][0].cpu().numpy(), out["t"][0].cpu().numpy(), out["inliers"].cpu().numpy()
+
+
+def relative_pose_error_batch(T_0to1: torch.Tensor, R: torch.Tensor, t: torch.Tensor, ignore_gt_t_thr: float = 0.0
+                              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`relative_pose_error` of src/utils/metrics.py:10-24 for a batch, on the device of its inputs: T_0to1 [n,4,4],
+    R [n,3,3], t [n,3] -> (t_err [n], R_err [n]) in degrees (float64)."""
+    T = T_0to1.to(dtype=torch.float64, device=R.device)
+    t_gt, R_gt = T[:, :3, 3], T[:, :3, :3]
+    n = t.norm(dim=1) * t_gt.norm(dim=1)
+    t_err = torch.rad2deg(torch.acos(torch.clamp((t * t_gt).sum(dim=1) / n, -1.0, 1.0)))
+    t_err = torch.minimum(t_err, 180.0 - t_err)                   # handle E ambiguity
+    t_err = torch.where(t_gt.norm(dim=1) < ignore_gt_t_thr, torch.zeros_like(t_err), t_err)
+    cos = ((R.transpose(1, 2) @ R_gt).diagonal(dim1=1, dim2=2).sum(dim=1) - 1.0) / 2.0
+    R_err = torch.rad2deg(torch.abs(torch.acos(torch.clamp(cos, -1.0, 1.0))))
+    return t_err, R_err
+
+
+def compute_pose_errors(data: dict, config, seed: int = 0) -> None:
+    """Drop-in for `compute_pose_errors(data, config)` of src/utils/metrics.py:97-133 (the validation step's pose metrics):
+    fills data['R_errs'], data['t_errs'] (lists of floats, inf where the reference's estimate_pose returns None) and
+    data['inliers'] (list of bool arrays).  All pairs are solved in one batched call on the device that holds the matches;
+    the only transfer is the result."""
+    pixel_thr = config.TRAINER.RANSAC_PIXEL_THR
+    conf = config.TRAINER.RANSAC_CONF
+    m_bids, pts0, pts1 = data["m_bids"], data["mkpts0_f"], data["mkpts1_f"]
+    n = int(data["K0"].shape[0])
+    order = torch.sort(m_bids, stable=True).indices           # the Matcher emits sorted ids; other callers may not
+    counts = torch.bincount(m_bids, minlength=n).to(torch.int32)
+    out = estimate_pose_batch(pts0[order].float(), pts1[order].float(), counts, data["K0"], data["K1"], pixel_thr, conf,
+                              seed=seed)
+    t_err, R_err = relative_pose_error_batch(data["T_0to1"], out["R"], out["t"], ignore_gt_t_thr=0.0)
+    ok = out["status"] == 1
+    inf = torch.full_like(t_err, float("inf"))
+    R_errs, t_errs = torch.where(ok, R_err, inf).cpu().tolist(), torch.where(ok, t_err, inf).cpu().tolist()
+    inl = torch.empty_like(out["inliers"])
+    inl[order] = out["inliers"]                                # back to the caller's match order
+    inl, m_host, ok_host = inl.cpu().numpy(), m_bids.cpu().numpy(), ok.cpu().tolist()
+    data.update({"R_errs": R_errs, "t_errs": t_errs,
+                 "inliers": [inl[m_host == b] if ok_host[b] else np.array([]).astype(bool) for b in range(n)]})

@@ -319,3 +319,41 @@ def test_gpu_pose_many_small_pairs_and_nonfinite_input():
                                    torch.from_numpy(K0), torch.from_numpy(K1), 0.5, 0.99, 64, seed=1)
     torch.cuda.synchronize()
     assert got["status"][p].item() == 0 and got["n_inliers"][p].item() == 0
+
+
+@pytest.mark.gpu
+def test_compute_pose_errors_drop_in(gold):
+    """metrics.py:97-133 through the batched device path, against the reference formulas applied to the oracle's poses;
+    the match order is shuffled to cover callers whose m_bids are not sorted."""
+    from types import SimpleNamespace
+    from pope_b200 import pose
+    dev = torch.device("cuda:0")
+    n = len(gold["counts"])
+    m_bids = np.repeat(np.arange(n), gold["counts"])
+    perm = np.random.default_rng(0).permutation(len(m_bids))
+    T = np.tile(np.eye(4), (n, 1, 1))
+    T[:, :3, :3], T[:, :3, 3] = gold["R_gt"], gold["t_gt"]
+    data = dict(m_bids=torch.from_numpy(m_bids[perm]).to(dev), mkpts0_f=torch.from_numpy(gold["mkpts0"][perm]).to(dev),
+                mkpts1_f=torch.from_numpy(gold["mkpts1"][perm]).to(dev), K0=torch.from_numpy(gold["K0"]).to(dev),
+                K1=torch.from_numpy(gold["K1"]).to(dev), T_0to1=torch.from_numpy(T).to(dev))
+    cfg = SimpleNamespace(TRAINER=SimpleNamespace(RANSAC_PIXEL_THR=0.5, RANSAC_CONF=0.99999))
+    pose.compute_pose_errors(data, cfg)
+    # the stable sort restores the fixture's own order within each pair only up to the shuffle, so rebuild the oracle input
+    order = np.argsort(m_bids[perm], kind="stable")
+    want = O.estimate_pose_batch(gold["mkpts0"][perm][order], gold["mkpts1"][perm][order], gold["counts"], gold["K0"],
+                                 gold["K1"], 0.5, 0.99999, 1000, seed=0)
+    off = np.concatenate([[0], np.cumsum(gold["counts"])])
+    assert len(data["R_errs"]) == len(data["t_errs"]) == len(data["inliers"]) == n
+    for b in range(n):
+        if not want["status"][b]:
+            assert data["R_errs"][b] == np.inf and data["t_errs"][b] == np.inf and data["inliers"][b].size == 0
+            continue
+        R, t, t_gt = want["R"][b], want["t"][b], gold["t_gt"][b]
+        t_err = np.rad2deg(np.arccos(np.clip(np.dot(t, t_gt) / (np.linalg.norm(t) * np.linalg.norm(t_gt)), -1.0, 1.0)))
+        t_err = np.minimum(t_err, 180 - t_err)
+        R_err = np.rad2deg(np.abs(np.arccos(np.clip((np.trace(np.dot(R.T, gold["R_gt"][b])) - 1) / 2, -1.0, 1.0))))
+        assert abs(data["R_errs"][b] - R_err) < 1e-6 and abs(data["t_errs"][b] - t_err) < 1e-6
+        inl_sorted = want["inliers"][off[b]:off[b + 1]]
+        back = np.empty(len(m_bids), dtype=bool)
+        back[order] = want["inliers"]
+        assert np.array_equal(data["inliers"][b], back[m_bids[perm] == b]) and data["inliers"][b].sum() == inl_sorted.sum()
