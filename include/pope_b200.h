@@ -246,6 +246,17 @@ int pope_write_match_files(const char* dir, const char* const* names, int n_pair
                            const float* mkpts1, const int32_t* counts, int64_t capacity, int min_matches, int n_threads,
                            int32_t* written);
 
+/* numpy.loadtxt(path, delimiter=' ') as pose/dataset.py:75-101 reads those files back: values separated by blanks, one row
+ * per line, '#' comments and empty lines skipped; values written with '%.18e' come back bit for bit.  out: host memory for
+ * `capacity` values; *rows, *cols receive the shape (0, 0 for an empty file).  POPE_ERR_CAPACITY if the file holds more
+ * values, POPE_ERR_SHAPE for ragged rows or a token that is not a number, POPE_ERR_IO if the file cannot be read. */
+int pope_loadtxt_f64(const char* path, double* out, int64_t capacity, int64_t* rows, int* cols);
+/* The inverse of pope_write_match_files: fills the per-pair slots mkpts0 / mkpts1 float32[n_pairs, capacity, 2] and counts
+ * int32[n_pairs] from <dir>/mkpts0/<names[p]>.txt and <dir>/mkpts1/<names[p]>.txt on n_threads host threads; counts[p] = -1
+ * where the pair has no files (pairs below min_matches were never written), lists longer than capacity are truncated. */
+int pope_read_match_files(const char* dir, const char* const* names, int n_pairs, float* mkpts0, float* mkpts1,
+                          int32_t* counts, int64_t capacity, int n_threads);
+
 /* ---- fine-level transformer and FinePreprocess Linears (bf16) ---------------------------------
  * Replace src/matcher/loftr_module/transformer.py:34-58,95-104 + linear_attention.py:21-47 (LocalFeatureTransformer with
  * d_model 128, 8 heads, 'linear' attention) and fine_preprocess.py:50-57 (down_proj / merge_feat) of the reference.

@@ -60,6 +60,60 @@ int write_txt(const char* path, const T* data, int64_t rows, int cols) {
 
 bool make_dir(const std::string& p) { return mkdir(p.c_str(), 0777) == 0 || errno == EEXIST; }
 
+// numpy.loadtxt(path, delimiter=' ') for the files above: one row per line, values separated by blanks, '#' starts a
+// comment, empty lines are skipped.  std::from_chars is the correctly rounded decimal -> binary conversion (CPython's float()
+// is too), so values written with '%.18e' come back bit for bit.  Returns POPE_ERR_SHAPE for a ragged file or a token that is
+// not a number.
+int parse_txt(const char* path, std::vector<double>& vals, int64_t* rows, int* cols) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return POPE_ERR_IO;
+  std::vector<char> buf;
+  char chunk[1 << 16];
+  size_t got;
+  while ((got = fread(chunk, 1, sizeof(chunk), f)) > 0) buf.insert(buf.end(), chunk, chunk + got);
+  const bool bad = ferror(f) != 0;
+  fclose(f);
+  if (bad) return POPE_ERR_IO;
+  *rows = 0;
+  *cols = 0;
+  const char* p = buf.data();
+  const char* end = p + buf.size();
+  while (p < end) {
+    const char* eol = static_cast<const char*>(memchr(p, '\n', size_t(end - p)));
+    const char* line_end = eol ? eol : end;
+    const char* stop = static_cast<const char*>(memchr(p, '#', size_t(line_end - p)));
+    if (!stop) stop = line_end;
+    int n = 0;
+    while (p < stop) {
+      while (p < stop && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+      if (p >= stop) break;
+      if (*p == '+') ++p;                                   // from_chars does not take a leading plus, float() does
+      double v;
+      const std::from_chars_result r = std::from_chars(p, stop, v);
+      if (r.ec == std::errc::result_out_of_range) {         // float() overflows to inf and underflows to 0 silently
+        const char* q = p;
+        const bool neg = *q == '-';
+        bool big = true;                                    // decide by the sign of the decimal exponent
+        for (; q < r.ptr; ++q) if ((*q == 'e' || *q == 'E') && q + 1 < r.ptr && q[1] == '-') big = false;
+        v = big ? (neg ? -HUGE_VAL : HUGE_VAL) : (neg ? -0.0 : 0.0);
+      } else if (r.ec != std::errc()) {
+        return POPE_ERR_SHAPE;
+      }
+      if (r.ptr < stop && !(*r.ptr == ' ' || *r.ptr == '\t' || *r.ptr == '\r')) return POPE_ERR_SHAPE;
+      vals.push_back(v);
+      ++n;
+      p = r.ptr;
+    }
+    if (n > 0) {
+      if (*rows == 0) *cols = n;
+      else if (n != *cols) return POPE_ERR_SHAPE;
+      ++*rows;
+    }
+    p = eol ? eol + 1 : end;
+  }
+  return POPE_OK;
+}
+
 }  // namespace
 
 extern "C" int pope_savetxt_f32(const char* path, const float* data, int64_t rows, int cols) {
@@ -70,6 +124,56 @@ extern "C" int pope_savetxt_f32(const char* path, const float* data, int64_t row
 extern "C" int pope_savetxt_f64(const char* path, const double* data, int64_t rows, int cols) {
   if (!path || (!data && rows > 0) || rows < 0 || cols <= 0) return POPE_ERR_INVALID_ARG;
   return write_txt<double>(path, data, rows, cols);
+}
+
+extern "C" int pope_loadtxt_f64(const char* path, double* out, int64_t capacity, int64_t* rows, int* cols) {
+  if (!path || !rows || !cols || capacity < 0 || (!out && capacity > 0)) return POPE_ERR_INVALID_ARG;
+  std::vector<double> vals;
+  const int rc = parse_txt(path, vals, rows, cols);
+  if (rc != POPE_OK) return rc;
+  if (int64_t(vals.size()) > capacity) return POPE_ERR_CAPACITY;
+  if (!vals.empty()) memcpy(out, vals.data(), vals.size() * sizeof(double));
+  return POPE_OK;
+}
+
+extern "C" int pope_read_match_files(const char* dir, const char* const* names, int n_pairs, float* mkpts0, float* mkpts1,
+                                     int32_t* counts, int64_t capacity, int n_threads) {
+  if (!dir || !names || !mkpts0 || !mkpts1 || !counts || n_pairs < 0 || capacity < 0) return POPE_ERR_INVALID_ARG;
+  const std::string root(dir);
+  if (n_threads <= 0) n_threads = int(sysconf(_SC_NPROCESSORS_ONLN));
+  if (n_threads <= 0) n_threads = 1;
+  if (n_threads > 64) n_threads = 64;
+  if (n_threads > n_pairs) n_threads = n_pairs > 0 ? n_pairs : 1;
+  std::atomic<int> next(0), status(POPE_OK);
+  auto work = [&]() {
+    std::vector<double> a, b;
+    for (int p = next.fetch_add(1); p < n_pairs; p = next.fetch_add(1)) {
+      counts[p] = -1;                                       // no such pair on disk (linemod.py skips pairs below 5 matches)
+      if (!names[p]) continue;
+      a.clear();
+      b.clear();
+      int64_t ra = 0, rb = 0;
+      int ca = 0, cb = 0;
+      const int rc0 = parse_txt((root + "/mkpts0/" + names[p] + ".txt").c_str(), a, &ra, &ca);
+      if (rc0 == POPE_ERR_IO) continue;
+      const int rc1 = parse_txt((root + "/mkpts1/" + names[p] + ".txt").c_str(), b, &rb, &cb);
+      if (rc0 != POPE_OK || rc1 != POPE_OK || ra != rb || (ra > 0 && (ca != 2 || cb != 2))) {
+        status.store(rc1 == POPE_ERR_IO ? POPE_ERR_IO : POPE_ERR_SHAPE);
+        continue;
+      }
+      const int64_t m = ra > capacity ? capacity : ra;
+      for (int64_t i = 0; i < m * 2; ++i) {
+        mkpts0[size_t(p) * capacity * 2 + i] = float(a[i]);
+        mkpts1[size_t(p) * capacity * 2 + i] = float(b[i]);
+      }
+      counts[p] = int32_t(m);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  return status.load();
 }
 
 extern "C" int pope_write_match_files(const char* dir, const char* const* names, int n_pairs, const float* mkpts0,

@@ -53,3 +53,30 @@ def write_match_files(out_dir: str, names: Sequence[str], out: Dict[str, torch.T
                                       int(min_matches), int(threads), C.byref(written))
     check(st, "pope_write_match_files")
     return int(written.value)
+
+
+def loadtxt(path: str) -> np.ndarray:
+    """np.loadtxt(path, delimiter=' ') as pose/dataset.py:75-101 uses it: float64, a single row or a single column comes
+    back 1-D, a single value 0-D, an empty file as an empty array."""
+    size = os.path.getsize(path)
+    buf = np.empty(size // 2 + 1, dtype=np.float64)              # a value takes at least two bytes of text
+    rows, cols = C.c_int64(0), C.c_int(0)
+    st = lib().pope_loadtxt_f64(os.fsencode(path), buf.ctypes.data, buf.size, C.byref(rows), C.byref(cols))
+    check(st, "pope_loadtxt_f64")
+    a = buf[: rows.value * cols.value].reshape(rows.value, cols.value).copy()
+    return np.squeeze(a) if a.size else np.empty(0, dtype=np.float64)
+
+
+def read_match_files(in_dir: str, names: Sequence[str], capacity: int, threads: int = 0) -> Dict[str, torch.Tensor]:
+    """The inverse of `write_match_files`: per-pair slots mkpts0_f / mkpts1_f [n, capacity, 2] float32 and counts [n] int32
+    (-1 where the pair has no files), pinned when CUDA is available so that they can go straight to the device."""
+    n = len(names)
+    pin = torch.cuda.is_available()
+    k0 = torch.zeros(n, capacity, 2, dtype=torch.float32, pin_memory=pin)
+    k1 = torch.zeros(n, capacity, 2, dtype=torch.float32, pin_memory=pin)
+    cnt = torch.zeros(n, dtype=torch.int32, pin_memory=pin)
+    arr = (C.c_char_p * max(n, 1))(*[os.fsencode(s) for s in names])
+    st = lib().pope_read_match_files(os.fsencode(in_dir), arr, n, k0.data_ptr(), k1.data_ptr(), cnt.data_ptr(), int(capacity),
+                                     int(threads))
+    check(st, "pope_read_match_files")
+    return {"mkpts0_f": k0, "mkpts1_f": k1, "counts": cnt}

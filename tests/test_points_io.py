@@ -62,3 +62,61 @@ def test_points_io_errors(tmp_path):
         points_io.savetxt(str(tmp_path / "no_such_dir" / "x.txt"), np.zeros((2, 2), dtype=np.float32))
     with pytest.raises(PopeError):
         points_io.savetxt(str(tmp_path / "x.txt"), np.zeros((2, 2, 2)))
+
+
+def _same_array(tmp_path, a, name, text=None):
+    """loadtxt must return what numpy.loadtxt(path, delimiter=' ') returns (pose/dataset.py:75-101)."""
+    path = tmp_path / f"{name}.txt"
+    if text is None:
+        np.savetxt(path, a)
+    else:
+        path.write_text(text)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.loadtxt(path, delimiter=" ") if text is None else np.loadtxt(path)
+    got = points_io.loadtxt(str(path))
+    assert got.dtype == np.float64 and got.shape == want.shape, (name, got.shape, want.shape)
+    assert np.array_equal(got, want, equal_nan=True), name
+    assert np.array_equal(np.signbit(got), np.signbit(want)), name
+
+
+def test_loadtxt_equals_numpy(tmp_path):
+    rng = np.random.default_rng(2)
+    _same_array(tmp_path, (rng.uniform(0, 640, (300, 2))).astype(np.float32), "mkpts")
+    _same_array(tmp_path, rng.standard_normal((500, 2)), "f64")
+    _same_array(tmp_path, np.array([12.0, 40.5, 300.25, 411.0]), "bbox_1d")
+    _same_array(tmp_path, np.array([[572.4114, 0.0, 325.2611], [0.0, 573.57043, 242.04899], [0.0, 0.0, 1.0]]), "K")
+    _same_array(tmp_path, rng.standard_normal((1, 2)), "single_row")
+    _same_array(tmp_path, np.array([3.25]), "single_value")
+    _same_array(tmp_path, np.array([[0.0, -0.0], [1e-45, -3.4028235e38], [np.inf, -np.inf], [np.nan, 5e-324]]), "special")
+    _same_array(tmp_path, None, "empty", text="")
+    _same_array(tmp_path, None, "comments", text="# header\n1 2 3\n\n4 5 6  # tail\n")
+    _same_array(tmp_path, None, "free_form", text="+1.5\t2e3   -7\r\n1e400 -1e400 1e-400\n")
+    (tmp_path / "ragged.txt").write_text("1 2\n3\n")
+    with pytest.raises(Exception):
+        points_io.loadtxt(str(tmp_path / "ragged.txt"))
+    (tmp_path / "word.txt").write_text("1 two\n")
+    with pytest.raises(Exception):
+        points_io.loadtxt(str(tmp_path / "word.txt"))
+    with pytest.raises(Exception):
+        points_io.loadtxt(str(tmp_path / "missing.txt"))
+
+
+def test_read_match_files_round_trip(tmp_path):
+    rng = np.random.default_rng(3)
+    n, cap = 7, 50
+    out = {"mkpts0_f": torch.from_numpy(rng.uniform(0, 640, (n, cap, 2)).astype(np.float32)),
+           "mkpts1_f": torch.from_numpy(rng.uniform(0, 480, (n, cap, 2)).astype(np.float32)),
+           "counts": torch.tensor([50, 4, 17, 0, 5, 33, 9], dtype=torch.int32)}
+    names = [f"{i:04d}-{i + 1:04d}" for i in range(n)]
+    assert points_io.write_match_files(str(tmp_path / "obj"), names, out) == 5
+    back = points_io.read_match_files(str(tmp_path / "obj"), names, cap, threads=3)
+    assert back["counts"].tolist() == [50, -1, 17, -1, 5, 33, 9]
+    for p, m in enumerate(back["counts"].tolist()):
+        if m > 0:
+            assert torch.equal(back["mkpts0_f"][p, :m], out["mkpts0_f"][p, :m])
+            assert torch.equal(back["mkpts1_f"][p, :m], out["mkpts1_f"][p, :m])
+    short = points_io.read_match_files(str(tmp_path / "obj"), names, 10)          # truncation at the slot capacity
+    assert short["counts"].tolist() == [10, -1, 10, -1, 5, 10, 9]
+    assert torch.equal(short["mkpts0_f"][0], out["mkpts0_f"][0, :10])

@@ -1,4 +1,4 @@
-"""Throughput of the native on-disk match writer against a numpy.savetxt loop on the bench workload's shape
+"""Throughput of the native on-disk match writer / reader against numpy.savetxt / numpy.loadtxt loops on the bench workload's shape
 (n pairs x ~2 544 matches, mkpts0 + mkpts1; default n = 512).  Host only."""
 import os, shutil, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -32,4 +32,19 @@ dt = time.perf_counter() - t0
 same = all(open(d + f"/np/{s}/{names[p]}.txt", "rb").read() == open(d + f"/b0/{s}/{names[p]}.txt", "rb").read()
            for p in range(n_np) for s in ("mkpts0", "mkpts1"))
 print(f"numpy.savetxt loop over {n_np} pairs: {1e3 * dt:.1f} ms ({n_np / dt:.0f} pairs/s); files byte-identical: {same}; host cores: {os.cpu_count()}")
+# the reader side (pose/dataset.py reads every file with numpy.loadtxt)
+for thr in (1, 0):
+    dt = 1e9
+    for rep in range(3):
+        t0 = time.perf_counter()
+        back = points_io.read_match_files(d + "/b0", names, cap, threads=thr)
+        dt = min(dt, time.perf_counter() - t0)
+    print(f"native reader, threads={'all' if thr == 0 else thr}: {1e3 * dt:.1f} ms for {n} pairs ({n / dt:.0f} pairs/s)")
+ok = all(torch.equal(back["mkpts0_f"][p, :counts[p]], out["mkpts0_f"][p, :counts[p]]) for p in range(n))
+t0 = time.perf_counter()
+for p in range(n_np):
+    a = np.loadtxt(d + f"/b0/mkpts0/{names[p]}.txt", delimiter=" ")
+    b = np.loadtxt(d + f"/b0/mkpts1/{names[p]}.txt", delimiter=" ")
+dt = time.perf_counter() - t0
+print(f"numpy.loadtxt loop over {n_np} pairs: {1e3 * dt:.1f} ms ({n_np / dt:.0f} pairs/s); round trip exact: {ok}")
 shutil.rmtree(d)
