@@ -393,3 +393,20 @@ def test_full_chain_recovers_planted_pose(hw_c, n, dtype):
                                      K.numpy(), 1.0, 0.99999, 1000, seed=0)
         for k in ("status", "iters", "n_inliers", "R", "t"):
             assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+
+
+@pytest.mark.gpu
+def test_pose_call_is_graph_capturable(gold):
+    """No host synchronisation and no allocation outside torch's pool inside the call: it can be captured once and replayed."""
+    from pope_b200 import pose
+    dev = torch.device("cuda:0")
+    args = [torch.from_numpy(gold[k]).to(dev) for k in ("mkpts0", "mkpts1", "counts", "K0", "K1")]
+    eager = pose.estimate_pose_batch(*args, 0.5, 0.99999)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = pose.estimate_pose_batch(*args, 0.5, 0.99999, workspace=eager["workspace"])
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    for k in ("status", "iters", "n_inliers", "inliers", "R", "t", "E"):
+        assert torch.equal(out[k], eager[k]), k

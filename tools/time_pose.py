@@ -38,9 +38,23 @@ for conf in (0.99, 0.99999):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    # the call is stream-ordered and free of host synchronisation, so it can be captured once and replayed as a CUDA graph
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        gout = pose.estimate_pose_batch(mk0, mk1, counts, K0, K1, 0.5, conf, workspace=ws)
+    graph.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_graph = e0.elapsed_time(e1) / reps
+    same = all(torch.equal(gout[k], out[k]) for k in ("R", "t", "inliers", "iters"))
     R = out["R"].cpu().numpy()
     errs = [ang(R[p], sc[p][4]) for p in range(n)]
-    line = (f"conf {conf}: {n} pairs x {m} matches ({outl:.0%} outliers): {ms:.3f} ms per batch = {n / ms * 1e3:,.0f} pairs/s; "
+    line = (f"conf {conf}: {n} pairs x {m} matches ({outl:.0%} outliers): {ms:.3f} ms per batch = {n / ms * 1e3:,.0f} pairs/s "
+            f"(as a replayed CUDA graph {ms_graph:.3f} ms, same result: {same}); "
             f"iters median {int(out['iters'].median())} max {int(out['iters'].max())}; R error median {np.median(errs):.3f} max {max(errs):.3f} deg; "
             f"inlier frac {float(out['n_inliers'].float().mean()) / m:.3f}")
     try:
