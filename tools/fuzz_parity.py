@@ -1,7 +1,7 @@
 """Randomised parity soak of the coarse + fine path against the oracle: random ragged shapes, channel counts, dtypes,
 thresholds, border widths, temperatures, feature statistics and implementations.  Index sets must agree except at near-ties
 (tests/parity_utils.py), confidences and fine coordinates within the dtype's tolerance.
-    python tools/fuzz_parity.py [cases] [seed]"""
+    python tools/fuzz_parity.py [cases] [seed] [max_cells_per_side=40]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -12,12 +12,13 @@ from tests.parity_utils import compare_match_lists, oracle_with_margins
 
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+hi = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 dev = torch.device("cuda:0")
 t0 = time.time()
 tot = dict(cases=0, same=0, near=0, bad=0, conf_fail=0, fine_fail=0, flagged=0, empty=0)
 for case in range(cases):
     n = int(rng.integers(1, 4))
-    h0, w0, h1, w1 = (int(rng.integers(3, 41)) for _ in range(4))
+    h0, w0, h1, w1 = (int(rng.integers(3, hi + 1)) for _ in range(4))
     C = int(rng.choice([64, 128, 192, 256]))
     dtype = torch.bfloat16 if rng.random() < 0.6 else torch.float32
     thr = float(rng.choice([0.05, 0.1, 0.2, 0.3, 0.5, 0.9]))
