@@ -336,7 +336,7 @@ extern "C" int pope_estimate_pose_batch(const float* mkpts0, const float* mkpts1
                                         size_t workspace_bytes, void* stream) {
     if (n_pairs == 0) return POPE_OK;
     if (n_pairs < 0 || n_pairs > 65535 || capacity < 0 || max_iters < 1 || max_iters > POPE_POSE_MAX_ITERS || !(thresh > 0.0) || !counts || !K0 || !K1 || !R || !t || !E ||
-        !inliers || !n_inliers || !status || !iters || (capacity > 0 && (!mkpts0 || !mkpts1)))
+        !n_inliers || !status || !iters || (capacity > 0 && (!mkpts0 || !mkpts1 || !inliers)))
         return POPE_ERR_INVALID_ARG;
     PoseWs w;
     if (!workspace || workspace_bytes < carve(&w, workspace, n_pairs, capacity)) return POPE_ERR_WORKSPACE;

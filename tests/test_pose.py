@@ -311,6 +311,11 @@ def test_gpu_pose_many_small_pairs_and_nonfinite_input():
     got2 = pose.estimate_pose_batch(torch.from_numpy(mk0).to(dev), torch.from_numpy(mk1).to(dev), torch.from_numpy(lying).to(dev),
                                     torch.from_numpy(K0), torch.from_numpy(K1), 0.5, 0.99, 64, seed=1)
     assert torch.equal(got2["R"][:-1], got["R"][:-1]) and torch.equal(got2["inliers"], got["inliers"])
+    # a batch without a single match is valid input (every pair `None`)
+    none = pose.estimate_pose_batch(torch.zeros(0, 2, device=dev), torch.zeros(0, 2, device=dev),
+                                    torch.zeros(3, dtype=torch.int32, device=dev), torch.from_numpy(K0[:3]), torch.from_numpy(K1[:3]),
+                                    0.5, 0.99)
+    assert none["status"].tolist() == [0, 0, 0] and none["inliers"].numel() == 0
     # non-finite coordinates must neither hang nor produce a pose for the poisoned pair
     bad0 = mk0.copy()
     p = int(np.argmax(counts))
