@@ -192,7 +192,8 @@ extern "C" int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, con
 
 extern "C" int pope_match_scores(const float* mconf, const int32_t* counts, int n_pairs, int group, float thr,
                                  int32_t* scores, int32_t* best, void* stream) {
-  if (!mconf || !counts || !scores || !best || n_pairs <= 0 || group <= 0) return POPE_ERR_INVALID_ARG;
+  // mconf may be NULL when no pair has a match (an empty list has no storage); the kernel then never reads it
+  if (!counts || !scores || !best || n_pairs <= 0 || group <= 0) return POPE_ERR_INVALID_ARG;
   const int groups = (n_pairs + group - 1) / group;
   match_score_kernel<<<groups, 256, 0, static_cast<cudaStream_t>(stream)>>>(mconf, counts, n_pairs, group, thr, scores, best);
   return int(cudaGetLastError());

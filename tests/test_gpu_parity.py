@@ -465,6 +465,9 @@ def test_match_scores_vs_oracle():
     cnt = torch.tensor([2, 1, 2, 1, 6, 0], dtype=torch.int32, device=DEV)      # pairs 0..3 (+ total, flags)
     s2, b2 = ops.match_scores(conf, cnt, 4, group=4, thr=0.9)
     assert s2.tolist() == [2, 0, 2, 0] and b2.tolist() == [0]
+    # no match in any pair: an empty list (no storage behind it) is valid input
+    s3, b3 = ops.match_scores(torch.zeros(0, device=DEV), torch.zeros(5, dtype=torch.int32, device=DEV), 5, group=3, thr=0.9)
+    assert s3.tolist() == [0] * 5 and b3.tolist() == [0, 0]
 
 
 def test_pack_records_kernel_equals_torch_packing():
