@@ -348,7 +348,8 @@ extern "C" int pope_estimate_pose_batch(const float* mkpts0, const float* mkpts1
         const int ws = wave_size(wv);
         const bool last = (wv == kWaves - 1) || (start + ws >= max_iters);
         pose_solve_kernel<<<(n_pairs * ws + 31) / 32, 32, 0, st>>>(n_pairs, start, ws, wv, seed, w);
-        pose_score_kernel<<<(int)std::min<int64_t>(((int64_t)n_pairs * ws * 4 + 3) / 4, 148 * 16), kScoreThreads, 0, st>>>(wv, w);
+        // about four models per sample: one block of four warps per sample, capped at a few waves of the machine
+        pose_score_kernel<<<(int)std::min<int64_t>((int64_t)n_pairs * ws, 148 * 16), kScoreThreads, 0, st>>>(wv, w);
         pose_scan_kernel<<<(n_pairs + 3) / 4, 128, 0, st>>>(n_pairs, start, ws, conf, last ? 1 : 0, w);
         start += ws;
     }
