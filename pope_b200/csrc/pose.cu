@@ -174,13 +174,32 @@ __global__ void __launch_bounds__(kScoreThreads) pose_score_kernel(int wave, Pos
         for (int e = 0; e < 9; ++e) E[e] = w.models[(size_t)id * 9 + e];
         const int64_t lo = w.offsets[p], hi = w.offsets[p + 1];
         const double thr2 = w.thr2[p];
+        // The scan only acts on a count that exceeds the best count of the earlier waves (and 4), so a model that can no
+        // longer get there is dropped: every 256 matches the warp compares its count plus the matches still ahead.
+        const int need = max(w.state[p].best_cnt, 4);
         int cnt = 0;
+        bool dropped = false;
+        if (need <= 4) {                              // first wave: nothing to compare with yet
 #pragma unroll 2
-        for (int64_t i = lo + lane; i < hi; i += 32) {
-            const double4 q = reinterpret_cast<const double4*>(w.pts)[i];
-            cnt += pm::sampson_inlier(E, q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
+            for (int64_t i = lo + lane; i < hi; i += 32) {
+                const double4 q = reinterpret_cast<const double4*>(w.pts)[i];
+                cnt += pm::sampson_inlier(E, q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
+            }
+        } else {
+            int it = 0;
+            for (int64_t base = lo; base < hi; base += 32) {
+                const int64_t i = base + lane;
+                if (i < hi) {
+                    const double4 q = reinterpret_cast<const double4*>(w.pts)[i];
+                    cnt += pm::sampson_inlier(E, q.x, q.y, q.z, q.w, thr2) ? 1 : 0;
+                }
+                if ((++it & 7) == 0) {
+                    const int64_t ahead = hi - (base + 32);
+                    if (__reduce_add_sync(0xffffffffu, cnt) + ahead <= need) { dropped = true; break; }
+                }
+            }
         }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        cnt = dropped ? 0 : __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) w.mcount[id] = cnt;
     }
 }
