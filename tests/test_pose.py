@@ -108,6 +108,27 @@ def test_fewer_than_five_matches_is_none():
     assert out["status"] == 0 and out["iters"] == 0
 
 
+def test_oracle_chain_recovers_planted_pose():
+    """The CPU restatement of the whole chain on geometry-consistent synthetic features (synth.posed_pair_features): the
+    match oracle finds the planted correspondences within the 2 px fine grid and the pose oracle gets the motion back."""
+    from oracle import pope_oracle as MO
+    from pope_b200 import synth
+    n, hw = 2, (30, 40)
+    d = synth.posed_pair_features(3, n, hw_c=hw)
+    w = MO.match_pairs(d["feat_c0"], d["feat_c1"], d["feat_f0"].float(), d["feat_f1"].float(), (240, 320), hw, hw)
+    planted = int((~torch.isnan(d["proj"][..., 0])).sum())
+    assert len(w["b_ids"]) > 0.6 * planted
+    resid = (w["mkpts1_f"].double() - d["proj"][w["b_ids"], w["i_ids"]]).norm(dim=1)
+    assert int(resid.isnan().sum()) == 0 and float(resid.median()) < 1.0
+    counts = np.bincount(w["b_ids"].numpy(), minlength=n).astype(np.int32)
+    K = np.tile(d["K"].numpy(), (n, 1, 1))
+    o = O.estimate_pose_batch(w["mkpts0_f"].numpy(), w["mkpts1_f"].numpy(), counts, K, K, 1.0, 0.99999, 1000, 0)
+    assert o["status"].tolist() == [1, 1]
+    for p in range(n):
+        assert rot_angle(o["R"][p], d["R"][p].numpy()) < 2.0
+        assert o["n_inliers"][p] > 0.7 * counts[p]
+
+
 @pytest.fixture(scope="module")
 def host_math(tmp_path_factory):
     """pope_b200/csrc/pose_math.cuh compiled for the host (the file the device runs), without multiply-add contraction."""
