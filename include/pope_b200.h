@@ -257,6 +257,15 @@ int pope_loadtxt_f64(const char* path, double* out, int64_t capacity, int64_t* r
 int pope_read_match_files(const char* dir, const char* const* names, int n_pairs, float* mkpts0, float* mkpts1,
                           int32_t* counts, int64_t capacity, int n_threads);
 
+/* The two crops the reference stores beside the match files (linemod.py:172-173: cv2.imwrite(<dir>/img0/<pair>.png, crop)),
+ * read back with cv2.imread (pose/dataset.py:102-103).  img: host memory, 8 bits per channel in OpenCV's order ([height,
+ * width, channels] with channels = 1 grey, 3 BGR, 4 BGRA), `pitch` bytes between rows; level = zlib level 0..9 (OpenCV's
+ * default is 1).  The file decodes to exactly the input pixels; its bytes are not libpng's (other filter choice). */
+int pope_write_png(const char* path, const unsigned char* img, int height, int width, int channels, int64_t pitch, int level);
+/* n densely packed images of possibly different sizes on n_threads host threads (<= 0: all cores). */
+int pope_write_png_batch(const char* const* paths, const unsigned char* const* imgs, const int32_t* heights,
+                         const int32_t* widths, int channels, int n, int level, int n_threads);
+
 /* ---- fine-level transformer and FinePreprocess Linears (bf16) ---------------------------------
  * Replace src/matcher/loftr_module/transformer.py:34-58,95-104 + linear_attention.py:21-47 (LocalFeatureTransformer with
  * d_model 128, 8 heads, 'linear' attention) and fine_preprocess.py:50-57 (down_proj / merge_feat) of the reference.

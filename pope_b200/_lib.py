@@ -45,6 +45,8 @@ SIGNATURES = {
     "pope_write_match_files": (_i, [C.c_char_p, C.POINTER(C.c_char_p), _i, _p, _p, _p, _i64, _i, _i, C.POINTER(C.c_int32)]),
     "pope_loadtxt_f64": (_i, [C.c_char_p, _p, _i64, C.POINTER(_i64), C.POINTER(_i)]),
     "pope_read_match_files": (_i, [C.c_char_p, C.POINTER(C.c_char_p), _i, _p, _p, _p, _i64, _i]),
+    "pope_write_png": (_i, [C.c_char_p, _p, _i, _i, _i, _i64, _i]),
+    "pope_write_png_batch": (_i, [C.POINTER(C.c_char_p), C.POINTER(_p), _p, _p, _i, _i, _i, _i]),
     "pope_pack_records": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p]),
     "pope_match_scores": (_i, [_p, _p, _i, _i, _f, _p, _p, _p]),
     "pope_pose_workspace_bytes": (_sz, [_i, _i64]),

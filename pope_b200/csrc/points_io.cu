@@ -12,6 +12,7 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include <atomic>
 #include <charconv>
@@ -124,6 +125,113 @@ extern "C" int pope_savetxt_f32(const char* path, const float* data, int64_t row
 extern "C" int pope_savetxt_f64(const char* path, const double* data, int64_t rows, int cols) {
   if (!path || (!data && rows > 0) || rows < 0 || cols <= 0) return POPE_ERR_INVALID_ARG;
   return write_txt<double>(path, data, rows, cols);
+}
+
+// ---- PNG crops (linemod.py:172-173 writes them with cv2.imwrite, pose/dataset.py:102-103 reads them with cv2.imread) --------
+namespace {
+
+void put_be32(std::vector<unsigned char>& v, uint32_t x) {
+  v.push_back((unsigned char)(x >> 24)); v.push_back((unsigned char)(x >> 16)); v.push_back((unsigned char)(x >> 8)); v.push_back((unsigned char)x);
+}
+void put_chunk(std::vector<unsigned char>& out, const char* type, const unsigned char* data, size_t n) {
+  put_be32(out, uint32_t(n));
+  const size_t at = out.size();
+  out.insert(out.end(), type, type + 4);
+  if (n) out.insert(out.end(), data, data + n);
+  put_be32(out, uint32_t(crc32(0L, out.data() + at, uInt(n + 4))));
+}
+
+// 8-bit image in OpenCV's memory order ([h, w, c] with c = 1 grey, 3 BGR, 4 BGRA; row pitch in bytes) -> PNG file: channels
+// swapped to PNG's RGB(A) order, every scanline predicted from its left neighbour ('Sub' filter), one zlib stream.
+// raw / z / out: scratch owned by the calling thread and reused from image to image (fresh megabyte-sized allocations per
+// image serialise the threads of the batch writer in the kernel's page-fault path)
+int write_png(const char* path, const unsigned char* img, int h, int w, int c, int64_t pitch, int level,
+              std::vector<unsigned char>& raw, std::vector<unsigned char>& z, std::vector<unsigned char>& out) {
+  if (h <= 0 || w <= 0 || (c != 1 && c != 3 && c != 4)) return POPE_ERR_SHAPE;
+  const size_t row = size_t(w) * c;
+  if (raw.size() < (row + 1) * size_t(h)) raw.resize((row + 1) * size_t(h));
+  const size_t raw_len = (row + 1) * size_t(h);
+  for (int y = 0; y < h; ++y) {
+    const unsigned char* src = img + size_t(y) * pitch;
+    unsigned char* dst = raw.data() + (row + 1) * size_t(y);
+    *dst++ = 1;                                             // filter type Sub
+    if (c == 3) {                                           // BGR -> RGB, the common case
+      unsigned char pr = 0, pg = 0, pb = 0;
+      for (int x = 0; x < w; ++x) {
+        const unsigned char b = src[3 * x], g = src[3 * x + 1], r = src[3 * x + 2];
+        dst[3 * x] = (unsigned char)(r - pr); dst[3 * x + 1] = (unsigned char)(g - pg); dst[3 * x + 2] = (unsigned char)(b - pb);
+        pr = r; pg = g; pb = b;
+      }
+    } else {
+      for (int x = 0; x < w; ++x)
+        for (int k = 0; k < c; ++k) {
+          const int ks = (c == 4 && k < 3) ? 2 - k : k;     // BGRA -> RGBA
+          const unsigned char cur = src[size_t(x) * c + ks], left = x ? src[size_t(x - 1) * c + ks] : 0;
+          dst[size_t(x) * c + k] = (unsigned char)(cur - left);
+        }
+    }
+  }
+  // run-length strategy: what OpenCV's encoder uses by default, fast on filtered scanlines
+  z_stream zs;
+  memset(&zs, 0, sizeof(zs));
+  if (deflateInit2(&zs, level, Z_DEFLATED, 15, 8, Z_RLE) != Z_OK) return POPE_ERR_IO;
+  uLongf zlen = deflateBound(&zs, uLong(raw_len));
+  if (z.size() < zlen) z.resize(zlen);
+  zs.next_in = raw.data(); zs.avail_in = uInt(raw_len);
+  zs.next_out = z.data(); zs.avail_out = uInt(zlen);
+  const int zrc = deflate(&zs, Z_FINISH);
+  zlen = zs.total_out;
+  deflateEnd(&zs);
+  if (zrc != Z_STREAM_END) return POPE_ERR_IO;
+  out.clear();
+  out.reserve(zlen + 64);
+  static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  out.insert(out.end(), sig, sig + 8);
+  std::vector<unsigned char> hdr;
+  put_be32(hdr, uint32_t(w));
+  put_be32(hdr, uint32_t(h));
+  const unsigned char tail[5] = {8, (unsigned char)(c == 1 ? 0 : c == 3 ? 2 : 6), 0, 0, 0};   // depth, colour type, deflate, filter, no interlace
+  hdr.insert(hdr.end(), tail, tail + 5);
+  put_chunk(out, "IHDR", hdr.data(), hdr.size());
+  put_chunk(out, "IDAT", z.data(), zlen);
+  put_chunk(out, "IEND", nullptr, 0);
+  FILE* f = fopen(path, "wb");
+  if (!f) return POPE_ERR_IO;
+  const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+  return (fclose(f) == 0 && ok) ? POPE_OK : POPE_ERR_IO;
+}
+
+}  // namespace
+
+extern "C" int pope_write_png(const char* path, const unsigned char* img, int height, int width, int channels, int64_t pitch,
+                              int level) {
+  if (!path || !img || pitch < int64_t(width) * channels || level < 0 || level > 9) return POPE_ERR_INVALID_ARG;
+  std::vector<unsigned char> raw, z, out;
+  return write_png(path, img, height, width, channels, pitch, level, raw, z, out);
+}
+
+extern "C" int pope_write_png_batch(const char* const* paths, const unsigned char* const* imgs, const int32_t* heights,
+                                    const int32_t* widths, int channels, int n, int level, int n_threads) {
+  if (!paths || !imgs || !heights || !widths || n < 0 || level < 0 || level > 9) return POPE_ERR_INVALID_ARG;
+  if (n_threads <= 0) n_threads = int(sysconf(_SC_NPROCESSORS_ONLN));
+  if (n_threads <= 0) n_threads = 1;
+  if (n_threads > 64) n_threads = 64;
+  if (n_threads > n) n_threads = n > 0 ? n : 1;
+  std::atomic<int> next(0), status(POPE_OK);
+  auto work = [&]() {
+    std::vector<unsigned char> raw, z, out;
+    for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
+      if (!paths[i] || !imgs[i]) { status.store(POPE_ERR_INVALID_ARG); continue; }
+      const int rc = write_png(paths[i], imgs[i], heights[i], widths[i], channels, int64_t(widths[i]) * channels, level, raw, z,
+                               out);
+      if (rc != POPE_OK) status.store(rc);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  return status.load();
 }
 
 extern "C" int pope_loadtxt_f64(const char* path, double* out, int64_t capacity, int64_t* rows, int* cols) {

@@ -80,3 +80,34 @@ def read_match_files(in_dir: str, names: Sequence[str], capacity: int, threads: 
                                      int(threads))
     check(st, "pope_read_match_files")
     return {"mkpts0_f": k0, "mkpts1_f": k1, "counts": cnt}
+
+
+def imwrite_png(path: str, img, level: int = 1) -> None:
+    """cv2.imwrite(path, img) for an 8-bit [h, w], [h, w, 1], [h, w, 3] (BGR) or [h, w, 4] (BGRA) array: the PNG decodes to
+    exactly these pixels (linemod.py:172-173 / pose/dataset.py:102-103)."""
+    a = img.detach().cpu().numpy() if torch.is_tensor(img) else np.asarray(img)
+    if a.dtype != np.uint8 or a.ndim not in (2, 3):
+        raise PopeError("imwrite_png takes uint8 arrays of shape [h, w] or [h, w, c]")
+    a = np.ascontiguousarray(a)
+    h, w = a.shape[:2]
+    c = 1 if a.ndim == 2 else a.shape[2]
+    check(lib().pope_write_png(os.fsencode(path), a.ctypes.data, h, w, c, w * c, int(level)), "pope_write_png")
+
+
+def imwrite_png_batch(paths: Sequence[str], imgs: Sequence[np.ndarray], level: int = 1, threads: int = 0) -> None:
+    """All crops of a batch on native threads; imgs: uint8 arrays with the same channel count, any sizes."""
+    n = len(paths)
+    if n != len(imgs):
+        raise PopeError("one path per image is required")
+    if n == 0:
+        return
+    arrs = [np.ascontiguousarray(i.detach().cpu().numpy() if torch.is_tensor(i) else i) for i in imgs]
+    cs = {1 if a.ndim == 2 else a.shape[2] for a in arrs}
+    if len(cs) != 1 or any(a.dtype != np.uint8 or a.ndim not in (2, 3) for a in arrs):
+        raise PopeError("imwrite_png_batch takes uint8 images with one common channel count")
+    p = (C.c_char_p * n)(*[os.fsencode(s) for s in paths])
+    d = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    hs = np.array([a.shape[0] for a in arrs], dtype=np.int32)
+    ws = np.array([a.shape[1] for a in arrs], dtype=np.int32)
+    check(lib().pope_write_png_batch(p, d, hs.ctypes.data, ws.ctypes.data, cs.pop(), n, int(level), int(threads)),
+          "pope_write_png_batch")

@@ -120,3 +120,33 @@ def test_read_match_files_round_trip(tmp_path):
     short = points_io.read_match_files(str(tmp_path / "obj"), names, 10)          # truncation at the slot capacity
     assert short["counts"].tolist() == [10, -1, 10, -1, 5, 10, 9]
     assert torch.equal(short["mkpts0_f"][0], out["mkpts0_f"][0, :10])
+
+
+def test_png_crops_decode_to_the_input(tmp_path):
+    """linemod.py:172-173 writes the two crops with cv2.imwrite, pose/dataset.py:102-103 reads them with cv2.imread: the
+    native writer's files must decode to the same pixels as cv2's own files (and as the input)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    yy, xx = np.mgrid[0:97, 0:131]
+    smooth = np.stack([128 + 100 * np.sin(xx / 17.0 + yy / 29.0), 128 + 90 * np.cos(xx / 23.0), yy * 2.0], 2).clip(0, 255).astype(np.uint8)
+    cases = [rng.integers(0, 256, (37, 53, 3), dtype=np.uint8), smooth, rng.integers(0, 256, (64, 64), dtype=np.uint8),
+             rng.integers(0, 256, (20, 31, 1), dtype=np.uint8), rng.integers(0, 256, (15, 17, 4), dtype=np.uint8),
+             np.zeros((1, 1, 3), np.uint8), np.full((5, 300, 3), 255, np.uint8)]
+    for k, a in enumerate(cases):
+        ours, ref = str(tmp_path / f"a{k}.png"), str(tmp_path / f"b{k}.png")
+        points_io.imwrite_png(ours, a)
+        assert cv2.imwrite(ref, a)
+        for flag in (cv2.IMREAD_UNCHANGED, cv2.IMREAD_COLOR):
+            x, y = cv2.imread(ours, flag), cv2.imread(ref, flag)
+            assert x is not None and x.shape == y.shape and np.array_equal(x, y), (k, flag)
+        assert np.array_equal(cv2.imread(ours, cv2.IMREAD_UNCHANGED).reshape(a.shape), a)
+    paths = [str(tmp_path / f"batch{k}.png") for k in range(3)]
+    points_io.imwrite_png_batch(paths, [cases[0], cases[1], torch.from_numpy(cases[6])], threads=2)
+    for p, a in zip(paths, (cases[0], cases[1], cases[6])):
+        assert np.array_equal(cv2.imread(p), a)
+    with pytest.raises(Exception):
+        points_io.imwrite_png(str(tmp_path / "bad.png"), np.zeros((4, 4, 2), np.uint8))
+    with pytest.raises(Exception):
+        points_io.imwrite_png(str(tmp_path / "bad.png"), np.zeros((4, 4, 3), np.float32))
+    with pytest.raises(Exception):
+        points_io.imwrite_png(str(tmp_path / "no_such_dir" / "x.png"), cases[0])

@@ -47,4 +47,30 @@ for p in range(n_np):
     b = np.loadtxt(d + f"/b0/mkpts1/{names[p]}.txt", delimiter=" ")
 dt = time.perf_counter() - t0
 print(f"numpy.loadtxt loop over {n_np} pairs: {1e3 * dt:.1f} ms ({n_np / dt:.0f} pairs/s); round trip exact: {ok}")
+# the two crops per pair (linemod.py:172-173 writes them with cv2.imwrite)
+try:
+    import cv2
+    cv2.setNumThreads(1)
+    yy, xx = np.mgrid[0:480, 0:640]
+    img = np.stack([128 + 100 * np.sin(xx / 37.0 + yy / 91.0), 128 + 90 * np.cos(xx / 53.0), yy / 2.0], 2)
+    img = (img + rng.normal(0, 4, img.shape)).clip(0, 255).astype(np.uint8)
+    crops = [np.ascontiguousarray(img[: rng.integers(200, 480), : rng.integers(200, 640)]) for _ in range(128)]
+    os.makedirs(d + "/png")
+    t0 = time.perf_counter()
+    for i, c in enumerate(crops):
+        cv2.imwrite(d + f"/png/c{i}.png", c)
+    t_cv = time.perf_counter() - t0
+    line = f"128 crops (200-480 x 200-640 BGR): cv2.imwrite loop {1e3 * t_cv:.0f} ms"
+    for thr in (1, 0):
+        dt = 1e9
+        for rep in range(3):
+            t0 = time.perf_counter()
+            points_io.imwrite_png_batch([d + f"/png/p{i}.png" for i in range(128)], crops, threads=thr)
+            dt = min(dt, time.perf_counter() - t0)
+        line += f"; native, threads={'all' if thr == 0 else thr}: {1e3 * dt:.0f} ms"
+    same = all(np.array_equal(cv2.imread(d + f"/png/p{i}.png"), crops[i]) for i in range(128))
+    size = lambda pre: sum(os.path.getsize(d + f"/png/{pre}{i}.png") for i in range(128)) >> 10
+    print(line + f"; decoded equal: {same}; {size('c')} KB (cv2) vs {size('p')} KB")
+except ImportError:
+    print("cv2 not importable: PNG comparison skipped")
 shutil.rmtree(d)
