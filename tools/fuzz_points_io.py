@@ -24,4 +24,17 @@ for case in range(400):
         got=points_io.loadtxt(p1)
     if got.shape!=want.shape or not np.array_equal(got,want,equal_nan=True) or not np.array_equal(np.signbit(got[~np.isnan(got)]),np.signbit(want[~np.isnan(want)])):
         bad+=1; print("loadtxt differs",case,a.shape,got.shape,want.shape)
+try:
+    import cv2
+    for case in range(300):
+        h,w=int(rng.integers(1,70)),int(rng.integers(1,70)); c=int(rng.choice([1,3,4]))
+        a=rng.integers(0,256,(h,w,c),dtype=np.uint8) if rng.random()<0.5 else np.repeat(rng.integers(0,256,(h,1,c),dtype=np.uint8),w,1)
+        if c==1 and rng.random()<0.5: a=a[:,:,0].copy()
+        p1,p2=os.path.join(d,"a.png"),os.path.join(d,"b.png")
+        points_io.imwrite_png(p1,a,level=int(rng.integers(0,10))); cv2.imwrite(p2,a)
+        x,y=cv2.imread(p1,cv2.IMREAD_UNCHANGED),cv2.imread(p2,cv2.IMREAD_UNCHANGED)
+        if x is None or x.shape!=y.shape or not np.array_equal(x,y): bad+=1; print("png differs",case,a.shape)
+    print("png: 300 cases")
+except ImportError:
+    print("cv2 not importable: PNG cases skipped")
 print("points_io fuzz: 400 cases,",bad,"failures")
