@@ -111,3 +111,29 @@ def imwrite_png_batch(paths: Sequence[str], imgs: Sequence[np.ndarray], level: i
     ws = np.array([a.shape[1] for a in arrs], dtype=np.int32)
     check(lib().pope_write_png_batch(p, d, hs.ctypes.data, ws.ctypes.data, cs.pop(), n, int(level), int(threads)),
           "pope_write_png_batch")
+
+
+def write_pair_records(out_dir: str, names: Sequence[str], out: Dict[str, torch.Tensor], pre_bbox, pre_K, crops0=None,
+                       crops1=None, min_matches: int = 5, threads: int = 0) -> int:
+    """Everything linemod.py:147-173 stores for the pairs of one object directory, for a whole batch:
+    <out_dir>/{pre_bbox,mkpts0,mkpts1,pre_K}/<name>.txt and, when crops are given, <out_dir>/{img0,img1}/<name>.png.
+    `out`: the host pipeline's per-pair slots (see write_match_files); pre_bbox [n, 4], pre_K [n, 3, 3]; crops0 / crops1:
+    lists of uint8 BGR images.  Pairs with fewer than `min_matches` matches or a pre_K that is not 3 x 3 are skipped like the
+    reference does (:142-146).  Returns the number of pairs written."""
+    n = len(names)
+    counts = out["counts"].tolist()
+    pre_bbox, pre_K = np.asarray(pre_bbox, dtype=np.float64), np.asarray(pre_K, dtype=np.float64)
+    if pre_bbox.shape[0] != n or pre_K.shape[0] != n or pre_K.shape[1:] != (3, 3):
+        raise PopeError("pre_bbox [n, 4] and pre_K [n, 3, 3] are required, one per pair")
+    for sub in ("pre_bbox", "pre_K") + (("img0", "img1") if crops0 is not None else ()):
+        os.makedirs(os.path.join(out_dir, sub), exist_ok=True)
+    written = write_match_files(out_dir, names, out, min_matches, threads)
+    live = [p for p in range(n) if counts[p] >= min_matches]
+    for p in live:                                               # two tiny files per pair
+        savetxt(os.path.join(out_dir, "pre_bbox", names[p] + ".txt"), pre_bbox[p])
+        savetxt(os.path.join(out_dir, "pre_K", names[p] + ".txt"), pre_K[p])
+    if crops0 is not None:
+        imwrite_png_batch([os.path.join(out_dir, "img0", names[p] + ".png") for p in live] +
+                          [os.path.join(out_dir, "img1", names[p] + ".png") for p in live],
+                          [crops0[p] for p in live] + [crops1[p] for p in live], threads=threads)
+    return written

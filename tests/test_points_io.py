@@ -150,3 +150,40 @@ def test_png_crops_decode_to_the_input(tmp_path):
         points_io.imwrite_png(str(tmp_path / "bad.png"), np.zeros((4, 4, 3), np.float32))
     with pytest.raises(Exception):
         points_io.imwrite_png(str(tmp_path / "no_such_dir" / "x.png"), cases[0])
+
+
+def test_write_pair_records_equals_the_reference_loop(tmp_path):
+    """The six per-pair artefacts of linemod.py:147-173 for a batch, against that loop restated with numpy / cv2."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    n, cap = 5, 30
+    out = {"mkpts0_f": torch.from_numpy(rng.uniform(0, 640, (n, cap, 2)).astype(np.float32)),
+           "mkpts1_f": torch.from_numpy(rng.uniform(0, 480, (n, cap, 2)).astype(np.float32)),
+           "counts": torch.tensor([30, 3, 12, 5, 0], dtype=torch.int32)}
+    names = [f"{i:04d}-{i + 7:04d}" for i in range(n)]
+    bbox = rng.uniform(0, 400, (n, 4))
+    Ks = np.tile(np.array([[572.4, 0, 325.3], [0, 573.6, 242.0], [0, 0, 1.0]]), (n, 1, 1)) + rng.normal(0, 1, (n, 3, 3))
+    c0 = [rng.integers(0, 256, (int(rng.integers(8, 40)), int(rng.integers(8, 40)), 3), dtype=np.uint8) for _ in range(n)]
+    c1 = [rng.integers(0, 256, (int(rng.integers(8, 40)), int(rng.integers(8, 40)), 3), dtype=np.uint8) for _ in range(n)]
+    got, ref = tmp_path / "got", tmp_path / "ref"
+    assert points_io.write_pair_records(str(got), names, out, bbox, Ks, c0, c1) == 3
+    for p in range(n):                                           # the reference loop (linemod.py:142-173)
+        m = int(out["counts"][p])
+        if m < 5:
+            continue
+        for sub in ("pre_bbox", "mkpts0", "mkpts1", "pre_K", "img0", "img1"):
+            (ref / sub).mkdir(parents=True, exist_ok=True)
+        np.savetxt(ref / "pre_bbox" / f"{names[p]}.txt", bbox[p])
+        np.savetxt(ref / "mkpts0" / f"{names[p]}.txt", out["mkpts0_f"][p, :m].numpy())
+        np.savetxt(ref / "mkpts1" / f"{names[p]}.txt", out["mkpts1_f"][p, :m].numpy())
+        np.savetxt(ref / "pre_K" / f"{names[p]}.txt", Ks[p])
+        cv2.imwrite(str(ref / "img0" / f"{names[p]}.png"), c0[p])
+        cv2.imwrite(str(ref / "img1" / f"{names[p]}.png"), c1[p])
+    for sub in ("pre_bbox", "mkpts0", "mkpts1", "pre_K", "img0", "img1"):
+        want = sorted(os.listdir(ref / sub))
+        assert sorted(os.listdir(got / sub)) == want and len(want) == 3, sub
+        for f in want:
+            if f.endswith(".txt"):
+                assert (got / sub / f).read_bytes() == (ref / sub / f).read_bytes(), (sub, f)
+            else:
+                assert np.array_equal(cv2.imread(str(got / sub / f)), cv2.imread(str(ref / sub / f))), (sub, f)
