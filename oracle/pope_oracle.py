@@ -101,6 +101,54 @@ def coarse_match(feat_c0: torch.Tensor, feat_c1: torch.Tensor, hw0_i, hw0_c, hw1
     return {k: torch.cat([o[k] for o in outs]) for k in outs[0]}
 
 
+def _interior_padded(mask2d: torch.Tensor, bd: int) -> torch.Tensor:
+    """Bool [h*w]: cells that survive `mask_border_with_padding` (coarse_matching.py:28-43) for one image whose valid
+    (unpadded) area is given by mask2d [h, w]: the first bd rows / columns and everything from (valid height - bd) /
+    (valid width - bd) on are cleared, with the valid extents taken as the reference takes them (:38-39: the largest
+    column sum and the largest row sum of the mask) and with Python's slice semantics for the upper bounds."""
+    h, w = mask2d.shape
+    keep = torch.ones(h, w, dtype=torch.bool)
+    if bd <= 0:
+        return keep.reshape(-1)
+    hv = int(mask2d.sum(0).max())
+    wv = int(mask2d.sum(1).max())
+    keep[:bd] = False
+    keep[:, :bd] = False
+    keep[hv - bd:] = False
+    keep[:, wv - bd:] = False
+    return keep.reshape(-1)
+
+
+def coarse_match_masked(feat_c0: torch.Tensor, feat_c1: torch.Tensor, hw0_i, hw0_c, hw1_c, mask0: torch.Tensor,
+                        mask1: torch.Tensor, thr: float = THR, border_rm: int = BORDER_RM,
+                        temperature: float = DSMAX_TEMPERATURE) -> Dict[str, torch.Tensor]:
+    """CoarseMatching.forward with padding masks (the MegaDepth-style batches of the reference): mask0 [N, h0c, w0c],
+    mask1 [N, h1c, w1c] bool, True = valid cell.  Follows coarse_matching.py:115-118 (similarities of invalid cells filled
+    with -1e9 before the two softmaxes), :176-184 with `mask_border_with_padding` (:28-43) instead of `mask_border`,
+    :187-196 and :239-259 as in `coarse_match_from_conf`."""
+    n, l, c = feat_c0.shape
+    s = feat_c1.shape[1]
+    m0, m1 = mask0.reshape(n, l).bool(), mask1.reshape(n, s).bool()
+    sim = torch.einsum("nlc,nsc->nls", feat_c0.float() / c ** 0.5, feat_c1.float() / c ** 0.5) / temperature
+    sim = sim.masked_fill(~(m0[:, :, None] & m1[:, None, :]), -1e9)
+    conf = F.softmax(sim, 1) * F.softmax(sim, 2)
+    keep0 = torch.stack([_interior_padded(mask0[b].bool(), border_rm) for b in range(n)])
+    keep1 = torch.stack([_interior_padded(mask1[b].bool(), border_rm) for b in range(n)])
+    sel = (conf > thr) & keep0[:, :, None] & keep1[:, None, :]
+    sel &= conf == conf.max(dim=2, keepdim=True)[0]
+    sel &= conf == conf.max(dim=1, keepdim=True)[0]
+    row_has, row_arg = sel.max(dim=2)
+    b_ids, i_ids = torch.where(row_has)
+    j_ids = row_arg[b_ids, i_ids]
+    mconf = conf[b_ids, i_ids, j_ids]
+    scale = hw0_i[0] / hw0_c[0]
+    mk0 = torch.stack([i_ids % hw0_c[1], i_ids // hw0_c[1]], dim=1) * scale
+    mk1 = torch.stack([j_ids % hw1_c[1], j_ids // hw1_c[1]], dim=1) * scale
+    live = mconf != 0
+    return {"b_ids": b_ids, "i_ids": i_ids, "j_ids": j_ids, "gt_mask": mconf == 0, "m_bids": b_ids[live],
+            "mkpts0_c": mk0[live], "mkpts1_c": mk1[live], "mconf": mconf[live], "conf_matrix": conf}
+
+
 def fine_windows(feat_f: torch.Tensor, b_ids: torch.Tensor, cell_ids: torch.Tensor, W: int = FINE_WINDOW,
                  stride: int = 4) -> torch.Tensor:
     """The unfold + gather of src/matcher/loftr_module/fine_preprocess.py:40-47 for one image:
