@@ -62,10 +62,11 @@ def _worker(rank, world, port, n_pairs, q):
     job.add(res, lo)
     recs, sizes = job.finish(rank, world)
     if rank == 0:
-        payload = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in got.items()}
+        # numpy arrays travel through the queue by value; tensors would travel as file descriptors that die with this process
+        payload = {k: (v.numpy().copy() if torch.is_tensor(v) else v) for k, v in got.items()}
         payload["job_sizes"] = sizes
-        payload["job_b"] = torch.cat([recs[r, :sizes[r], 0] for r in range(world)]).clone()
-        payload["job_conf"] = torch.cat([recs[r, :sizes[r], 3] for r in range(world)]).view(torch.float32).clone()
+        payload["job_b"] = torch.cat([recs[r, :sizes[r], 0] for r in range(world)]).numpy().copy()
+        payload["job_conf"] = torch.cat([recs[r, :sizes[r], 3] for r in range(world)]).view(torch.float32).numpy().copy()
         q.put(payload)
     dist.barrier()
     dist.destroy_process_group()
@@ -85,6 +86,7 @@ def test_two_rank_gather_equals_single_process():
     for p in procs:
         p.start()
     got = q.get(timeout=180)
+    got = {k: (torch.from_numpy(v) if hasattr(v, "dtype") else v) for k, v in got.items()}
     for p in procs:
         p.join(60)
         assert p.exitcode == 0

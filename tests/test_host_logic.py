@@ -59,8 +59,10 @@ def test_hot_path_has_no_cpu_fallback():
         pope_b200.FineMatching().eval()(torch.randn(4, 25, 128), torch.randn(4, 25, 128),
                                         {"hw0_i": (64, 64), "hw0_f": (32, 32), "mconf": torch.ones(4),
                                          "mkpts0_c": torch.zeros(4, 2), "mkpts1_c": torch.zeros(4, 2)})
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_lib.PopeError):                                       # the padded-batch route is CUDA-only as well
         cm(torch.randn(1, 64, 256), torch.randn(1, 64, 256), data, mask_c0=torch.ones(1, 64), mask_c1=torch.ones(1, 64))
+    with pytest.raises(NotImplementedError):                                  # the training-time sampling branch is not built
+        cm.train()(torch.randn(1, 64, 256), torch.randn(1, 64, 256), data)
 
 
 def test_product_package_never_imports_the_oracle():
