@@ -320,3 +320,48 @@ def run_sharded(n_pairs: int, rank: int, world: int, local_fn: Callable[[int, in
     lo, hi = shard_range(n_pairs, rank, world)
     local = local_fn(lo, hi)
     return gather_matches(local, n_pairs, rank, world, group, device)
+
+
+# ---- the pair loop of the evaluation scripts (eval_linemod_json.py:103-122, :146-149) ---------------------------------------
+
+def bgr_to_gray(img: torch.Tensor) -> torch.Tensor:
+    """cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) for a uint8 [..., H, W, 3] tensor, on the tensor's device: OpenCV's 8-bit
+    path (4.x) is the fixed-point sum (B * 3735 + G * 19235 + R * 9798 + 16384) >> 15, reproduced exactly (checked over all
+    2^24 colours in tests/test_driver_sharding.py)."""
+    if img.dtype != torch.uint8 or img.shape[-1] != 3:
+        raise _lib.PopeError("bgr_to_gray takes uint8 images with three channels last")
+    x = img.to(torch.int32)
+    return ((x[..., 0] * 3735 + x[..., 1] * 19235 + x[..., 2] * 9798 + 16384) >> 15).to(torch.uint8)
+
+
+def match_crops(matcher, image0: torch.Tensor, crops: Sequence[torch.Tensor], conf_thr: float = 0.9):
+    """The reference's per-query loop (eval_linemod_json.py:103-122, :146-149): the query image against each of the
+    retrieved crops -- grey conversion, / 255, one Matcher call per crop, `matching_score` = number of matches with
+    mconf > 0.9, best crop = first arg-max.  Here crops of equal size go through ONE Matcher call (image0 repeated), and the
+    scores and the arg-max are computed on the device (`pope_match_scores`); the only host reads are the ones the Matcher
+    itself needs.  image0 / crops: uint8 BGR [H, W, 3] tensors on the matcher's device.
+    Returns (per-crop list of dicts with mkpts0_f / mkpts1_f / mconf, scores int32 [n_crops] (device), best int)."""
+    from . import ops
+    dev = image0.device
+    g0 = (bgr_to_gray(image0).float() / 255.0)[None, None]
+    results = [None] * len(crops)
+    scores = torch.zeros(len(crops), dtype=torch.int32, device=dev)
+    by_size = {}
+    for k, c in enumerate(crops):
+        by_size.setdefault(tuple(c.shape[:2]), []).append(k)
+    for size, ks in by_size.items():
+        g1 = torch.stack([bgr_to_gray(crops[k]).float() / 255.0 for k in ks])[:, None]
+        batch = {"image0": g0.expand(len(ks), -1, -1, -1).contiguous(), "image1": g1}
+        with torch.no_grad():
+            matcher(batch)
+        counts = torch.bincount(batch["b_ids"], minlength=len(ks)).to(torch.int32)
+        if batch["mconf"].numel():
+            sc, _ = ops.match_scores(batch["mconf"].contiguous(), counts, len(ks), group=len(ks), thr=conf_thr)
+        else:
+            sc = torch.zeros(len(ks), dtype=torch.int32, device=dev)
+        for slot, k in enumerate(ks):
+            sel = batch["b_ids"] == slot
+            results[k] = {"mkpts0_f": batch["mkpts0_f"][sel], "mkpts1_f": batch["mkpts1_f"][sel], "mconf": batch["mconf"][sel]}
+            scores[k] = sc[slot]
+    best = int(torch.argmax(scores).item()) if len(crops) else -1        # torch.argmax returns the first maximum, like np.argmax
+    return results, scores, best

@@ -2,6 +2,8 @@
 the checker here, the thing under test is the partition + the single gather)."""
 import os
 
+import pytest
+
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -106,3 +108,15 @@ def test_two_rank_gather_equals_single_process():
     want_b = torch.cat([want["b_ids"][off[r]:off[r + 1]].repeat(2) for r in range(2)]).to(torch.int32)
     want_c = torch.cat([want["mconf"][off[r]:off[r + 1]].repeat(2) for r in range(2)])
     assert torch.equal(got["job_b"], want_b) and torch.equal(got["job_conf"], want_c)
+
+
+def test_bgr_to_gray_equals_cv2_for_every_colour():
+    """The grey conversion of the evaluation loop (eval_linemod_json.py:103, :109) on the device = cv2's 8-bit path."""
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    from pope_b200 import driver
+    r = np.arange(256, dtype=np.uint8)
+    for b in range(0, 256, 8):                               # 32 slabs of 8 x 256 x 256 colours = all 2^24
+        bb = np.arange(b, b + 8, dtype=np.uint8)
+        cube = np.stack(np.meshgrid(bb, r, r, indexing="ij"), -1).reshape(8, 65536, 3)
+        assert np.array_equal(driver.bgr_to_gray(torch.from_numpy(cube)).numpy(), cv2.cvtColor(cube, cv2.COLOR_BGR2GRAY)), b

@@ -519,3 +519,48 @@ def test_device_batch_runner_equals_sequential_steps():
         assert res.total() == m and m > 100
         for k in ("b_ids", "i_ids", "j_ids", "mconf", "mkpts1_f", "expec_f"):
             assert torch.equal(res[k][:m], want[k][:m]), k
+
+
+def test_match_crops_equals_the_reference_pair_loop():
+    """driver.match_crops against the loop of eval_linemod_json.py:103-122 / :146 restated with cv2 + numpy.  A stand-in
+    matcher whose output is a deterministic function of its two input images makes the comparison non-vacuous (the real
+    Matcher with random weights finds no match); the real Matcher then runs through the same helper for the flow."""
+    import cv2
+    import pope_b200
+    from pope_b200 import driver
+
+    def fake_matcher(batch):
+        n = batch["image0"].shape[0]
+        b, conf, k0, k1 = [], [], [], []
+        for p in range(n):
+            key1 = int((batch["image1"][p] * 255).round().long().sum().item())       # exact, whatever the batching
+            key0 = int((batch["image0"][p] * 255).round().long().sum().item())
+            m = key1 % 40 + 3
+            s = float(key0 % 7)
+            t = torch.arange(m, device=batch["image1"].device, dtype=torch.float32)
+            b.append(torch.full((m,), p, device=t.device, dtype=torch.int64))
+            conf.append(((t * 37 + key1 % 100) % 100) / 100.0)
+            k0.append(torch.stack([t * s, t + 1], 1))
+            k1.append(torch.stack([t + 2, t * 3], 1))
+        batch.update(b_ids=torch.cat(b), mconf=torch.cat(conf), mkpts0_f=torch.cat(k0), mkpts1_f=torch.cat(k1))
+
+    rng = np.random.default_rng(8)
+    image0 = rng.integers(0, 256, (48, 64, 3), dtype=np.uint8)
+    crops = [rng.integers(0, 256, s + (3,), dtype=np.uint8) for s in ((32, 40), (24, 24), (32, 40), (32, 40), (24, 24))]
+    res, scores, best = driver.match_crops(fake_matcher, torch.from_numpy(image0).to(DEV), [torch.from_numpy(c).to(DEV) for c in crops])
+    want_scores = []
+    for k, c in enumerate(crops):                              # the reference loop, one call per crop
+        g0 = torch.from_numpy(cv2.cvtColor(image0, cv2.COLOR_BGR2GRAY)).float()[None] / 255.
+        g1 = torch.from_numpy(cv2.cvtColor(c, cv2.COLOR_BGR2GRAY)).float()[None] / 255.
+        batch = {"image0": g0.unsqueeze(0).to(DEV), "image1": g1.unsqueeze(0).to(DEV)}
+        fake_matcher(batch)
+        conf = batch["mconf"].cpu().numpy()
+        want_scores.append(int(np.where(conf > 0.9)[0].shape[0]))
+        assert torch.equal(res[k]["mconf"], batch["mconf"]) and torch.equal(res[k]["mkpts0_f"], batch["mkpts0_f"])
+        assert torch.equal(res[k]["mkpts1_f"], batch["mkpts1_f"])
+    assert scores.tolist() == want_scores and best == int(np.argmax(want_scores)) and max(want_scores) > 0
+    # flow with the real module (random weights: no matches, every score 0, first crop wins like np.argmax)
+    torch.manual_seed(0)
+    matcher = pope_b200.Matcher(pope_b200.make_default_cfg()).eval().to(DEV)
+    res, scores, best = driver.match_crops(matcher, torch.from_numpy(image0).to(DEV), [torch.from_numpy(c).to(DEV) for c in crops[:3]])
+    assert len(res) == 3 and scores.tolist() == [0, 0, 0] and best == 0 and res[1]["mkpts0_f"].shape == (0, 2)
