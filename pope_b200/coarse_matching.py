@@ -3,7 +3,9 @@
 Same constructor config keys, same call signature `forward(feat_c0, feat_c1, data, mask_c0=None, mask_c1=None)`,
 same keys written into `data` (b_ids, i_ids, j_ids, gt_mask, m_bids, mkpts0_c, mkpts1_c, mconf) with the same
 dtypes and (b, i) ordering.  Deviations, all documented in DESIGN.md:
-  * `data['conf_matrix']` is not produced (the L x S matrix never exists; only the training loss reads it).
+  * `data['conf_matrix']` is not produced (the L x S matrix never exists; only the training loss reads it) unless the
+    debug switch `materialize_conf_matrix` is set: then it is written with the reference's own torch op sequence on the
+    device (an extra output for inspection; the match list still comes from the CUDA path and never reads it).
   * padding masks (`mask_c0/mask_c1`, `data['mask0']`; :115-118, :28-43, :180-182) are handled by running the CUDA path on
     the valid cells of every pair (an invalid cell has similarity -1e9 in the reference, i.e. weight exactly 0 in both
     softmaxes and no match) and clearing the padded border afterwards -- see `_forward_masked`.
@@ -32,12 +34,19 @@ class CoarseMatching(nn.Module):
                                       "imports a superglue.py it does not ship)")
         self.temperature = config["dsmax_temperature"]
         self.impl = _lib.COARSE_AUTO      # POPE_COARSE_AUTO | _SIMT | _TCGEN05
+        self.materialize_conf_matrix = False     # debug: also write data['conf_matrix'] (92 MB per 480x640 pair)
         self._workspace = None
 
     @torch.no_grad()
     def forward(self, feat_c0, feat_c1, data, mask_c0=None, mask_c1=None):
         if self.training:
             raise NotImplementedError("the CUDA coarse matcher is inference-only (call .eval())")
+        if self.materialize_conf_matrix:          # coarse_matching.py:106-119, verbatim op sequence, inspection only
+            c = feat_c0.shape[-1]
+            sim = torch.einsum("nlc,nsc->nls", feat_c0.float() / c ** 0.5, feat_c1.float() / c ** 0.5) / self.temperature
+            if mask_c0 is not None:
+                sim.masked_fill_(~(mask_c0[..., None] * mask_c1[:, None]).bool(), -1e9)
+            data["conf_matrix"] = torch.softmax(sim, 1) * torch.softmax(sim, 2)
         if mask_c0 is not None or mask_c1 is not None or "mask0" in data:
             return self._forward_masked(feat_c0, feat_c1, data, mask_c0, mask_c1)
         res = ops.coarse_match(feat_c0, feat_c1, data["hw0_c"], data["hw1_c"],

@@ -68,6 +68,7 @@ def test_cuda_coarse_matching_with_padding_masks(dtype, mask_in_data):
     m0, m1 = masks(CASE)
     hw0_c, hw1_c = CASE["hw0_c"], CASE["hw1_c"]
     cm = pope_b200.CoarseMatching(pope_b200.make_default_cfg()["match_coarse"]).eval()
+    cm.materialize_conf_matrix = dtype == torch.float32            # the debug output, checked below
     data = {"hw0_i": torch.Size(_hw_i(CASE)), "hw1_i": torch.Size((hw1_c[0] * 8, hw1_c[1] * 8)),
             "hw0_c": torch.Size(hw0_c), "hw1_c": torch.Size(hw1_c)}
     if mask_in_data:
@@ -94,3 +95,7 @@ def test_cuda_coarse_matching_with_padding_masks(dtype, mask_in_data):
             for k in ("b_ids", "i_ids", "j_ids"):
                 assert np.array_equal(got[k].numpy(), g[k]), k
     assert data["gt_mask"].dtype == torch.bool and torch.equal(data["m_bids"], data["b_ids"])
+    if dtype == torch.float32:
+        assert torch.allclose(data["conf_matrix"].cpu(), conf, rtol=1e-4, atol=1e-7)
+    else:
+        assert "conf_matrix" not in data
