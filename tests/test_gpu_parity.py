@@ -525,7 +525,7 @@ def test_match_crops_equals_the_reference_pair_loop():
     """driver.match_crops against the loop of eval_linemod_json.py:103-122 / :146 restated with cv2 + numpy.  A stand-in
     matcher whose output is a deterministic function of its two input images makes the comparison non-vacuous (the real
     Matcher with random weights finds no match); the real Matcher then runs through the same helper for the flow."""
-    import cv2
+    cv2 = pytest.importorskip("cv2")
     import pope_b200
     from pope_b200 import driver
 
