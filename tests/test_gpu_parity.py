@@ -564,3 +564,42 @@ def test_match_crops_equals_the_reference_pair_loop():
     matcher = pope_b200.Matcher(pope_b200.make_default_cfg()).eval().to(DEV)
     res, scores, best = driver.match_crops(matcher, torch.from_numpy(image0).to(DEV), [torch.from_numpy(c).to(DEV) for c in crops[:3]])
     assert len(res) == 3 and scores.tolist() == [0, 0, 0] and best == 0 and res[1]["mkpts0_f"].shape == (0, 2)
+
+
+@pytest.mark.parametrize("impl", list(IMPLS))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_kat_border_veto_and_threshold_straddle(impl, dtype):
+    """Known answers of SURVEY.md 8(c) on the CUDA path: (2) a border cell that holds the row maximum vetoes the interior
+    candidate of its row and is itself removed; (3) two equal-strength columns split the row softmax, which puts the
+    confidence on either side of the threshold depending on the third column's weight."""
+    _need_tc(impl, 64, 64, 64)
+    h = w = 8
+    L = h * w
+    i, j_in, j_bd = 3 * w + 3, 4 * w + 4, 0 * w + 5
+    f0, f1 = torch.zeros(1, L, 64), torch.zeros(1, L, 64)
+    f0[0, i, 0] = 16.0
+    f1[0, j_in, 0], f1[0, j_bd, 0] = 8.0, 8.1875                              # exactly representable in bf16
+    conf = O.dual_softmax_conf(f0, f1)
+    assert conf[0, i, j_bd] > conf[0, i, j_in] > 0.2                          # the interior candidate alone would pass thr
+    out = _run_coarse(f0, f1, (h, w), (h, w), IMPLS[impl], dtype, thr=0.2)
+    assert out["i_ids"].numel() == 0                                          # vetoed by the border cell, which is removed
+    out = _run_coarse(f0, f1, (h, w), (h, w), IMPLS[impl], dtype, thr=0.2, border_rm=0)
+    assert out["i_ids"].tolist() == [i] and out["j_ids"].tolist() == [j_bd]   # without border removal the border cell matches
+    f1[0, j_bd, 0] = 6.0                                                      # now the interior cell wins
+    out = _run_coarse(f0, f1, (h, w), (h, w), IMPLS[impl], dtype, thr=0.2)
+    want = O.coarse_match(f0, f1, (64, 64), (h, w), (h, w), thr=0.2)
+    assert out["i_ids"].tolist() == [i] and out["j_ids"].tolist() == [j_in] == want["j_ids"].tolist()
+    assert torch.allclose(out["mconf"], want["mconf"], rtol=1e-2 if dtype == torch.bfloat16 else 1e-4, atol=0)
+    # (3) one query row, two interior columns of equal strength: no unique row maximum pair above thr unless one is lowered
+    f0, f1 = torch.zeros(1, L, 64), torch.zeros(1, L, 64)
+    ja, jb = 2 * w + 2, 5 * w + 5
+    f0[0, i, 0] = 16.0
+    for strength_b, n_expected in ((16.0, None), (8.0, 1)):
+        f1[0, ja, 0], f1[0, jb, 0] = 16.0, strength_b
+        want = O.coarse_match(f0, f1, (64, 64), (h, w), (h, w), thr=0.2)
+        out = _run_coarse(f0, f1, (h, w), (h, w), IMPLS[impl], dtype, thr=0.2)
+        if n_expected is None:      # an exact tie: both columns hold the row maximum; `mask.max(dim=2)` keeps the first
+            assert out["i_ids"].tolist() == want["i_ids"].tolist() and out["j_ids"].tolist() == want["j_ids"].tolist()
+        else:
+            assert out["j_ids"].tolist() == [ja] == want["j_ids"].tolist()
+            assert torch.allclose(out["mconf"], want["mconf"], rtol=1e-2 if dtype == torch.bfloat16 else 1e-4, atol=0)
