@@ -224,7 +224,8 @@ int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t*
  * n_inliers / status / iters int32 [n_pairs]; status 0 is the reference's `return None` (fewer than 5 matches, no model, or
  * no point in front of both cameras), iters the number of minimal samples the equivalent sequential loop consumed.
  * Results equal a sequential RANSAC over the same samples with OpenCV's adaptive iteration bound; they are deterministic in
- * (inputs, seed).  All arithmetic is float64.  Workspace: about 0.37 MB per pair plus 33 bytes per row of capacity. */
+ * (inputs, seed).  All arithmetic is float64.  Workspace: about 0.37 MB per pair plus 33 bytes per row of capacity.
+ * n_pairs <= 65535 per call.  The call is stream-ordered without host synchronisation (CUDA-graph capturable). */
 #define POPE_POSE_MAX_ITERS 1024
 size_t pope_pose_workspace_bytes(int n_pairs, int64_t capacity);
 int pope_estimate_pose_batch(const float* mkpts0, const float* mkpts1, const int32_t* counts, int n_pairs, int64_t capacity,
