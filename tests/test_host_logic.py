@@ -105,3 +105,25 @@ def test_argument_errors_are_reported_before_touching_the_gpu():
     assert h.pope_fine_match(None, None, 0, 0, None, 25, 128, None, 4.0, None, None, None) == 0     # M == 0 is a no-op
     assert h.pope_cosine_topk(None, None, 0, 4, 4, 3, 1e-8, None, None, None, None) == -1
     assert b"workspace" in h.pope_status_string(-3)
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C ABI: include/pope_b200.h must compile as C99 (no C++ in the declarations) and a C program must
+    link against the library and call it without any Python or torch in the process."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include <stdio.h>\n#include "pope_b200.h"\n'
+                   'int main(void) {\n'
+                   '  if (pope_abi_version() != 1) return 1;\n'
+                   '  if (pope_coarse_workspace_bytes(0, 1, 1) != 0) return 2;\n'
+                   '  if (pope_coarse_match(0, 0, 0, 1, 64, 64, 256, 8, 8, 8, 8, 8.0f, 0.1f, 0.2f, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 64, 0) >= 0) return 3;\n'
+                   '  puts(pope_status_string(-3));\n  return 0;\n}\n')
+    exe = tmp_path / "c_abi"
+    libdir = os.path.join(ROOT, "pope_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-L", libdir, "-lpope_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "workspace" in out
