@@ -211,6 +211,13 @@ int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t*
                       const float* mkpts0_f, const float* mkpts1_f, const int32_t* m_dev, int64_t capacity,
                       int pair_offset, int32_t* records, const int64_t* base_dev, void* stream);
 
+/* The compact form of the same record, 20 bytes (int32[5]: global pair index, i | j << 16, mconf, x1, y1): the keypoint of
+ * image 0 is implied by i (mkpts0_f = mkpts0_c = (i % w0c, i / w0c) * pixel_scale, fine_matching.py:66).  Needs
+ * L, S <= 65536.  records: int32[capacity * 5]; the other arguments as pope_pack_records. */
+int pope_pack_records_compact(const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids, const float* mconf,
+                              const float* mkpts1_f, const int32_t* m_dev, int64_t capacity, int pair_offset,
+                              int32_t* records, const int64_t* base_dev, void* stream);
+
 /* ---- batched relative pose from the match lists --------------------------------------------------
  * Replaces the per-pair `estimate_pose(kpts0, kpts1, K0, K1, thresh, conf)` of the reference (src/utils/metrics.py:69-94:
  * cv2.findEssentialMat(..., threshold, prob=conf, method=cv2.RANSAC) followed by cv2.recoverPose) for a whole batch of match

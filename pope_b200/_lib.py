@@ -48,6 +48,7 @@ SIGNATURES = {
     "pope_write_png": (_i, [C.c_char_p, _p, _i, _i, _i, _i64, _i]),
     "pope_write_png_batch": (_i, [C.POINTER(C.c_char_p), C.POINTER(_p), _p, _p, _i, _i, _i, _i]),
     "pope_pack_records": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p]),
+    "pope_pack_records_compact": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _p, _p, _p]),
     "pope_match_scores": (_i, [_p, _p, _i, _i, _f, _p, _p, _p]),
     "pope_pose_workspace_bytes": (_sz, [_i, _i64]),
     "pope_estimate_pose_batch": (_i, [_p, _p, _p, _i, _i64, _p, _p, C.c_double, C.c_double, _i, C.c_uint64, _p, _p, _p, _p,

@@ -191,11 +191,11 @@ __global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ 
   rowbest[r] = best;
 }
 
-// tcgen05 two-sweep path: one thread per row i evaluates the cells its four epilogue threads listed during the row
-// sweep (a superset of the cells with p_row > thr: the test there ran against the RUNNING log-sum-exp, which only
-// grows).  Same arithmetic as cand_eval_kernel.
-// mode 0: lists of raw accumulators (two-sweep kernels).  mode 1: single-sweep launch sequence -- the lists hold 2^x
-// unless POPE_FLAG_ROBUST_PATH is set, in which case the gated two-sweep launch has rewritten them with raw accumulators.
+// tcgen05 paths: one thread per row i evaluates the cells its four epilogue threads listed during the row sweep (a
+// superset of the cells with p_row > thr: the test there ran against the RUNNING row sum, which only grows).  Same
+// arithmetic as cand_eval_kernel; the lists hold raw accumulators on every path (single sweep, its gated online-softmax
+// redo of flagged pairs, two-sweep).  mode 2 (fp32 split path): nothing at all once POPE_FLAG_ROBUST_PATH is set -- the
+// fp32-FMA fallback evaluates its own lists.
 // Every row's rowbest is written (0 = no candidate), so the caller need not clear it.
 __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
                                                              const float* __restrict__ lse_r,
@@ -204,22 +204,23 @@ __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restr
                                                              u64* __restrict__ colbest, const int32_t* __restrict__ flags,
                                                              int mode) {
   if (mode == 2 && (uint32_t(*flags) & POPE_FLAG_ROBUST_PATH)) return;
-  const bool exp_lists = mode == 2 || (mode == 1 && !(uint32_t(*flags) & POPE_FLAG_ROBUST_PATH));
   const size_t r = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= size_t(n_pairs) * L) return;
-  const uint32_t c4 = uint32_t(cand_cnt[r]);
+  const uint2 cw = reinterpret_cast<const uint2*>(cand_cnt)[r];       // four uint16: nibble counts of the row's 16 sub-lists
   u64 best = 0;
-  if (c4 != 0) {
+  if ((cw.x | cw.y) != 0u) {
     const int n = int(r / L), i = int(r - size_t(n) * L);
     const float lr = lse_r[r];
-#pragma unroll
-    for (int q = 0; q < kListGroups; ++q) {
-      const int c = min(int((c4 >> (8 * q)) & 0xffu), kCandSlots);
+    u64 todo = u64(cw.x) | (u64(cw.y) << 32);
+    while (todo) {                                          // the non-empty sub-lists only (usually one or two per row)
+      const int sub = (__ffsll((long long)todo) - 1) >> 2;
+      const int c = min(int((todo >> (4 * sub)) & 0xfull), kLaneSlots);
+      todo &= ~(0xfull << (4 * sub));
       for (int k = 0; k < c; ++k) {
-        const u64 rec = cand[(r * kListGroups + q) * kCandSlots + k];
+        const u64 rec = cand[(r * (kListGroups * kListStride / kLaneSlots) + sub) * kLaneSlots + k];
         const int j = int(uint32_t(rec));
         const float val = __uint_as_float(uint32_t(rec >> 32));
-        const float x = exp_lists ? log2f(val) : val * scale;
+        const float x = val * scale;
         if (!(x - lr > log2_thr - 0.01f)) continue;         // conf <= p_row: stale entries of the running-bound test go here
         const float t2 = (x - lr) + (x - lse_c[size_t(n) * S + j]);
         if (t2 > log2_thr) {
@@ -233,29 +234,52 @@ __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restr
   rowbest[r] = best;
 }
 
-// single-sweep path: column sums of 2^x from the per-32-row partial sums written by the sweep -> column log-sum-exp
-// (also clears the column's best-candidate record and the pair's "count published" word: the single-sweep launch
-// sequence needs no memset of the scratch).  HBM-bound: n * ceil(L/32) * S * 4 bytes are read once; a thread owns VEC
-// adjacent columns and keeps 4 x VEC loads in flight; the summation order over the groups is fixed.
+// single-sweep path: column log-sum-exp from the per-32-row partial sums written by the sweep.  Partial (group g, column j)
+// is a sum of 2^(x - m) with m = cshift[g][j / 32], an integer, so moving it to another domain is an exact scaling; the
+// column's total is taken in the domain of the largest shift that occurs (usually all shifts of a column are equal and no
+// exponential is evaluated).  A total below 2^-90 of that domain may have lost terms to underflow: the pair is flagged for
+// the online-softmax kernels.  Also clears the column's best-candidate record and the pair's "count published" word (the
+// single-sweep launch sequence needs no memset of the scratch).  HBM-bound: n * ceil(L/32) * S * 4 bytes are read once; a
+// thread owns VEC adjacent columns (one 32-column block) and keeps 4 x VEC loads in flight; the order over the groups is
+// fixed.
 template <int VEC>
-__global__ void __launch_bounds__(128) colsum_reduce_kernel(const float* __restrict__ colpart, int ngroups, int S,
-                                                           float* __restrict__ lse_c, u64* __restrict__ colbest,
-                                                           int* __restrict__ ready, int32_t* __restrict__ flags) {
+__global__ void __launch_bounds__(128) colsum_reduce_kernel(const float* __restrict__ colpart, const float* __restrict__ cshift,
+                                                           int ngroups, int S, int nblk, float* __restrict__ lse_c,
+                                                           u64* __restrict__ colbest, int* __restrict__ ready,
+                                                           int32_t* __restrict__ flags, int* __restrict__ pairflag) {
   const int j = (blockIdx.x * 128 + threadIdx.x) * VEC, n = blockIdx.y;
   if (j >= S) return;
   if (j == 0) ready[n] = 0;
   const float* p = colpart + size_t(n) * ngroups * S + j;
-  float acc[4][VEC];
+  const float* sh = cshift + size_t(n) * ngroups * nblk + (j >> 5);
+  float acc[4][VEC], mtop[4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < 4; ++u) {
+    mtop[u] = -INFINITY;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[u][v] = 0.f;
+  }
   auto load_add = [&](int g, int u) {
+    float q[VEC];
     if (VEC == 4) {
       const float4 t = __ldcs(reinterpret_cast<const float4*>(p + size_t(g) * S));
-      acc[u][0] += t.x; acc[u][1 % VEC] += t.y; acc[u][2 % VEC] += t.z; acc[u][3 % VEC] += t.w;
+      q[0] = t.x; q[1 % VEC] = t.y; q[2 % VEC] = t.z; q[3 % VEC] = t.w;
     } else {
-      acc[u][0] += __ldcs(p + size_t(g) * S);
+      q[0] = __ldcs(p + size_t(g) * S);
+    }
+    const float m = __ldg(sh + size_t(g) * nblk);
+    if (m == mtop[u]) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[u][v] += q[v];
+    } else if (m < mtop[u]) {
+      const float f = ex2_approx(m - mtop[u]);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[u][v] = fmaf(q[v], f, acc[u][v]);
+    } else {                                          // also the first group: 2^(-inf) = 0 times a zero sum
+      const float f = ex2_approx(mtop[u] - m);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[u][v] = fmaf(acc[u][v], f, q[v]);
+      mtop[u] = m;
     }
   };
   int g = 0;
@@ -263,15 +287,22 @@ __global__ void __launch_bounds__(128) colsum_reduce_kernel(const float* __restr
     load_add(g, 0); load_add(g + 1, 1); load_add(g + 2, 2); load_add(g + 3, 3);
   }
   for (; g < ngroups; ++g) load_add(g, 0);
+  const float mall = fmaxf(fmaxf(mtop[0], mtop[1]), fmaxf(mtop[2], mtop[3]));
+  float f[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) f[u] = (mtop[u] == mall) ? 1.f : ex2_approx(mtop[u] - mall);    // -inf (unused chain) -> 0
   bool bad = false;
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    const float tot = (acc[0][v] + acc[1][v]) + (acc[2][v] + acc[3][v]);
-    lse_c[size_t(n) * S + j + v] = log2f(tot);
+    const float tot = (acc[0][v] * f[0] + acc[1][v] * f[1]) + (acc[2][v] * f[2] + acc[3][v] * f[3]);
+    lse_c[size_t(n) * S + j + v] = mall + log2f(tot);
     colbest[size_t(n) * S + j + v] = 0ull;
     bad |= !(tot > kSumLo && tot < kSumHi);
   }
-  if (bad) atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_ROBUST_PATH);
+  if (bad) {
+    atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_ROBUST_PATH);
+    *reinterpret_cast<volatile int*>(pairflag + n) = 1;
+  }
 }
 
 }  // namespace
@@ -304,13 +335,15 @@ cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, 
 }
 
 cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
-  const int ngroups = (p.L + 31) / 32;
+  const int ngroups = (p.L + 31) / 32, nblk = (p.S + 31) / 32;
   if (p.S % 4 == 0) {   // rows of the partial-sum array are then 16-byte aligned (the array itself is 256-byte aligned)
     dim3 grid((p.S / 4 + 127) / 128, p.n);
-    colsum_reduce_kernel<4><<<grid, 128, 0, st>>>(w.colpart, ngroups, p.S, w.lse_c, w.colbest, w.ready, flags);
+    colsum_reduce_kernel<4><<<grid, 128, 0, st>>>(w.colpart, w.cshift, ngroups, p.S, nblk, w.lse_c, w.colbest, w.ready, flags,
+                                                  w.pairflag);
   } else {
     dim3 grid((p.S + 127) / 128, p.n);
-    colsum_reduce_kernel<1><<<grid, 128, 0, st>>>(w.colpart, ngroups, p.S, w.lse_c, w.colbest, w.ready, flags);
+    colsum_reduce_kernel<1><<<grid, 128, 0, st>>>(w.colpart, w.cshift, ngroups, p.S, nblk, w.lse_c, w.colbest, w.ready, flags,
+                                                  w.pairflag);
   }
   return cudaGetLastError();
 }

@@ -176,8 +176,11 @@ struct SweepParams {
   u64* colbest;
   int* cand_cnt;            // two-sweep path: per row of S, one count byte per column quarter
   u64* cand;                //   [n, L0, kListGroups, kCandSlots] (raw accumulator bits << 32 | column)
-  float* colpart;           // single-sweep path: [n, ceil(L0/32), L1] column sums of 2^x over each 32-row group
-  int gate;                 // != 0: the launch is a no-op unless POPE_FLAG_ROBUST_PATH is set in *flags
+  float* colpart;           // single-sweep path: [n, ceil(L0/32), L1] column sums of 2^(x - shift) over each 32-row group
+  float* cshift;            //   [n, ceil(L0/32), ceil(L1/32)] the shift of each (32-row group, 32-column block)
+  int* pairflag;            //   [n] != 0: the pair left the single sweep's range and is redone by the gated launch
+  int gate;                 // != 0: the launch is a no-op unless POPE_FLAG_ROBUST_PATH is set in *flags, and then only
+                            //       the pairs with pairflag[n] != 0 are swept
   int32_t* flags;
   unsigned long long* trace;   // developer diagnostics (POPE_TC_TRACE): clock stamps of CTA pair 0, or nullptr
   int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps
@@ -250,19 +253,28 @@ __device__ __forceinline__ float lse_update(const float (&v)[32], int vc, float 
   return cmax;      // raw-accumulator units
 }
 
-// two-sweep path: append cell (value v, column col) to the calling thread's private list.  A full list is first
-// re-filtered against the current bound (the running row sum only grows, so entries below it are dead for good; fewer
-// than 1/thr < kCandSlots cells can stay above it).
-__device__ __noinline__ int list_push(u64* __restrict__ list, int cnt, float bound, float v, int col, int32_t* __restrict__ flags) {
-  if (cnt >= kCandSlots) {
+// append cell (raw accumulator v, column col) to one of the calling thread's private lists (SLOTS entries).  A full list is
+// first re-filtered against the current bound (raw-accumulator units): the running row sum only grows, so entries below it
+// are dead for good, and fewer than 1/thr cells can stay above it (heavy-tailed similarities list many early cells that a
+// later, larger cell of the row makes irrelevant).  A list that is still full: two-sweep kernels raise
+// POPE_FLAG_CAND_OVERFLOW (nan inputs), the single sweep hands the pair to the online-softmax launch.
+template <int SLOTS>
+__device__ __noinline__ int list_push(u64* __restrict__ list, int cnt, float bound, float v, int col, int32_t* __restrict__ flags,
+                                      int* __restrict__ pairflag) {
+  if (cnt >= SLOTS) {
     int kept = 0;
-    for (int k = 0; k < kCandSlots; ++k) {
+    for (int k = 0; k < SLOTS; ++k) {
       const u64 rec = list[k];
       if (__uint_as_float(uint32_t(rec >> 32)) > bound) list[kept++] = rec;
     }
     cnt = kept;
-    if (cnt >= kCandSlots) {
-      atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_CAND_OVERFLOW);
+    if (cnt >= SLOTS) {
+      if (pairflag) {
+        atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_ROBUST_PATH);
+        *reinterpret_cast<volatile int*>(pairflag) = 1;
+      } else {
+        atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_CAND_OVERFLOW);
+      }
       return cnt;
     }
   }
@@ -304,18 +316,25 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
   asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 __device__ __forceinline__ u64 add2(u64 a, u64 b) {
   u64 r;
   asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
 
-// v <- 2^(v * scale) in place (0 for masked rows / columns); the (even, odd) column pairs of a row are adjacent
-// registers, so scaling, row sums (rowacc2[rho] = {even-column sum, odd-column sum}) and the per-thread column sums
+// e = 2^(v * scale - m) for the 32 raw accumulators of a thread (0 for masked rows / columns; v itself is kept: the rare
+// paths -- candidate scan, shift change -- work on the raw values); the (even, odd) column pairs of a row are adjacent
+// registers, so scaling, the chunk's row sums (rc2[rho] = {even-column sum, odd-column sum}) and the per-thread column sums
 // (cp2[k] = {column 8k+2p, column 8k+2p+1} over the thread's four rows) run on packed fp32x2 instructions
 template <bool FULL>
-__device__ __forceinline__ void ss_chunk(float (&v)[32], u64 scale2, u64 (&rowacc2)[4], u64 (&cp2)[4], uint32_t rowmask,
-                                         int vc, int p) {
+__device__ __forceinline__ void ss_chunk(const float (&v)[32], float scale, float negm, u64 (&rc2)[4], u64 (&cp2)[4],
+                                         uint32_t rowmask, int vc, int p) {
+  const u64 scale2 = pack2(scale, scale), negm2 = pack2(negm, negm);
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -324,7 +343,7 @@ __device__ __forceinline__ void ss_chunk(float (&v)[32], u64 scale2, u64 (&rowac
       for (int r = 0; r < 2; ++r) {
         const int idx = 16 * h + 4 * k + 2 * r, rho = 2 * h + r;
         float a, b;
-        unpack2(mul2(pack2(v[idx], v[idx + 1]), scale2), a, b);
+        unpack2(fma2(pack2(v[idx], v[idx + 1]), scale2, negm2), a, b);
         a = ex2_approx(a);
         b = ex2_approx(b);
         if (!FULL) {
@@ -333,10 +352,8 @@ __device__ __forceinline__ void ss_chunk(float (&v)[32], u64 scale2, u64 (&rowac
           if (!rowok || col >= vc) a = 0.f;
           if (!rowok || col + 1 >= vc) b = 0.f;
         }
-        v[idx] = a;
-        v[idx + 1] = b;
         const u64 e2 = pack2(a, b);
-        rowacc2[rho] = add2(rowacc2[rho], e2);
+        rc2[rho] = (k == 0) ? e2 : add2(rc2[rho], e2);
         cp2[k] = (rho == 0) ? e2 : add2(cp2[k], e2);
       }
 }
@@ -360,20 +377,15 @@ __device__ __forceinline__ float ss_col_reduce(const float (&cp)[8], int lane) {
   return keep + __shfl_xor_sync(kFullMask, send, 4);
 }
 
-// append (2^x, column) to the (row, column group) list; the slot counter lives in shared memory for the unit
-__device__ __noinline__ void ss_push(int* cnt, u64* __restrict__ list, float e, int col, int32_t* __restrict__ flags) {
-  const int slot = atomicAdd(cnt, 1);
-  if (slot < kCandSlots) list[slot] = (u64(__float_as_uint(e)) << 32) | uint32_t(col);
-  else atomicOr(reinterpret_cast<unsigned*>(flags), POPE_FLAG_ROBUST_PATH);
-}
-
 // MODE 0: row log-sum-exp of the stationary operand's rows.
 // MODE 1: candidate sweep of the three-sweep path (needs both log-sum-exps; direction 0 only).
 // MODE 2: MODE 0 + in direction 0 (rows of S stationary) every thread lists the cells of its row that exceed thr x the
 //         running row sum in its private slots (two-sweep path; both directions run in one launch).
-// MODE 3: single sweep over the rows of S (direction 0 only): unshifted 2^x, row sums per thread, column sums through a
-//         shuffle reduction and per-32-row partial sums in global memory, candidate lists as in MODE 2.  Valid while the
-//         sums stay in fp32 range; otherwise POPE_FLAG_ROBUST_PATH is raised and a gated MODE 2 launch redoes the batch.
+// MODE 3: single sweep over the rows of S (direction 0 only): 2^(x - m) with one lazily raised shift m per epilogue warp
+//         (32 rows), row sums per thread, column sums through a shuffle reduction and per-32-row partial sums (plus the
+//         shift they were taken at) in global memory, candidate lists as in MODE 2.  A pair whose sums lose precision
+//         (rows more than ~150 log2 units apart inside one 32-row group, inf / nan) raises POPE_FLAG_ROBUST_PATH and its
+//         own flag, and a gated MODE 2 launch redoes that pair.
 // MODE 4: MODE 3 for FP32 features at fp32 accuracy on the bf16 tensor cores.  Every feature value is split into three bf16
 //         terms a = a1 + a2 + a3 (24 mantissa bits, split3_kernel) and the contraction is the six significant products
 //         a1b1 + a2b1 + a3b1 + a1b2 + a2b2 + a1b3 (the dropped ones are below 2^-24 of |a||b|) accumulated in fp32 in
@@ -451,6 +463,10 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     rb = v - n * rbs;
   };
 
+  // gated launch (the fallback behind the single sweep): only the pairs the single sweep gave up on are swept; the
+  // flags are final before this launch starts, so all roles of both CTAs skip the same units
+  auto skip_pair = [&](int n) { return MODE == 2 && P.gate && *reinterpret_cast<const volatile int*>(P.pairflag + n) == 0; };
+
   if (warp == 0) {
     // =============================== TMA producer (both CTAs) ===============================
     if (lane == 0) {
@@ -458,6 +474,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       for (int u = pair; u < P.total_units; u += npairs) {
         int dir, n, rb;
         decode(u, dir, n, rb);
+        if (skip_pair(n)) continue;
         const CUtensorMap* mapA = dir ? &map1 : &map0;
         const CUtensorMap* mapB = dir ? &map0 : &map1;
         const int arow = rb * kUnitRows + int(rank) * kBoxRows;
@@ -498,6 +515,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       for (int u = pair; u < P.total_units; u += npairs) {
         int dir, n, rb;
         decode(u, dir, n, rb);
+        if (skip_pair(n)) continue;
         const int ntiles = ((dir ? P.L0 : P.L1) + kTileCols - 1) / kTileCols;
         if (!(P.debug & 4) || u == pair) {
           mbar_wait(bar_a_full, a_phase);
@@ -580,20 +598,25 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     }
   } else if (MODE == 3 || MODE == 4) {
     // =============================== single-sweep epilogue (16 warps: 4 lane quadrants x 4 groups of 64 columns) =====
+    // Every warp keeps one integer-valued shift m for its 32 rows: e = 2^(x - m).  m is chosen from the data at the first
+    // chunk of a unit and raised (never lowered) when a thread's running row sum passes 2^104 -- the chunk is then redone
+    // from the raw accumulators still in registers and the row sums are rescaled by an exact power of two.  Column sums
+    // leave the warp once per chunk together with the shift they were taken at; the merge kernel combines them.
     const int g = lane >> 2, p = lane & 3;
     const int cg = (warp - 2) >> 2, quad = warp & 3;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    int* scnt = reinterpret_cast<int*>(smem + kSmemLc);              // [128 rows][4 column groups] list fill counts
-    float* mergef = reinterpret_cast<float*>(smem + kSmemMerge);     // [3][128] row sums of column groups 1..3
+    float2* mergef = reinterpret_cast<float2*>(smem + kSmemMerge);   // [3][128] (row sum, shift) of column groups 1..3
     const int rin = quad * 32 + g + 8 * p;                           // the row of the CTA this lane writes results for
-    scnt[(quad * 32 + lane) * kListGroups + cg] = 0;                 // entries (row, cg) are private to warp (quad(row), cg)
-    __syncwarp();
-    const u64 scale2 = pack2(P.scale_log2, P.scale_log2);
+    const float scale = P.scale_log2;
     const float thrm = exp2f(P.log2_thr) * 0.99f;
     const int LA = P.L0, LB = P.L1;
-    const int ntiles = (LB + kTileCols - 1) / kTileCols, ngroups = (LA + 31) / 32;
+    const int ntiles = (LB + kTileCols - 1) / kTileCols, ngroups = (LA + 31) / 32, nblk = (LB + 31) / 32;
     const int ccol = 8 * (g >> 1) + 2 * p + (g & 1);                 // chunk column whose sum ss_col_reduce leaves in this lane
+    // the warps of the odd column groups run half a tile behind the even ones (they finish a tile's second chunk after the
+    // next tile's accumulator is ready), so that the four warps of a scheduler are not all in their MUFU phase at once
+    const bool lag = (cg & 1) && !(P.debug & 32);
     uint32_t tile_ctr = 0;
+    float mshift = 0.f;
     for (int u = pair; u < P.total_units; u += npairs) {
       int dir, n, rb;
       decode(u, dir, n, rb);
@@ -602,47 +625,101 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       uint32_t rowmask = 0;
 #pragma unroll
       for (int rho = 0; rho < 4; ++rho) rowmask |= (g + 8 * rho < rows_valid) ? (1u << rho) : 0u;
-      u64 rowacc2[4] = {0ull, 0ull, 0ull, 0ull};                     // per row: {sum over even columns, sum over odd columns}
-      float rsum[4] = {0.f, 0.f, 0.f, 0.f};                          // the thread's row sums as of the previous chunk
-      float* const cpart = P.colpart + (size_t(n) * ngroups + (rowbase >> 5)) * LB;
-      u64* const lists = P.cand + (size_t(n) * LA + rowbase) * (kListGroups * kCandSlots) + cg * kCandSlots;
+      float rowacc[4] = {0.f, 0.f, 0.f, 0.f};                        // the thread's row sums (its 2 of every 8 columns)
+      bool fresh = true;                                             // no chunk of this unit processed yet
+      uint32_t cnts = 0;                                             // fill counts of the thread's four private lists (a byte each)
+      const uint32_t gidx = uint32_t(n) * ngroups + (rowbase >> 5);  // (pair, 32-row group): row of colpart / cshift
+      bool waited = false;
 
       for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
         const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
         const int col0 = ct * kTileCols;
         const int nvalid = min(LB - col0, kTileCols) - cg * kSpan;
         const bool active = rows_valid > 0 && nvalid > 0 && !(P.debug & 1);
-        mbar_wait(bar_acc_full + 8 * s, acc_phase);
+        if (!waited) mbar_wait(bar_acc_full + 8 * s, acc_phase);
+        waited = false;
         tc_fence_after();
         const uint32_t tbase = tmem_base + lane_addr + s * kTileCols + cg * kSpan;
         float v[32];
-        auto process = [&](int cc) {
-          const int vc = nvalid - cc * 32;
-          u64 cp2[4];
-          if (rows_valid == 32 && vc >= 32) ss_chunk<true>(v, scale2, rowacc2, cp2, rowmask, vc, p);
-          else ss_chunk<false>(v, scale2, rowacc2, cp2, rowmask, vc, p);
-          float cp[8];
+        // new shift for the warp from the raw values of the chunk in v (forced: first chunk of a unit); returns the exact
+        // power of two that takes sums from the old domain to the new one
+        auto rebase = [&](bool forced) {
+          // (every value goes through an identity shuffle first: a warp-synchronous instruction is not speculated across
+          //  the branch, so the 32-way maximum stays out of the common path -- ptxas otherwise hoists it into every chunk)
+          float cm = -INFINITY;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) unpack2(cp2[k], cp[2 * k], cp[2 * k + 1]);
-          const float cs = ss_col_reduce(cp, lane);
+          for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __shfl_sync(kFullMask, v[j], lane));
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(kFullMask, cm, o));
+          float mnew = floorf(cm * scale) - kShiftBack;
+          if (!forced) mnew = fmaxf(mnew, mshift + 24.f);
+          if (!(fabsf(mnew) < 1e30f)) mnew = mshift;                 // inf / nan inputs: keep the shift, the sums get flagged
+          const float f = ex2_approx(mshift - mnew);
+          mshift = mnew;
+          return f;
+        };
+        // the two 32-column chunks of the thread, one copy of the code: chunk 0, then chunk 1's TMEM load, the hand-back of
+        // the accumulator stage, and chunk 1's arithmetic after it
+#pragma unroll 1
+        for (int cc = 0; cc < kChunks; ++cc) {
+          const int vc = nvalid - cc * 32;
           const int colb = col0 + cg * kSpan + cc * 32;
-          if (ccol < vc) cpart[colb + ccol] = cs;
+          const bool on = active && vc > 0;
+          if (on) tmem_ld_frag(tbase + cc * 32, v);
+          if (cc == kChunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
+            if (lag && ct + 1 < ntiles) {
+              mbar_wait(bar_acc_full + 8 * (s ^ 1), ((tile_ctr + 1) >> 1) & 1);
+              waited = true;
+            }
+          }
+          if (!on) continue;
+          if (fresh) {                               // first chunk of the unit: shift from the data
+            rebase(true);
+            fresh = false;
+          }
+          u64 cp2[4], rc2[4];
+          float d[4], now[4];
+          bool pass;
+          if (rows_valid == 32 && vc >= 32) ss_chunk<true>(v, scale, -mshift, rc2, cp2, rowmask, vc, p);
+          else ss_chunk<false>(v, scale, -mshift, rc2, cp2, rowmask, vc, p);
           // A cell can only have p_row > thr if it exceeds thr x (running row sum).  Level 1, no communication: this
           // chunk's contribution d[rho] to the thread's own row sum against that sum (true for the first chunks of a
           // unit by construction).  Level 2: the same against the row sum over the 4 lanes that share the row.  Level 3
           // (a real candidate, or the first chunk of a unit): the row's 8 cells one by one.
-          float d[4], now[4];
-          bool pass = false;
+          auto row_deltas = [&]() {
+            pass = false;
 #pragma unroll
-          for (int rho = 0; rho < 4; ++rho) {
-            float x, y;
-            unpack2(rowacc2[rho], x, y);
-            now[rho] = x + y;
-            d[rho] = now[rho] - rsum[rho];
-            rsum[rho] = now[rho];
-            pass |= d[rho] > thrm * now[rho];
+            for (int rho = 0; rho < 4; ++rho) {
+              float x, y;
+              unpack2(rc2[rho], x, y);
+              d[rho] = x + y;
+              now[rho] = rowacc[rho] + d[rho];
+              pass |= d[rho] > thrm * now[rho];
+            }
+          };
+          row_deltas();
+          const bool over = !((now[0] + now[1]) + (now[2] + now[3]) < kBumpTrig);      // outside the window; also inf / nan
+          const bool rare = __any_sync(kFullMask, pass | over);
+          if (rare && __any_sync(kFullMask, over)) {
+            // a higher shift from the raw values of the chunk, the running sums moved to it, the chunk once more
+            const float f = rebase(false);
+#pragma unroll
+            for (int rho = 0; rho < 4; ++rho) rowacc[rho] *= f;
+            ss_chunk<false>(v, scale, -mshift, rc2, cp2, rowmask, vc, p);
+            row_deltas();
           }
-          if (__any_sync(kFullMask, pass) && !(P.debug & 2)) {
+#pragma unroll
+          for (int rho = 0; rho < 4; ++rho) rowacc[rho] = now[rho];
+          float cp[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) unpack2(cp2[k], cp[2 * k], cp[2 * k + 1]);
+          const float cs = ss_col_reduce(cp, lane);
+          if (ccol < vc) P.colpart[size_t(gidx) * LB + (colb + ccol)] = cs;
+          if (lane == 0) P.cshift[size_t(gidx) * nblk + (colb >> 5)] = mshift;
+          if (rare && __any_sync(kFullMask, pass) && !(P.debug & 2)) {
             float bound[4];
             bool hit = false;
 #pragma unroll
@@ -654,59 +731,76 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               hit |= d[rho] > bound[rho];
             }
             if (hit) {
+              const float inv_scale = 1.f / scale;
 #pragma unroll
               for (int rho = 0; rho < 4; ++rho) {
-                if (d[rho] > bound[rho]) {
-                  const int rq = g + 8 * rho;
+                if (d[rho] > bound[rho] && ((rowmask >> rho) & 1u)) {
+                  // the bound in raw-accumulator units, margin on the safe side (the lists are a superset anyway)
+                  const float b = (lg2_approx(bound[rho]) + mshift) * inv_scale;
+                  const float rawb = b - (1e-5f * fabsf(b) + 0.005f * inv_scale);
+                  u64* const mylist = P.cand + (((size_t(n) * LA + rowbase + g + 8 * rho) * kListGroups + cg) * 4 + p) * kLaneSlots;
+                  int c = int((cnts >> (8 * rho)) & 0xffu);
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                      const int idx = 16 * (rho >> 1) + 4 * k + 2 * (rho & 1) + c;
-                      if (v[idx] > bound[rho])
-                        ss_push(scnt + (quad * 32 + rq) * kListGroups + cg, lists + size_t(rq) * (kListGroups * kCandSlots),
-                                v[idx], colb + 8 * k + 2 * p + c, P.flags);
+                    for (int cc2 = 0; cc2 < 2; ++cc2) {
+                      const int idx = 16 * (rho >> 1) + 4 * k + 2 * (rho & 1) + cc2;
+                      const int cin = 8 * k + 2 * p + cc2;
+                      if (v[idx] > rawb && cin < vc)
+                        c = list_push<kLaneSlots>(mylist, c, rawb, v[idx], colb + cin, P.flags, P.pairflag + n);
                     }
+                  cnts = (cnts & ~(0xffu << (8 * rho))) | (uint32_t(c) << (8 * rho));
                 }
               }
             }
           }
-        };
-        if (active) {
-          tmem_ld_frag(tbase, v);
-          process(0);
         }
-        if (active && nvalid > 32) tmem_ld_frag(tbase + 32, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
-        if (active && nvalid > 32) process(1);
       }
 
-      // unit end: row sums over the 4 lanes of a row, then over the 4 column groups through shared memory
-      float rowacc[4];
+      // unit end: row sums over the 4 lanes of a row (same warp, same shift), then over the 4 column groups (one shift
+      // each) through shared memory
 #pragma unroll
       for (int rho = 0; rho < 4; ++rho) {
-        float x, y;
-        unpack2(rowacc2[rho], x, y);
-        rowacc[rho] = x + y;
         rowacc[rho] += __shfl_xor_sync(kFullMask, rowacc[rho], 1);
         rowacc[rho] += __shfl_xor_sync(kFullMask, rowacc[rho], 2);
       }
       const float mine = p == 0 ? rowacc[0] : p == 1 ? rowacc[1] : p == 2 ? rowacc[2] : rowacc[3];
-      if (cg > 0) mergef[(cg - 1) * 128 + rin] = mine;
+      // list counts: row (g + 8 rho)'s uint16 = the nibbles of its four lanes; lane p publishes row rho = p
+      uint32_t myfield = 0;
+#pragma unroll
+      for (int rho = 0; rho < 4; ++rho) {
+        uint32_t f = ((cnts >> (8 * rho)) & 0xfu) << (4 * p);
+        f |= __shfl_xor_sync(kFullMask, f, 1);
+        f |= __shfl_xor_sync(kFullMask, f, 2);
+        myfield = (p == rho) ? f : myfield;
+      }
+      if (cg > 0) mergef[(cg - 1) * 128 + rin] = make_float2(mine, mshift);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       const int row = rb * kUnitRows + int(rank) * kBoxRows + rin;
       if (row < LA) {
         if (cg == 0) {
-          const float tot = ((mine + mergef[rin]) + mergef[128 + rin]) + mergef[256 + rin];
-          P.lse_out0[size_t(n) * LA + row] = log2f(tot);
-          if (!(tot > kSumLo && tot < kSumHi)) atomicOr(reinterpret_cast<unsigned*>(P.flags), POPE_FLAG_ROBUST_PATH);
+          // domain of the total = the largest shift among the column groups that hold anything
+          float sk[4] = {mine, 0.f, 0.f, 0.f}, mk[4] = {mshift, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            const float2 t = mergef[(q - 1) * 128 + rin];
+            sk[q] = t.x;
+            mk[q] = t.y;
+          }
+          float mtop = -INFINITY;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mtop = (sk[q] != 0.f) ? fmaxf(mtop, mk[q]) : mtop;
+          float tot = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tot += (sk[q] != 0.f) ? sk[q] * ex2_approx(mk[q] - mtop) : 0.f;
+          P.lse_out0[size_t(n) * LA + row] = mtop + log2f(tot);
+          if (!(tot > kSumLo && tot < kSumHi)) {
+            atomicOr(reinterpret_cast<unsigned*>(P.flags), POPE_FLAG_ROBUST_PATH);
+            *reinterpret_cast<volatile int*>(P.pairflag + n) = 1;
+          }
         }
-        reinterpret_cast<uint8_t*>(P.cand_cnt)[(size_t(n) * LA + row) * kListGroups + cg] =
-            uint8_t(min(scnt[rin * kListGroups + cg], 255));
+        reinterpret_cast<uint16_t*>(P.cand_cnt)[(size_t(n) * LA + row) * kListGroups + cg] = uint16_t(myfield);
       }
-      scnt[rin * kListGroups + cg] = 0;
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
   } else {
@@ -725,6 +819,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     for (int u = pair; u < P.total_units; u += npairs) {
       int dir, n, rb;
       decode(u, dir, n, rb);
+      if (skip_pair(n)) continue;
       const int LA = dir ? P.L1 : P.L0, LB = dir ? P.L0 : P.L1;
       const int ntiles = (LB + kTileCols - 1) / kTileCols;
       const int row = rb * kUnitRows + int(rank) * kBoxRows + row_in_cta;
@@ -733,7 +828,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       const float inv_s = 1.f / (2.f * scale);
       const bool listing = (MODE == 2) && dir == 0 && row < LA;     // MODE 2: this thread lists candidates of its row
       const float inv_scale = 1.f / scale;
-      u64* const mylist = P.cand + ((size_t(n) * LA + row) * kListGroups + colq) * kCandSlots;
+      u64* const mylist = P.cand + ((size_t(n) * LA + row) * kListGroups + colq) * kListStride;
       int list_cnt = 0;
 
       float m_run = -INFINITY, s_run = 0.f;         // log-sum-exp state
@@ -822,7 +917,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               const int colb = col0 + colq * kSpan + cc * 32;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (v[j] > bound && j < vc) list_cnt = list_push(mylist, list_cnt, bound, v[j], colb + j, P.flags);
+                if (v[j] > bound && j < vc) list_cnt = list_push<kCandSlots>(mylist, list_cnt, bound, v[j], colb + j, P.flags, nullptr);
             }
           };
           const bool skip = (P.debug & 1) != 0;
@@ -865,7 +960,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           }
         }
       }
-      if (listing) reinterpret_cast<uint8_t*>(P.cand_cnt)[(size_t(n) * LA + row) * kListGroups + colq] = uint8_t(list_cnt);
+      if (listing)      // nibble counts of the quarter's sub-lists: the thread's entries are contiguous from entry 0
+        reinterpret_cast<uint16_t*>(P.cand_cnt)[(size_t(n) * LA + row) * kListGroups + colq] =
+            uint16_t(min(list_cnt, 4) | (max(list_cnt - 4, 0) << 4));
       if (kLse) {
         // the four column quarters of a row merge their (max, sum) through shared memory
         if (colq > 0) merge[(colq - 1) * 128 + row_in_cta] = make_float2(m_run, s_run);
@@ -1000,9 +1097,10 @@ cudaError_t coarse_tc_split_run(const CoarseProblem& p, const CoarseScratch& w, 
   P.n = p.n; P.L0 = p.L; P.L1 = p.S; P.kchunks = p.C / kBoxK;
   P.scale_log2 = p.scale_log2; P.log2_thr = p.log2_thr;
   P.lse_out0 = w.lse_r; P.lse_out1 = w.lse_c; P.lse_r = w.lse_r; P.lse_c = w.lse_c; P.rowbest = w.rowbest; P.colbest = w.colbest;
-  P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags; P.colpart = w.colpart;
+  P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags; P.colpart = w.colpart; P.cshift = w.cshift; P.pairflag = w.pairflag;
   const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows);
   P.units_dir0 = u0; P.total_units = u0;
+  if ((e = cudaMemsetAsync(w.pairflag, 0, sizeof(int) * p.n, st)) != cudaSuccess) return e;
   k4<<<2 * min(u0, sms / 2), kThreads, kSmemAlloc, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = colsum_reduce_run(p, w, flags, st)) != cudaSuccess) return e;
@@ -1039,7 +1137,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   P.scale_log2 = p.scale_log2; P.log2_thr = p.log2_thr;
   P.lse_out0 = w.lse_r; P.lse_out1 = w.lse_c;
   P.lse_r = w.lse_r; P.lse_c = w.lse_c; P.rowbest = w.rowbest; P.colbest = w.colbest;
-  P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags; P.colpart = w.colpart;
+  P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags; P.colpart = w.colpart; P.cshift = w.cshift; P.pairflag = w.pairflag;
   const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows), u1 = p.n * ((p.S + kUnitRows - 1) / kUnitRows);
   const int max_pairs = sms / 2;
   // A cell with conf > thr has p_row > thr, and a row has fewer than 1/thr such cells: with thr > 1/kCandSlots the
@@ -1050,6 +1148,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
       // single sweep over the rows of S: row sums, column partial sums and candidate lists in one pass; raises
       // POPE_FLAG_ROBUST_PATH when the unshifted exponentials leave the safe range (debug bit4 skips it)
       P.units_dir0 = u0; P.total_units = u0;
+      if ((e = cudaMemsetAsync(w.pairflag, 0, sizeof(int) * p.n, st)) != cudaSuccess) return e;
       k3<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, map0, map1, map0, map1, P);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       if ((e = colsum_reduce_run(p, w, flags, st)) != cudaSuccess) return e;
@@ -1061,7 +1160,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
     P.trace = trace_mode == 2 ? g_trace : nullptr;
     k2<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, map0, map1, map0, map1, P);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return cand_eval_lists_run(p, w, flags, P.gate, st);
+    return cand_eval_lists_run(p, w, flags, 0, st);
   }
   // three sweeps (small thresholds): both log-sum-exp directions in one launch, then the candidate sweep
   P.units_dir0 = u0; P.total_units = u0 + u1;

@@ -43,24 +43,34 @@ __device__ __forceinline__ float lg2_approx(float x) {
 
 // ---- coarse-match scratch layout -------------------------------------------------------------------------
 constexpr int kCandSlots = 8;   // per-row candidate slots of the two-sweep paths (thr > 1/8 => at most 7 cells pass)
-// tcgen05 two-sweep path: every epilogue thread (row, quarter of the columns) keeps a PRIVATE list of kCandSlots cells,
-// so the sweep needs no atomics; the per-quarter counts are the four bytes of the row's cand_cnt word.
+// tcgen05 paths: every epilogue thread keeps PRIVATE candidate lists, so the sweeps need no atomics.  A row owns
+// kListGroups (column quarters) x kListStride entries.  Two-sweep kernels: thread (row, quarter) fills the first kCandSlots
+// entries of its quarter.  Single sweep: the four lanes that share a row in a quarter own kLaneSlots entries each.
+// Counts: one uint16 per (row, quarter) = four nibbles, nibble p = entries used in sub-list p (entries [4p, 4p + 4)).
 constexpr int kListGroups = 4;
-// single-sweep path: row / column sums of 2^x must stay inside [2^-90, 2^110] for the unshifted exponentials to be exact
-// enough (terms lost to underflow < 2^-36 of the sum, no overflow); otherwise POPE_FLAG_ROBUST_PATH is raised
+constexpr int kListStride = 16;
+constexpr int kLaneSlots = 4;
+// single-sweep path: every epilogue warp keeps a lazily raised, integer-valued shift m (e = 2^(x - m)); a term that
+// underflows is below 2^-126 in its sum's final domain, so a row / column sum inside [2^-90, 2^110] of that domain has lost
+// less than 2^-22 of its value (<= 2^14 terms); outside it the pair is handed to the online-softmax kernels
+// (POPE_FLAG_ROBUST_PATH; happens when rows whose maxima are more than ~150 log2 units apart share a 32-row group)
 constexpr float kSumLo = 8.0779357e-28f, kSumHi = 1.2980742e33f;
+constexpr float kShiftBack = 64.f;           // a freshly chosen shift leaves the chunk's largest cell at 2^64
+constexpr float kBumpTrig = 2.0282410e31f;   // 2^104: a thread's running row sums above this raise the warp's shift
 
 struct CoarseScratch {
   float* lse_r;   // [n, L]  log2-domain log-sum-exp of every row of S
   float* lse_c;   // [n, S]  ... of every column
   u64* rowbest;   // [n, L]  best above-threshold candidate of the row   (pack_best(t2, j))
   u64* colbest;   // [n, S]  best above-threshold candidate of the column (pack_best(t2, i))
-  int* cand_cnt;  // [n, L]  two-sweep paths: number of listed cells of the row (tcgen05: one byte per column quarter)
-  u64* cand;      // [n, L, kListGroups, kCandSlots]  (raw accumulator bits << 32 | column); SIMT uses [n, L, kCandSlots]
+  int* cand_cnt;  // [n, L, 2]  tcgen05: four uint16 per row (above); SIMT: [n, L] ints, number of listed cells of the row
+  u64* cand;      // [n, L, kListGroups, kListStride]  (raw accumulator bits << 32 | column); SIMT uses [n, L, kCandSlots]
   float* cbound;  // [n, 32*ceil(L/32)]  two-sweep path: raw-accumulator bound above which a cell of row i has p_row > thr
   float* cminb;   // [n, ceil(L/32)]  minimum of cbound over each group of 32 rows
-  float* colpart; // [n, ceil(L/32), S]  single-sweep tcgen05 path: column sums of 2^x over each group of 32 rows
+  float* colpart; // [n, ceil(L/32), S]  single-sweep tcgen05 path: column sums of 2^(x - shift) over each group of 32 rows
+  float* cshift;  // [n, ceil(L/32), ceil(S/32)]  ... the shift of each (32-row group, 32-column block) of colpart
   int* ready;     // [n]  count_emit_kernel: "this pair's count is published" (cleared before every call)
+  int* pairflag;  // [n]  single-sweep path: != 0 = this pair is recomputed by the gated online-softmax launch
   size_t zero_bytes;   // rowbest, colbest, cand_cnt, ready are adjacent and cleared by one memset
   size_t bytes;
 };
@@ -71,15 +81,17 @@ inline CoarseScratch carve_coarse_scratch(void* base, int n, int L, int S) {
   size_t off = 0;
   w.rowbest = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L, 256);
   w.colbest = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * S, 256);
-  w.cand_cnt = reinterpret_cast<int*>(p + off); off += align_up(sizeof(int) * size_t(n) * L, 256);
+  w.cand_cnt = reinterpret_cast<int*>(p + off); off += align_up(sizeof(int) * size_t(n) * L * 2, 256);
   w.ready = reinterpret_cast<int*>(p + off); off += align_up(sizeof(int) * size_t(n), 256);
   w.zero_bytes = off;
   w.lse_r = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * L, 256);
   w.lse_c = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * S, 256);
-  w.cand = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L * kListGroups * kCandSlots, 256);
+  w.cand = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L * kListGroups * kListStride, 256);
   w.cbound = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32) * 32, 256);
   w.cminb = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32), 256);
   w.colpart = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32) * S, 256);
+  w.cshift = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * ((L + 31) / 32) * ((S + 31) / 32), 256);
+  w.pairflag = reinterpret_cast<int*>(p + off); off += align_up(sizeof(int) * size_t(n), 256);
   w.bytes = off;
   return w;
 }
@@ -113,11 +125,11 @@ cudaError_t cand_eval_run(const CoarseProblem& p, const CoarseScratch& w, cudaSt
 // zero `bytes` (multiple of 16) at ptr if POPE_FLAG_ROBUST_PATH is set in *gate
 cudaError_t gated_clear_run(void* ptr, size_t bytes, const int32_t* gate, cudaStream_t st);
 // evaluation of the per-thread (row, column quarter) lists written by the tcgen05 row sweep
-// (mode 1: after the single-sweep launch sequence -- the list format follows POPE_FLAG_ROBUST_PATH in *flags;
-//  mode 2: 2^x lists, and nothing at all if the flag is set: the fp32 fallback evaluates its own lists)
+// (the lists hold raw accumulators on every path; mode 2 = fp32 split path: nothing at all if POPE_FLAG_ROBUST_PATH is set,
+//  the fp32-FMA fallback evaluates its own lists)
 cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, int mode, cudaStream_t st);
-// single-sweep tcgen05 path: column log-sum-exp from the per-32-row partial sums; evaluation of its lists (which hold
-// 2^x instead of the raw accumulator); both set / honour POPE_FLAG_ROBUST_PATH
+// single-sweep tcgen05 path: column log-sum-exp from the per-32-row partial sums and their shifts (a log-sum-exp merge);
+// sets POPE_FLAG_ROBUST_PATH and the pair's flag when a column sum lost precision
 cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st);
 // does coarse_tc_run need rowbest / colbest / cand_cnt cleared beforehand?  (not on the single-sweep launch sequence)
 bool coarse_tc_needs_clear(const CoarseProblem& p);

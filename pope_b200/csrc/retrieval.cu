@@ -168,10 +168,44 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const int64_t* __rest
   }
 }
 
+// The compact form of the record, 20 bytes (int32[5]): global pair index, i | j << 16, mconf, x1, y1 -- the keypoint of
+// image 0 is implied by i (mkpts0_f = mkpts0_c = (i % w0c, i / w0c) * pixel_scale, fine_matching.py:66), so the gather moves
+// 20 instead of 32 bytes per match.  Needs L, S <= 65536.
+__global__ void __launch_bounds__(256) pack_records5_kernel(const int64_t* __restrict__ b_ids, const int64_t* __restrict__ i_ids,
+                                                           const int64_t* __restrict__ j_ids, const float* __restrict__ mconf,
+                                                           const float2* __restrict__ mk1, const int32_t* __restrict__ m_dev,
+                                                           int64_t capacity, int pair_offset, int32_t* __restrict__ rec,
+                                                           const int64_t* __restrict__ base_dev) {
+  const int64_t m = min(int64_t(*m_dev), capacity);
+  if (base_dev) rec += 5 * *base_dev;
+  for (int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < m; k += int64_t(gridDim.x) * blockDim.x) {
+    const float2 b = mk1[k];
+    int32_t* r = rec + 5 * k;
+    r[0] = int(b_ids[k]) + pair_offset;
+    r[1] = int(uint32_t(i_ids[k]) | (uint32_t(j_ids[k]) << 16));
+    r[2] = __float_as_int(mconf[k]);
+    r[3] = __float_as_int(b.x);
+    r[4] = __float_as_int(b.y);
+  }
+}
+
 }  // namespace
 }  // namespace pope
 
 using namespace pope;
+
+extern "C" int pope_pack_records_compact(const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids, const float* mconf,
+                                         const float* mkpts1_f, const int32_t* m_dev, int64_t capacity, int pair_offset,
+                                         int32_t* records, const int64_t* base_dev, void* stream) {
+  if (!b_ids || !i_ids || !j_ids || !mconf || !mkpts1_f || !m_dev || !records || capacity < 0) return POPE_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(mkpts1_f) & 7u || reinterpret_cast<uintptr_t>(records) & 3u) return POPE_ERR_ALIGNMENT;
+  if (capacity == 0) return POPE_OK;
+  const int64_t want = (capacity + 255) / 256;
+  const unsigned blocks = unsigned(want < 148 * 8 ? want : 148 * 8);
+  pack_records5_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      b_ids, i_ids, j_ids, mconf, reinterpret_cast<const float2*>(mkpts1_f), m_dev, capacity, pair_offset, records, base_dev);
+  return int(cudaGetLastError());
+}
 
 extern "C" int pope_pack_records(const int64_t* b_ids, const int64_t* i_ids, const int64_t* j_ids, const float* mconf,
                                  const float* mkpts0_f, const float* mkpts1_f, const int32_t* m_dev, int64_t capacity,

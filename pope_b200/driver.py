@@ -199,77 +199,138 @@ def gather_matches(local: Dict[str, torch.Tensor], n_pairs: int, rank: int, worl
             "mkpts0_f": fl[:, 1:3], "mkpts1_f": fl[:, 3:5], "per_rank_matches": totals}
 
 
-def pack_records(res, pair_offset: int, out: Optional[torch.Tensor] = None, base: Optional[torch.Tensor] = None
-                 ) -> torch.Tensor:
-    """Capacity-sized result -> packed int32 records [cap, 8] = (b_global, i, j, mconf, x0, y0, x1, y1; floats as bit
-    patterns); rows past the live count are not written.  One kernel (`pope_pack_records`), no host sync.
+def pack_records(res, pair_offset: int, out: Optional[torch.Tensor] = None, base: Optional[torch.Tensor] = None,
+                 compact: bool = False) -> torch.Tensor:
+    """Capacity-sized result -> packed int32 records; rows past the live count are not written.  One kernel, no host sync.
+      compact=False: [cap, 8] = (b_global, i, j, mconf, x0, y0, x1, y1; floats as bit patterns)   (`pope_pack_records`)
+      compact=True : [cap, 5] = (b_global, i | j << 16, mconf, x1, y1) -- 20 instead of 32 bytes per match: the keypoint of
+                     image 0 is implied by i (`unpack_records` restores it); needs L, S <= 65536  (`pope_pack_records_compact`)
     `base` (device int64[1]): the batch is appended to `out` behind the `base` records already there."""
     cap = res["i_ids"].shape[0]
     dev = res["i_ids"].device
+    words = 5 if compact else 8
     if dev.type != "cuda":
         # host-side bookkeeping of already-computed results (the world_size-2 gloo tests of the sharding logic); the
         # records themselves are produced on the GPU in every real run
-        rec = torch.cat([(res["b_ids"] + pair_offset).to(torch.int32)[:, None], res["i_ids"].to(torch.int32)[:, None],
-                         res["j_ids"].to(torch.int32)[:, None], res["mconf"].view(torch.int32)[:, None],
-                         res["mkpts0_f"].view(torch.int32), res["mkpts1_f"].view(torch.int32)], 1)
+        head = [(res["b_ids"] + pair_offset).to(torch.int32)[:, None]]
+        if compact:
+            ij = (res["i_ids"] | (res["j_ids"] << 16)).to(torch.int64)
+            ij = torch.where(ij >= 2 ** 31, ij - 2 ** 32, ij).to(torch.int32)
+            rec = torch.cat(head + [ij[:, None], res["mconf"].view(torch.int32)[:, None], res["mkpts1_f"].view(torch.int32)], 1)
+        else:
+            rec = torch.cat(head + [res["i_ids"].to(torch.int32)[:, None], res["j_ids"].to(torch.int32)[:, None],
+                                    res["mconf"].view(torch.int32)[:, None], res["mkpts0_f"].view(torch.int32),
+                                    res["mkpts1_f"].view(torch.int32)], 1)
         if out is None:
             return rec
         m, b = int(res["counts"][res["n_pairs"]]), (int(base) if base is not None else 0)
         out[b:b + m] = rec[:m]
         return out
     if out is None:
-        out = torch.empty(cap, 8, dtype=torch.int32, device=dev)
+        out = torch.empty(cap, words, dtype=torch.int32, device=dev)
     n = res["n_pairs"]
+    base_ptr = None if base is None else base.data_ptr()
     with torch.cuda.device(dev):
-        st = _lib.lib().pope_pack_records(res["b_ids"].data_ptr(), res["i_ids"].data_ptr(), res["j_ids"].data_ptr(),
-                                          res["mconf"].data_ptr(), res["mkpts0_f"].contiguous().data_ptr(),
-                                          res["mkpts1_f"].contiguous().data_ptr(), res["counts"][n:n + 1].data_ptr(), cap,
-                                          int(pair_offset), out.data_ptr(), None if base is None else base.data_ptr(),
-                                          _lib.stream_ptr(dev))
+        if compact:
+            st = _lib.lib().pope_pack_records_compact(res["b_ids"].data_ptr(), res["i_ids"].data_ptr(), res["j_ids"].data_ptr(),
+                                                      res["mconf"].data_ptr(), res["mkpts1_f"].contiguous().data_ptr(),
+                                                      res["counts"][n:n + 1].data_ptr(), cap, int(pair_offset), out.data_ptr(),
+                                                      base_ptr, _lib.stream_ptr(dev))
+        else:
+            st = _lib.lib().pope_pack_records(res["b_ids"].data_ptr(), res["i_ids"].data_ptr(), res["j_ids"].data_ptr(),
+                                              res["mconf"].data_ptr(), res["mkpts0_f"].contiguous().data_ptr(),
+                                              res["mkpts1_f"].contiguous().data_ptr(), res["counts"][n:n + 1].data_ptr(), cap,
+                                              int(pair_offset), out.data_ptr(), base_ptr, _lib.stream_ptr(dev))
     _lib.check(st, "pope_pack_records")
     return out
+
+
+def unpack_records(rec: torch.Tensor, w0c: Optional[int] = None, pixel_scale: Optional[float] = None) -> Dict[str, torch.Tensor]:
+    """Packed int32 records [M, 8] or [M, 5] (`pack_records`) -> the reference's match-list tensors (ids int64, the rest fp32).
+    The compact form needs the width of image 0's coarse grid and hw0_i[0] / hw0_c[0] to restore mkpts0_f from i."""
+    if rec.shape[1] == 8:
+        fl = rec[:, 3:8].contiguous().view(torch.float32)
+        return {"b_ids": rec[:, 0].long(), "i_ids": rec[:, 1].long(), "j_ids": rec[:, 2].long(), "mconf": fl[:, 0],
+                "mkpts0_f": fl[:, 1:3], "mkpts1_f": fl[:, 3:5]}
+    if w0c is None or pixel_scale is None:
+        raise _lib.PopeError("compact records need w0c and pixel_scale to restore mkpts0_f")
+    ij = rec[:, 1].long() & 0xFFFFFFFF
+    i, j = ij & 0xFFFF, ij >> 16
+    fl = rec[:, 2:5].contiguous().view(torch.float32)
+    mk0 = torch.stack([(i % w0c).float() * pixel_scale, (i // w0c).float() * pixel_scale], 1)
+    return {"b_ids": rec[:, 0].long(), "i_ids": i, "j_ids": j, "mconf": fl[:, 0], "mkpts0_f": mk0, "mkpts1_f": fl[:, 1:3]}
 
 
 class JobGather:
     """The single cross-GPU step of a sharded job: every rank appends the packed records of each
     of its steps behind the previous ones in one device buffer (no sync, no collective, no compaction: the running count
-    stays on the device); `finish()` runs once at the end of the job -- one host read of the rank's total, one all-gather
-    of the totals and ONE collective on the records: a gather to rank 0 (default) or an all-gather (`to_all=True`)."""
+    stays on the device); `finish()` runs once at the end of the job -- one all-gather of the totals (with the job's one
+    host read) and ONE collective on the records: a gather to rank 0 (default) or an all-gather (`to_all=True`).
 
-    def __init__(self, steps: int, cap: int, device):
-        self.rec = torch.empty(steps * cap, 8, dtype=torch.int32, device=device)
+    Nothing is allocated after the constructor: rank 0's receive buffer [world, steps * cap, words] exists from the start
+    and the gather lands in views of it (a job's first `finish()` is as fast as any later one).
+    `add()` is stream-safe by itself: appends may be issued from different streams (e.g. `DeviceBatchRunner.submit(after=)`
+    on alternating streams); each one waits for the previous append's event before it reads the running count, and
+    `finish()` waits for the last."""
+
+    def __init__(self, steps: int, cap: int, device, rank: int = 0, world: int = 1, compact: bool = False, to_all: bool = False):
+        self.words = 5 if compact else 8
+        self.compact, self.rank, self.world, self.to_all = compact, rank, world, to_all
+        self.rec = torch.empty(steps * cap, self.words, dtype=torch.int32, device=device)
         self.total = torch.zeros(1, dtype=torch.int64, device=device)
+        self.sizes = torch.zeros(max(world, 1), dtype=torch.int64, device=device)
+        self.recv = (torch.empty(world, steps * cap, self.words, dtype=torch.int32, device=device)
+                     if world > 1 and (rank == 0 or to_all) else None)
+        self._last = None                    # event after the most recent append (cuda only)
 
     def add(self, res, pair_offset: int):
         n = res["n_pairs"]
-        pack_records(res, pair_offset, out=self.rec, base=self.total)
+        cuda = self.rec.device.type == "cuda"
+        if cuda:
+            cur = torch.cuda.current_stream(self.rec.device)
+            if self._last is not None:
+                cur.wait_event(self._last)          # the previous append has advanced the count
+        pack_records(res, pair_offset, out=self.rec, base=self.total, compact=self.compact)
         self.total += res["counts"][n:n + 1]
+        if cuda:
+            self._last = torch.cuda.Event()
+            self._last.record(cur)
 
-    def finish(self, rank: int, world: int, group=None, to_all: bool = False):
-        """Returns (records [world, max_total, 8], totals): rank r's records are records[r, :totals[r]], sorted by (b, i)
+    def finish(self, group=None):
+        """Returns (records [world, max_total, words], totals): rank r's records are records[r, :totals[r]], sorted by (b, i)
         within each step.  With the default gather only rank 0 receives the records (the others get None)."""
         import torch.distributed as dist
-        mine = int(self.total.item())                           # the job's one host read
-        if world == 1:
+        if self.rec.device.type == "cuda" and self._last is not None:
+            torch.cuda.current_stream(self.rec.device).wait_event(self._last)
+            self._last = None
+        if self.world == 1:
+            mine = int(self.total.item())                       # the job's one host read
             self.total.zero_()
             return self.rec[:mine].unsqueeze(0), [mine]
-        sizes = torch.empty(world, dtype=torch.int64, device=self.rec.device)
-        dist.all_gather_into_tensor(sizes, self.total, group=group)
-        sizes = sizes.tolist()
+        dist.all_gather_into_tensor(self.sizes, self.total, group=group)
+        sizes = self.sizes.tolist()                             # the job's one host read (every rank's total)
         mx = max(max(sizes), 1)
         send = self.rec[:mx]                                    # rows past the rank's own total are never read
         out = None
-        if to_all:
-            out = torch.empty(world * mx, 8, dtype=torch.int32, device=self.rec.device)
+        if self.to_all:
+            out = self.recv.view(-1, self.words)[:self.world * mx]
             dist.all_gather_into_tensor(out, send, group=group)
-            out = out.view(world, mx, 8)
+            out = out.view(self.world, mx, self.words)
         else:
-            parts = [torch.empty(mx, 8, dtype=torch.int32, device=self.rec.device) for _ in range(world)] if rank == 0 else None
+            parts = [self.recv[r, :mx] for r in range(self.world)] if self.rank == 0 else None
             dist.gather(send, parts, dst=0, group=group)
-            if rank == 0:
-                out = torch.stack(parts)
+            if self.rank == 0:
+                out = self.recv[:, :mx]
         self.total.zero_()
         return out, sizes
+
+    def checksum(self, records: Optional[torch.Tensor] = None, totals=None) -> torch.Tensor:
+        """int64 word sum of the live records: of this rank's own buffer (no arguments; call before `finish()` clears the
+        count, or pass the count), or per rank of a gathered [world, max_total, words] tensor -> [world]."""
+        if records is None:
+            m = int(self.total.item()) if totals is None else int(totals)
+            return self.rec[:m].to(torch.int64).sum().reshape(1)
+        return torch.stack([records[r, :int(t)].to(torch.int64).sum() for r, t in enumerate(totals)])
 
 
 def bind_host_to_gpu(device_index: int):

@@ -59,16 +59,31 @@ def _worker(rank, world, port, n_pairs, q):
     for k in ("b_ids", "i_ids", "j_ids", "mconf", "mkpts0_f", "mkpts1_f"):
         res[k][:m] = loc[k] if k != "b_ids" else loc[k] - lo
     res["counts"][hi - lo] = m
-    job = driver.JobGather(2, cap, torch.device("cpu"))
+    job = driver.JobGather(2, cap, torch.device("cpu"), rank=rank, world=world)
     job.add(res, lo)
     job.add(res, lo)
-    recs, sizes = job.finish(rank, world)
+    recs, sizes = job.finish()
+    # the compact 20-byte records (mkpts0_f implied by i) through the same gather, with the per-rank checksums bench.py uses
+    jobc = driver.JobGather(2, cap, torch.device("cpu"), rank=rank, world=world, compact=True)
+    jobc.add(res, lo)
+    jobc.add(res, lo)
+    mine = jobc.checksum()
+    sums = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(sums, mine)
+    recs_c, sizes_c = jobc.finish()
     if rank == 0:
         # numpy arrays travel through the queue by value; tensors would travel as file descriptors that die with this process
         payload = {k: (v.numpy().copy() if torch.is_tensor(v) else v) for k, v in got.items()}
         payload["job_sizes"] = sizes
         payload["job_b"] = torch.cat([recs[r, :sizes[r], 0] for r in range(world)]).numpy().copy()
         payload["job_conf"] = torch.cat([recs[r, :sizes[r], 3] for r in range(world)]).view(torch.float32).numpy().copy()
+        assert sizes_c == sizes and recs_c.shape[2] == 5
+        assert torch.equal(jobc.checksum(recs_c, sizes_c), torch.cat(sums))
+        for r in range(world):
+            full = driver.unpack_records(recs[r, :sizes[r]])
+            comp = driver.unpack_records(recs_c[r, :sizes[r]], hw[1], 8.0)
+            for k in full:
+                assert torch.equal(full[k], comp[k]), k
         q.put(payload)
     dist.barrier()
     dist.destroy_process_group()

@@ -107,8 +107,49 @@ def test_coarse_hard_set_bf16(impl):
     assert not bad, bad[:5]
     assert same > 100
     if impl == "tcgen05":
-        # |S| log2(e) reaches the hundreds: the unshifted single sweep must have detected it and handed over
+        # a x50 row sits 500+ log2 units above the other 31 rows of its 32-row group: more than one warp-uniform fp32 shift
+        # can hold, so the single sweep must have detected it and handed these pairs to the online-softmax launch
         assert out["_flags"] & _lib.FLAG_ROBUST_PATH
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_coarse_large_norm_stays_on_the_single_sweep(dtype):
+    """Token norm ~ 49 (what the coarse transformer emits): |S| log2(e) reaches ~135, far outside what
+    unshifted fp32 exponentials hold.  The lazily shifted single sweep must stay on the fast path (no flag) and agree with
+    the oracle; so must a batch that mixes weak pairs (sigma 0.25: every similarity below 1) with such strong ones."""
+    h0, w0, h1, w1 = 40, 48, 36, 56
+    _need_tc("tcgen05", 256, h0 * w0, h1 * w1)
+    fa0, fa1 = synth.coarse_features(91, 2, h0 * w0, h1 * w1, 256, sigma=49.0 / 16.0, dtype=dtype)
+    fb0, fb1 = synth.coarse_features(92, 1, h0 * w0, h1 * w1, 256, sigma=0.25, noise=0.05, dtype=dtype)
+    f0, f1 = torch.cat([fa0[:1], fb0, fa0[1:]]), torch.cat([fa1[:1], fb1, fa1[1:]])
+    want, mg = oracle_with_margins(f0.float(), f1.float(), (h0 * 8, w0 * 8), (h0, w0), (h1, w1))
+    out = _run_coarse(f0, f1, (h0, w0), (h1, w1), _lib.COARSE_TCGEN05, dtype)
+    assert out["_flags"] == 0
+    same, near, bad = compare_match_lists(out, want, mg)
+    assert not bad, bad[:5]
+    assert same > 1500 and len(near) <= 6
+    if not near:
+        assert torch.allclose(out["mconf"], want["mconf"], rtol=1e-2 if dtype == torch.bfloat16 else 1e-4, atol=0)
+
+
+def test_coarse_mixed_batch_only_flagged_pairs_take_the_robust_launch():
+    """A batch of ordinary pairs with one hard-set pair in the middle: the flag is raised, the result of every pair equals
+    what the pair gives when it is run alone (the gated launch redoes the flagged pair only; the others keep the
+    single-sweep results bit for bit)."""
+    h0, w0, h1, w1 = 40, 48, 36, 56
+    _need_tc("tcgen05", 256, h0 * w0, h1 * w1)
+    fa0, fa1 = synth.coarse_features(93, 2, h0 * w0, h1 * w1, 256, sigma=0.9, dtype=torch.bfloat16)
+    fh0, fh1 = synth.hard_coarse_features(94, 1, h0 * w0, h1 * w1, 256, sigma=0.9, dtype=torch.bfloat16)
+    f0, f1 = torch.cat([fa0[:1], fh0, fa0[1:]]), torch.cat([fa1[:1], fh1, fa1[1:]])
+    out = _run_coarse(f0, f1, (h0, w0), (h1, w1), _lib.COARSE_TCGEN05, torch.bfloat16)
+    assert out["_flags"] & _lib.FLAG_ROBUST_PATH
+    for b in range(3):
+        solo = _run_coarse(f0[b:b + 1], f1[b:b + 1], (h0, w0), (h1, w1), _lib.COARSE_TCGEN05, torch.bfloat16)
+        assert bool(solo["_flags"] & _lib.FLAG_ROBUST_PATH) == (b == 1)
+        sel = out["b_ids"] == b
+        assert int(sel.sum()) == solo["b_ids"].numel() > 100
+        for k in ("i_ids", "j_ids", "mconf", "mkpts1_c"):
+            assert torch.equal(out[k][sel], solo[k]), (b, k)
 
 
 def test_coarse_fp32_on_tensor_cores_vs_fp32_fma():
@@ -133,7 +174,7 @@ def test_coarse_fp32_on_tensor_cores_vs_fp32_fma():
 
 
 def test_coarse_single_sweep_vs_robust_path():
-    """tcgen05: the single-sweep kernel (unshifted 2^x, shuffle-reduced column sums) and the two-sweep online-softmax
+    """tcgen05: the single-sweep kernel (lazily shifted 2^(x - m), shuffle-reduced column sums) and the two-sweep online-softmax
     kernels it falls back to must produce the same match lists on in-range data (ragged L != S, 3 pairs)."""
     L, S = 50 * 70, 44 * 60
     _need_tc("tcgen05", 256, L, S)
@@ -182,6 +223,7 @@ def test_coarse_permutation_property_full_size(impl):
         f1[b, p] = f0[b]
         perms.append(p)
     out = _run_coarse(f0, f1, (h, w), (h, w), IMPLS[impl], torch.bfloat16)
+    assert out["_flags"] == 0        # |S| log2(e) ~ 130 on the diagonal: the lazily shifted single sweep holds it
     keep = O._interior(h, w, 2)
     want_b, want_i, want_j = [], [], []
     for b in range(n):
