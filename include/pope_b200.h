@@ -59,9 +59,13 @@ typedef enum { POPE_COARSE_AUTO = 0, POPE_COARSE_SIMT = 1, POPE_COARSE_TCGEN05 =
 /* bits of counts[n_pairs + 1] written by pope_coarse_match */
 #define POPE_FLAG_NONFINITE_LSE 1u   /* a row/column log-sum-exp was inf/nan (inputs contain inf/nan) */
 #define POPE_FLAG_CAND_OVERFLOW 2u   /* a row had more above-threshold cells than 1/thr allows (inputs contain nan) */
-#define POPE_FLAG_ROBUST_PATH   4u   /* informational: the similarities left the range the single-sweep tcgen05 kernel
-                                        handles without per-row shifts (|S| log2(e) > ~90) or a candidate list filled up,
-                                        so the two-sweep online-softmax kernels recomputed the batch; results are valid */
+#define POPE_FLAG_ROBUST_PATH   4u   /* informational: in some pair the single-sweep tcgen05 kernel found rows (or columns) whose
+                                        maxima lie more than ~186 log2 units below the strongest cell of their 32-row group
+                                        (one lazily raised shift per group cannot hold both in fp32), or inf / nan; the flagged
+                                        pairs were recomputed by the two-sweep online-softmax kernels; results are valid */
+
+#define POPE_FLAG_CAPACITY      8u   /* more matches than `capacity` (possible only for L > S, when several rows tie bit for bit
+                                        on one column): the lists hold the first `capacity` matches, counts[n_pairs] = capacity */
 
 int pope_abi_version(void);
 const char* pope_status_string(int status);
@@ -150,6 +154,12 @@ int pope_match_order_by_ref(const int32_t* counts, int n_pairs, int S, const int
  *   q [D], refs [R, D] contiguous, k <= 16.  Outputs scores float[R], slot_scores float[k], slot_idx int32[k] (-1 = empty). */
 int pope_cosine_topk(const void* q, const void* refs, int dtype, int R, int D, int k, float eps,
                      float* scores, float* slot_scores, int32_t* slot_idx, void* stream);
+
+/* The running top-k of the retrieval loop alone (eval_linemod_json.py:95-101) over R scores that are already on the device, in
+ * crop order -- the last step of a retrieval whose crops were scored on several GPUs (each rank scores its shard with
+ * pope_cosine_topk, the R scores are all-gathered in crop order, every rank runs this; the slot contents depend on the whole
+ * arrival order, so they cannot be merged from per-shard top-k lists).  Outputs as pope_cosine_topk. */
+int pope_running_topk(const float* scores, int R, int k, float* slot_scores, int32_t* slot_idx, void* stream);
 
 /* Pair-batching driver with HOST buffers (the end-to-end entry point): coarse match -> window gather -> fine
  * match for n_pairs pairs, processed in chunks of `chunk_pairs` with host->device copies, kernels and

@@ -16,6 +16,7 @@ COARSE_AUTO, COARSE_SIMT, COARSE_TCGEN05 = 0, 1, 2
 FLAG_NONFINITE_LSE = 1
 FLAG_CAND_OVERFLOW = 2
 FLAG_ROBUST_PATH = 4
+FLAG_CAPACITY = 8
 FINE_TF_LAYER_BYTES = 329728      # include/pope_b200.h: packed weights of one LoFTREncoderLayer (d_model 128)
 FINE_PRE_BYTES = 132096           # ... of FinePreprocess' down_proj + merge_feat
 
@@ -53,6 +54,7 @@ SIGNATURES = {
     "pope_pose_workspace_bytes": (_sz, [_i, _i64]),
     "pope_estimate_pose_batch": (_i, [_p, _p, _p, _i, _i64, _p, _p, C.c_double, C.c_double, _i, C.c_uint64, _p, _p, _p, _p,
                                       _p, _p, _p, _p, _sz, _p]),
+    "pope_running_topk": (_i, [_p, _i, _i, _p, _p, _p]),
     "pope_cosine_topk": (_i, [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "pope_debug_trace_read": (_i, [_p, _i]),
     "pope_pipeline_create": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i]),

@@ -86,17 +86,24 @@ class CoarseMatching(nn.Module):
         S = feat_c1.shape[1]
         hw0_c, hw1_c = tuple(data["hw0_c"]), tuple(data["hw1_c"])
         dev = feat_c0.device
-        m0 = (mask_c0 if mask_c0 is not None else data["mask0"].flatten(-2)).reshape(n, L).bool()
-        m1 = (mask_c1 if mask_c1 is not None else data["mask1"].flatten(-2)).reshape(n, S).bool()
+        # like the reference, the similarity matrix is masked only when mask_c0 is passed (:115-118); data['mask0'] alone
+        # selects the padded border handling (:180-182) and nothing else
+        fill = mask_c0 is not None
+        if fill:
+            m0 = mask_c0.reshape(n, L).bool()
+            m1 = (mask_c1 if mask_c1 is not None else torch.ones(n, S, dtype=torch.bool, device=dev)).reshape(n, S).bool()
+        all0, all1 = torch.arange(L, device=dev), torch.arange(S, device=dev)
         scale = data["hw0_i"][0] / data["hw0_c"][0]
         parts = {k: [] for k in ("b_ids", "i_ids", "j_ids", "mconf")}
         for b in range(n):
-            v0, v1 = torch.nonzero(m0[b]).reshape(-1), torch.nonzero(m1[b]).reshape(-1)
+            v0 = torch.nonzero(m0[b]).reshape(-1) if fill else all0
+            v1 = torch.nonzero(m1[b]).reshape(-1) if fill else all1
             if v0.numel() == 0 or v1.numel() == 0:
                 continue
             res = ops.coarse_match(feat_c0[b, v0][None].contiguous(), feat_c1[b, v1][None].contiguous(), (v0.numel(), 1),
                                    (v1.numel(), 1), pixel_scale=scale, thr=self.thr, border_rm=0,
-                                   temperature=self.temperature, impl=self.impl)
+                                   temperature=self.temperature, impl=self.impl, workspace=self._workspace)
+            self._workspace = res["workspace"]        # sized for the largest pair so far, reused for the others
             out = res.sliced()
             i_ids, j_ids = v0[out["i_ids"]], v1[out["j_ids"]]
             if "mask0" in data:

@@ -97,6 +97,6 @@ extern "C" int pope_coarse_match(const void* feat_c0, const void* feat_c1, int d
     e = use_tc ? coarse_tc_run(p, w, counts + n_pairs + 1, st) : coarse_simt_run(p, w, counts + n_pairs + 1, st);
   }
   if (e != cudaSuccess) return int(e);
-  e = coarse_finalize_run(p, w, b_ids, i_ids, j_ids, mconf, mkpts0_c, mkpts1_c, counts, st);
+  e = coarse_finalize_run(p, w, b_ids, i_ids, j_ids, mconf, mkpts0_c, mkpts1_c, counts, capacity, st);
   return int(e);
 }

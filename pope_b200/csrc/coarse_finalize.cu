@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(FT) count_emit_kernel(const u64* __restrict__ 
                                                        int32_t* __restrict__ counts, int n_pairs, int* __restrict__ ready,
                                                        int64_t* __restrict__ b_ids, int64_t* __restrict__ i_ids,
                                                        int64_t* __restrict__ j_ids, float* __restrict__ mconf,
-                                                       float* __restrict__ mk0, float* __restrict__ mk1, int phase) {
+                                                       float* __restrict__ mk0, float* __restrict__ mk1, int phase,
+                                                       int64_t capacity) {
   __shared__ int smem[32];
   __shared__ int warp_off[FT / 32];
   const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -97,7 +98,12 @@ __global__ void __launch_bounds__(FT) count_emit_kernel(const u64* __restrict__ 
     part += *reinterpret_cast<volatile int32_t*>(counts + p);
   }
   int base = block_sum(part, smem);
-  if (n == n_pairs - 1 && threadIdx.x == 0) counts[n_pairs] = base + c;
+  if (n == n_pairs - 1 && threadIdx.x == 0) {
+    // one match per row, so n * L always suffices; the documented minimum n * min(L, S) can fall short only when L > S and
+    // several rows hold bit-identical confidences in one column (the reference emits them all, too)
+    counts[n_pairs] = int32_t(min(int64_t(base + c), capacity));
+    if (base + c > capacity) atomicOr(reinterpret_cast<unsigned*>(counts + n_pairs + 1), POPE_FLAG_CAPACITY);
+  }
   for (int i0 = 0; i0 < L; i0 += FT) {
     const int i = i0 + threadIdx.x;
     int j = 0; float t2 = 0.f;
@@ -117,8 +123,8 @@ __global__ void __launch_bounds__(FT) count_emit_kernel(const u64* __restrict__ 
       if (lane == 31) smem[0] = incl;
     }
     __syncthreads();
-    if (hit) {
-      const int64_t pos = base + warp_off[warp] + __popc(ballot & ((1u << lane) - 1u));
+    const int64_t pos = base + warp_off[warp] + __popc(ballot & ((1u << lane) - 1u));
+    if (hit && pos < capacity) {
       b_ids[pos] = n; i_ids[pos] = i; j_ids[pos] = j;
       mconf[pos] = exp2f(t2);
       mk0[2 * pos + 0] = float(i % g0.w) * pixel_scale; mk0[2 * pos + 1] = float(i / g0.w) * pixel_scale;
@@ -193,8 +199,8 @@ __global__ void __launch_bounds__(256) cand_eval_kernel(const int* __restrict__ 
 
 // tcgen05 paths: one thread per row i evaluates the cells its four epilogue threads listed during the row sweep (a
 // superset of the cells with p_row > thr: the test there ran against the RUNNING row sum, which only grows).  Same
-// arithmetic as cand_eval_kernel; the lists hold raw accumulators on every path (single sweep, its gated online-softmax
-// redo of flagged pairs, two-sweep).  mode 2 (fp32 split path): nothing at all once POPE_FLAG_ROBUST_PATH is set -- the
+// arithmetic as cand_eval_kernel; the lists hold similarities in log2 units on every path (single sweep, its gated
+// online-softmax redo of flagged pairs, two-sweep).  mode 2 (fp32 split path): nothing at all once POPE_FLAG_ROBUST_PATH is set -- the
 // fp32-FMA fallback evaluates its own lists.
 // Every row's rowbest is written (0 = no candidate), so the caller need not clear it.
 __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restrict__ cand_cnt, const u64* __restrict__ cand,
@@ -219,8 +225,7 @@ __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restr
       for (int k = 0; k < c; ++k) {
         const u64 rec = cand[(r * (kListGroups * kListStride / kLaneSlots) + sub) * kLaneSlots + k];
         const int j = int(uint32_t(rec));
-        const float val = __uint_as_float(uint32_t(rec >> 32));
-        const float x = val * scale;
+        const float x = __uint_as_float(uint32_t(rec >> 32));   // the similarity in log2 units
         if (!(x - lr > log2_thr - 0.01f)) continue;         // conf <= p_row: stale entries of the running-bound test go here
         const float t2 = (x - lr) + (x - lse_c[size_t(n) * S + j]);
         if (t2 > log2_thr) {
@@ -272,13 +277,11 @@ __global__ void __launch_bounds__(128) colsum_reduce_kernel(const float* __restr
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[u][v] += q[v];
     } else if (m < mtop[u]) {
-      const float f = ex2_approx(m - mtop[u]);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[u][v] = fmaf(q[v], f, acc[u][v]);
-    } else {                                          // also the first group: 2^(-inf) = 0 times a zero sum
-      const float f = ex2_approx(mtop[u] - m);
+      for (int v = 0; v < VEC; ++v) acc[u][v] += scale_pow2(q[v], m - mtop[u]);
+    } else {                                          // also the first group (mtop = -inf, zero sums)
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[u][v] = fmaf(acc[u][v], f, q[v]);
+      for (int v = 0; v < VEC; ++v) acc[u][v] = scale_pow2(acc[u][v], mtop[u] - m) + q[v];
       mtop[u] = m;
     }
   };
@@ -288,13 +291,13 @@ __global__ void __launch_bounds__(128) colsum_reduce_kernel(const float* __restr
   }
   for (; g < ngroups; ++g) load_add(g, 0);
   const float mall = fmaxf(fmaxf(mtop[0], mtop[1]), fmaxf(mtop[2], mtop[3]));
-  float f[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) f[u] = (mtop[u] == mall) ? 1.f : ex2_approx(mtop[u] - mall);    // -inf (unused chain) -> 0
   bool bad = false;
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    const float tot = (acc[0][v] * f[0] + acc[1][v] * f[1]) + (acc[2][v] * f[2] + acc[3][v] * f[3]);
+    float t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) t[u] = (mtop[u] == mall) ? acc[u][v] : scale_pow2(acc[u][v], mtop[u] - mall);   // unused chain: 0
+    const float tot = (t[0] + t[1]) + (t[2] + t[3]);
     lse_c[size_t(n) * S + j + v] = mall + log2f(tot);
     colbest[size_t(n) * S + j + v] = 0ull;
     bad |= !(tot > kSumLo && tot < kSumHi);
@@ -349,7 +352,7 @@ cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, in
 }
 
 cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, int64_t* b_ids, int64_t* i_ids,
-                                int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts,
+                                int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts, int64_t capacity,
                                 cudaStream_t st) {
   Grid2 g0{p.h0c, p.w0c, p.border}, g1{p.h1c, p.w1c, p.border};
   int dev = 0, sms = 0;
@@ -359,7 +362,7 @@ cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, 
   const bool one_launch = p.n <= 2 * sms;            // two 1024-thread CTAs per SM: every CTA of the grid is resident
   for (int phase = one_launch ? 0 : 1; phase <= (one_launch ? 0 : 2); ++phase)
     count_emit_kernel<<<p.n, FT, 0, st>>>(w.rowbest, w.colbest, w.lse_r, w.lse_c, p.L, p.S, g0, g1, p.pixel_scale, counts, p.n,
-                                          w.ready, b_ids, i_ids, j_ids, mconf, mk0, mk1, phase);
+                                          w.ready, b_ids, i_ids, j_ids, mconf, mk0, mk1, phase, capacity);
   return cudaGetLastError();
 }
 

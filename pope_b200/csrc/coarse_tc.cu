@@ -2,28 +2,38 @@
 //
 // Replaces src/matcher/utils/coarse_matching.py:106-119 and :175-189 of the reference (einsum -> /T -> dual softmax
 // -> threshold -> mutual max) without ever writing the L x S matrix.  Sweeps over S = f0 f1^T (log2 units):
-//   sweep 1+2 (one launch): row log-sum-exp of S and of S^T (= column log-sum-exp of S), online softmax per row.
-//                           Two-sweep path (thr > 1/8): while sweeping the rows of S every epilogue thread also lists,
-//                           in a private slot array (no atomics), the cells that exceed thr x the RUNNING row sum --
-//                           a superset of the cells with p_row > thr, of which a row has fewer than 1/thr; a small
-//                           kernel evaluates the listed cells once both log-sum-exps are known.
-//   sweep 3 (thr <= 1/8)  : recompute S, t2 = log2 conf = (x - lse_r[i]) + (x - lse_c[j]); cells above log2(thr) update
+//   single sweep (thr > 0.15, the default 0.2): one pass over the rows of S computes 2^(x - m) with a lazily raised integer
+//                           shift m per epilogue warp (32 rows): row sums per thread, column sums through a shuffle reduction
+//                           as per-32-row partial sums (+ the shift they were taken at) that a small kernel merges into the
+//                           column log-sum-exp, and per-thread candidate lists (below).  Pairs whose sums lose precision
+//                           (rows more than ~186 log2 units apart inside one 32-row group, inf / nan) are flagged one by one
+//                           and redone by a gated launch of the two-sweep kernel.
+//   two sweeps (one launch): row log-sum-exp of S and of S^T (= column log-sum-exp of S), online softmax per row.  While
+//                           sweeping the rows of S every epilogue thread also lists, in private slots (no atomics), the
+//                           cells that exceed thr x the RUNNING row sum -- a superset of the cells with p_row > thr, of
+//                           which a row has fewer than 1/thr; a small kernel evaluates the listed cells once both
+//                           log-sum-exps are known.
+//   sweep 3 (thr <= 0.15)  : recompute S, t2 = log2 conf = (x - lse_r[i]) + (x - lse_c[j]); cells above log2(thr) update
 //                           the best-candidate record of their row and column (rare 64-bit atomicMax)
 //
-// Kernel anatomy (persistent, one CTA PAIR per two SMs, cta_group::2, 576 threads per CTA):
+// Kernel anatomy (persistent, one CTA PAIR per two SMs, cta_group::2, 640 threads per CTA):
 //   work unit   = (direction, pair, 256-row block of the stationary operand "A"); CTA r of the pair keeps rows
 //                 [128r, 128r+128) of the block (64 KB) in its shared memory for the whole unit while 256-row tiles of
 //                 the streamed operand "B" pass through an 8-stage ring: per stage each CTA TMA-loads ITS half of the
 //                 tile (128 rows x 64 k, 16 KB, 128B-swizzled).  One tcgen05.mma.cta_group::2 (M=256, N=256, K=16)
 //                 reads A and half of B from each SM: 64 B/clk of shared-memory reads and 32 B/clk of L2 traffic per
 //                 SM (a single-CTA M=128 x N=128 tile needs 128 B/clk of shared-memory reads, i.e. all of it).
-//   warp 0      = TMA producer (one elected lane, both CTAs; transaction bytes land on the leader's barrier)
-//   warp 1      = TMEM allocator (both CTAs) + tcgen05.mma issuer (leader CTA, one elected lane); accumulators are
+//   warps 0-15  = epilogue (four whole warpgroups): four threads per row (64 of the tile's 256 columns each); tcgen05.ld 32
+//                 columns at a time; single sweep: FMNMX3 guard + FFMA2 + MUFU.EX2 + packed adds per element, a 7-shuffle
+//                 column reduction and a candidate pre-test per 32x32 block; two-sweep: online softmax (FMNMX + FFMA +
+//                 MUFU.EX2 + FADD per element); three-sweep: candidate test (FADD + FSETP per element, one warp vote per block)
+//   warp 16     = TMA producer (one elected lane, both CTAs; transaction bytes land on the leader's barrier)
+//   warp 17     = TMEM allocator (both CTAs) + tcgen05.mma issuer (leader CTA, one elected lane); accumulators are
 //                 128 lanes x 256 fp32 columns per CTA, double-buffered (2 x 256 = all 512 TMEM columns); commits are
 //                 multicast to the barriers of both CTAs
-//   warps 2-17  = epilogue: four threads per row (64 of the tile's 256 columns each); tcgen05.ld 32 columns at a time;
-//                 online softmax (FMNMX + FFMA + MUFU.EX2 + FADD per element) or the candidate test (FADD + FSETP per
-//                 element, one warp vote per 32x32 block)
+//   warps 18-19 = idle (they complete the fifth warpgroup): setmaxnreg moves registers from that warpgroup (40 per thread)
+//                 to the epilogue warpgroups (104 per thread; a 640-thread CTA starts at 96, where the single-sweep epilogue
+//                 spilled and re-derived thread constants from SR_TID for every tile)
 //   barriers    = a_full/a_empty (stationary block), b_full/b_empty[8] (ring), acc_full/acc_empty[2] (TMEM stages);
 //                 *_full of the operands and acc_empty live in the leader CTA (the issuer waits on them)
 #include <cuda.h>
@@ -47,7 +57,12 @@ constexpr int kChunks = (256 / 32) / kColGroups;     // 32-column chunks per thr
 constexpr int kSpan = kChunks * 32;                  // columns per thread and tile
 static_assert(kColGroups == kListGroups, "one private candidate list per (row, column group) thread");
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;
+// warps 0..15 = epilogue (four whole warpgroups), warp 16 = TMA producer, warp 17 = TMEM allocator + MMA issuer, warps 18-19 idle:
+// the epilogue warpgroups and the producer / issuer warpgroup trade registers with setmaxnreg (a 640-thread CTA starts at 96
+// per thread; the data-movement warps need a fraction of that, the epilogue is short of registers at 96)
+constexpr int kWarpProducer = kEpiWarps, kWarpMma = kEpiWarps + 1;
+constexpr int kThreads = kEpiThreads + 128;
+constexpr int kRegsEpi = 104, kRegsAux = 40;   // 16 x 32 x 104 + 4 x 32 x 40 = 58 368 <= the CTA's 640 x 96 = 61 440 registers (the pool is per CTA)
 constexpr uint32_t kTmemCols = 512;
 constexpr bool kLoadAll = (kEpiWarps == 8);          // all chunks TMEM -> registers before any arithmetic (needs the
                                                      // 204-register budget of the 8-warp layout; spills with 16 warps)
@@ -175,7 +190,7 @@ struct SweepParams {
   u64* rowbest;
   u64* colbest;
   int* cand_cnt;            // two-sweep path: per row of S, one count byte per column quarter
-  u64* cand;                //   [n, L0, kListGroups, kCandSlots] (raw accumulator bits << 32 | column)
+  u64* cand;                //   [n, L0, kListGroups, kListStride] (similarity in log2 units, float bits << 32 | column)
   float* colpart;           // single-sweep path: [n, ceil(L0/32), L1] column sums of 2^(x - shift) over each 32-row group
   float* cshift;            //   [n, ceil(L0/32), ceil(L1/32)] the shift of each (32-row group, 32-column block)
   int* pairflag;            //   [n] != 0: the pair left the single sweep's range and is redone by the gated launch
@@ -183,7 +198,7 @@ struct SweepParams {
                             //       the pairs with pairflag[n] != 0 are swept
   int32_t* flags;
   unsigned long long* trace;   // developer diagnostics (POPE_TC_TRACE): clock stamps of CTA pair 0, or nullptr
-  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps
+  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps, bit4 = no single sweep, bit6 = no gated redo after the single sweep
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -253,8 +268,8 @@ __device__ __forceinline__ float lse_update(const float (&v)[32], int vc, float 
   return cmax;      // raw-accumulator units
 }
 
-// append cell (raw accumulator v, column col) to one of the calling thread's private lists (SLOTS entries).  A full list is
-// first re-filtered against the current bound (raw-accumulator units): the running row sum only grows, so entries below it
+// append cell (similarity x in log2 units, column col) to one of the calling thread's private lists (SLOTS entries).  A full
+// list is first re-filtered against the current bound (same units): the running row sum only grows, so entries below it
 // are dead for good, and fewer than 1/thr cells can stay above it (heavy-tailed similarities list many early cells that a
 // later, larger cell of the row makes irrelevant).  A list that is still full: two-sweep kernels raise
 // POPE_FLAG_CAND_OVERFLOW (nan inputs), the single sweep hands the pair to the online-softmax launch.
@@ -304,6 +319,13 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// three-input maximum (sm_100 FMNMX3)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 // packed fp32x2 arithmetic (sm_100: one issue slot for two lanes of a 64-bit register pair)
 __device__ __forceinline__ u64 pack2(float a, float b) {
   u64 r;
@@ -327,13 +349,12 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
   return r;
 }
 
-// e = 2^(v * scale - m) for the 32 raw accumulators of a thread (0 for masked rows / columns; v itself is kept: the rare
-// paths -- candidate scan, shift change -- work on the raw values); the (even, odd) column pairs of a row are adjacent
-// registers, so scaling, the chunk's row sums (rc2[rho] = {even-column sum, odd-column sum}) and the per-thread column sums
-// (cp2[k] = {column 8k+2p, column 8k+2p+1} over the thread's four rows) run on packed fp32x2 instructions
-template <bool FULL>
-__device__ __forceinline__ void ss_chunk(const float (&v)[32], float scale, float negm, u64 (&rc2)[4], u64 (&cp2)[4],
-                                         uint32_t rowmask, int vc, int p) {
+// v <- e = 2^(v * scale - m) in place for the 32 raw accumulators of a thread (cells of ragged tiles that do not exist were
+// set to -inf by the caller and come out as 0): all the multiply-adds can issue before the first exponential retires.  The
+// (even, odd) column pairs of a row are adjacent registers, so scaling, the chunk's row sums (rc2[rho] = {even-column sum,
+// odd-column sum}) and the per-thread column sums (cp2[k] = {column 8k+2p, column 8k+2p+1} over the thread's four rows) run
+// on packed fp32x2 instructions
+__device__ __forceinline__ void ss_chunk(float (&v)[32], float scale, float negm, u64 (&rc2)[4], u64 (&cp2)[4]) {
   const u64 scale2 = pack2(scale, scale), negm2 = pack2(negm, negm);
 #pragma unroll
   for (int h = 0; h < 2; ++h)
@@ -346,16 +367,51 @@ __device__ __forceinline__ void ss_chunk(const float (&v)[32], float scale, floa
         unpack2(fma2(pack2(v[idx], v[idx + 1]), scale2, negm2), a, b);
         a = ex2_approx(a);
         b = ex2_approx(b);
-        if (!FULL) {
-          const int col = 8 * k + 2 * p;
-          const bool rowok = (rowmask >> rho) & 1u;
-          if (!rowok || col >= vc) a = 0.f;
-          if (!rowok || col + 1 >= vc) b = 0.f;
-        }
+        v[idx] = a;
+        v[idx + 1] = b;
         const u64 e2 = pack2(a, b);
         rc2[rho] = (k == 0) ? e2 : add2(rc2[rho], e2);
         cp2[k] = (rho == 0) ? e2 : add2(cp2[k], e2);
       }
+}
+
+// ragged tiles: the cells of rows / columns that do not exist become -inf (2^-inf = 0 in every sum; no effect on the
+// maximum that guards the shift).  Runs for the last tile / unit of a pair only.
+__device__ __forceinline__ void ss_mask(float (&v)[32], uint32_t rowmask, int vc, int p) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int idx = 16 * h + 4 * k + 2 * r, rho = 2 * h + r;
+        const int col = 8 * k + 2 * p;
+        const bool rowok = (rowmask >> rho) & 1u;
+        if (!rowok || col >= vc) v[idx] = -INFINITY;
+        if (!rowok || col + 1 >= vc) v[idx + 1] = -INFINITY;
+      }
+}
+
+// log2 of a positive normal float: exponent exactly, mantissa through lg2.approx (absolute error 2^-22)
+__device__ __forceinline__ float log2_split(float e) {
+  const uint32_t b = __float_as_uint(e);
+  return float(int(b >> 23) - 127) + lg2_approx(__uint_as_float((b & 0x007fffffu) | 0x3f800000u));
+}
+
+// the 8 cells of one row of a chunk (e = 2^(x - m)) against the row's bound; cells above it go to the thread's private list
+// as similarities in log2 units, x = log2(e) + m.  Returns the list's new fill count.  Out of line on purpose: the epilogue's
+// hot loop must stay inside the instruction cache (64 KB of code cost 30 % of the kernel's time).
+__device__ __noinline__ int ss_scan_row(float e0, float e1, float e2, float e3, float e4, float e5, float e6, float e7, float bound,
+                                        float mshift, u64* __restrict__ list, int cnt, int col, int32_t* __restrict__ flags,
+                                        int* __restrict__ pairflag) {
+  // the bound a full list is re-filtered with, same units as the entries (margin on the safe side: the lists are a
+  // superset anyway)
+  const float xb = lg2_approx(bound) + mshift - 0.01f;
+  const float e[8] = {e0, e1, e2, e3, e4, e5, e6, e7};
+#pragma unroll
+  for (int q = 0; q < 8; ++q)       // cell q: column col + 8 (q / 2) + q % 2
+    if (e[q] > bound) cnt = list_push<kLaneSlots>(list, cnt, xb, log2_split(e[q]) + mshift, col + 8 * (q >> 1) + (q & 1), flags, pairflag);
+  return cnt;
 }
 
 // transposed reduction of the 8 per-thread column sums over the 8 lanes with the same lane%4: lane l ends up with the
@@ -429,7 +485,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpProducer && lane == 0) {
     prefetch_tmap(&map0);
     prefetch_tmap(&map1);
     // operand "full" barriers: one arrival (the leader's expect_tx) + the bytes of both CTAs' TMA loads
@@ -442,7 +498,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemTmemPtr), "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -467,7 +523,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   // flags are final before this launch starts, so all roles of both CTAs skip the same units
   auto skip_pair = [&](int n) { return MODE == 2 && P.gate && *reinterpret_cast<const volatile int*>(P.pairflag + n) == 0; };
 
-  if (warp == 0) {
+  if (warp >= kEpiWarps) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
+  if (warp == kWarpProducer) {
     // =============================== TMA producer (both CTAs) ===============================
     if (lane == 0) {
       uint32_t a_phase = 0, b_stage = 0, b_phase = 0;
@@ -508,7 +566,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // =============================== MMA issuer (leader CTA only) ===============================
     if (rank == 0 && lane == 0) {
       uint32_t a_phase = 0, b_stage = 0, b_phase = 0, tile_ctr = 0;
@@ -596,27 +654,33 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         if (!(P.debug & 4)) umma_commit_2sm(bar_a_empty);   // stationary blocks may be overwritten
       }
     }
-  } else if (MODE == 3 || MODE == 4) {
+  }
+  // (warps 18-19 only complete the last warpgroup)
+  } else {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+  if (MODE == 3 || MODE == 4) {
     // =============================== single-sweep epilogue (16 warps: 4 lane quadrants x 4 groups of 64 columns) =====
-    // Every warp keeps one integer-valued shift m for its 32 rows: e = 2^(x - m).  m is chosen from the data at the first
-    // chunk of a unit and raised (never lowered) when a thread's running row sum passes 2^104 -- the chunk is then redone
-    // from the raw accumulators still in registers and the row sums are rescaled by an exact power of two.  Column sums
-    // leave the warp once per chunk together with the shift they were taken at; the merge kernel combines them.
+    // Every warp keeps one integer-valued shift m for its 32 rows: e = 2^(x - m).  Before the exponentials of a chunk each
+    // thread takes the maximum of its 32 raw accumulators (16 three-input FMNMX); if any of them would land above 2^110 the
+    // warp raises m to (chunk maximum - 96) and rescales its running row sums by that exact power of two -- so nothing ever
+    // overflows and nothing is computed twice.  m is chosen from the data at the first chunk of a unit and never lowered.
+    // Column sums leave the warp once per chunk together with the shift they were taken at; the merge kernel combines them.
     const int g = lane >> 2, p = lane & 3;
-    const int cg = (warp - 2) >> 2, quad = warp & 3;
+    const int cg = warp >> 2, quad = warp & 3;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     float2* mergef = reinterpret_cast<float2*>(smem + kSmemMerge);   // [3][128] (row sum, shift) of column groups 1..3
     const int rin = quad * 32 + g + 8 * p;                           // the row of the CTA this lane writes results for
-    const float scale = P.scale_log2;
+    const float scale = P.scale_log2, inv_scale = 1.f / P.scale_log2;
     const float thrm = exp2f(P.log2_thr) * 0.99f;
     const int LA = P.L0, LB = P.L1;
     const int ntiles = (LB + kTileCols - 1) / kTileCols, ngroups = (LA + 31) / 32, nblk = (LB + 31) / 32;
     const int ccol = 8 * (g >> 1) + 2 * p + (g & 1);                 // chunk column whose sum ss_col_reduce leaves in this lane
-    // the warps of the odd column groups run half a tile behind the even ones (they finish a tile's second chunk after the
-    // next tile's accumulator is ready), so that the four warps of a scheduler are not all in their MUFU phase at once
-    const bool lag = (cg & 1) && !(P.debug & 32);
+    // (made opaque: the compiler otherwise re-derives these from SR_TID.X for every tile -- ~40 instructions per tile --
+    //  instead of spending two registers on them)
+    uint32_t tb0 = tmem_base + lane_addr + cg * kSpan;               // TMEM address of the thread's columns in stage 0
+    int colofs = cg * kSpan;                                         // the warp's first column within a tile
+    asm volatile("" : "+r"(tb0), "+r"(colofs));
     uint32_t tile_ctr = 0;
-    float mshift = 0.f;
     for (int u = pair; u < P.total_units; u += npairs) {
       int dir, n, rb;
       decode(u, dir, n, rb);
@@ -626,135 +690,105 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
 #pragma unroll
       for (int rho = 0; rho < 4; ++rho) rowmask |= (g + 8 * rho < rows_valid) ? (1u << rho) : 0u;
       float rowacc[4] = {0.f, 0.f, 0.f, 0.f};                        // the thread's row sums (its 2 of every 8 columns)
-      bool fresh = true;                                             // no chunk of this unit processed yet
+      float mshift = 0.f, rawlim = -INFINITY;                        // raw accumulators above rawlim raise the shift (first chunk: always)
       uint32_t cnts = 0;                                             // fill counts of the thread's four private lists (a byte each)
       const uint32_t gidx = uint32_t(n) * ngroups + (rowbase >> 5);  // (pair, 32-row group): row of colpart / cshift
-      bool waited = false;
 
       for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
         const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
         const int col0 = ct * kTileCols;
-        const int nvalid = min(LB - col0, kTileCols) - cg * kSpan;
+        const int nvalid = min(LB - col0, kTileCols) - colofs;
         const bool active = rows_valid > 0 && nvalid > 0 && !(P.debug & 1);
-        if (!waited) mbar_wait(bar_acc_full + 8 * s, acc_phase);
-        waited = false;
+        mbar_wait(bar_acc_full + 8 * s, acc_phase);
         tc_fence_after();
-        const uint32_t tbase = tmem_base + lane_addr + s * kTileCols + cg * kSpan;
+        const uint32_t tbase = tb0 + s * kTileCols;
         float v[32];
-        // new shift for the warp from the raw values of the chunk in v (forced: first chunk of a unit); returns the exact
-        // power of two that takes sums from the old domain to the new one
-        auto rebase = [&](bool forced) {
-          // (every value goes through an identity shuffle first: a warp-synchronous instruction is not speculated across
-          //  the branch, so the 32-way maximum stays out of the common path -- ptxas otherwise hoists it into every chunk)
-          float cm = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) cm = fmaxf(cm, __shfl_sync(kFullMask, v[j], lane));
-#pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(kFullMask, cm, o));
-          float mnew = floorf(cm * scale) - kShiftBack;
-          if (!forced) mnew = fmaxf(mnew, mshift + 24.f);
-          if (!(fabsf(mnew) < 1e30f)) mnew = mshift;                 // inf / nan inputs: keep the shift, the sums get flagged
-          const float f = ex2_approx(mshift - mnew);
-          mshift = mnew;
-          return f;
-        };
-        // the two 32-column chunks of the thread, one copy of the code: chunk 0, then chunk 1's TMEM load, the hand-back of
-        // the accumulator stage, and chunk 1's arithmetic after it
-#pragma unroll 1
-        for (int cc = 0; cc < kChunks; ++cc) {
+        auto process = [&](int cc) {
           const int vc = nvalid - cc * 32;
-          const int colb = col0 + cg * kSpan + cc * 32;
-          const bool on = active && vc > 0;
-          if (on) tmem_ld_frag(tbase + cc * 32, v);
-          if (cc == kChunks - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
-            if (lag && ct + 1 < ntiles) {
-              mbar_wait(bar_acc_full + 8 * (s ^ 1), ((tile_ctr + 1) >> 1) & 1);
-              waited = true;
+          const int colb = col0 + colofs + cc * 32;
+          if (rows_valid < 32 || vc < 32) ss_mask(v, rowmask, vc, p);
+          // ---- shift guard on the raw accumulators
+          float t0 = fmax3(v[0], v[1], v[2]), t1 = fmax3(v[3], v[4], v[5]);
+#pragma unroll
+          for (int j = 6; j < 30; j += 4) {
+            t0 = fmax3(t0, v[j], v[j + 1]);
+            t1 = fmax3(t1, v[j + 2], v[j + 3]);
+          }
+          t0 = fmax3(t0, v[30], v[31]);
+          const float tmax = fmaxf(t0, t1);
+          if (__any_sync(kFullMask, tmax > rawlim)) {
+            float cm = tmax;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(kFullMask, cm, o));
+            const bool first = rawlim == -INFINITY;                  // first chunk of the unit: no sums yet, any shift
+            float mnew = floorf(cm * scale) - kShiftBack;
+            if (!first) mnew = fmaxf(mnew, mshift);                  // afterwards the shift only rises
+            if (!(fabsf(mnew) < 1e30f)) mnew = first ? 0.f : mshift; // inf inputs: the sums get flagged
+            if (!first) {
+#pragma unroll
+              for (int rho = 0; rho < 4; ++rho) rowacc[rho] = scale_pow2(rowacc[rho], mshift - mnew);
             }
+            mshift = mnew;
+            rawlim = (mnew + kShiftHead) * inv_scale;
           }
-          if (!on) continue;
-          if (fresh) {                               // first chunk of the unit: shift from the data
-            rebase(true);
-            fresh = false;
-          }
+          // ---- exponentials, row and column sums
           u64 cp2[4], rc2[4];
-          float d[4], now[4];
-          bool pass;
-          if (rows_valid == 32 && vc >= 32) ss_chunk<true>(v, scale, -mshift, rc2, cp2, rowmask, vc, p);
-          else ss_chunk<false>(v, scale, -mshift, rc2, cp2, rowmask, vc, p);
-          // A cell can only have p_row > thr if it exceeds thr x (running row sum).  Level 1, no communication: this
-          // chunk's contribution d[rho] to the thread's own row sum against that sum (true for the first chunks of a
-          // unit by construction).  Level 2: the same against the row sum over the 4 lanes that share the row.  Level 3
-          // (a real candidate, or the first chunk of a unit): the row's 8 cells one by one.
-          auto row_deltas = [&]() {
-            pass = false;
-#pragma unroll
-            for (int rho = 0; rho < 4; ++rho) {
-              float x, y;
-              unpack2(rc2[rho], x, y);
-              d[rho] = x + y;
-              now[rho] = rowacc[rho] + d[rho];
-              pass |= d[rho] > thrm * now[rho];
-            }
-          };
-          row_deltas();
-          const bool over = !((now[0] + now[1]) + (now[2] + now[3]) < kBumpTrig);      // outside the window; also inf / nan
-          const bool rare = __any_sync(kFullMask, pass | over);
-          if (rare && __any_sync(kFullMask, over)) {
-            // a higher shift from the raw values of the chunk, the running sums moved to it, the chunk once more
-            const float f = rebase(false);
-#pragma unroll
-            for (int rho = 0; rho < 4; ++rho) rowacc[rho] *= f;
-            ss_chunk<false>(v, scale, -mshift, rc2, cp2, rowmask, vc, p);
-            row_deltas();
-          }
-#pragma unroll
-          for (int rho = 0; rho < 4; ++rho) rowacc[rho] = now[rho];
+          ss_chunk(v, scale, -mshift, rc2, cp2);
           float cp[8];
 #pragma unroll
           for (int k = 0; k < 4; ++k) unpack2(cp2[k], cp[2 * k], cp[2 * k + 1]);
           const float cs = ss_col_reduce(cp, lane);
           if (ccol < vc) P.colpart[size_t(gidx) * LB + (colb + ccol)] = cs;
           if (lane == 0) P.cshift[size_t(gidx) * nblk + (colb >> 5)] = mshift;
-          if (rare && __any_sync(kFullMask, pass) && !(P.debug & 2)) {
+          // ---- candidates.  A cell can only have p_row > thr if it exceeds thr x (running row sum).  Level 1, no
+          // communication: this chunk's contribution d[rho] to the thread's own row sum against that sum (true for the first
+          // chunks of a unit by construction).  Level 2: the same against the row sum over the 4 lanes that share the row.
+          // Level 3 (a real candidate, or the first chunk of a unit): the row's 8 cells one by one.
+          float d[4];
+          bool pass = false;
+#pragma unroll
+          for (int rho = 0; rho < 4; ++rho) {
+            float x, y;
+            unpack2(rc2[rho], x, y);
+            d[rho] = x + y;
+            rowacc[rho] += d[rho];
+            pass |= d[rho] > thrm * rowacc[rho];
+          }
+          if (__any_sync(kFullMask, pass) && !(P.debug & 2)) {
             float bound[4];
             bool hit = false;
 #pragma unroll
             for (int rho = 0; rho < 4; ++rho) {
-              float rs = now[rho];
+              float rs = rowacc[rho];
               rs += __shfl_xor_sync(kFullMask, rs, 1);
               rs += __shfl_xor_sync(kFullMask, rs, 2);
               bound[rho] = thrm * rs;
               hit |= d[rho] > bound[rho];
             }
             if (hit) {
-              const float inv_scale = 1.f / scale;
 #pragma unroll
               for (int rho = 0; rho < 4; ++rho) {
-                if (d[rho] > bound[rho] && ((rowmask >> rho) & 1u)) {
-                  // the bound in raw-accumulator units, margin on the safe side (the lists are a superset anyway)
-                  const float b = (lg2_approx(bound[rho]) + mshift) * inv_scale;
-                  const float rawb = b - (1e-5f * fabsf(b) + 0.005f * inv_scale);
+                if (d[rho] > bound[rho]) {
+                  const int i0 = 16 * (rho >> 1) + 2 * (rho & 1);
                   u64* const mylist = P.cand + (((size_t(n) * LA + rowbase + g + 8 * rho) * kListGroups + cg) * 4 + p) * kLaneSlots;
-                  int c = int((cnts >> (8 * rho)) & 0xffu);
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int cc2 = 0; cc2 < 2; ++cc2) {
-                      const int idx = 16 * (rho >> 1) + 4 * k + 2 * (rho & 1) + cc2;
-                      const int cin = 8 * k + 2 * p + cc2;
-                      if (v[idx] > rawb && cin < vc)
-                        c = list_push<kLaneSlots>(mylist, c, rawb, v[idx], colb + cin, P.flags, P.pairflag + n);
-                    }
+                  const int c = ss_scan_row(v[i0], v[i0 + 1], v[i0 + 4], v[i0 + 5], v[i0 + 8], v[i0 + 9], v[i0 + 12], v[i0 + 13],
+                                            bound[rho], mshift, mylist, int((cnts >> (8 * rho)) & 0xffu), colb + 2 * p, P.flags,
+                                            P.pairflag + n);
                   cnts = (cnts & ~(0xffu << (8 * rho))) | (uint32_t(c) << (8 * rho));
                 }
               }
             }
           }
+        };
+        if (active) {
+          tmem_ld_frag(tbase, v);
+          process(0);
         }
+        if (active && nvalid > 32) tmem_ld_frag(tbase + 32, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
+        if (active && nvalid > 32) process(1);
       }
 
       // unit end: row sums over the 4 lanes of a row (same warp, same shift), then over the 4 column groups (one shift
@@ -792,7 +826,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           for (int q = 0; q < 4; ++q) mtop = (sk[q] != 0.f) ? fmaxf(mtop, mk[q]) : mtop;
           float tot = 0.f;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) tot += (sk[q] != 0.f) ? sk[q] * ex2_approx(mk[q] - mtop) : 0.f;
+          for (int q = 0; q < 4; ++q) tot += (sk[q] != 0.f) ? scale_pow2(sk[q], mk[q] - mtop) : 0.f;
           P.lse_out0[size_t(n) * LA + row] = mtop + log2f(tot);
           if (!(tot > kSumLo && tot < kSumHi)) {
             atomicOr(reinterpret_cast<unsigned*>(P.flags), POPE_FLAG_ROBUST_PATH);
@@ -807,8 +841,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     // =============================== epilogue (16 warps; four threads per row, 64 columns of the tile each) =========
     constexpr bool kLse = (MODE == 0 || MODE == 2);      // online log-sum-exp of the thread's row
     constexpr bool kStage = (MODE == 1);                 // per-column terms staged in shared memory (three-sweep path)
-    const int e = threadIdx.x - 64;                 // 0..511
-    const int colq = (warp - 2) >> 2;               // which kSpan of the tile's 256 columns (4 consecutive warps = 4 quadrants)
+    const int e = threadIdx.x;                      // 0..511
+    const int colq = warp >> 2;                     // which kSpan of the tile's 256 columns (4 consecutive warps = 4 quadrants)
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
     const int row_in_cta = quad * 32 + lane;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
@@ -858,7 +892,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
-        const bool etr = TRACE && P.trace && pair == 0 && rank == 0 && warp == 2 && lane == 0 && tile_ctr < kTraceTiles;
+        const bool etr = TRACE && P.trace && pair == 0 && rank == 0 && warp == 0 && lane == 0 && tile_ctr < kTraceTiles;
         unsigned long long* erec = P.trace + size_t(kTraceTiles + tile_ctr) * 8;
         if (etr) erec[0] = clock64();
         mbar_wait(bar_acc_full + 8 * s, acc_phase);
@@ -917,7 +951,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               const int colb = col0 + colq * kSpan + cc * 32;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (v[j] > bound && j < vc) list_cnt = list_push<kCandSlots>(mylist, list_cnt, bound, v[j], colb + j, P.flags, nullptr);
+                if (v[j] > bound && j < vc)
+                  list_cnt = list_push<kCandSlots>(mylist, list_cnt, bound * scale, v[j] * scale, colb + j, P.flags, nullptr);
             }
           };
           const bool skip = (P.debug & 1) != 0;
@@ -962,7 +997,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       }
       if (listing)      // nibble counts of the quarter's sub-lists: the thread's entries are contiguous from entry 0
         reinterpret_cast<uint16_t*>(P.cand_cnt)[(size_t(n) * LA + row) * kListGroups + colq] =
-            uint16_t(min(list_cnt, 4) | (max(list_cnt - 4, 0) << 4));
+            uint16_t(min(list_cnt, kLaneSlots) | (max(list_cnt - kLaneSlots, 0) << 4));
       if (kLse) {
         // the four column quarters of a row merge their (max, sum) through shared memory
         if (colq > 0) merge[(colq - 1) * 128 + row_in_cta] = make_float2(m_run, s_run);
@@ -983,10 +1018,12 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     }
   }
 
+  }
+
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                // the peer may still be signalling / reading this CTA's memory
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
@@ -1153,6 +1190,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       if ((e = colsum_reduce_run(p, w, flags, st)) != cudaSuccess) return e;
       P.gate = 1;
+      if (P.debug & 64) return cand_eval_lists_run(p, w, flags, 0, st);      // developer knob: no gated redo (inspect the single sweep)
     }
     // robust two-sweep path (online softmax per row, both directions in one launch; the direction-0 units also fill the
     // per-thread candidate lists); after the single sweep it only runs if the flag was raised

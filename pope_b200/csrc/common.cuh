@@ -41,22 +41,38 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return y;
 }
 
+// x * 2^d for x >= 0 and an integer-valued d <= 0, by exponent arithmetic: exact, and correct when 2^d itself is below the
+// normal range (a factor 2^-146 would flush to zero although 2^68 * 2^-146 is an ordinary number).  Results below 2^-126
+// flush to zero; 0, inf and nan pass through.  Used wherever a sum moves to a higher shift domain.
+__device__ __forceinline__ float scale_pow2(float x, float d) {
+  const int b = __float_as_int(x);
+  if (!(x > 0.f) || b >= 0x7f800000) return x;
+  if (!(d > -280.f)) return 0.f;
+  const int e = b + (int(d) << 23);
+  return e >= 0x00800000 ? __int_as_float(e) : 0.f;
+}
+
 // ---- coarse-match scratch layout -------------------------------------------------------------------------
 constexpr int kCandSlots = 8;   // per-row candidate slots of the two-sweep paths (thr > 1/8 => at most 7 cells pass)
 // tcgen05 paths: every epilogue thread keeps PRIVATE candidate lists, so the sweeps need no atomics.  A row owns
 // kListGroups (column quarters) x kListStride entries.  Two-sweep kernels: thread (row, quarter) fills the first kCandSlots
-// entries of its quarter.  Single sweep: the four lanes that share a row in a quarter own kLaneSlots entries each.
-// Counts: one uint16 per (row, quarter) = four nibbles, nibble p = entries used in sub-list p (entries [4p, 4p + 4)).
+// entries of its quarter.  Single sweep: the four lanes that share a row in a quarter own kLaneSlots entries each -- at most
+// 1 / (0.99 thr) cells of a row can exceed thr x (row sum) at any time (5 for thr = 0.2), and a full list is re-filtered
+// against the current sum before it takes another cell, so six slots cannot overflow for thr > 1/6, wherever the cells fall.
+// Counts: one uint16 per (row, quarter) = four nibbles, nibble p = entries used in sub-list p (entries [6p, 6p + 6)).
 constexpr int kListGroups = 4;
-constexpr int kListStride = 16;
-constexpr int kLaneSlots = 4;
-// single-sweep path: every epilogue warp keeps a lazily raised, integer-valued shift m (e = 2^(x - m)); a term that
-// underflows is below 2^-126 in its sum's final domain, so a row / column sum inside [2^-90, 2^110] of that domain has lost
-// less than 2^-22 of its value (<= 2^14 terms); outside it the pair is handed to the online-softmax kernels
-// (POPE_FLAG_ROBUST_PATH; happens when rows whose maxima are more than ~150 log2 units apart share a 32-row group)
-constexpr float kSumLo = 8.0779357e-28f, kSumHi = 1.2980742e33f;
-constexpr float kShiftBack = 64.f;           // a freshly chosen shift leaves the chunk's largest cell at 2^64
-constexpr float kBumpTrig = 2.0282410e31f;   // 2^104: a thread's running row sums above this raise the warp's shift
+constexpr int kListStride = 24;
+constexpr int kLaneSlots = 6;
+// single-sweep path: every epilogue warp keeps an integer-valued shift m (e = 2^(x - m)).  A fresh shift leaves the chunk's
+// largest cell at 2^96, and no cell is ever allowed above 2^110 (the warp raises m first), so sums of <= 2^16 terms stay
+// below 2^126.  The window is deliberately lopsided: the risk is at the bottom, where rows / columns whose maxima lie far
+// below the strongest cell of their 32-row group underflow.  A term that underflows is below 2^-126 in its sum's final
+// domain, so a row / column sum above 2^-90 of that domain has lost less than 2^-20 of its value; below it the pair is
+// handed to the online-softmax kernels (POPE_FLAG_ROBUST_PATH): rows whose maxima are more than ~186 log2 units (129 in
+// natural-log similarity) below the strongest row of their group.
+constexpr float kSumLo = 8.0779357e-28f, kSumHi = 1.7014118e38f;
+constexpr float kShiftBack = 96.f;           // a freshly chosen shift leaves the chunk's largest cell at 2^96
+constexpr float kShiftHead = 110.f;          // a cell that would land above 2^110 raises the warp's shift first
 
 struct CoarseScratch {
   float* lse_r;   // [n, L]  log2-domain log-sum-exp of every row of S
@@ -64,7 +80,7 @@ struct CoarseScratch {
   u64* rowbest;   // [n, L]  best above-threshold candidate of the row   (pack_best(t2, j))
   u64* colbest;   // [n, S]  best above-threshold candidate of the column (pack_best(t2, i))
   int* cand_cnt;  // [n, L, 2]  tcgen05: four uint16 per row (above); SIMT: [n, L] ints, number of listed cells of the row
-  u64* cand;      // [n, L, kListGroups, kListStride]  (raw accumulator bits << 32 | column); SIMT uses [n, L, kCandSlots]
+  u64* cand;      // [n, L, kListGroups, kListStride]  (tcgen05: similarity in log2 units, float bits << 32 | column); SIMT uses [n, L, kCandSlots] raw accumulators
   float* cbound;  // [n, 32*ceil(L/32)]  two-sweep path: raw-accumulator bound above which a cell of row i has p_row > thr
   float* cminb;   // [n, ceil(L/32)]  minimum of cbound over each group of 32 rows
   float* colpart; // [n, ceil(L/32), S]  single-sweep tcgen05 path: column sums of 2^(x - shift) over each group of 32 rows
@@ -137,7 +153,7 @@ bool coarse_tc_needs_clear(const CoarseProblem& p);
 inline bool two_sweeps_possible(const CoarseProblem& p) { return exp2f(p.log2_thr) * float(kCandSlots) > 1.2f; }
 // coarse_finalize.cu -- mutual test, border removal, ordered compaction
 cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, int64_t* b_ids, int64_t* i_ids,
-                                int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts,
+                                int64_t* j_ids, float* mconf, float* mk0, float* mk1, int32_t* counts, int64_t capacity,
                                 cudaStream_t st);
 
 }  // namespace pope

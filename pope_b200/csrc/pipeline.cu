@@ -15,7 +15,7 @@ namespace pope {
 namespace {
 
 // packed (sorted by pair) -> fixed per-pair slots, so that the host copy has a size known without a sync
-__global__ void __launch_bounds__(256) slot_kernel(const int32_t* __restrict__ counts, int cap,
+__global__ void __launch_bounds__(256) slot_kernel(const int32_t* __restrict__ counts, int n_pairs, int cap,
                                                   const int64_t* __restrict__ i_ids, const int64_t* __restrict__ j_ids,
                                                   const float* __restrict__ mconf, const float* __restrict__ mk0,
                                                   const float* __restrict__ mk1f, int64_t* __restrict__ o_i,
@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(256) slot_kernel(const int32_t* __restrict__ c
     s_base = base;
   }
   __syncthreads();
-  const int base = s_base, cnt = counts[b];
+  // (a pair can exceed its slot, and the packed list its capacity, only through bit-identical ties -- POPE_FLAG_CAPACITY)
+  const int base = s_base, cnt = min(min(counts[b], cap), max(counts[n_pairs] - s_base, 0));
   for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
     const size_t src = size_t(base) + r, dst = size_t(b) * cap + r;
     o_i[dst] = i_ids[src]; o_j[dst] = j_ids[src]; o_conf[dst] = mconf[src];
@@ -198,7 +199,7 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
                               pl->fstride, pl->W, s.b_ids, s.i_ids, s.j_ids, int64_t(capt), s.counts + n, nullptr, s.mk1,
                               coord_scale, s.expec, s.mk1f, pl->s_comp);
     if (rc) goto fail;
-    slot_kernel<<<n, 256, 0, pl->s_comp>>>(s.counts, int(cap), s.i_ids, s.j_ids, s.mconf, s.mk0, s.mk1f, s.o_i, s.o_j,
+    slot_kernel<<<n, 256, 0, pl->s_comp>>>(s.counts, n, int(cap), s.i_ids, s.j_ids, s.mconf, s.mk0, s.mk1f, s.o_i, s.o_j,
                                            s.o_conf, s.o_mk0, s.o_mk1);
     PL_CUDA(cudaGetLastError());
     PL_CUDA(cudaEventRecord(s.computed, pl->s_comp));

@@ -233,6 +233,12 @@ extern "C" int pope_match_scores(const float* mconf, const int32_t* counts, int 
   return int(cudaGetLastError());
 }
 
+extern "C" int pope_running_topk(const float* scores, int R, int k, float* slot_scores, int32_t* slot_idx, void* stream) {
+  if (!scores || !slot_scores || !slot_idx || R <= 0 || k <= 0 || k > kTopkMaxK) return POPE_ERR_INVALID_ARG;
+  running_topk_kernel<<<1, kTopkThreads, 0, static_cast<cudaStream_t>(stream)>>>(scores, R, k, slot_scores, slot_idx);
+  return int(cudaGetLastError());
+}
+
 extern "C" int pope_cosine_topk(const void* q, const void* refs, int dtype, int R, int D, int k, float eps,
                                 float* scores, float* slot_scores, int32_t* slot_idx, void* stream) {
   if (!q || !refs || !scores || !slot_scores || !slot_idx || R <= 0 || D <= 0 || k <= 0 || k > kTopkMaxK) return POPE_ERR_INVALID_ARG;

@@ -29,7 +29,15 @@ class CoarseResult(dict):
         return int(self["counts"][self["n_pairs"] + 1].item())
 
     def sliced(self) -> Dict[str, torch.Tensor]:
-        m = self.total()
+        n = self["n_pairs"]
+        m, fl = self["counts"][n:n + 2].tolist()          # one transfer: the total and the flag word
+        if fl & ~_lib.FLAG_ROBUST_PATH:                   # ROBUST_PATH is informational; anything else the caller must hear of
+            import warnings
+            what = [name for bit, name in ((_lib.FLAG_NONFINITE_LSE, "inf / nan in the features (non-finite log-sum-exp)"),
+                                           (_lib.FLAG_CAND_OVERFLOW, "candidate list overflow (nan in the features)"),
+                                           (_lib.FLAG_CAPACITY, "more matches than the output capacity: list truncated"))
+                    if fl & bit]
+            warnings.warn("pope_coarse_match: " + "; ".join(what), RuntimeWarning, stacklevel=2)
         out = {k: self[k][:m] for k in ("b_ids", "i_ids", "j_ids")}
         mconf = self["mconf"][:m]
         out["gt_mask"] = mconf == 0
@@ -57,7 +65,7 @@ def coarse_match(feat_c0: torch.Tensor, feat_c1: torch.Tensor, hw0_c: Sequence[i
             else h.pope_coarse_workspace_bytes_ex(n, L, S, feat_c0.shape[2], dtype_code(feat_c0)))
     if workspace is None or workspace.numel() < need or workspace.device != dev:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-    cap = n * min(L, S)
+    cap = n * L           # one match per row: never truncated (the C ABI's documented minimum is n * min(L, S))
     i64 = dict(dtype=torch.int64, device=dev)
     f32 = dict(dtype=torch.float32, device=dev)
     res = CoarseResult(
@@ -271,6 +279,19 @@ def cosine_topk(q: torch.Tensor, refs: torch.Tensor, k: int = 3, eps: float = 1e
     return scores, slot_s, slot_i
 
 
+def running_topk(scores: torch.Tensor, k: int = 3):
+    """The running top-k of eval_linemod_json.py:95-101 over device scores [R] in crop order -> (slot_scores [k],
+    slot_idx [k] int32; -1 = empty slot)."""
+    dev = require_cuda(scores)
+    scores = scores.reshape(-1).contiguous().float()
+    slot_s = torch.empty(k, dtype=torch.float32, device=dev)
+    slot_i = torch.empty(k, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().pope_running_topk(ptr(scores), scores.numel(), k, ptr(slot_s), ptr(slot_i), stream_ptr(dev))
+    check(st, "pope_running_topk")
+    return slot_s, slot_i
+
+
 def match_pairs_device(feat_c0, feat_c1, feat_f0, feat_f1, hw0_i, hw0_c, hw1_c, thr=0.2, border_rm=2,
                        temperature=0.1, W=5, impl=_lib.COARSE_AUTO, workspace=None, fused_fine=None) -> CoarseResult:
     """The hot path on device-resident inputs with NO host synchronisation: coarse match -> window gather ->
@@ -298,15 +319,19 @@ def match_pairs_device(feat_c0, feat_c1, feat_f0, feat_f1, hw0_i, hw0_c, hw1_c, 
 
 def scratch_views(workspace: torch.Tensor, n: int, L: int, S: int) -> Dict[str, torch.Tensor]:
     """Debug/test view of the coarse scratch (layout of carve_coarse_scratch in csrc/common.cuh): the row/column
-    log-sum-exp (log2 units) and the best-candidate records left by the last pope_coarse_match call."""
+    log-sum-exp (log2 units), the best-candidate records, and the single sweep's column partial sums / shifts / per-pair
+    flags left by the last pope_coarse_match call."""
     def up(x):
         return (x + 255) // 256 * 256
-    o_rb = 0
-    o_cb = o_rb + up(8 * n * L)
-    o_cc = o_cb + up(8 * n * S)
-    o_lr = o_cc + up(4 * n * L)
-    o_lc = o_lr + up(4 * n * L)
-    return {"rowbest": workspace[o_rb:o_rb + 8 * n * L].view(torch.int64).view(n, L),
-            "colbest": workspace[o_cb:o_cb + 8 * n * S].view(torch.int64).view(n, S),
-            "lse_r": workspace[o_lr:o_lr + 4 * n * L].view(torch.float32).view(n, L),
-            "lse_c": workspace[o_lc:o_lc + 4 * n * S].view(torch.float32).view(n, S)}
+    G, B = (L + 31) // 32, (S + 31) // 32
+    off, out = 0, {}
+    for name, nbytes, dt, shape in (("rowbest", 8 * n * L, torch.int64, (n, L)), ("colbest", 8 * n * S, torch.int64, (n, S)),
+                                    ("cand_cnt", 8 * n * L, torch.int16, (n, L, 4)), ("ready", 4 * n, torch.int32, (n,)),
+                                    ("lse_r", 4 * n * L, torch.float32, (n, L)), ("lse_c", 4 * n * S, torch.float32, (n, S)),
+                                    ("cand", 8 * n * L * 4 * 24, torch.int64, (n, L, 16, 6)),
+                                    ("cbound", 4 * n * G * 32, torch.float32, (n, G * 32)), ("cminb", 4 * n * G, torch.float32, (n, G)),
+                                    ("colpart", 4 * n * G * S, torch.float32, (n, G, S)), ("cshift", 4 * n * G * B, torch.float32, (n, G, B)),
+                                    ("pairflag", 4 * n, torch.int32, (n,))):
+        out[name] = workspace[off:off + nbytes].view(dt).view(*shape)
+        off += up(nbytes)
+    return out

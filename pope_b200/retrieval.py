@@ -31,3 +31,33 @@ def retrieve_topk_images(model, ref_image: torch.Tensor, crop_images: torch.Tens
     ref_fea = cls_tokens(model, ref_image, batch)
     crop_feas = cls_tokens(model, crop_images, batch)
     return retrieve_topk(ref_fea, crop_feas, k, eps)
+
+
+def retrieve_topk_sharded(local_scores: torch.Tensor, n_crops: int, rank: int, world: int, k: int = 3, group=None,
+                          topk_fn=None) -> Tuple[torch.Tensor, List[float], List[int]]:
+    """Retrieval with the R crops sharded over the ranks of one box: rank r scores the contiguous
+    block `driver.shard_range(n_crops, r, world)` of the crops (ViT forwards + `ops.cosine_topk` on its own GPU -- that is
+    where the time goes) and passes its scores [hi - lo] here.  ONE small collective, an all-gather of the R scores in crop
+    order, then every rank runs the running top-k over all of them.  The slots of the reference loop
+    (eval_linemod_json.py:95-101: a crop that beats any slot overwrites the current arg-min slot) depend on the whole arrival
+    order -- an element that is evicted later still decides which slot its successor lands in -- so per-shard top-k lists
+    cannot be merged into the same slots; the full score vector (R floats) can.
+    Returns (scores [R], slot_scores, slot_indices), identical on every rank and to the single-GPU `retrieve_topk`.
+    `topk_fn(scores, k) -> (slot_scores, slot_idx)`: defaults to the CUDA kernel (`ops.running_topk`)."""
+    import torch.distributed as dist
+    from .driver import shard_range
+    spans = [shard_range(n_crops, r, world) for r in range(world)]
+    lo, hi = spans[rank]
+    if local_scores.numel() != hi - lo:
+        raise ValueError(f"rank {rank} owns crops [{lo}, {hi}) but passed {local_scores.numel()} scores")
+    width = max(b - a for a, b in spans)
+    send = torch.zeros(width, dtype=torch.float32, device=local_scores.device)
+    send[:hi - lo] = local_scores.float()
+    if world > 1:
+        recv = torch.empty(world * width, dtype=torch.float32, device=local_scores.device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        scores = torch.cat([recv[r * width:r * width + (b - a)] for r, (a, b) in enumerate(spans)])
+    else:
+        scores = send[:n_crops]
+    slot_s, slot_i = (topk_fn or ops.running_topk)(scores, k)
+    return scores, [float(v) for v in slot_s], [int(v) for v in slot_i]

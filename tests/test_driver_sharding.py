@@ -71,10 +71,18 @@ def _worker(rank, world, port, n_pairs, q):
     sums = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(sums, mine)
     recs_c, sizes_c = jobc.finish()
+    # retrieval sharded over the ranks: each rank scores its block of the crops, one all-gather of the scores, then the running
+    # top-k over all of them (the oracle stands in for the two CUDA kernels)
+    from pope_b200 import retrieval
+    q_tok, ref_tok = synth.retrieval_tokens(9, 37, 48)
+    rlo, rhi = driver.shard_range(37, rank, world)
+    ret = retrieval.retrieve_topk_sharded(O.cosine_scores(q_tok, ref_tok[rlo:rhi]), 37, rank, world, 3,
+                                          topk_fn=lambda sc, k: O.running_topk(sc.tolist(), k))
     if rank == 0:
         # numpy arrays travel through the queue by value; tensors would travel as file descriptors that die with this process
         payload = {k: (v.numpy().copy() if torch.is_tensor(v) else v) for k, v in got.items()}
         payload["job_sizes"] = sizes
+        payload["retrieval"] = (ret[0].numpy().copy(), ret[1], ret[2])
         payload["job_b"] = torch.cat([recs[r, :sizes[r], 0] for r in range(world)]).numpy().copy()
         payload["job_conf"] = torch.cat([recs[r, :sizes[r], 3] for r in range(world)]).view(torch.float32).numpy().copy()
         assert sizes_c == sizes and recs_c.shape[2] == 5
@@ -103,7 +111,7 @@ def test_two_rank_gather_equals_single_process():
     for p in procs:
         p.start()
     got = q.get(timeout=180)
-    got = {k: (torch.from_numpy(v) if hasattr(v, "dtype") else v) for k, v in got.items()}
+    got = {k: (torch.from_numpy(v) if hasattr(v, "dtype") else v) for k, v in got.items()}      # (tuples pass through)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -116,6 +124,12 @@ def test_two_rank_gather_equals_single_process():
     assert torch.equal(got["mconf"], want["mconf"])
     assert torch.equal(got["mkpts1_f"], want["mkpts1_f"]) and torch.equal(got["mkpts0_f"], want["mkpts0_f"])
     assert sum(got["per_rank_matches"]) == want["b_ids"].numel()
+    # sharded retrieval: the same scores, slot scores and slot indices as the one-process loop over all 37 crops
+    q_tok, ref_tok = synth.retrieval_tokens(9, 37, 48)
+    all_scores = O.cosine_scores(q_tok, ref_tok)
+    want_s, want_i = O.running_topk(all_scores.tolist(), 3)
+    r_scores, r_slot_s, r_slot_i = got["retrieval"]
+    assert torch.equal(torch.as_tensor(r_scores), all_scores) and r_slot_i == want_i and r_slot_s == want_s and min(want_i) >= 0
     # job-level gather: each rank contributed its matches twice (two identical steps)
     assert got["job_sizes"] == [2 * x for x in got["per_rank_matches"]]
     per = torch.tensor(got["per_rank_matches"])
