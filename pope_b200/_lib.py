@@ -9,7 +9,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpope_b200.so")
+# POPE_B200_LIB: developer override (experiment builds of tools/build_variant.sh); the product library is the in-tree one
+LIB_PATH = os.environ.get("POPE_B200_LIB") or os.path.join(_HERE, "libpope_b200.so")
 
 POPE_F32, POPE_BF16 = 0, 1
 COARSE_AUTO, COARSE_SIMT, COARSE_TCGEN05 = 0, 1, 2

@@ -62,7 +62,11 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 // per thread; the data-movement warps need a fraction of that, the epilogue is short of registers at 96)
 constexpr int kWarpProducer = kEpiWarps, kWarpMma = kEpiWarps + 1;
 constexpr int kThreads = kEpiThreads + 128;
-constexpr int kRegsEpi = 104, kRegsAux = 40;   // 16 x 32 x 104 + 4 x 32 x 40 = 58 368 <= the CTA's 640 x 96 = 61 440 registers (the pool is per CTA)
+#ifndef POPE_VAR_REGS_EPI
+#define POPE_VAR_REGS_EPI 104
+#define POPE_VAR_REGS_AUX 40
+#endif
+constexpr int kRegsEpi = POPE_VAR_REGS_EPI, kRegsAux = POPE_VAR_REGS_AUX;   // 16 x 32 x 104 + 4 x 32 x 40 = 58 368 <= the CTA's 640 x 96 = 61 440 registers (the pool is per CTA)
 constexpr uint32_t kTmemCols = 512;
 constexpr bool kLoadAll = (kEpiWarps == 8);          // all chunks TMEM -> registers before any arithmetic (needs the
                                                      // 204-register budget of the 8-warp layout; spills with 16 warps)
@@ -90,6 +94,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Experiment switches of the developer builds (tools/build_variant.sh); the defaults are the product configuration.
+#ifndef POPE_VAR_WAIT_HINT
+#define POPE_VAR_WAIT_HINT 0          // > 0: suspend-time hint (ns) of the epilogue's accumulator wait
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -99,13 +107,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must become a launch failure, never a hung GPU.
+// the same with a suspend-time hint: the warp may sleep up to `ns` inside the instruction instead of polling
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ long long clock_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+// Bounded wait: a protocol bug must become a launch failure, never a hung GPU.  The clock is only read every 1024 polls
+// (read on every poll, the nine instructions of the time-out test were a fifth of all instructions the sweep issued).
+template <int HINT = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000ll) __trap();     // ~2 s at 2 GHz
+  if (HINT > 0 ? mbar_try_wait_hint(bar, parity, HINT) : mbar_try_wait(bar, parity)) return;
+  long long t0 = 0;
+  for (;;) {
+#pragma unroll 1
+    for (int k = 0; k < 1024; ++k)
+      if (HINT > 0 ? mbar_try_wait_hint(bar, parity, HINT) : mbar_try_wait(bar, parity)) return;
+    const long long t = clock_now();
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 4000000000ll) __trap();     // ~2 s at 2 GHz
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -198,7 +227,7 @@ struct SweepParams {
                             //       the pairs with pairflag[n] != 0 are swept
   int32_t* flags;
   unsigned long long* trace;   // developer diagnostics (POPE_TC_TRACE): clock stamps of CTA pair 0, or nullptr
-  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps, bit4 = no single sweep, bit6 = no gated redo after the single sweep
+  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps, bit4 = no single sweep, bit5 = single sweep without the per-cell candidate scan, bit6 = no gated redo after the single sweep
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -693,13 +722,18 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       float mshift = 0.f, rawlim = -INFINITY;                        // raw accumulators above rawlim raise the shift (first chunk: always)
       uint32_t cnts = 0;                                             // fill counts of the thread's four private lists (a byte each)
       const uint32_t gidx = uint32_t(n) * ngroups + (rowbase >> 5);  // (pair, 32-row group): row of colpart / cshift
+      // where this lane's column sum / this warp's shift of the current tile's first chunk go (advanced tile by tile)
+      float* cp_ptr = P.colpart + size_t(gidx) * LB + (colofs + ccol);
+      float* cs_ptr = P.cshift + size_t(gidx) * nblk + (colofs >> 5);
+      // the thread's private candidate list of row (g + 8 rho) starts at listbase + rho * (8 rows of lists)
+      u64* const listbase = P.cand + (((size_t(n) * LA + rowbase + g) * kListGroups + cg) * 4 + p) * kLaneSlots;
 
       for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
         const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
         const int col0 = ct * kTileCols;
         const int nvalid = min(LB - col0, kTileCols) - colofs;
         const bool active = rows_valid > 0 && nvalid > 0 && !(P.debug & 1);
-        mbar_wait(bar_acc_full + 8 * s, acc_phase);
+        mbar_wait<POPE_VAR_WAIT_HINT>(bar_acc_full + 8 * s, acc_phase);
         tc_fence_after();
         const uint32_t tbase = tb0 + s * kTileCols;
         float v[32];
@@ -738,8 +772,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < 4; ++k) unpack2(cp2[k], cp[2 * k], cp[2 * k + 1]);
           const float cs = ss_col_reduce(cp, lane);
-          if (ccol < vc) P.colpart[size_t(gidx) * LB + (colb + ccol)] = cs;
-          if (lane == 0) P.cshift[size_t(gidx) * nblk + (colb >> 5)] = mshift;
+          if (ccol < vc) cp_ptr[cc * 32] = cs;
+          if (lane == 0) cs_ptr[cc] = mshift;
           // ---- candidates.  A cell can only have p_row > thr if it exceeds thr x (running row sum).  Level 1, no
           // communication: this chunk's contribution d[rho] to the thread's own row sum against that sum (true for the first
           // chunks of a unit by construction).  Level 2: the same against the row sum over the 4 lanes that share the row.
@@ -765,16 +799,36 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               bound[rho] = thrm * rs;
               hit |= d[rho] > bound[rho];
             }
-            if (hit) {
+            // Level 3: a row whose chunk contribution reaches a fifth of its running sum.  Only a CELL above the bound is a
+            // candidate, so the row's largest cell decides (4 instructions), and the lists are touched for real candidates
+            // only -- not for the rows of a unit's first chunks, where every contribution passes by construction.  One cell
+            // above the bound (the rest of the contribution cannot hold another one) is stored in line; several cells, or a
+            // full list, go through the out-of-line scan.
+            if (__any_sync(kFullMask, hit) && !(P.debug & 32)) {
 #pragma unroll
               for (int rho = 0; rho < 4; ++rho) {
-                if (d[rho] > bound[rho]) {
-                  const int i0 = 16 * (rho >> 1) + 2 * (rho & 1);
-                  u64* const mylist = P.cand + (((size_t(n) * LA + rowbase + g + 8 * rho) * kListGroups + cg) * 4 + p) * kLaneSlots;
-                  const int c = ss_scan_row(v[i0], v[i0 + 1], v[i0 + 4], v[i0 + 5], v[i0 + 8], v[i0 + 9], v[i0 + 12], v[i0 + 13],
-                                            bound[rho], mshift, mylist, int((cnts >> (8 * rho)) & 0xffu), colb + 2 * p, P.flags,
-                                            P.pairflag + n);
-                  cnts = (cnts & ~(0xffu << (8 * rho))) | (uint32_t(c) << (8 * rho));
+                const int i0 = 16 * (rho >> 1) + 2 * (rho & 1);
+                const float e0 = v[i0], e1 = v[i0 + 1], e2 = v[i0 + 4], e3 = v[i0 + 5], e4 = v[i0 + 8], e5 = v[i0 + 9],
+                            e6 = v[i0 + 12], e7 = v[i0 + 13];
+                const float emax = fmax3(fmax3(e0, e1, e2), fmax3(e3, e4, e5), fmaxf(e6, e7));
+                const bool cand = emax > bound[rho];
+                if (__any_sync(kFullMask, cand)) {
+                  if (cand) {
+                    u64* const mylist = listbase + rho * (8 * kListGroups * 4 * kLaneSlots);
+                    int c = int((cnts >> (8 * rho)) & 0xffu);
+                    if (d[rho] - emax <= bound[rho] && c < kLaneSlots) {
+                      int q = 0;
+                      q = e1 == emax ? 1 : q; q = e2 == emax ? 2 : q; q = e3 == emax ? 3 : q; q = e4 == emax ? 4 : q;
+                      q = e5 == emax ? 5 : q; q = e6 == emax ? 6 : q; q = e7 == emax ? 7 : q;
+                      const int col = colb + 2 * p + 8 * (q >> 1) + (q & 1);
+                      mylist[c] = (u64(__float_as_uint(log2_split(emax) + mshift)) << 32) | uint32_t(col);
+                      ++c;
+                    } else {
+                      c = ss_scan_row(e0, e1, e2, e3, e4, e5, e6, e7, bound[rho], mshift, mylist, c, colb + 2 * p, P.flags,
+                                      P.pairflag + n);
+                    }
+                    cnts = (cnts & ~(0xffu << (8 * rho))) | (uint32_t(c) << (8 * rho));
+                  }
                 }
               }
             }
@@ -789,6 +843,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
         if (active && nvalid > 32) process(1);
+        cp_ptr += kTileCols;
+        cs_ptr += kTileCols / 32;
       }
 
       // unit end: row sums over the 4 lanes of a row (same warp, same shift), then over the 4 column groups (one shift
