@@ -245,59 +245,79 @@ __global__ void __launch_bounds__(256) cand_eval_lists_kernel(const int* __restr
 // exponential is evaluated).  A total below 2^-90 of that domain may have lost terms to underflow: the pair is flagged for
 // the online-softmax kernels.  Also clears the column's best-candidate record and the pair's "count published" word (the
 // single-sweep launch sequence needs no memset of the scratch).  HBM-bound: n * ceil(L/32) * S * 4 bytes are read once; a
-// thread owns VEC adjacent columns (one 32-column block) and keeps 4 x VEC loads in flight; the order over the groups is
-// fixed.
+// thread owns VEC adjacent columns (inside one 32-column block) for every eighth row group.
+constexpr int kMergeWarps = 4, kMergeBatch = 5;    // tools/micro/merge_bench.cu: 41 us for 184 MB (8 warps: 45, 16 warps: 76)
 template <int VEC>
-__global__ void __launch_bounds__(128) colsum_reduce_kernel(const float* __restrict__ colpart, const float* __restrict__ cshift,
-                                                           int ngroups, int S, int nblk, float* __restrict__ lse_c,
-                                                           u64* __restrict__ colbest, int* __restrict__ ready,
-                                                           int32_t* __restrict__ flags, int* __restrict__ pairflag) {
-  const int j = (blockIdx.x * 128 + threadIdx.x) * VEC, n = blockIdx.y;
-  if (j >= S) return;
-  if (j == 0) ready[n] = 0;
-  const float* p = colpart + size_t(n) * ngroups * S + j;
-  const float* sh = cshift + size_t(n) * ngroups * nblk + (j >> 5);
-  float acc[4][VEC], mtop[4];
+__global__ void __launch_bounds__(32 * kMergeWarps) colsum_reduce_kernel(const float* __restrict__ colpart,
+                                                                        const float* __restrict__ cshift, int ngroups, int S,
+                                                                        int nblk, float* __restrict__ lse_c,
+                                                                        u64* __restrict__ colbest, int* __restrict__ ready,
+                                                                        int32_t* __restrict__ flags, int* __restrict__ pairflag) {
+  // block = kMergeWarps warps x (32 lanes x VEC adjacent columns): warp w takes the row groups g = w, w + kMergeWarps, ...,
+  // kMergeBatch loads in flight per thread; the partial results of a column meet in shared memory and are merged in warp
+  // order (fixed order: deterministic)
+  __shared__ float s_acc[kMergeWarps][32 * VEC];
+  __shared__ float s_m[kMergeWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = (blockIdx.x * 32 + lane) * VEC, n = blockIdx.y;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ready[n] = 0;
+  float acc[VEC], mtop = -INFINITY;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    mtop[u] = -INFINITY;
+  for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+  if (j < S) {
+    const float* p = colpart + size_t(n) * ngroups * S + j;
+    const float* sh = cshift + size_t(n) * ngroups * nblk + (j >> 5);
+    for (int g0 = warp; g0 < ngroups; g0 += kMergeWarps * kMergeBatch) {
+      float q[kMergeBatch][VEC], m[kMergeBatch];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[u][v] = 0.f;
-  }
-  auto load_add = [&](int g, int u) {
-    float q[VEC];
-    if (VEC == 4) {
-      const float4 t = __ldcs(reinterpret_cast<const float4*>(p + size_t(g) * S));
-      q[0] = t.x; q[1 % VEC] = t.y; q[2 % VEC] = t.z; q[3 % VEC] = t.w;
-    } else {
-      q[0] = __ldcs(p + size_t(g) * S);
+      for (int b = 0; b < kMergeBatch; ++b) {
+        const int g = g0 + b * kMergeWarps;
+        m[b] = -INFINITY;                                  // past the last group: (0, -inf) is neutral below
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) q[b][v] = 0.f;
+        if (g < ngroups) {
+          if (VEC == 4) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(p + size_t(g) * S));
+            q[b][0] = t.x; q[b][1 % VEC] = t.y; q[b][2 % VEC] = t.z; q[b][3 % VEC] = t.w;
+          } else {
+            q[b][0] = __ldcs(p + size_t(g) * S);
+          }
+          m[b] = __ldg(sh + size_t(g) * nblk);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kMergeBatch; ++b) {
+        if (m[b] == mtop) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] += q[b][v];
+        } else if (m[b] < mtop) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] += scale_pow2(q[b][v], m[b] - mtop);
+        } else {                                          // also the first group (mtop = -inf, zero sums)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] = scale_pow2(acc[v], mtop - m[b]) + q[b][v];
+          mtop = m[b];
+        }
+      }
     }
-    const float m = __ldg(sh + size_t(g) * nblk);
-    if (m == mtop[u]) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[u][v] += q[v];
-    } else if (m < mtop[u]) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[u][v] += scale_pow2(q[v], m - mtop[u]);
-    } else {                                          // also the first group (mtop = -inf, zero sums)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[u][v] = scale_pow2(acc[u][v], mtop[u] - m) + q[v];
-      mtop[u] = m;
-    }
-  };
-  int g = 0;
-  for (; g + 4 <= ngroups; g += 4) {
-    load_add(g, 0); load_add(g + 1, 1); load_add(g + 2, 2); load_add(g + 3, 3);
   }
-  for (; g < ngroups; ++g) load_add(g, 0);
-  const float mall = fmaxf(fmaxf(mtop[0], mtop[1]), fmaxf(mtop[2], mtop[3]));
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) s_acc[warp][lane * VEC + v] = acc[v];
+  s_m[warp][lane] = mtop;
+  __syncthreads();
+  if (warp != 0 || j >= S) return;
+  float mall = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < kMergeWarps; ++w) mall = fmaxf(mall, s_m[w][lane]);
   bool bad = false;
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    float t[4];
+    float tot = 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) t[u] = (mtop[u] == mall) ? acc[u][v] : scale_pow2(acc[u][v], mtop[u] - mall);   // unused chain: 0
-    const float tot = (t[0] + t[1]) + (t[2] + t[3]);
+    for (int w = 0; w < kMergeWarps; ++w) {
+      const float a = s_acc[w][lane * VEC + v], m = s_m[w][lane];
+      tot += (m == mall) ? a : scale_pow2(a, m - mall);          // a warp without groups holds (0, -inf)
+    }
     lse_c[size_t(n) * S + j + v] = mall + log2f(tot);
     colbest[size_t(n) * S + j + v] = 0ull;
     bad |= !(tot > kSumLo && tot < kSumHi);
@@ -340,12 +360,12 @@ cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, 
 cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
   const int ngroups = (p.L + 31) / 32, nblk = (p.S + 31) / 32;
   if (p.S % 4 == 0) {   // rows of the partial-sum array are then 16-byte aligned (the array itself is 256-byte aligned)
-    dim3 grid((p.S / 4 + 127) / 128, p.n);
-    colsum_reduce_kernel<4><<<grid, 128, 0, st>>>(w.colpart, w.cshift, ngroups, p.S, nblk, w.lse_c, w.colbest, w.ready, flags,
+    dim3 grid((p.S / 4 + 31) / 32, p.n);
+    colsum_reduce_kernel<4><<<grid, 32 * kMergeWarps, 0, st>>>(w.colpart, w.cshift, ngroups, p.S, nblk, w.lse_c, w.colbest, w.ready, flags,
                                                   w.pairflag);
   } else {
-    dim3 grid((p.S + 127) / 128, p.n);
-    colsum_reduce_kernel<1><<<grid, 128, 0, st>>>(w.colpart, w.cshift, ngroups, p.S, nblk, w.lse_c, w.colbest, w.ready, flags,
+    dim3 grid((p.S + 31) / 32, p.n);
+    colsum_reduce_kernel<1><<<grid, 32 * kMergeWarps, 0, st>>>(w.colpart, w.cshift, ngroups, p.S, nblk, w.lse_c, w.colbest, w.ready, flags,
                                                   w.pairflag);
   }
   return cudaGetLastError();

@@ -62,11 +62,14 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 // per thread; the data-movement warps need a fraction of that, the epilogue is short of registers at 96)
 constexpr int kWarpProducer = kEpiWarps, kWarpMma = kEpiWarps + 1;
 constexpr int kThreads = kEpiThreads + 128;
-#ifndef POPE_VAR_REGS_EPI
-#define POPE_VAR_REGS_EPI 104
-#define POPE_VAR_REGS_AUX 40
+#ifndef POPE_VAR_LOADBOTH
+#define POPE_VAR_LOADBOTH 0        // 1: single sweep loads both chunks of a tile before any arithmetic
 #endif
-constexpr int kRegsEpi = POPE_VAR_REGS_EPI, kRegsAux = POPE_VAR_REGS_AUX;   // 16 x 32 x 104 + 4 x 32 x 40 = 58 368 <= the CTA's 640 x 96 = 61 440 registers (the pool is per CTA)
+#ifndef POPE_VAR_REGS_EPI
+#define POPE_VAR_REGS_EPI 112
+#define POPE_VAR_REGS_AUX 32
+#endif
+constexpr int kRegsEpi = POPE_VAR_REGS_EPI, kRegsAux = POPE_VAR_REGS_AUX;   // 16 x 32 x 112 + 4 x 32 x 32 = 61 440 = the CTA's 640 x 96 registers (the pool is per CTA)
 constexpr uint32_t kTmemCols = 512;
 constexpr bool kLoadAll = (kEpiWarps == 8);          // all chunks TMEM -> registers before any arithmetic (needs the
                                                      // 204-register budget of the 8-warp layout; spills with 16 warps)
@@ -699,6 +702,13 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     float2* mergef = reinterpret_cast<float2*>(smem + kSmemMerge);   // [3][128] (row sum, shift) of column groups 1..3
     const int rin = quad * 32 + g + 8 * p;                           // the row of the CTA this lane writes results for
+    // [128] per row of the CTA: log2 of the largest partial row sum any column group has published + kBndBias (float bits
+    // compared as integers: positive floats order like their bits; 0 = nothing yet)
+    constexpr float kBndBias = 16384.f;
+    int* rowbnd = reinterpret_cast<int*>(smem + kSmemLc);
+    const uint32_t rowbnd_addr = sbase + kSmemLc + 4 * (quad * 32 + g);   // this thread's rows: + 32 bytes per rho
+    if (threadIdx.x < 128) rowbnd[threadIdx.x] = 0;
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     const float scale = P.scale_log2, inv_scale = 1.f / P.scale_log2;
     const float thrm = exp2f(P.log2_thr) * 0.99f;
     const int LA = P.L0, LB = P.L1;
@@ -719,6 +729,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
 #pragma unroll
       for (int rho = 0; rho < 4; ++rho) rowmask |= (g + 8 * rho < rows_valid) ? (1u << rho) : 0u;
       float rowacc[4] = {0.f, 0.f, 0.f, 0.f};                        // the thread's row sums (its 2 of every 8 columns)
+      float tb[4] = {0.f, 0.f, 0.f, 0.f};                            // thr x (what is known of the rest of the row's sum)
       float mshift = 0.f, rawlim = -INFINITY;                        // raw accumulators above rawlim raise the shift (first chunk: always)
       uint32_t cnts = 0;                                             // fill counts of the thread's four private lists (a byte each)
       const uint32_t gidx = uint32_t(n) * ngroups + (rowbase >> 5);  // (pair, 32-row group): row of colpart / cshift
@@ -737,7 +748,10 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         tc_fence_after();
         const uint32_t tbase = tb0 + s * kTileCols;
         float v[32];
-        auto process = [&](int cc) {
+#if POPE_VAR_LOADBOTH
+        float v2[32];
+#endif
+        auto process = [&](float (&v)[32], int cc) {
           const int vc = nvalid - cc * 32;
           const int colb = col0 + colofs + cc * 32;
           if (rows_valid < 32 || vc < 32) ss_mask(v, rowmask, vc, p);
@@ -760,7 +774,10 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             if (!(fabsf(mnew) < 1e30f)) mnew = first ? 0.f : mshift; // inf inputs: the sums get flagged
             if (!first) {
 #pragma unroll
-              for (int rho = 0; rho < 4; ++rho) rowacc[rho] = scale_pow2(rowacc[rho], mshift - mnew);
+              for (int rho = 0; rho < 4; ++rho) {
+                rowacc[rho] = scale_pow2(rowacc[rho], mshift - mnew);
+                tb[rho] = scale_pow2(tb[rho], mshift - mnew);
+              }
             }
             mshift = mnew;
             rawlim = (mnew + kShiftHead) * inv_scale;
@@ -774,10 +791,16 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           const float cs = ss_col_reduce(cp, lane);
           if (ccol < vc) cp_ptr[cc * 32] = cs;
           if (lane == 0) cs_ptr[cc] = mshift;
-          // ---- candidates.  A cell can only have p_row > thr if it exceeds thr x (running row sum).  Level 1, no
-          // communication: this chunk's contribution d[rho] to the thread's own row sum against that sum (true for the first
-          // chunks of a unit by construction).  Level 2: the same against the row sum over the 4 lanes that share the row.
-          // Level 3 (a real candidate, or the first chunk of a unit): the row's 8 cells one by one.
+          // ---- candidates.  A cell can only have p_row > thr if it exceeds thr x (a lower bound of the row's final sum).
+          // Level 1, no communication: this chunk's contribution d[rho] to the thread's own row sum against thr x (that sum
+          // + what the thread last learnt about the rest of the row, tb[]); true for the first chunks of a unit by
+          // construction.  Level 2, per row position rho and only if some lane passed level 1 for it: the row sum over the 4
+          // lanes that share the row, and what the other column groups of the CTA have published about the row (rowbnd:
+          // log2 of a partial row sum + kBndBias, raised with a shared-memory atomicMax; ANY lower bound of the final row
+          // sum is a valid pruning bound, whenever it was taken).  Level 3: only a CELL above the bound is a candidate, so
+          // the row's largest cell decides, and the lists are touched for real candidates only.  One cell above the bound
+          // (the rest of the contribution cannot hold another one) is stored in line; several cells, or a full list, go
+          // through the out-of-line scan.
           float d[4];
           bool pass = false;
 #pragma unroll
@@ -786,63 +809,63 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             unpack2(rc2[rho], x, y);
             d[rho] = x + y;
             rowacc[rho] += d[rho];
-            pass |= d[rho] > thrm * rowacc[rho];
+            pass |= d[rho] > fmaf(thrm, rowacc[rho], tb[rho]);
           }
-          if (__any_sync(kFullMask, pass) && !(P.debug & 2)) {
-            float bound[4];
-            bool hit = false;
+          if (__any_sync(kFullMask, pass) && !(P.debug & 2)) {       // (one vote per chunk on the common path)
 #pragma unroll
             for (int rho = 0; rho < 4; ++rho) {
+              if (!__any_sync(kFullMask, d[rho] > fmaf(thrm, rowacc[rho], tb[rho]))) continue;
               float rs = rowacc[rho];
               rs += __shfl_xor_sync(kFullMask, rs, 1);
               rs += __shfl_xor_sync(kFullMask, rs, 2);
-              bound[rho] = thrm * rs;
-              hit |= d[rho] > bound[rho];
-            }
-            // Level 3: a row whose chunk contribution reaches a fifth of its running sum.  Only a CELL above the bound is a
-            // candidate, so the row's largest cell decides (4 instructions), and the lists are touched for real candidates
-            // only -- not for the rows of a unit's first chunks, where every contribution passes by construction.  One cell
-            // above the bound (the rest of the contribution cannot hold another one) is stored in line; several cells, or a
-            // full list, go through the out-of-line scan.
-            if (__any_sync(kFullMask, hit) && !(P.debug & 32)) {
-#pragma unroll
-              for (int rho = 0; rho < 4; ++rho) {
-                const int i0 = 16 * (rho >> 1) + 2 * (rho & 1);
-                const float e0 = v[i0], e1 = v[i0 + 1], e2 = v[i0 + 4], e3 = v[i0 + 5], e4 = v[i0 + 8], e5 = v[i0 + 9],
-                            e6 = v[i0 + 12], e7 = v[i0 + 13];
-                const float emax = fmax3(fmax3(e0, e1, e2), fmax3(e3, e4, e5), fmaxf(e6, e7));
-                const bool cand = emax > bound[rho];
-                if (__any_sync(kFullMask, cand)) {
-                  if (cand) {
-                    u64* const mylist = listbase + rho * (8 * kListGroups * 4 * kLaneSlots);
-                    int c = int((cnts >> (8 * rho)) & 0xffu);
-                    if (d[rho] - emax <= bound[rho] && c < kLaneSlots) {
-                      int q = 0;
-                      q = e1 == emax ? 1 : q; q = e2 == emax ? 2 : q; q = e3 == emax ? 3 : q; q = e4 == emax ? 4 : q;
-                      q = e5 == emax ? 5 : q; q = e6 == emax ? 6 : q; q = e7 == emax ? 7 : q;
-                      const int col = colb + 2 * p + 8 * (q >> 1) + (q & 1);
-                      mylist[c] = (u64(__float_as_uint(log2_split(emax) + mshift)) << 32) | uint32_t(col);
-                      ++c;
-                    } else {
-                      c = ss_scan_row(e0, e1, e2, e3, e4, e5, e6, e7, bound[rho], mshift, mylist, c, colb + 2 * p, P.flags,
-                                      P.pairflag + n);
-                    }
-                    cnts = (cnts & ~(0xffu << (8 * rho))) | (uint32_t(c) << (8 * rho));
-                  }
+              const float other = ex2_approx(lds32(rowbnd_addr + 32 * rho) - (kBndBias + mshift));
+              const float bound = thrm * fmaxf(rs, other);
+              tb[rho] = fmaxf(tb[rho], fmaf(-thrm, rowacc[rho], bound));
+              if (p == 0 && fabsf(mshift) < 0.5f * kBndBias)
+                atomicMax(rowbnd + (quad * 32 + g + 8 * rho), __float_as_int(lg2_approx(rs) + (mshift + kBndBias - 0.004f)));
+              if (P.debug & 32) continue;
+              const int i0 = 16 * (rho >> 1) + 2 * (rho & 1);
+              const float e0 = v[i0], e1 = v[i0 + 1], e2 = v[i0 + 4], e3 = v[i0 + 5], e4 = v[i0 + 8], e5 = v[i0 + 9],
+                          e6 = v[i0 + 12], e7 = v[i0 + 13];
+              const float emax = fmax3(fmax3(e0, e1, e2), fmax3(e3, e4, e5), fmaxf(e6, e7));
+              if (emax > bound) {
+                u64* const mylist = listbase + rho * (8 * kListGroups * 4 * kLaneSlots);
+                int c = int((cnts >> (8 * rho)) & 0xffu);
+                if (d[rho] - emax <= bound && c < kLaneSlots) {
+                  int q = 0;
+                  q = e1 == emax ? 1 : q; q = e2 == emax ? 2 : q; q = e3 == emax ? 3 : q; q = e4 == emax ? 4 : q;
+                  q = e5 == emax ? 5 : q; q = e6 == emax ? 6 : q; q = e7 == emax ? 7 : q;
+                  const int col = colb + 2 * p + 8 * (q >> 1) + (q & 1);
+                  mylist[c] = (u64(__float_as_uint(log2_split(emax) + mshift)) << 32) | uint32_t(col);
+                  ++c;
+                } else {
+                  c = ss_scan_row(e0, e1, e2, e3, e4, e5, e6, e7, bound, mshift, mylist, c, colb + 2 * p, P.flags, P.pairflag + n);
                 }
+                cnts = (cnts & ~(0xffu << (8 * rho))) | (uint32_t(c) << (8 * rho));
               }
             }
           }
         };
+#if POPE_VAR_LOADBOTH
+        // both chunks in registers first, the TMEM stage handed back before any arithmetic
+        if (active) tmem_ld_frag(tbase, v);
+        if (active && nvalid > 32) tmem_ld_frag(tbase + 32, v2);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
+        if (active) process(v, 0);
+        if (active && nvalid > 32) process(v2, 1);
+#else
         if (active) {
           tmem_ld_frag(tbase, v);
-          process(0);
+          process(v, 0);
         }
         if (active && nvalid > 32) tmem_ld_frag(tbase + 32, v);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
-        if (active && nvalid > 32) process(1);
+        if (active && nvalid > 32) process(v, 1);
+#endif
         cp_ptr += kTileCols;
         cs_ptr += kTileCols / 32;
       }
@@ -891,6 +914,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         }
         reinterpret_cast<uint16_t*>(P.cand_cnt)[(size_t(n) * LA + row) * kListGroups + cg] = uint16_t(myfield);
       }
+      if (threadIdx.x < 128) rowbnd[threadIdx.x] = 0;                 // (every warp is past its last tile of the unit)
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
   } else {
