@@ -69,7 +69,8 @@ constexpr int kThreads = kEpiThreads + 128;
 #define POPE_VAR_REGS_EPI 112
 #define POPE_VAR_REGS_AUX 32
 #endif
-constexpr int kRegsEpi = POPE_VAR_REGS_EPI, kRegsAux = POPE_VAR_REGS_AUX;   // 16 x 32 x 112 + 4 x 32 x 32 = 61 440 = the CTA's 640 x 96 registers (the pool is per CTA)
+constexpr int kRegsEpi = POPE_VAR_REGS_EPI, kRegsAux = POPE_VAR_REGS_AUX;
+static_assert(16 * 32 * kRegsEpi + 4 * 32 * kRegsAux <= 640 * 96, "setmaxnreg would wait for registers the CTA does not own");   // 16 x 32 x 112 + 4 x 32 x 32 = 61 440 = the CTA's 640 x 96 registers (the pool is per CTA)
 constexpr uint32_t kTmemCols = 512;
 constexpr bool kLoadAll = (kEpiWarps == 8);          // all chunks TMEM -> registers before any arithmetic (needs the
                                                      // 204-register budget of the 8-warp layout; spills with 16 warps)
