@@ -47,11 +47,16 @@ __device__ __forceinline__ int block_sum(int v, int* smem) {
   return t;
 }
 
-// One CTA per pair: count the pair's matches, publish the count, wait for the counts of all earlier pairs (CTAs are
-// dispatched in blockIdx order, so an earlier pair's CTA is always running or done), then emit in (pair, i) order.
-// ready[n] must be 0 on entry for every pair; the kernel leaves it set (the caller clears it with the flag words).
-// phase 0: count, look back, emit in one launch (all CTAs co-resident: n_pairs <= 2 x SMs).  Larger batches do not rely
-// on the dispatch order: phase 1 = count only, phase 2 = emit only, as two launches.
+// One CTA per pair: count the pair's matches, publish the count, wait for the counts of all earlier pairs, then emit in
+// (pair, i) order.  ready[0..n) must be 0 on entry and ready[n] (the ticket counter) too; the kernel leaves them set (the
+// caller's memset / the column-merge kernel clears them).
+// phase 0: count, look back, emit in one launch.  The pair a CTA works on is a TICKET drawn when the CTA starts, not its
+// blockIdx: a CTA only ever waits for pairs whose CTAs drew their tickets earlier, i.e. are running or done, whatever
+// order the hardware dispatches the grid in and whatever else occupies the SMs.  Batches of more than 2 x SMs pairs keep the
+// two-launch form (phase 1 = count only, phase 2 = emit only).
+// Rows are matched once: a thread keeps the outcome of its (up to kKeep x FT rows) in registers between counting and
+// emitting (L <= kKeep * FT; longer rows are matched again).
+constexpr int kKeep = 5;
 __global__ void __launch_bounds__(FT) count_emit_kernel(const u64* __restrict__ rowbest, const u64* __restrict__ colbest,
                                                        const float* __restrict__ lse_r, const float* __restrict__ lse_c,
                                                        int L, int S, Grid2 g0, Grid2 g1, float pixel_scale,
@@ -62,14 +67,36 @@ __global__ void __launch_bounds__(FT) count_emit_kernel(const u64* __restrict__ 
                                                        int64_t capacity) {
   __shared__ int smem[32];
   __shared__ int warp_off[FT / 32];
-  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int s_pair;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (phase == 0) {
+    if (threadIdx.x == 0) s_pair = atomicAdd(ready + n_pairs, 1);
+    __syncthreads();
+  }
+  const int n = phase == 0 ? s_pair : int(blockIdx.x);
   rowbest += size_t(n) * L; colbest += size_t(n) * S;
+  const bool keep = L <= kKeep * FT;
+  int kj[kKeep];
+  float kt[kKeep];
+  uint32_t khit = 0;
   int c = 0, bad = 0;
   if (phase != 2) {
-    for (int i = threadIdx.x; i < L; i += FT) {
-      int j; float t2;
-      c += row_match(rowbest, colbest, L, S, i, g0, g1, j, t2) ? 1 : 0;
-      bad |= !isfinite(lse_r[size_t(n) * L + i]);
+    if (keep) {
+#pragma unroll
+      for (int k = 0; k < kKeep; ++k) {
+        const int i = k * FT + threadIdx.x;
+        kj[k] = 0; kt[k] = 0.f;
+        if (i < L) {
+          if (row_match(rowbest, colbest, L, S, i, g0, g1, kj[k], kt[k])) { khit |= 1u << k; ++c; }
+          bad |= !isfinite(lse_r[size_t(n) * L + i]);
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < L; i += FT) {
+        int j; float t2;
+        c += row_match(rowbest, colbest, L, S, i, g0, g1, j, t2) ? 1 : 0;
+        bad |= !isfinite(lse_r[size_t(n) * L + i]);
+      }
     }
     for (int j = threadIdx.x; j < S; j += FT) bad |= !isfinite(lse_c[size_t(n) * S + j]);
     c = block_sum(c, smem);
@@ -91,7 +118,7 @@ __global__ void __launch_bounds__(FT) count_emit_kernel(const u64* __restrict__ 
       const long long t0 = clock64();
       while (atomicAdd(ready + p, 0) == 0) {
         __nanosleep(64);
-        if (clock64() - t0 > 4000000000ll) __trap();   // never hang the GPU
+        if (clock64() - t0 > 4000000000ll) __trap();   // a pair with an earlier ticket always publishes: unreachable
       }
       __threadfence();
     }
@@ -104,10 +131,18 @@ __global__ void __launch_bounds__(FT) count_emit_kernel(const u64* __restrict__ 
     counts[n_pairs] = int32_t(min(int64_t(base + c), capacity));
     if (base + c > capacity) atomicOr(reinterpret_cast<unsigned*>(counts + n_pairs + 1), POPE_FLAG_CAPACITY);
   }
-  for (int i0 = 0; i0 < L; i0 += FT) {
+  for (int i0 = 0, k = 0; i0 < L; i0 += FT, ++k) {
     const int i = i0 + threadIdx.x;
     int j = 0; float t2 = 0.f;
-    const bool hit = (i < L) && row_match(rowbest, colbest, L, S, i, g0, g1, j, t2);
+    bool hit;
+    if (keep && phase == 0) {
+      hit = false;
+#pragma unroll
+      for (int q = 0; q < kKeep; ++q)
+        if (q == k) { hit = (khit >> q) & 1u; j = kj[q]; t2 = kt[q]; }
+    } else {
+      hit = (i < L) && row_match(rowbest, colbest, L, S, i, g0, g1, j, t2);
+    }
     const unsigned ballot = __ballot_sync(kFullMask, hit);
     __syncthreads();
     if (lane == 0) warp_off[warp] = __popc(ballot);
@@ -260,7 +295,10 @@ __global__ void __launch_bounds__(32 * kMergeWarps) colsum_reduce_kernel(const f
   __shared__ float s_m[kMergeWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = (blockIdx.x * 32 + lane) * VEC, n = blockIdx.y;
-  if (blockIdx.x == 0 && threadIdx.x == 0) ready[n] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ready[n] = 0;
+    if (n == 0) ready[gridDim.y] = 0;                 // the compaction kernel's ticket counter
+  }
   float acc[VEC], mtop = -INFINITY;
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;

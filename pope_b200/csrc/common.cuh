@@ -85,7 +85,7 @@ struct CoarseScratch {
   float* cminb;   // [n, ceil(L/32)]  minimum of cbound over each group of 32 rows
   float* colpart; // [n, ceil(L/32), S]  single-sweep tcgen05 path: column sums of 2^(x - shift) over each group of 32 rows
   float* cshift;  // [n, ceil(L/32), ceil(S/32)]  ... the shift of each (32-row group, 32-column block) of colpart
-  int* ready;     // [n]  count_emit_kernel: "this pair's count is published" (cleared before every call)
+  int* ready;     // [n + 1]  count_emit_kernel: "this pair's count is published", then its ticket counter (cleared before every call)
   int* pairflag;  // [n]  single-sweep path: != 0 = this pair is recomputed by the gated online-softmax launch
   size_t zero_bytes;   // rowbest, colbest, cand_cnt, ready are adjacent and cleared by one memset
   size_t bytes;
@@ -98,7 +98,7 @@ inline CoarseScratch carve_coarse_scratch(void* base, int n, int L, int S) {
   w.rowbest = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * L, 256);
   w.colbest = reinterpret_cast<u64*>(p + off); off += align_up(sizeof(u64) * size_t(n) * S, 256);
   w.cand_cnt = reinterpret_cast<int*>(p + off); off += align_up(sizeof(int) * size_t(n) * L * 2, 256);
-  w.ready = reinterpret_cast<int*>(p + off); off += align_up(sizeof(int) * size_t(n), 256);
+  w.ready = reinterpret_cast<int*>(p + off); off += align_up(sizeof(int) * (size_t(n) + 1), 256);
   w.zero_bytes = off;
   w.lse_r = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * L, 256);
   w.lse_c = reinterpret_cast<float*>(p + off); off += align_up(sizeof(float) * size_t(n) * S, 256);
