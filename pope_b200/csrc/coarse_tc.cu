@@ -231,7 +231,7 @@ struct SweepParams {
                             //       the pairs with pairflag[n] != 0 are swept
   int32_t* flags;
   unsigned long long* trace;   // developer diagnostics (POPE_TC_TRACE): clock stamps of CTA pair 0, or nullptr
-  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps, bit4 = no single sweep, bit5 = single sweep without the per-cell candidate scan, bit6 = no gated redo after the single sweep
+  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps, bit4 = no single sweep, bit5 = single sweep without the per-cell candidate scan, bits 8.. = the epilogue warp POPE_TC_TRACE stamps, bit6 = no gated redo after the single sweep
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -745,7 +745,12 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         const int col0 = ct * kTileCols;
         const int nvalid = min(LB - col0, kTileCols) - colofs;
         const bool active = rows_valid > 0 && nvalid > 0 && !(P.debug & 1);
+        // developer diagnostics: epilogue warp POPE_TC_TRACE_WARP (default 0) of CTA pair 0, leader CTA
+        const bool etr = TRACE && P.trace && pair == 0 && rank == 0 && warp == (P.debug >> 8) && lane == 0 && tile_ctr < kTraceTiles;
+        unsigned long long* erec = P.trace + size_t(kTraceTiles + tile_ctr) * 8;
+        if (etr) erec[0] = clock64();
         mbar_wait<POPE_VAR_WAIT_HINT>(bar_acc_full + 8 * s, acc_phase);
+        if (etr) erec[1] = clock64();
         tc_fence_after();
         const uint32_t tbase = tb0 + s * kTileCols;
         float v[32];
@@ -865,7 +870,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(bar_acc_empty + 8 * s);
+        if (etr) erec[2] = clock64();
         if (active && nvalid > 32) process(v, 1);
+        if (etr) erec[3] = clock64();
 #endif
         cp_ptr += kTileCols;
         cs_ptr += kTileCols / 32;
@@ -1235,11 +1242,12 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
   // per-device attribute, cheap: set on every call so that any device of a multi-GPU process is covered
   auto k0 = sweep_tc_kernel<0, false>, k1 = sweep_tc_kernel<1, false>, k2 = sweep_tc_kernel<2, false>;
   auto k3 = sweep_tc_kernel<3, false>;
-  if ((e = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   const char* trace_env = getenv("POPE_TC_TRACE");         // developer diagnostics: "0" / "2" = trace that sweep mode
   const int trace_mode = trace_env ? atoi(trace_env) : -1;
   if (trace_mode == 0) k0 = sweep_tc_kernel<0, true>;
   if (trace_mode == 2) k2 = sweep_tc_kernel<2, true>;
+  if (trace_mode == 3) k3 = sweep_tc_kernel<3, true>;
+  if ((e = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc)) != cudaSuccess) return e;
@@ -1266,6 +1274,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
       // single sweep over the rows of S: row sums, column partial sums and candidate lists in one pass; raises
       // POPE_FLAG_ROBUST_PATH when the unshifted exponentials leave the safe range (debug bit4 skips it)
       P.units_dir0 = u0; P.total_units = u0;
+      P.trace = trace_mode == 3 ? g_trace : nullptr;
       if ((e = cudaMemsetAsync(w.pairflag, 0, sizeof(int) * p.n, st)) != cudaSuccess) return e;
       k3<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, map0, map1, map0, map1, P);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;

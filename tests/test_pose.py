@@ -34,30 +34,50 @@ def oracle_out(gold):
                                  float(gold["thresh"]), float(gold["conf_hi"]), 1000, seed=0)
 
 
+PLANAR, SMALL_BASELINE = (10, 12), (11,)       # scenes appended by oracle/gen_golden_pose.py in round 2
+
+
 @pytest.mark.parametrize("tag", ["hi", "lo"])
 def test_oracle_against_reference_cv2(gold, oracle_out, tag):
     """The pin: same scenes through the reference's estimate_pose (metrics.py:69-94) at its default confidence 0.99999
     ("hi") and at the 0.99 of eval_onepose_json.py:164 ("lo").  RANSAC draws differ and neither side refines the winning
     minimal-sample model, so the bar is statistical: same None / not-None, rotations within 2 (3) degrees of cv2's and 1.5
-    (2) of the truth, inlier masks agreeing on more than 94 % (80 %) of the matches."""
+    (2) of the truth, inlier masks agreeing with cv2's on more than 94 % (90 %) of the matches, precision >= 99.5 % and
+    recall >= 93 % against the correspondences that were planted.  At 0.99 cv2 stops after 5-78 draws and sometimes keeps a
+    model that misses a fifth of the planted matches (pairs 0 and 6); there the masks may differ by more, but only if the
+    oracle recalls at least 5 points of a hundred more of the planted matches than cv2 does.
+    Near-degenerate geometry: planar scenes have a two-fold ambiguity that costs both sides accuracy (cv2 is 6.7 degrees off
+    on pair 10), so only the masks and a 6 degree bar against the truth are held; with a baseline of 1/225 of the depth
+    (pair 11) recoverPose's cheirality vote is decided by noise -- cv2 returns one inlier / None -- so the oracle is held to
+    the truth alone there (documented divergence)."""
     conf = float(gold[f"conf_{tag}"])
     out = oracle_out if tag == "hi" else O.estimate_pose_batch(gold["mkpts0"], gold["mkpts1"], gold["counts"], gold["K0"],
                                                               gold["K1"], float(gold["thresh"]), conf, 1000, seed=0)
-    r_cv, r_gt, agree = (2.0, 1.5, 0.94) if tag == "hi" else (3.0, 2.0, 0.80)
+    r_cv, r_gt, agree = (2.0, 1.5, 0.94) if tag == "hi" else (3.0, 2.0, 0.90)
     off = np.concatenate([[0], np.cumsum(gold["counts"])])
-    assert np.array_equal(out["status"], gold[f"status_cv2_{tag}"])
     for p, m in enumerate(gold["counts"]):
-        mask_o, mask_c = out["inliers"][off[p]:off[p + 1]], gold[f"inliers_cv2_{tag}"][off[p]:off[p + 1]]
+        mask_o, mask_c = out["inliers"][off[p]:off[p + 1]].astype(bool), gold[f"inliers_cv2_{tag}"][off[p]:off[p + 1]].astype(bool)
+        planted = gold["planted"][off[p]:off[p + 1]]
+        if p in SMALL_BASELINE:
+            assert out["status"][p] == 1 and rot_angle(out["R"][p], gold["R_gt"][p]) < 1.0
+            assert (mask_o & planted).sum() >= 0.995 * mask_o.sum() and (mask_o & planted).sum() >= 0.80 * planted.sum()
+            continue
+        assert out["status"][p] == gold[f"status_cv2_{tag}"][p]
         if not gold[f"status_cv2_{tag}"][p]:
             assert out["n_inliers"][p] == 0 and not mask_o.any()
             continue
         if m == 5:      # a bare minimal sample has several exact solutions; only the count is comparable
             assert mask_o.sum() == mask_c.sum() == 5
             continue
-        assert rot_angle(out["R"][p], gold[f"R_cv2_{tag}"][p]) < r_cv
-        assert rot_angle(out["R"][p], gold["R_gt"][p]) < r_gt
-        assert dir_angle(out["t"][p], gold["t_gt"][p]) < 6.0
-        assert np.mean(mask_o == mask_c) > agree, (p, np.mean(mask_o == mask_c))
+        if p in PLANAR:
+            assert rot_angle(out["R"][p], gold["R_gt"][p]) < 6.0
+        else:
+            assert rot_angle(out["R"][p], gold[f"R_cv2_{tag}"][p]) < r_cv
+            assert rot_angle(out["R"][p], gold["R_gt"][p]) < r_gt
+            assert dir_angle(out["t"][p], gold["t_gt"][p]) < 6.0
+        rec_o, rec_c = (mask_o & planted).sum() / planted.sum(), (mask_c & planted).sum() / planted.sum()
+        assert (mask_o & planted).sum() >= 0.995 * mask_o.sum() and rec_o >= 0.93, (p, rec_o)
+        assert np.mean(mask_o == mask_c) > agree or rec_o >= rec_c + 0.05, (p, np.mean(mask_o == mask_c), rec_o, rec_c)
         assert int(mask_o.sum()) >= 0.9 * int(mask_c.sum())
         assert abs(np.linalg.det(out["R"][p]) - 1.0) < 1e-9 and abs(np.linalg.norm(out["t"][p]) - 1.0) < 1e-9
 
