@@ -62,6 +62,9 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 // per thread; the data-movement warps need a fraction of that, the epilogue is short of registers at 96)
 constexpr int kWarpProducer = kEpiWarps, kWarpMma = kEpiWarps + 1;
 constexpr int kThreads = kEpiThreads + 128;
+#ifndef POPE_VAR_ABUFS
+#define POPE_VAR_ABUFS 1           // single sweep: stationary blocks of two consecutive units resident (2: measured slower, the ring shrinks to 5 stages) or one (1)
+#endif
 #ifndef POPE_VAR_LOADBOTH
 #define POPE_VAR_LOADBOTH 0        // 1: single sweep loads both chunks of a tile before any arithmetic
 #endif
@@ -488,13 +491,17 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
                 const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
                 const __grid_constant__ CUtensorMap map4, const __grid_constant__ CUtensorMap map5, const SweepParams P) {
   // shared-memory layout: MODE 4 keeps two stationary blocks (a1, a2) and a shorter ring
-  constexpr int kAChunks = (MODE == 4) ? 2 * kMaxKChunks : kMaxKChunks;
-  constexpr int kRing = (MODE == 4) ? 5 : kStages;
+  // MODE 3 keeps the stationary blocks of TWO consecutive units (the next unit's block is loaded while this unit's tiles
+  // are swept, so the tensor pipe does not drain at a unit boundary: the reload used to cost about one tile time in twenty)
+  // and, like MODE 4 with its two resident planes, a 5-stage ring
+  constexpr int kABufs = (MODE == 3) ? POPE_VAR_ABUFS : 1;
+  constexpr int kAChunks = (MODE == 4 || kABufs == 2) ? 2 * kMaxKChunks : kMaxKChunks;
+  constexpr int kRing = (MODE == 4 || kABufs == 2) ? 5 : kStages;
   constexpr int kSmemB = kSmemA + kAChunks * kBoxBytes;
   constexpr int kSmemLc = kSmemB + kRing * kBoxBytes;
   constexpr int kSmemMerge = kSmemLc + 2 * 2 * kTileCols * 4;
   constexpr int kSmemBar = kSmemMerge + 3 * 128 * 8;
-  constexpr int kSmemTmemPtr = kSmemBar + (2 + 2 * kRing + 4) * 8;
+  constexpr int kSmemTmemPtr = kSmemBar + (4 + 2 * kRing + 4) * 8;
   static_assert(kSmemTmemPtr + 16 + 1024 <= kSmemAlloc, "shared-memory layout exceeds the allocation");
   constexpr int kStages = kRing;                    // shadows the file-level ring depth inside the kernel
   extern __shared__ uint8_t smem_raw[];
@@ -505,8 +512,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   asm volatile("" : "+r"(sbase_pin));
   const uint32_t sbase = sbase_pin;
   const uint32_t bar0 = sbase + kSmemBar;
-  const uint32_t bar_a_full = bar0, bar_a_empty = bar0 + 8;
-  const uint32_t bar_b_full = bar0 + 16, bar_b_empty = bar_b_full + 8 * kStages;
+  const uint32_t bar_a_full = bar0, bar_a_empty = bar0 + 16;          // [2] each (one per resident stationary block)
+  const uint32_t bar_b_full = bar0 + 32, bar_b_empty = bar_b_full + 8 * kStages;
   const uint32_t bar_acc_full = bar_b_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 16;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
 
@@ -522,8 +529,10 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     prefetch_tmap(&map0);
     prefetch_tmap(&map1);
     // operand "full" barriers: one arrival (the leader's expect_tx) + the bytes of both CTAs' TMA loads
-    mbar_init(bar_a_full, 1);
-    mbar_init(bar_a_empty, 1);                       // one multicast tcgen05.commit
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_a_full + 8 * b, 1);
+      mbar_init(bar_a_empty + 8 * b, 1);             // one multicast tcgen05.commit
+    }
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);            // one multicast tcgen05.commit
@@ -561,12 +570,27 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   if (warp == kWarpProducer) {
     // =============================== TMA producer (both CTAs) ===============================
     if (lane == 0) {
-      uint32_t a_phase = 0, b_stage = 0, b_phase = 0;
+      uint32_t a_phase[2] = {0, 0}, b_stage = 0, b_phase = 0, unit_ctr = 0;
+      // stationary block of unit uu into buffer `buf` (waits until the MMAs of the unit that used the buffer before are done)
+      auto load_a = [&](int uu, uint32_t buf) {
+        int dir, n, rb;
+        decode(uu, dir, n, rb);
+        const CUtensorMap* mapA = dir ? &map1 : &map0;
+        const int arow = rb * kUnitRows + int(rank) * kBoxRows;
+        mbar_wait(bar_a_empty + 8 * buf, a_phase[buf] ^ 1);
+        if (rank == 0) mbar_expect_tx(bar_a_full + 8 * buf, (MODE == 4 ? 4 : 2) * kchunks * kBoxBytes);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          tma_load_3d_2sm(sbase + kSmemA + (buf * kMaxKChunks + kc) * kBoxBytes, mapA, bar_a_full + 8 * buf, kc * kBoxK, arow, n);
+          if (MODE == 4)      // a2 block behind the a1 block
+            tma_load_3d_2sm(sbase + kSmemA + (kMaxKChunks + kc) * kBoxBytes, &map1, bar_a_full, kc * kBoxK, arow, n);
+        }
+        a_phase[buf] ^= 1;
+      };
+      if (kABufs == 2 && pair < P.total_units) load_a(pair, 0);
       for (int u = pair; u < P.total_units; u += npairs) {
         int dir, n, rb;
         decode(u, dir, n, rb);
         if (skip_pair(n)) continue;
-        const CUtensorMap* mapA = dir ? &map1 : &map0;
         const CUtensorMap* mapB = dir ? &map0 : &map1;
         const int arow = rb * kUnitRows + int(rank) * kBoxRows;
         auto ring_load = [&](const CUtensorMap* mp, int kc, int row) {
@@ -575,19 +599,15 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           tma_load_3d_2sm(sbase + kSmemB + b_stage * kBoxBytes, mp, bar_b_full + 8 * b_stage, kc * kBoxK, row, n);
           if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
         };
-        if (!(P.debug & 4) || u == pair) {            // debug bit2: timing experiment, the stationary block is loaded once
-          mbar_wait(bar_a_empty, a_phase ^ 1);
-          if (rank == 0) mbar_expect_tx(bar_a_full, (MODE == 4 ? 4 : 2) * kchunks * kBoxBytes);
-          for (int kc = 0; kc < kchunks; ++kc) {
-            tma_load_3d_2sm(sbase + kSmemA + kc * kBoxBytes, mapA, bar_a_full, kc * kBoxK, arow, n);
-            if (MODE == 4)      // a2 block behind the a1 block
-              tma_load_3d_2sm(sbase + kSmemA + (kMaxKChunks + kc) * kBoxBytes, &map1, bar_a_full, kc * kBoxK, arow, n);
-          }
-          a_phase ^= 1;
-        }
+        if (kABufs == 1 && (!(P.debug & 4) || u == pair)) load_a(u, 0);   // debug bit2: timing experiment, loaded once
+        const uint32_t abuf = (kABufs == 2) ? (unit_ctr & 1u) : 0u;
+        ++unit_ctr;
         const int ntiles = ((dir ? P.L0 : P.L1) + kTileCols - 1) / kTileCols;
         for (int ct = 0; ct < ntiles; ++ct) {
           const int brow = ct * kTileCols + int(rank) * kBoxRows;
+          // two resident blocks: the next unit's block follows this unit's third tile into the queue -- by then the MMAs of
+          // the previous unit, which read the other buffer, have long completed, so the wait inside does not hold up the ring
+          if (kABufs == 2 && ct == min(2, ntiles - 1) && u + npairs < P.total_units) load_a(u + npairs, abuf ^ 1u);
           if (MODE == 4) {
             // ring order = the issuer's order: (a3[c], b1[c]) for every k-chunk, then the b2 chunks, then the b3 chunks
             for (int kc = 0; kc < kchunks; ++kc) { ring_load(&map2, kc, arow); ring_load(&map3, kc, brow); }
@@ -602,15 +622,18 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   } else if (warp == kWarpMma) {
     // =============================== MMA issuer (leader CTA only) ===============================
     if (rank == 0 && lane == 0) {
-      uint32_t a_phase = 0, b_stage = 0, b_phase = 0, tile_ctr = 0;
+      uint32_t a_phase[2] = {0, 0}, b_stage = 0, b_phase = 0, tile_ctr = 0, unit_ctr = 0;
       for (int u = pair; u < P.total_units; u += npairs) {
         int dir, n, rb;
         decode(u, dir, n, rb);
         if (skip_pair(n)) continue;
         const int ntiles = ((dir ? P.L0 : P.L1) + kTileCols - 1) / kTileCols;
-        if (!(P.debug & 4) || u == pair) {
-          mbar_wait(bar_a_full, a_phase);
-          a_phase ^= 1;
+        const uint32_t abuf = (kABufs == 2) ? (unit_ctr & 1u) : 0u;
+        ++unit_ctr;
+        const uint32_t a_base = sbase + kSmemA + abuf * (kMaxKChunks * kBoxBytes);
+        if (kABufs == 2 || !(P.debug & 4) || u == pair) {
+          mbar_wait(bar_a_full + 8 * abuf, a_phase[abuf]);
+          a_phase[abuf] ^= 1;
         }
         tc_fence_after();
         for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
@@ -672,7 +695,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             mbar_wait(bar_b_full + 8 * b_stage, b_phase);
             if (tr && kc == 0) rec[2] = clock64();
             tc_fence_after();
-            const uint32_t a_addr = sbase + kSmemA + kc * kBoxBytes;
+            const uint32_t a_addr = a_base + kc * kBoxBytes;
             const uint32_t b_addr = sbase + kSmemB + b_stage * kBoxBytes;
 #pragma unroll
             for (int ks = 0; ks < kBoxK / 16; ++ks)
@@ -684,7 +707,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           umma_commit_2sm(bar_acc_full + 8 * s);         // accumulator stage complete (both CTAs' epilogues)
           if (tr) rec[3] = clock64();
         }
-        if (!(P.debug & 4)) umma_commit_2sm(bar_a_empty);   // stationary blocks may be overwritten
+        if (kABufs == 2 || !(P.debug & 4)) umma_commit_2sm(bar_a_empty + 8 * abuf);   // the stationary block may be overwritten
       }
     }
   }
