@@ -62,9 +62,6 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 // per thread; the data-movement warps need a fraction of that, the epilogue is short of registers at 96)
 constexpr int kWarpProducer = kEpiWarps, kWarpMma = kEpiWarps + 1;
 constexpr int kThreads = kEpiThreads + 128;
-#ifndef POPE_VAR_ABUFS
-#define POPE_VAR_ABUFS 1           // single sweep: stationary blocks of two consecutive units resident (2: measured slower, the ring shrinks to 5 stages) or one (1)
-#endif
 #ifndef POPE_VAR_LOADBOTH
 #define POPE_VAR_LOADBOTH 0        // 1: single sweep loads both chunks of a tile before any arithmetic
 #endif
@@ -168,6 +165,17 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// one lane of a converged warp (the way the tensor-core instructions are issued: ptxas keeps their operands in uniform
+// registers when the single-thread region is entered through elect.sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok));
+  return ok != 0;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -234,7 +242,7 @@ struct SweepParams {
                             //       the pairs with pairflag[n] != 0 are swept
   int32_t* flags;
   unsigned long long* trace;   // developer diagnostics (POPE_TC_TRACE): clock stamps of CTA pair 0, or nullptr
-  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit2 = A loaded once, bit3 = force three sweeps, bit4 = no single sweep, bit5 = single sweep without the per-cell candidate scan, bits 8.. = the epilogue warp POPE_TC_TRACE stamps, bit6 = no gated redo after the single sweep
+  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit3 = force three sweeps, bit4 = no single sweep, bit5 = single sweep without the per-cell candidate scan, bits 8.. = the epilogue warp POPE_TC_TRACE stamps, bit6 = no gated redo after the single sweep
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -491,17 +499,13 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
                 const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
                 const __grid_constant__ CUtensorMap map4, const __grid_constant__ CUtensorMap map5, const SweepParams P) {
   // shared-memory layout: MODE 4 keeps two stationary blocks (a1, a2) and a shorter ring
-  // MODE 3 keeps the stationary blocks of TWO consecutive units (the next unit's block is loaded while this unit's tiles
-  // are swept, so the tensor pipe does not drain at a unit boundary: the reload used to cost about one tile time in twenty)
-  // and, like MODE 4 with its two resident planes, a 5-stage ring
-  constexpr int kABufs = (MODE == 3) ? POPE_VAR_ABUFS : 1;
-  constexpr int kAChunks = (MODE == 4 || kABufs == 2) ? 2 * kMaxKChunks : kMaxKChunks;
-  constexpr int kRing = (MODE == 4 || kABufs == 2) ? 5 : kStages;
+  constexpr int kAChunks = (MODE == 4) ? 2 * kMaxKChunks : kMaxKChunks;
+  constexpr int kRing = (MODE == 4) ? 5 : kStages;
   constexpr int kSmemB = kSmemA + kAChunks * kBoxBytes;
   constexpr int kSmemLc = kSmemB + kRing * kBoxBytes;
   constexpr int kSmemMerge = kSmemLc + 2 * 2 * kTileCols * 4;
   constexpr int kSmemBar = kSmemMerge + 3 * 128 * 8;
-  constexpr int kSmemTmemPtr = kSmemBar + (4 + 2 * kRing + 4) * 8;
+  constexpr int kSmemTmemPtr = kSmemBar + (2 * kMaxKChunks + 2 * kRing + 4) * 8;
   static_assert(kSmemTmemPtr + 16 + 1024 <= kSmemAlloc, "shared-memory layout exceeds the allocation");
   constexpr int kStages = kRing;                    // shadows the file-level ring depth inside the kernel
   extern __shared__ uint8_t smem_raw[];
@@ -512,8 +516,11 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   asm volatile("" : "+r"(sbase_pin));
   const uint32_t sbase = sbase_pin;
   const uint32_t bar0 = sbase + kSmemBar;
-  const uint32_t bar_a_full = bar0, bar_a_empty = bar0 + 16;          // [2] each (one per resident stationary block)
-  const uint32_t bar_b_full = bar0 + 32, bar_b_empty = bar_b_full + 8 * kStages;
+  // one full / empty pair per 64-wide k-chunk of the stationary block: a chunk is reloaded for the next unit as soon as the
+  // unit's LAST tile has read it, while the MMAs of the remaining chunks still run (the reload of the whole block after the
+  // unit's last MMA used to cost about one tile time in twenty)
+  const uint32_t bar_a_full = bar0, bar_a_empty = bar0 + 8 * kMaxKChunks;
+  const uint32_t bar_b_full = bar0 + 16 * kMaxKChunks, bar_b_empty = bar_b_full + 8 * kStages;
   const uint32_t bar_acc_full = bar_b_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 16;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
 
@@ -529,7 +536,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     prefetch_tmap(&map0);
     prefetch_tmap(&map1);
     // operand "full" barriers: one arrival (the leader's expect_tx) + the bytes of both CTAs' TMA loads
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kMaxKChunks; ++b) {
       mbar_init(bar_a_full + 8 * b, 1);
       mbar_init(bar_a_empty + 8 * b, 1);             // one multicast tcgen05.commit
     }
@@ -568,25 +575,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   if (warp >= kEpiWarps) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
   if (warp == kWarpProducer) {
-    // =============================== TMA producer (both CTAs) ===============================
+    // =============================== TMA producer of the streamed operand (both CTAs) ===============================
     if (lane == 0) {
-      uint32_t a_phase[2] = {0, 0}, b_stage = 0, b_phase = 0, unit_ctr = 0;
-      // stationary block of unit uu into buffer `buf` (waits until the MMAs of the unit that used the buffer before are done)
-      auto load_a = [&](int uu, uint32_t buf) {
-        int dir, n, rb;
-        decode(uu, dir, n, rb);
-        const CUtensorMap* mapA = dir ? &map1 : &map0;
-        const int arow = rb * kUnitRows + int(rank) * kBoxRows;
-        mbar_wait(bar_a_empty + 8 * buf, a_phase[buf] ^ 1);
-        if (rank == 0) mbar_expect_tx(bar_a_full + 8 * buf, (MODE == 4 ? 4 : 2) * kchunks * kBoxBytes);
-        for (int kc = 0; kc < kchunks; ++kc) {
-          tma_load_3d_2sm(sbase + kSmemA + (buf * kMaxKChunks + kc) * kBoxBytes, mapA, bar_a_full + 8 * buf, kc * kBoxK, arow, n);
-          if (MODE == 4)      // a2 block behind the a1 block
-            tma_load_3d_2sm(sbase + kSmemA + (kMaxKChunks + kc) * kBoxBytes, &map1, bar_a_full, kc * kBoxK, arow, n);
-        }
-        a_phase[buf] ^= 1;
-      };
-      if (kABufs == 2 && pair < P.total_units) load_a(pair, 0);
+      uint32_t b_stage = 0, b_phase = 0;
       for (int u = pair; u < P.total_units; u += npairs) {
         int dir, n, rb;
         decode(u, dir, n, rb);
@@ -599,15 +590,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           tma_load_3d_2sm(sbase + kSmemB + b_stage * kBoxBytes, mp, bar_b_full + 8 * b_stage, kc * kBoxK, row, n);
           if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
         };
-        if (kABufs == 1 && (!(P.debug & 4) || u == pair)) load_a(u, 0);   // debug bit2: timing experiment, loaded once
-        const uint32_t abuf = (kABufs == 2) ? (unit_ctr & 1u) : 0u;
-        ++unit_ctr;
         const int ntiles = ((dir ? P.L0 : P.L1) + kTileCols - 1) / kTileCols;
         for (int ct = 0; ct < ntiles; ++ct) {
           const int brow = ct * kTileCols + int(rank) * kBoxRows;
-          // two resident blocks: the next unit's block follows this unit's third tile into the queue -- by then the MMAs of
-          // the previous unit, which read the other buffer, have long completed, so the wait inside does not hold up the ring
-          if (kABufs == 2 && ct == min(2, ntiles - 1) && u + npairs < P.total_units) load_a(u + npairs, abuf ^ 1u);
           if (MODE == 4) {
             // ring order = the issuer's order: (a3[c], b1[c]) for every k-chunk, then the b2 chunks, then the b3 chunks
             for (int kc = 0; kc < kchunks; ++kc) { ring_load(&map2, kc, arow); ring_load(&map3, kc, brow); }
@@ -621,24 +606,27 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     }
   } else if (warp == kWarpMma) {
     // =============================== MMA issuer (leader CTA only) ===============================
-    if (rank == 0 && lane == 0) {
-      uint32_t a_phase[2] = {0, 0}, b_stage = 0, b_phase = 0, tile_ctr = 0, unit_ctr = 0;
+    // The whole warp walks the loops (so that every counter and address is warp-uniform and stays in uniform registers:
+    // with a single lane inside, the descriptors went through five R2UR broadcasts per MMA and a k-chunk took 130 clk
+    // longer to issue); lane 0 alone issues the tcgen05 instructions.
+    if (rank == 0) {
+      uint32_t a_phase = 0, b_stage = 0, b_phase = 0, tile_ctr = 0;
       for (int u = pair; u < P.total_units; u += npairs) {
         int dir, n, rb;
         decode(u, dir, n, rb);
         if (skip_pair(n)) continue;
         const int ntiles = ((dir ? P.L0 : P.L1) + kTileCols - 1) / kTileCols;
-        const uint32_t abuf = (kABufs == 2) ? (unit_ctr & 1u) : 0u;
-        ++unit_ctr;
-        const uint32_t a_base = sbase + kSmemA + abuf * (kMaxKChunks * kBoxBytes);
-        if (kABufs == 2 || !(P.debug & 4) || u == pair) {
-          mbar_wait(bar_a_full + 8 * abuf, a_phase[abuf]);
-          a_phase[abuf] ^= 1;
-        }
-        tc_fence_after();
+        // k-chunk kc of the stationary block: awaited before its first use in the unit's first tile, handed back to the
+        // loader right after its last use in the unit's last tile
+        auto a_wait = [&](int ct, int kc) {
+          if (ct == 0) { mbar_wait(bar_a_full + 8 * kc, a_phase); tc_fence_after(); }
+        };
+        auto a_done = [&](int ct, int kc) {
+          if (ct == ntiles - 1 && elect_one()) umma_commit_2sm(bar_a_empty + 8 * kc);
+        };
         for (int ct = 0; ct < ntiles; ++ct, ++tile_ctr) {
           const uint32_t s = tile_ctr & 1, acc_phase = (tile_ctr >> 1) & 1;
-          const bool tr = TRACE && P.trace && pair == 0 && tile_ctr < kTraceTiles;
+          const bool tr = TRACE && P.trace && pair == 0 && tile_ctr < kTraceTiles && lane == 0;
           unsigned long long* rec = P.trace + size_t(tile_ctr) * 8;
           if (tr) rec[0] = clock64() | ((unsigned long long)(ct == 0) << 63);   // top bit: first tile of a unit
           mbar_wait(bar_acc_empty + 8 * s, acc_phase ^ 1);
@@ -649,11 +637,11 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             // six products per k-chunk: (a1 + a2 + a3) b1, (a1 + a2) b2, a1 b3; a1 / a2 resident, a3 and b* from the ring
             uint32_t first = 0;
             auto mma4 = [&](uint32_t a_addr, uint32_t b_addr) {
+              if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < kBoxK / 16; ++ks) {
-                umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), first);
-                first = 1u;
+                for (int ks = 0; ks < kBoxK / 16; ++ks) umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), first | uint32_t(ks));
               }
+              first = 1u;
             };
             auto ring_wait = [&]() {
               mbar_wait(bar_b_full + 8 * b_stage, b_phase);
@@ -662,10 +650,11 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               return addr;
             };
             auto ring_done = [&]() {
-              umma_commit_2sm(bar_b_empty + 8 * b_stage);
+              if (elect_one()) umma_commit_2sm(bar_b_empty + 8 * b_stage);
               if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
             };
             for (int kc = 0; kc < kchunks; ++kc) {
+              a_wait(ct, kc);
               const uint32_t a3 = ring_wait();
               const uint32_t a3_stage = b_stage;
               uint32_t nxt = b_stage + 1 == kStages ? 0 : b_stage + 1;
@@ -689,29 +678,56 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
               const uint32_t b3 = ring_wait();
               mma4(sbase + kSmemA + kc * kBoxBytes, b3);
               ring_done();
+              a_done(ct, kc);                                      // (the a2 chunk was last read in the loop above)
             }
           } else
           for (int kc = 0; kc < kchunks; ++kc) {
+            a_wait(ct, kc);
             mbar_wait(bar_b_full + 8 * b_stage, b_phase);
             if (tr && kc == 0) rec[2] = clock64();
             tc_fence_after();
-            const uint32_t a_addr = a_base + kc * kBoxBytes;
+            const uint32_t a_addr = sbase + kSmemA + kc * kBoxBytes;
             const uint32_t b_addr = sbase + kSmemB + b_stage * kBoxBytes;
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < kBoxK / 16; ++ks)
-              umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), (kc | ks) ? 1u : 0u);
-            umma_commit_2sm(bar_b_empty + 8 * b_stage);  // ring slot free in both CTAs once these MMAs have read it
+              for (int ks = 0; ks < kBoxK / 16; ++ks)
+                umma_bf16(d, umma_desc(a_addr + ks * 32), umma_desc(b_addr + ks * 32), (kc | ks) ? 1u : 0u);
+              umma_commit_2sm(bar_b_empty + 8 * b_stage);  // ring slot free in both CTAs once these MMAs have read it
+            }
+            a_done(ct, kc);
             if (tr && kc < 4) rec[4 + kc] = clock64();    // this chunk's four MMAs and its commit are issued
             if (++b_stage == kStages) { b_stage = 0; b_phase ^= 1; }
           }
-          umma_commit_2sm(bar_acc_full + 8 * s);         // accumulator stage complete (both CTAs' epilogues)
+          if (elect_one()) umma_commit_2sm(bar_acc_full + 8 * s);         // accumulator stage complete (both CTAs' epilogues)
           if (tr) rec[3] = clock64();
         }
-        if (kABufs == 2 || !(P.debug & 4)) umma_commit_2sm(bar_a_empty + 8 * abuf);   // the stationary block may be overwritten
+        a_phase ^= 1;
+      }
+    }
+  } else if (warp == kWarpMma + 1) {
+    // =============================== TMA loader of the stationary operand (both CTAs) ===============================
+    // A thread of its own: the loads of a unit's block wait for MMAs that the streamed operand's producer is two tiles
+    // ahead of, so they cannot share a queue with it.
+    if (lane == 0) {
+      uint32_t a_phase = 0;
+      for (int u = pair; u < P.total_units; u += npairs) {
+        int dir, n, rb;
+        decode(u, dir, n, rb);
+        if (skip_pair(n)) continue;
+        const CUtensorMap* mapA = dir ? &map1 : &map0;
+        const int arow = rb * kUnitRows + int(rank) * kBoxRows;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(bar_a_empty + 8 * kc, a_phase ^ 1);
+          if (rank == 0) mbar_expect_tx(bar_a_full + 8 * kc, (MODE == 4 ? 4 : 2) * kBoxBytes);
+          tma_load_3d_2sm(sbase + kSmemA + kc * kBoxBytes, mapA, bar_a_full + 8 * kc, kc * kBoxK, arow, n);
+          if (MODE == 4)      // a2 block behind the a1 block
+            tma_load_3d_2sm(sbase + kSmemA + (kMaxKChunks + kc) * kBoxBytes, &map1, bar_a_full + 8 * kc, kc * kBoxK, arow, n);
+        }
+        a_phase ^= 1;
       }
     }
   }
-  // (warps 18-19 only complete the last warpgroup)
+  // (warp 19 only completes the last warpgroup)
   } else {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
   if (MODE == 3 || MODE == 4) {
