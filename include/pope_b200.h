@@ -77,7 +77,7 @@ int pope_coarse_auto_impl(int dtype, int L, int S, int C);
 size_t pope_coarse_workspace_bytes(int n_pairs, int L, int S);
 /* The same plus, for POPE_F32 features with C % 64 == 0 && C <= 256, room for the three bf16 planes of every feature
  * value that the tensor-core path for fp32 inputs works on (fp32 accuracy: a = a1 + a2 + a3, six products).  With a
- * workspace of this size POPE_COARSE_AUTO / POPE_COARSE_TCGEN05 run fp32 features on the tensor cores (thr > 1/8);
+ * workspace of this size POPE_COARSE_AUTO / POPE_COARSE_TCGEN05 run fp32 features on the tensor cores (thr > 0.15);
  * with the smaller one fp32 features run the fp32-FMA kernels. */
 size_t pope_coarse_workspace_bytes_ex(int n_pairs, int L, int S, int C, int dtype);
 

@@ -69,7 +69,7 @@ extern "C" int pope_coarse_match(const void* feat_c0, const void* feat_c1, int d
   p.border = border_rm; p.pixel_scale = pixel_scale;
 
   // fp32 features: the tensor-core path splits every value into three bf16 terms (fp32 accuracy) and needs the larger
-  // workspace of pope_coarse_workspace_bytes_ex; with the plain workspace (or thr <= 1/8) fp32 runs the fp32-FMA kernels
+  // workspace of pope_coarse_workspace_bytes_ex; with the plain workspace (or thr <= 0.15, two_sweeps_possible) fp32 runs the fp32-FMA kernels
   const size_t std_bytes = align_up(w.bytes, 256);
   const bool split_ok = coarse_tc_split_supported(p) && workspace_bytes >= std_bytes + coarse_tc_split_bytes(n_pairs, L, S, C);
   bool use_tc, use_split = false;

@@ -1225,7 +1225,7 @@ bool coarse_tc_supported(const CoarseProblem& p) {
   return p.dtype == POPE_BF16 && p.C % kBoxK == 0 && p.C >= kBoxK && p.C <= kBoxK * kMaxKChunks;
 }
 
-// fp32 features on the tensor cores through the three-way bf16 split (single-sweep path only: thr > 1/8)
+// fp32 features on the tensor cores through the three-way bf16 split (single-sweep path only: thr > 0.15)
 bool coarse_tc_split_supported(const CoarseProblem& p) {
   return p.dtype == POPE_F32 && p.C % kBoxK == 0 && p.C >= kBoxK && p.C <= kBoxK * kMaxKChunks && two_sweeps_possible(p) &&
          !(debug_knob() & (8 | 16));
