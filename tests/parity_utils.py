@@ -33,17 +33,25 @@ def oracle_with_margins(f0, f1, hw0_i, hw0_c, hw1_c, thr=O.THR, border_rm=O.BORD
     return out, mg
 
 
+PARITY_LOG = []     # one entry per compare_match_lists call: printed by tests/conftest.py at the end of the run
+
+
 def _fragile(b, i, js, mg, thr):
+    """None, "tie" (top-2 gap of the row / column maximum below TIE_REL: the class BASELINE's north star names) or
+    "thr" (a maximum within THR_REL of the threshold: the extension of that class, counted separately)."""
     rm, r2 = mg["conf_rowmax"][b, i], mg["conf_row2nd"][b, i]
-    if abs(rm - thr) <= THR_REL * thr or (rm - r2) <= TIE_REL * rm:
-        return True
+    if (rm - r2) <= TIE_REL * rm:
+        return "tie"
+    kind = "thr" if abs(rm - thr) <= THR_REL * thr else None
     for j in js:
         if j is None:
             continue
         cm, c2 = mg["conf_colmax"][b, j], mg["conf_col2nd"][b, j]
-        if abs(cm - thr) <= THR_REL * thr or (cm - c2) <= TIE_REL * cm:
-            return True
-    return False
+        if (cm - c2) <= TIE_REL * cm:
+            return "tie"
+        if abs(cm - thr) <= THR_REL * thr:
+            kind = "thr"
+    return kind
 
 
 def compare_match_lists(got, want, mg, thr=O.THR):
@@ -51,14 +59,23 @@ def compare_match_lists(got, want, mg, thr=O.THR):
     `bad` are lists of (b, i, j_got, j_want); `bad` must be empty for parity."""
     g = {(int(b), int(i)): int(j) for b, i, j in zip(got["b_ids"].tolist(), got["i_ids"].tolist(), got["j_ids"].tolist())}
     w = {(int(b), int(i)): int(j) for b, i, j in zip(want["b_ids"].tolist(), want["i_ids"].tolist(), want["j_ids"].tolist())}
-    same, near, bad = 0, [], []
+    same, near, bad, kinds = 0, [], [], {"tie": 0, "thr": 0}
     for key in sorted(set(g) | set(w)):
         jg, jw = g.get(key), w.get(key)
         if jg == jw:
             same += 1
             continue
         rec = (key[0], key[1], jg, jw)
-        (near if _fragile(key[0], key[1], (jg, jw), mg, thr) else bad).append(rec)
+        kind = _fragile(key[0], key[1], (jg, jw), mg, thr)
+        if kind:
+            kinds[kind] += 1
+            near.append(rec)
+        else:
+            bad.append(rec)
+    import inspect
+    caller = next((f.function for f in inspect.stack()[1:] if f.function.startswith("test_")), "?")
+    PARITY_LOG.append({"test": caller, "rows_compared": same + len(near) + len(bad), "identical": same,
+                       "near_tie": kinds["tie"], "near_threshold": kinds["thr"], "unexplained": len(bad)})
     return same, near, bad
 
 

@@ -1,6 +1,7 @@
 """Parity of the CUDA path (through the C ABI) against the reference-generated golden fixtures and the oracle.
 Run on the B200 box:  python -m pytest tests -m gpu"""
 import json
+import math
 import os
 
 import numpy as np
@@ -129,6 +130,32 @@ def test_coarse_large_norm_stays_on_the_single_sweep(dtype):
     same, near, bad = compare_match_lists(out, want, mg)
     assert not bad, bad[:5]
     assert same > 1500 and len(near) <= 6
+    if not near:
+        assert torch.allclose(out["mconf"], want["mconf"], rtol=1e-2 if dtype == torch.bfloat16 else 1e-4, atol=0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_coarse_shift_rises_along_the_sweep(dtype):
+    """Columns whose norm grows geometrically from the first to the last tile (x1 ... x2.5: the planted similarities climb
+    from ~20 to ~100 log2 units along a row), so that an epilogue warp has to RAISE its shift several times while it sweeps
+    a row block (a raise is due whenever a cell exceeds the largest one so far by 14 units; the running row sums are
+    rescaled each time), and rows scaled the other way so that the 32-row groups start from different shifts and the column
+    merge has to combine partial sums taken under different shifts.  The spread inside a 32-row group (~95 units) is within
+    what one shift holds (186), so the pair must stay on the single sweep; results equal the oracle."""
+    h0, w0, h1, w1 = 40, 48, 36, 56
+    L, S = h0 * w0, h1 * w1
+    _need_tc("tcgen05", 256, L, S)
+    f0, f1 = synth.coarse_features(95, 2, L, S, 256, sigma=1.2, noise=0.2, dtype=torch.float32)
+    col_gain = torch.logspace(0, math.log10(2.5), S)                    # image-1 cells: x1 .. x2.5 in sweep order
+    row_gain = torch.logspace(math.log10(2.0), 0, L)                    # image-0 cells: x2 .. x1
+    f1 = (f1 * col_gain[None, :, None]).to(dtype)
+    f0 = (f0 * row_gain[None, :, None]).to(dtype)
+    want, mg = oracle_with_margins(f0.float(), f1.float(), (h0 * 8, w0 * 8), (h0, w0), (h1, w1))
+    out = _run_coarse(f0, f1, (h0, w0), (h1, w1), _lib.COARSE_TCGEN05, dtype)
+    assert out["_flags"] == 0
+    same, near, bad = compare_match_lists(out, want, mg)
+    assert not bad, bad[:5]
+    assert same > 500 and len(near) <= 6
     if not near:
         assert torch.allclose(out["mconf"], want["mconf"], rtol=1e-2 if dtype == torch.bfloat16 else 1e-4, atol=0)
 
