@@ -61,6 +61,14 @@ NORM49_SIGMA = 49.0 / 16.0           # |f| = sigma * sqrt(256)
 TRAFFIC_CSV = os.path.join(ROOT, "profiles", "r2_ncu_step.csv")
 
 
+def workload_config(n):
+    """The workload both arms are run on (the reference arm times a bounded sample of it per step): identical in both lines."""
+    return {"workload": ("batch of 64 pairs at 480x640, coarse+fine matching (BASELINE configs[1])" if n == 64 else
+                         f"batch of {n} pairs at 480x640, coarse+fine matching"),
+            "pairs_per_gpu_per_step": n, "coarse_tokens": [HC, WC], "d_coarse": C_COARSE, "d_fine": C_FINE, "window": WIN,
+            "l2_policy": "inputs_exceed_l2 (2.8 GB of features per step vs 126 MB L2)"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -245,8 +253,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "480x640 pairs, coarse 60x80 tokens d=256 + fine 5x5 windows d=128 (BASELINE configs[1])",
-                   "pairs_per_step": n},
+        "config": workload_config(args.pairs),
+        "details": {"pairs_per_step_timed": n, "note": "every step times a bounded sample of the workload's batch on the host cores"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -596,15 +604,11 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "batch of 64 pairs at 480x640, coarse+fine matching (BASELINE configs[1])" if n == 64 else
-                   f"batch of {n} pairs at 480x640, coarse+fine matching",
-                   "pairs_per_gpu_per_step": n, "coarse_tokens": [HC, WC], "d_coarse": C_COARSE, "d_fine": C_FINE,
-                   "window": WIN, "coarse_impl": ("tcgen05" if dtype == torch.bfloat16 else "tcgen05 on a three-way bf16 split of the fp32 features") if tc else "simt-fp32fma", "fine_map_layout": "channels_last",
-                   "l2_policy": "inputs_exceed_l2 (2.8 GB of features per step vs 126 MB L2)",
-                   "streams": n_streams,
-                   "matches_per_step": M, "flags": flags,
-                   "gather": ("one NCCL gather of the job's live 20-byte match records to rank 0 after the K steps (inside the "
-                              "timed region; receive buffer preallocated)") if world > 1 else "none"},
+        "config": workload_config(n),
+        "details": {"coarse_impl": ("tcgen05" if dtype == torch.bfloat16 else "tcgen05 on a three-way bf16 split of the fp32 features") if tc else "simt-fp32fma",
+                    "fine_map_layout": "channels_last", "streams": n_streams, "matches_per_step": M, "flags": flags,
+                    "gather": ("one NCCL gather of the job's live 20-byte match records to rank 0 after the K steps (inside the "
+                               "timed region; receive buffer preallocated)") if world > 1 else "none"},
         "clocks": clocks,
         "stage_ms": {"coarse": coarse_ms, "fine_gather_match_fused": fine_ms},
         "one_stream": {"value": n / ((coarse_ms + fine_ms) / 1e3), "unit": UNIT, "ms_per_step": coarse_ms + fine_ms,
