@@ -8,6 +8,7 @@
 //   drain stream  : device -> host copies of chunk k-1
 // One host synchronisation at the very end.
 #include <new>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -161,12 +162,21 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
   // addressable under UVA) the fused fine kernel fetches those pixels straight from host memory (M x 256 B per chunk
   // instead of copying the whole 1/2-resolution map); pageable buffers fall back to the bulk copy.
   const char* f0_dev_view = nullptr;
-  {
+  const char* f1_dev_view = nullptr;
+  auto host_view = [](const void* p) -> const char* {
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, feat_f0) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
-      f0_dev_view = static_cast<const char*>(attr.devicePointer);
-    else
-      cudaGetLastError();   // clear the "invalid value" some drivers report for pageable pointers
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      return static_cast<const char*>(attr.devicePointer);
+    cudaGetLastError();   // clear the "invalid value" some drivers report for pageable pointers
+    return nullptr;
+  };
+  f0_dev_view = host_view(feat_f0);
+  // Image 1's 5x5 windows are read in place as well when its buffer is page-locked: M x 25 x 256 B per chunk (16.3 MB per
+  // 480x640 pair at 2 544 matches) instead of the whole 19.7 MB map; the reads reach ~90 % of the link's copy rate, which
+  // nets +5 % end to end (profiles/r2_history.md).  POPE_PIPELINE_WINDOWS_IN_PLACE=0 restores the bulk copy.
+  {
+    const char* env = getenv("POPE_PIPELINE_WINDOWS_IN_PLACE");
+    if (!(env && env[0] == '0')) f1_dev_view = host_view(feat_f1);
   }
   int64_t h2d = 0;
   int32_t flag_acc = 0;
@@ -187,15 +197,17 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
     PL_CUDA(cudaMemcpyAsync(s.fc1, static_cast<const char*>(feat_c1) + p0 * fc1_pair, n * fc1_pair, cudaMemcpyHostToDevice, pl->s_copy));
     if (!f0_dev_view)
       PL_CUDA(cudaMemcpyAsync(s.ff0, static_cast<const char*>(feat_f0) + p0 * ff0_pair, n * ff0_pair, cudaMemcpyHostToDevice, pl->s_copy));
-    h2d += int64_t(n) * int64_t(fc0_pair + fc1_pair + ff1_pair + (f0_dev_view ? 0 : ff0_pair));
-    PL_CUDA(cudaMemcpyAsync(s.ff1, static_cast<const char*>(feat_f1) + p0 * ff1_pair, n * ff1_pair, cudaMemcpyHostToDevice, pl->s_copy));
+    h2d += int64_t(n) * int64_t(fc0_pair + fc1_pair + (f1_dev_view ? 0 : ff1_pair) + (f0_dev_view ? 0 : ff0_pair));
+    if (!f1_dev_view)
+      PL_CUDA(cudaMemcpyAsync(s.ff1, static_cast<const char*>(feat_f1) + p0 * ff1_pair, n * ff1_pair, cudaMemcpyHostToDevice, pl->s_copy));
     PL_CUDA(cudaEventRecord(s.uploaded, pl->s_copy));
     PL_CUDA(cudaStreamWaitEvent(pl->s_comp, s.uploaded, 0));
     rc = pope_coarse_match(s.fc0, s.fc1, pl->dtype, n, pl->L, pl->S, pl->C, pl->h0c, pl->w0c, pl->h1c, pl->w1c,
                            pl->pixel_scale, pl->temperature, pl->thr, pl->border, pl->impl, s.ws, pl->ws_bytes, s.b_ids,
                            s.i_ids, s.j_ids, s.mconf, s.mk0, s.mk1, s.counts, int64_t(capt), pl->s_comp);
     if (rc) goto fail;
-    rc = pope_fine_match_maps(f0_dev_view ? static_cast<const void*>(f0_dev_view + p0 * ff0_pair) : s.ff0, s.ff1, pl->dtype, n, pl->Cf, Hf0, Wf0, st0, Hf1, Wf1, st1, pl->w0c, pl->w1c,
+    rc = pope_fine_match_maps(f0_dev_view ? static_cast<const void*>(f0_dev_view + p0 * ff0_pair) : s.ff0,
+                              f1_dev_view ? static_cast<const void*>(f1_dev_view + p0 * ff1_pair) : s.ff1, pl->dtype, n, pl->Cf, Hf0, Wf0, st0, Hf1, Wf1, st1, pl->w0c, pl->w1c,
                               pl->fstride, pl->W, s.b_ids, s.i_ids, s.j_ids, int64_t(capt), s.counts + n, nullptr, s.mk1,
                               coord_scale, s.expec, s.mk1f, pl->s_comp);
     if (rc) goto fail;
@@ -220,6 +232,7 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
     int64_t m = 0;
     for (int p = 0; p < n_pairs; ++p) m += counts[p];
     h2d += m * int64_t(Cf * e);
+    if (f1_dev_view) h2d += m * int64_t(pl->W * pl->W) * int64_t(Cf * e);   // (upper bound: overlapping windows may hit L2)
   }
   pl->last_h2d_bytes = h2d;
   return POPE_OK;

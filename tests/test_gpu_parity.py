@@ -529,14 +529,24 @@ def test_host_pipeline_equals_device_path():
     m = res.total()
     # pageable host buffers (bulk copies of everything) ...
     out = driver.match_pairs_host(f0, f1, ff0, ff1, (h * 8, w * 8), (h, w), (h, w), chunk_pairs=2, device=0)
-    # ... and page-locked ones (image 0's centre pixels are read in place by the fine kernel, its map is not copied)
-    pl = driver.Pipeline(torch.bfloat16, 2, (h * 8, w * 8), (h, w), (h, w), device=0)
+    # ... and page-locked ones: the fine kernel reads image 0's centre pixels and image 1's 5x5 windows in place over the host
+    # link, neither fine map is copied (POPE_PIPELINE_WINDOWS_IN_PLACE=0: image 1's map is copied in bulk as before)
     nhwc0, nhwc1 = ff0.permute(0, 2, 3, 1).contiguous().pin_memory(), ff1.permute(0, 2, 3, 1).contiguous().pin_memory()
-    out_pinned = pl.run(f0.pin_memory(), f1.pin_memory(), nhwc0, nhwc1)
     full = sum(t.numel() * t.element_size() for t in (f0, f1, nhwc0, nhwc1))
-    assert pl.last_h2d_bytes == full - nhwc0.numel() * 2 + m * 128 * 2
-    pl.close()
-    for o in (out, out_pinned):
+    outs = [out]
+    for in_place in ("1", "0"):
+        os.environ["POPE_PIPELINE_WINDOWS_IN_PLACE"] = in_place
+        try:
+            pl = driver.Pipeline(torch.bfloat16, 2, (h * 8, w * 8), (h, w), (h, w), device=0)
+            outs.append(pl.run(f0.pin_memory(), f1.pin_memory(), nhwc0, nhwc1))
+            want = full - nhwc0.numel() * 2 + m * 128 * 2
+            if in_place == "1":
+                want += -nhwc1.numel() * 2 + m * 25 * 128 * 2
+            assert pl.last_h2d_bytes == want
+            pl.close()
+        finally:
+            del os.environ["POPE_PIPELINE_WINDOWS_IN_PLACE"]
+    for o in outs:
         assert int(o["counts"].sum()) == m
         cat = driver.flatten_slots(o)
         for k in ("b_ids", "i_ids", "j_ids"):
