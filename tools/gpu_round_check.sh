@@ -10,3 +10,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"sweep_tc|colsum|cand_eval|count_emit|fine_match" -s 5 -c 6 -o gpurun_out/r2_step -f python tools/profile_step.py 64 3 > gpurun_out/ncu_full.log 2>&1
 ncu -i gpurun_out/r2_step.ncu-rep --page raw --csv > gpurun_out/r2_step_raw.csv 2>/dev/null
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/sweeps.log
+python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; echo "ref rc=$?"
