@@ -15,7 +15,7 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 hi = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 dev = torch.device("cuda:0")
 t0 = time.time()
-tot = dict(cases=0, same=0, near=0, bad=0, conf_fail=0, fine_fail=0, flagged=0, empty=0)
+tot = dict(cases=0, same=0, near=0, bad=0, conf_fail=0, fine_fail=0, flagged=0, empty=0, robust_path=0)
 for case in range(cases):
     n = int(rng.integers(1, 4))
     h0, w0, h1, w1 = (int(rng.integers(3, hi + 1)) for _ in range(4))
@@ -24,12 +24,18 @@ for case in range(cases):
     thr = float(rng.choice([0.05, 0.1, 0.2, 0.3, 0.5, 0.9]))
     border = int(rng.integers(0, 3))
     temp = float(rng.choice([0.1, 0.1, 0.2, 0.05]))
-    sigma = float(rng.uniform(0.5, 1.3))
+    # a third of the cases with large norms (token norm up to 64: similarities in the hundreds of log2 units at T = 0.05)
+    sigma = float(rng.uniform(0.5, 1.3)) if rng.random() < 0.67 else float(rng.uniform(1.3, 4.0))
     noise = float(rng.choice([0.0, 0.1, 0.3, 0.6]))
     planted = float(rng.uniform(0.0, 1.0))
     impl = _lib.COARSE_SIMT if rng.random() < 0.25 else _lib.COARSE_AUTO
     L, S = h0 * w0, h1 * w1
     f0, f1 = synth.coarse_features(1000 + case, n, L, S, C, sigma=sigma, planted=planted, noise=noise, dtype=dtype)
+    if rng.random() < 0.2:                                      # norms that grow / shrink along the sweep: the lazy shift must rise
+        g1 = torch.logspace(0, float(rng.uniform(0.0, 0.5)), S)
+        g0 = torch.logspace(float(rng.uniform(0.0, 0.3)), 0, L)
+        f1 = (f1.float() * (g1 if rng.random() < 0.5 else g1.flip(0))[None, :, None]).to(dtype)
+        f0 = (f0.float() * g0[None, :, None]).to(dtype)
     if rng.random() < 0.15:                                     # duplicated rows: exact ties
         f1[:, : S // 2] = f1[:, S - S // 2:]
     ff0, _ = synth.fine_feature_maps(2000 + case, n, h0 * 4, w0 * 4, 128, dtype=dtype)
@@ -47,6 +53,7 @@ for case in range(cases):
         tot["flagged"] += 1
         print(desc, "-> flags", flags)
         continue
+    tot["robust_path"] += int(bool(flags & _lib.FLAG_ROBUST_PATH))
     m = res.total()
     got = {k: res[k][:m].cpu() for k in ("b_ids", "i_ids", "j_ids", "mconf", "mkpts0_f", "mkpts1_f")}
     want, mg = oracle_with_margins(f0.float(), f1.float(), (h0 * 8, w0 * 8), (h0, w0), (h1, w1), thr=thr, border_rm=border,
