@@ -384,6 +384,19 @@ def retrieval_block(dev):
         ms, r = _timed(lambda: ops.cosine_topk(q, refs, 3), 20, dev, warm=3)
         byts = 257 * D * q.element_size()
         out[name] = {"us_per_query": ms * 1e3, "gbs": byts / (ms / 1e3) / 1e9, "top3": r[2].tolist()}
+        try:        # the same call replayed from a CUDA graph: what the kernels take without the Python / launch overhead
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                ops.cosine_topk(q, refs, 3)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    keep = ops.cosine_topk(q, refs, 3)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            gms, _ = _timed(graph.replay, 50, dev, warm=3)
+            out[name].update(us_per_query_graph=gms * 1e3, gbs_graph=byts / (gms / 1e3) / 1e9, top3_graph=keep[2].tolist())
+        except Exception as e:
+            out[name]["graph_error"] = repr(e)[:200]
     try:
         from pope_b200.dino_vit import DinoViT
         torch.manual_seed(3)

@@ -4,6 +4,8 @@
 //   score = F.cosine_similarity(ref_fea, fea, dim=1, eps=1e-8); if (score.item() > similarity_score).any(): ...
 // of eval_linemod_json.py:94-101 (one `.item()` host sync per crop in the reference; none here).
 // torch's cosine_similarity normalises each vector by max(|v|, eps) before the dot product.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pope {
@@ -29,8 +31,8 @@ template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bflo
 // One CTA per reference row (kCosThreads threads): HBM-bound for long rows (the patch-token shape streams 50-100 MB), so
 // every thread keeps several 16-byte loads of the row in flight; the query is re-read from L2.  VEC: rows are 16-byte
 // aligned and D % 8 == 0.
-constexpr int kCosThreads = 128;
-template <typename T, bool VEC>
+constexpr int kCosThreadsShort = 128, kCosThreadsLong = 1024;    // long rows (>= 64 KB): 256 rows must fill 148 SMs by themselves
+template <typename T, bool VEC, int kCosThreads>
 __global__ void __launch_bounds__(kCosThreads) cosine_kernel(const T* __restrict__ q, const T* __restrict__ refs, int R, int D,
                                                             float eps, float* __restrict__ scores) {
   __shared__ float red[3][kCosThreads / 32];
@@ -80,6 +82,48 @@ __global__ void __launch_bounds__(kCosThreads) cosine_kernel(const T* __restrict
   }
 }
 
+// The eval loop's slot update (eval_linemod_json.py:95-101) over nr scores in shared memory, continuing from the slots in
+// registers: `if (score > slots).any(): slots[argmin(slots)] = score` -- i.e. a score enters iff it exceeds the smallest slot
+// (first arg-min, like np.argmin).  Slots live in registers (fully unrolled over kTopkMaxK) and the smallest slot is cached:
+// one shared-memory load and one compare per crop once the slots have filled (walking the slots in shared memory cost
+// ~150 clk per crop: 20 us for 256 crops, the whole cost of the CLS-token case).
+struct TopkSlots {
+  float ss[16];
+  int si[16];
+  float smin;
+  int lo;
+};
+__device__ __forceinline__ void topk_init(TopkSlots& T, int k) {
+#pragma unroll
+  for (int t = 0; t < 16; ++t) { T.ss[t] = t < k ? 0.f : INFINITY; T.si[t] = -1; }
+  T.smin = 0.f;
+  T.lo = 0;
+}
+__device__ __forceinline__ void topk_feed(TopkSlots& T, const float* sc, int nr, int r0) {
+  auto feed = [&](float s, int r) {
+    if (!(s > T.smin)) return;
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      if (t == T.lo) { T.ss[t] = s; T.si[t] = r0 + r; }
+    T.smin = T.ss[0];
+    T.lo = 0;
+#pragma unroll
+    for (int t = 1; t < 16; ++t)
+      if (T.ss[t] < T.smin) { T.smin = T.ss[t]; T.lo = t; }     // (slots past k hold +inf)
+  };
+  int r = 0;
+  for (; r + 4 <= nr; r += 4) {                                  // sc is 16-byte aligned: four crops per load
+    const float4 v = *reinterpret_cast<const float4*>(sc + r);
+    feed(v.x, r); feed(v.y, r + 1); feed(v.z, r + 2); feed(v.w, r + 3);
+  }
+  for (; r < nr; ++r) feed(sc[r], r);
+}
+__device__ __forceinline__ void topk_store(const TopkSlots& T, int k, float* slot_scores, int32_t* slot_idx) {
+#pragma unroll
+  for (int t = 0; t < 16; ++t)
+    if (t < k) { slot_scores[t] = T.ss[t]; slot_idx[t] = T.si[t]; }
+}
+
 // Sequential by construction (slot order depends on arrival order); R is a few hundred.  The scores are staged in shared
 // memory by the whole block first: one thread walking global memory pays a full L2 round trip per crop (measured 50 us
 // for R = 256).
@@ -87,31 +131,93 @@ constexpr int kTopkThreads = 256, kTopkChunk = 2048, kTopkMaxK = 16;
 __global__ void __launch_bounds__(kTopkThreads) running_topk_kernel(const float* __restrict__ scores, int R, int k,
                                                                    float* __restrict__ slot_scores,
                                                                    int32_t* __restrict__ slot_idx) {
-  __shared__ float sc[kTopkChunk];
-  __shared__ float ss[kTopkMaxK];
-  __shared__ int si[kTopkMaxK];
-  if (threadIdx.x == 0)
-    for (int t = 0; t < k; ++t) { ss[t] = 0.f; si[t] = -1; }
+  __shared__ __align__(16) float sc[kTopkChunk];
+  TopkSlots T;
+  topk_init(T, k);
   for (int r0 = 0; r0 < R; r0 += kTopkChunk) {
     const int nr = min(kTopkChunk, R - r0);
     __syncthreads();
     for (int r = threadIdx.x; r < nr; r += kTopkThreads) sc[r] = scores[r0 + r];
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int r = 0; r < nr; ++r) {
-        const float s = sc[r];
-        bool any = false;
-        int lo = 0;
-        for (int t = 0; t < k; ++t) {
-          any |= s > ss[t];
-          if (ss[t] < ss[lo]) lo = t;     // first arg-min, like np.argmin
+    if (threadIdx.x == 0) topk_feed(T, sc, nr, r0);
+  }
+  if (threadIdx.x == 0) topk_store(T, k, slot_scores, slot_idx);
+}
+
+// The CLS-token case of the eval loop (R = a few hundred crops, D = 384: 0.4 MB) is bound by launch latency, not by memory:
+// ONE CTA computes all scores (a warp per row, rows w, w + 32, ...; same per-lane accumulation and shuffle order for every
+// row) and then runs the slot update over them -- one launch instead of two and no trip through global memory in between.
+constexpr int kSmallThreads = 1024, kSmallMaxBytes = 2 << 20;
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kSmallThreads) cosine_topk_small_kernel(const T* __restrict__ q, const T* __restrict__ refs, int R,
+                                                                          int D, float eps, int k, float* __restrict__ scores,
+                                                                          float* __restrict__ slot_scores,
+                                                                          int32_t* __restrict__ slot_idx) {
+  __shared__ __align__(16) float sc[kTopkChunk];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float qq = 0.f;                                   // |q|^2: every warp computes it once, in the order it uses for the rows
+  if (VEC) {
+    for (int d = lane * 8; d < D; d += 256) {
+      float a[8];
+      load8<T>(q + d, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) qq = fmaf(a[e], a[e], qq);
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) { const float a = to_f<T>(q[d]); qq = fmaf(a, a, qq); }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) qq += __shfl_xor_sync(kFullMask, qq, o);
+  // four rows of the warp at a time: their loads are in flight together (a warp has R / 32 rows; one at a time pays a full
+  // memory round trip per row)
+  constexpr int kRowsAtOnce = 4, kWarps = kSmallThreads / 32;
+  for (int r0 = warp; r0 < R; r0 += kRowsAtOnce * kWarps) {
+    float xx[kRowsAtOnce], qx[kRowsAtOnce];
+#pragma unroll
+    for (int u = 0; u < kRowsAtOnce; ++u) xx[u] = qx[u] = 0.f;
+    if (VEC) {
+      for (int d = lane * 8; d < D; d += 256) {
+        float a[8], b[kRowsAtOnce][8];
+#pragma unroll
+        for (int u = 0; u < kRowsAtOnce; ++u) {
+          const int r = min(r0 + u * kWarps, R - 1);            // (rows past the end repeat the last one; not stored)
+          load8<T>(refs + size_t(r) * D + d, b[u]);
         }
-        if (any) { ss[lo] = s; si[lo] = r0 + r; }
+        load8<T>(q + d, a);
+#pragma unroll
+        for (int u = 0; u < kRowsAtOnce; ++u)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { xx[u] = fmaf(b[u][e], b[u][e], xx[u]); qx[u] = fmaf(a[e], b[u][e], qx[u]); }
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) {
+        const float a = to_f<T>(q[d]);
+#pragma unroll
+        for (int u = 0; u < kRowsAtOnce; ++u) {
+          const float b = to_f<T>(refs[size_t(min(r0 + u * kWarps, R - 1)) * D + d]);
+          xx[u] = fmaf(b, b, xx[u]); qx[u] = fmaf(a, b, qx[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRowsAtOnce; ++u) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) { xx[u] += __shfl_xor_sync(kFullMask, xx[u], o); qx[u] += __shfl_xor_sync(kFullMask, qx[u], o); }
+      const int r = r0 + u * kWarps;
+      if (lane == 0 && r < R) {
+        const float sres = qx[u] / (fmaxf(sqrtf(qq), eps) * fmaxf(sqrtf(xx[u]), eps));
+        sc[r] = sres;
+        scores[r] = sres;
       }
     }
   }
   __syncthreads();
-  if (threadIdx.x < k) { slot_scores[threadIdx.x] = ss[threadIdx.x]; slot_idx[threadIdx.x] = si[threadIdx.x]; }
+  if (threadIdx.x == 0) {
+    TopkSlots T;
+    topk_init(T, k);
+    topk_feed(T, sc, R, 0);
+    topk_store(T, k, slot_scores, slot_idx);
+  }
 }
 
 // Match-list consumer of the eval loop (eval_linemod_json.py:118-119, :146): for every pair the number of matches with
@@ -247,17 +353,33 @@ extern "C" int pope_cosine_topk(const void* q, const void* refs, int dtype, int 
   const size_t esz = dtype == POPE_BF16 ? 2 : 4;
   const bool vec = D % 8 == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(refs)) & 15u) == 0 &&
                    (size_t(D) * esz) % 16 == 0;
-  if (dtype == POPE_BF16) {
-    const __nv_bfloat16* qq = static_cast<const __nv_bfloat16*>(q);
-    const __nv_bfloat16* rr = static_cast<const __nv_bfloat16*>(refs);
-    if (vec) cosine_kernel<__nv_bfloat16, true><<<R, kCosThreads, 0, st>>>(qq, rr, R, D, eps, scores);
-    else cosine_kernel<__nv_bfloat16, false><<<R, kCosThreads, 0, st>>>(qq, rr, R, D, eps, scores);
-  } else {
-    const float* qq = static_cast<const float*>(q);
-    const float* rr = static_cast<const float*>(refs);
-    if (vec) cosine_kernel<float, true><<<R, kCosThreads, 0, st>>>(qq, rr, R, D, eps, scores);
-    else cosine_kernel<float, false><<<R, kCosThreads, 0, st>>>(qq, rr, R, D, eps, scores);
+  if (R <= kTopkChunk && size_t(R) * D * esz <= size_t(kSmallMaxBytes)) {      // small problems: one launch, one CTA
+    if (dtype == POPE_BF16) {
+      const __nv_bfloat16* qq = static_cast<const __nv_bfloat16*>(q);
+      const __nv_bfloat16* rr = static_cast<const __nv_bfloat16*>(refs);
+      if (vec) cosine_topk_small_kernel<__nv_bfloat16, true><<<1, kSmallThreads, 0, st>>>(qq, rr, R, D, eps, k, scores, slot_scores, slot_idx);
+      else cosine_topk_small_kernel<__nv_bfloat16, false><<<1, kSmallThreads, 0, st>>>(qq, rr, R, D, eps, k, scores, slot_scores, slot_idx);
+    } else {
+      const float* qq = static_cast<const float*>(q);
+      const float* rr = static_cast<const float*>(refs);
+      if (vec) cosine_topk_small_kernel<float, true><<<1, kSmallThreads, 0, st>>>(qq, rr, R, D, eps, k, scores, slot_scores, slot_idx);
+      else cosine_topk_small_kernel<float, false><<<1, kSmallThreads, 0, st>>>(qq, rr, R, D, eps, k, scores, slot_scores, slot_idx);
+    }
+    return int(cudaGetLastError());
   }
+  const bool long_rows = size_t(D) * esz >= (64u << 10);
+  auto launch = [&](auto qq, auto rr) {
+    using T = typename std::remove_cv<typename std::remove_pointer<decltype(qq)>::type>::type;
+    if (long_rows) {
+      if (vec) cosine_kernel<T, true, kCosThreadsLong><<<R, kCosThreadsLong, 0, st>>>(qq, rr, R, D, eps, scores);
+      else cosine_kernel<T, false, kCosThreadsLong><<<R, kCosThreadsLong, 0, st>>>(qq, rr, R, D, eps, scores);
+    } else {
+      if (vec) cosine_kernel<T, true, kCosThreadsShort><<<R, kCosThreadsShort, 0, st>>>(qq, rr, R, D, eps, scores);
+      else cosine_kernel<T, false, kCosThreadsShort><<<R, kCosThreadsShort, 0, st>>>(qq, rr, R, D, eps, scores);
+    }
+  };
+  if (dtype == POPE_BF16) launch(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(refs));
+  else launch(static_cast<const float*>(q), static_cast<const float*>(refs));
   running_topk_kernel<<<1, kTopkThreads, 0, st>>>(scores, R, k, slot_scores, slot_idx);
   return int(cudaGetLastError());
 }
