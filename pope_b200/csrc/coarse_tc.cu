@@ -242,13 +242,16 @@ struct SweepParams {
                             //       the pairs with pairflag[n] != 0 are swept
   int32_t* flags;
   unsigned long long* trace;   // developer diagnostics (POPE_TC_TRACE): clock stamps of CTA pair 0, or nullptr
-  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit3 = force three sweeps, bit4 = no single sweep, bit5 = single sweep without the per-cell candidate scan, bits 8.. = the epilogue warp POPE_TC_TRACE stamps, bit6 = no gated redo after the single sweep
+  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit3 = force three sweeps, bit4 = no single sweep, bit5 = single sweep without the per-cell candidate scan, bit7 = single sweep without the shared-memory row-bound exchange, bit9 = no candidate levels 2/3 in a unit's first tile (timing only: drops its candidates), bits 10.. = the epilogue warp POPE_TC_TRACE stamps, bit6 = no gated redo after the single sweep
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 r;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
   return r;
+}
+__device__ __forceinline__ void red_max_shared(uint32_t addr, int v) {
+  asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ float lds32(uint32_t addr) {
   float r;
@@ -785,7 +788,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         const int nvalid = min(LB - col0, kTileCols) - colofs;
         const bool active = rows_valid > 0 && nvalid > 0 && !(P.debug & 1);
         // developer diagnostics: epilogue warp POPE_TC_TRACE_WARP (default 0) of CTA pair 0, leader CTA
-        const bool etr = TRACE && P.trace && pair == 0 && rank == 0 && warp == (P.debug >> 8) && lane == 0 && tile_ctr < kTraceTiles;
+        const bool etr = TRACE && P.trace && pair == 0 && rank == 0 && warp == (P.debug >> 10) && lane == 0 && tile_ctr < kTraceTiles;
         unsigned long long* erec = P.trace + size_t(kTraceTiles + tile_ctr) * 8;
         if (etr) erec[0] = clock64();
         mbar_wait<POPE_VAR_WAIT_HINT>(bar_acc_full + 8 * s, acc_phase);
@@ -856,18 +859,19 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             rowacc[rho] += d[rho];
             pass |= d[rho] > fmaf(thrm, rowacc[rho], tb[rho]);
           }
-          if (__any_sync(kFullMask, pass) && !(P.debug & 2)) {       // (one vote per chunk on the common path)
+          if (__any_sync(kFullMask, pass) && !(P.debug & 2) && !((P.debug & 512) && ct == 0)) {       // (one vote per chunk on the common path)
 #pragma unroll
             for (int rho = 0; rho < 4; ++rho) {
               if (!__any_sync(kFullMask, d[rho] > fmaf(thrm, rowacc[rho], tb[rho]))) continue;
               float rs = rowacc[rho];
               rs += __shfl_xor_sync(kFullMask, rs, 1);
               rs += __shfl_xor_sync(kFullMask, rs, 2);
-              const float other = ex2_approx(lds32(rowbnd_addr + 32 * rho) - (kBndBias + mshift));
+              const float other = (P.debug & 128) ? 0.f : ex2_approx(lds32(rowbnd_addr + 32 * rho) - (kBndBias + mshift));
               const float bound = thrm * fmaxf(rs, other);
               tb[rho] = fmaxf(tb[rho], fmaf(-thrm, rowacc[rho], bound));
-              if (p == 0 && fabsf(mshift) < 0.5f * kBndBias)
-                atomicMax(rowbnd + (quad * 32 + g + 8 * rho), __float_as_int(lg2_approx(rs) + (mshift + kBndBias - 0.004f)));
+              if (p == 0 && fabsf(mshift) < 0.5f * kBndBias && !(P.debug & 128))     // (explicit shared-space reduction: through the
+                red_max_shared(rowbnd_addr + 32 * rho,                              //  generic pointer it compiled to ATOM.E...GPU)
+                               __float_as_int(lg2_approx(rs) + (mshift + kBndBias - 0.004f)));
               if (P.debug & 32) continue;
               const int i0 = 16 * (rho >> 1) + 2 * (rho & 1);
               const float e0 = v[i0], e1 = v[i0 + 1], e2 = v[i0 + 4], e3 = v[i0 + 5], e4 = v[i0 + 8], e5 = v[i0 + 9],
