@@ -110,6 +110,45 @@ __global__ void __launch_bounds__(TPB) merge_shfl(const float* __restrict__ colp
   }
 }
 
+
+// NV float4 vectors per lane, adjacent in memory (a warp covers NV * 512 B of a row), W warps split the groups, B loads of each in flight
+template <int W, int B, int NV>
+__global__ void __launch_bounds__(32 * W) merge_wide(const float* __restrict__ colpart, const float* __restrict__ cshift, int ngroups,
+                                                     int S, int nblk, float* __restrict__ lse_c) {
+  __shared__ float s_acc[W][128 * NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = blockIdx.x * 128 * NV, n = blockIdx.y;
+  float acc[NV][4];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+  const float* p = colpart + size_t(n) * ngroups * S + j0 + lane * 4;
+  for (int g0 = warp; g0 < ngroups; g0 += W * B) {
+    float4 q[B][NV];
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int g = g0 + b * W, j = j0 + lane * 4 + k * 128;
+        q[b][k] = (g < ngroups && j < S) ? __ldcs(reinterpret_cast<const float4*>(p + size_t(g) * S + k * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+#pragma unroll
+      for (int k = 0; k < NV; ++k) { acc[k][0] += q[b][k].x; acc[k][1] += q[b][k].y; acc[k][2] += q[b][k].z; acc[k][3] += q[b][k].w; }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) s_acc[warp][k * 128 + lane * 4 + v] = acc[k][v];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 128 * NV; c += 32 * W) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < W; ++w) tot += s_acc[w][c];
+    if (j0 + c < S) lse_c[size_t(n) * S + j0 + c] = log2f(tot);
+  }
+}
+
 int main() {
   const int n = 64, L = 4800, S = 4800, ng = (L + 31) / 32, nblk = (S + 31) / 32;
   float *cp, *cs, *out, *flush;
@@ -140,5 +179,9 @@ int main() {
   { dim3 g((S / 32 + 3) / 4, n); time("shfl B=10 128thr", [&] { merge_shfl<10, 128><<<g, 128>>>(cp, cs, ng, S, nblk, out); }); }
   { dim3 g((S / 32 + 7) / 8, n); time("shfl B=5 256thr", [&] { merge_shfl<5, 256><<<g, 256>>>(cp, cs, ng, S, nblk, out); }); }
   { dim3 g((S / 32 + 1) / 2, n); time("shfl B=8 64thr", [&] { merge_shfl<8, 64><<<g, 64>>>(cp, cs, ng, S, nblk, out); }); }
+  { dim3 g((S + 255) / 256, n); time("wide W=4 B=4 NV=2 (no shifts)", [&] { merge_wide<4, 4, 2><<<g, 128>>>(cp, cs, ng, S, nblk, out); }); }
+  { dim3 g((S + 511) / 512, n); time("wide W=4 B=2 NV=4 (no shifts)", [&] { merge_wide<4, 2, 4><<<g, 128>>>(cp, cs, ng, S, nblk, out); }); }
+  { dim3 g((S + 511) / 512, n); time("wide W=8 B=2 NV=4 (no shifts)", [&] { merge_wide<8, 2, 4><<<g, 256>>>(cp, cs, ng, S, nblk, out); }); }
+  { dim3 g((S + 127) / 128, n); time("wide W=4 B=5 NV=1 (no shifts)", [&] { merge_wide<4, 5, 1><<<g, 128>>>(cp, cs, ng, S, nblk, out); }); }
   return 0;
 }
