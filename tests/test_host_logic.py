@@ -127,3 +127,24 @@ def test_header_is_plain_c_and_a_c_program_links(tmp_path):
                     "-L", libdir, "-lpope_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert "workspace" in out
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port, rank 0 only): one JSON line with the contract's
+    keys, and the SAME `config` the CUDA arm prints for the same workload (the arm-specific facts sit in `details`)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample-pairs", "1"], capture_output=True, text=True, timeout=600, check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, root)
+    import bench
+    assert line["config"] == bench.workload_config(64) and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
