@@ -646,6 +646,7 @@ def main():
                                   "dram_frac the DRAM bytes of the ncu capture",
                           "algorithmic_bytes_per_launch": fine_bytes},
         "gpu_launches": args.steps * (_lib.KERNELS_PER_STEP[("tcgen05" if dtype == torch.bfloat16 else "tcgen05_f32") if tc else "simt"]
+                                      + (1 if (tc and dtype == torch.bfloat16 and _lib.single_sweep_is_split(n, L)) else 0)
                                       + (1 if world > 1 else 0)),
     }
     if world > 1:

@@ -73,6 +73,20 @@ SIGNATURES = {
 # unless the fallback flag is raised), count+emit, fused fine match.
 KERNELS_PER_STEP = {"tcgen05": 6, "tcgen05_f32": 12, "simt": 6}
 
+
+def single_sweep_is_split(n_pairs: int, L: int, sms: int = 148) -> bool:
+    """Does the bf16 single sweep run as two launches (head + tail, csrc/coarse_tc.cu::coarse_tc_run)?  One more kernel per step
+    then: the head's pairs fill whole rounds of the static unit schedule, the tail's fit the last, part-empty round, and the
+    column merge of the head runs beside the tail."""
+    cta_pairs, upp = sms // 2, -(-L // 256)
+    units = n_pairs * upp
+    if n_pairs <= 1 or units <= cta_pairs or units % cta_pairs == 0:
+        return False
+    head = ((units // cta_pairs) * cta_pairs) // upp
+    ua, ub = head * upp, units - head * upp
+    rounds = lambda u: -(-u // cta_pairs)
+    return 0 < head < n_pairs and rounds(ua) + rounds(ub) == rounds(units) and 2 * ub <= cta_pairs + cta_pairs // 2
+
 _lib: Optional[C.CDLL] = None
 
 

@@ -287,17 +287,21 @@ __global__ void __launch_bounds__(32 * kMergeWarps) colsum_reduce_kernel(const f
                                                                         const float* __restrict__ cshift, int ngroups, int S,
                                                                         int nblk, float* __restrict__ lse_c,
                                                                         u64* __restrict__ colbest, int* __restrict__ ready,
-                                                                        int32_t* __restrict__ flags, int* __restrict__ pairflag) {
+                                                                        int32_t* __restrict__ flags, int* __restrict__ pairflag,
+                                                                        int n_base, int n_total, int wait_from) {
   // block = kMergeWarps warps x (32 lanes x VEC adjacent columns): warp w takes the row groups g = w, w + kMergeWarps, ...,
   // kMergeBatch loads in flight per thread; the partial results of a column meet in shared memory and are merged in warp
   // order (fixed order: deterministic)
   __shared__ float s_acc[kMergeWarps][32 * VEC];
   __shared__ float s_m[kMergeWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = (blockIdx.x * 32 + lane) * VEC, n = blockIdx.y;
+  const int j = (blockIdx.x * 32 + lane) * VEC, n = n_base + blockIdx.y;
+  // launched beside the tail of a split sweep (programmatic stream serialisation): the pairs of the head are complete, the
+  // blocks of the tail's pairs -- the last ones of the grid -- wait here until that sweep has finished and its stores are visible
+  if (n >= wait_from) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ready[n] = 0;
-    if (n == 0) ready[gridDim.y] = 0;                 // the compaction kernel's ticket counter
+    if (n == 0) ready[n_total] = 0;                   // the compaction kernel's ticket counter
   }
   float acc[VEC], mtop = -INFINITY;
 #pragma unroll
@@ -395,18 +399,28 @@ cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, 
   return cudaGetLastError();
 }
 
-cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st) {
+cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st, int n_base,
+                              int n_count, int wait_from) {
+  const bool overlap_previous = wait_from >= 0;
+  if (wait_from < 0) wait_from = 0x7fffffff;
   const int ngroups = (p.L + 31) / 32, nblk = (p.S + 31) / 32;
-  if (p.S % 4 == 0) {   // rows of the partial-sum array are then 16-byte aligned (the array itself is 256-byte aligned)
-    dim3 grid((p.S / 4 + 31) / 32, p.n);
-    colsum_reduce_kernel<4><<<grid, 32 * kMergeWarps, 0, st>>>(w.colpart, w.cshift, ngroups, p.S, nblk, w.lse_c, w.colbest, w.ready, flags,
-                                                  w.pairflag);
-  } else {
-    dim3 grid((p.S + 31) / 32, p.n);
-    colsum_reduce_kernel<1><<<grid, 32 * kMergeWarps, 0, st>>>(w.colpart, w.cshift, ngroups, p.S, nblk, w.lse_c, w.colbest, w.ready, flags,
-                                                  w.pairflag);
-  }
-  return cudaGetLastError();
+  const bool vec4 = p.S % 4 == 0;   // rows of the partial-sum array are then 16-byte aligned (the array itself is 256-byte aligned)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = vec4 ? dim3((p.S / 4 + 31) / 32, n_count) : dim3((p.S + 31) / 32, n_count);
+  cfg.blockDim = dim3(32 * kMergeWarps);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = overlap_previous ? 1 : 0;
+  const float* colpart = w.colpart;
+  const float* cshift = w.cshift;
+  if (vec4)
+    return cudaLaunchKernelEx(&cfg, colsum_reduce_kernel<4>, colpart, cshift, ngroups, p.S, nblk, w.lse_c, w.colbest, w.ready, flags,
+                              w.pairflag, n_base, p.n, wait_from);
+  return cudaLaunchKernelEx(&cfg, colsum_reduce_kernel<1>, colpart, cshift, ngroups, p.S, nblk, w.lse_c, w.colbest, w.ready, flags,
+                            w.pairflag, n_base, p.n, wait_from);
 }
 
 cudaError_t coarse_finalize_run(const CoarseProblem& p, const CoarseScratch& w, int64_t* b_ids, int64_t* i_ids,

@@ -220,7 +220,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 struct SweepParams {
   // direction d: stationary operand = feature set d (rows LA[d]), streamed operand = the other one
-  int n;
+  int n;                    // pairs covered by this launch ...
+  int n_base;               // ... starting at this pair
   int L0, L1;               // rows of feature set 0 / 1; direction d has LA = L_d, LB = L_(1-d)
   int kchunks;
   int units_dir0;           // work units of direction 0 (direction 1 follows)
@@ -242,7 +243,7 @@ struct SweepParams {
                             //       the pairs with pairflag[n] != 0 are swept
   int32_t* flags;
   unsigned long long* trace;   // developer diagnostics (POPE_TC_TRACE): clock stamps of CTA pair 0, or nullptr
-  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit3 = force three sweeps, bit4 = no single sweep, bit5 = single sweep without the per-cell candidate scan, bit7 = single sweep without the shared-memory row-bound exchange, bit9 = no candidate levels 2/3 in a unit's first tile (timing only: drops its candidates), bits 10.. = the epilogue warp POPE_TC_TRACE stamps, bit6 = no gated redo after the single sweep
+  int debug;                // developer knob (env POPE_TC_DEBUG): bit0 = epilogue does no math, bit1 = no rare path, bit3 = force three sweeps, bit4 = no single sweep, bit5 = single sweep without the per-cell candidate scan, bit7 = single sweep without the shared-memory row-bound exchange, bit9 = no candidate levels 2/3 in a unit's first tile (timing only: drops its candidates), bit10 = single sweep as one launch (no head / tail split), bits 11.. = the epilogue warp POPE_TC_TRACE stamps, bit6 = no gated redo after the single sweep
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -527,6 +528,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   const uint32_t bar_acc_full = bar_b_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 16;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
 
+  // (a kernel launched behind this one WITH programmatic stream serialisation may start while this one runs: the column
+  //  merge of the head of a split single sweep, coarse_tc_run; ordinary launches are not affected)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (P.gate && !(uint32_t(*reinterpret_cast<const volatile int32_t*>(P.flags)) & POPE_FLAG_ROBUST_PATH)) return;
   // (volatile read: the compiler otherwise re-derives lane bits from SR_TID.X inside the epilogue loops, ~6 S2R per chunk)
   uint32_t lane_u;
@@ -567,8 +571,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     dir = (u >= P.units_dir0) ? 1 : 0;
     const int v = dir ? u - P.units_dir0 : u;
     const int rbs = ((dir ? P.L1 : P.L0) + kUnitRows - 1) / kUnitRows;
-    n = v / rbs;
-    rb = v - n * rbs;
+    const int q = v / rbs;
+    rb = v - q * rbs;
+    n = P.n_base + q;          // (a launch may cover the pairs [n_base, n_base + n) only)
   };
 
   // gated launch (the fallback behind the single sweep): only the pairs the single sweep gave up on are swept; the
@@ -788,7 +793,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         const int nvalid = min(LB - col0, kTileCols) - colofs;
         const bool active = rows_valid > 0 && nvalid > 0 && !(P.debug & 1);
         // developer diagnostics: epilogue warp POPE_TC_TRACE_WARP (default 0) of CTA pair 0, leader CTA
-        const bool etr = TRACE && P.trace && pair == 0 && rank == 0 && warp == (P.debug >> 10) && lane == 0 && tile_ctr < kTraceTiles;
+        const bool etr = TRACE && P.trace && pair == 0 && rank == 0 && warp == (P.debug >> 11) && lane == 0 && tile_ctr < kTraceTiles;
         unsigned long long* erec = P.trace + size_t(kTraceTiles + tile_ctr) * 8;
         if (etr) erec[0] = clock64();
         mbar_wait<POPE_VAR_WAIT_HINT>(bar_acc_full + 8 * s, acc_phase);
@@ -1271,7 +1276,7 @@ cudaError_t coarse_tc_split_run(const CoarseProblem& p, const CoarseScratch& w, 
   if ((e = cudaMemsetAsync(w.pairflag, 0, sizeof(int) * p.n, st)) != cudaSuccess) return e;
   k4<<<2 * min(u0, sms / 2), kThreads, kSmemAlloc, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if ((e = colsum_reduce_run(p, w, flags, st)) != cudaSuccess) return e;
+  if ((e = colsum_reduce_run(p, w, flags, st, 0, p.n)) != cudaSuccess) return e;
   return cand_eval_lists_run(p, w, flags, 2, st);       // mode 2: 2^x lists; a no-op once the fallback flag is up
 }
 
@@ -1316,12 +1321,41 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
     if (!(P.debug & 16)) {
       // single sweep over the rows of S: row sums, column partial sums and candidate lists in one pass; raises
       // POPE_FLAG_ROBUST_PATH when the unshifted exponentials leave the safe range (debug bit4 skips it)
-      P.units_dir0 = u0; P.total_units = u0;
       P.trace = trace_mode == 3 ? g_trace : nullptr;
       if ((e = cudaMemsetAsync(w.pairflag, 0, sizeof(int) * p.n, st)) != cudaSuccess) return e;
-      k3<<<2 * min(P.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, map0, map1, map0, map1, P);
-      if ((e = cudaGetLastError()) != cudaSuccess) return e;
-      if ((e = colsum_reduce_run(p, w, flags, st)) != cudaSuccess) return e;
+      // The unit schedule is static: u0 units over max_pairs CTA pairs run in ceil(u0 / max_pairs) rounds, and the last round
+      // is usually part empty (64 pairs at 480x640: 1 216 units = 16 rounds of 74 + 32).  When the pairs can be cut into a
+      // head that fills whole rounds and a tail that fits the last round without adding one, the sweep is launched twice --
+      // head, then tail -- and the column merge of the head's pairs runs on the SMs the tail leaves idle: the sweep kernel
+      // announces its dependents at once (griddepcontrol.launch_dependents) and merge(head), which needs nothing from the
+      // tail (the head sweep has completed before the tail started), is launched behind the tail with programmatic stream
+      // serialisation: ONE merge launch over all pairs, whose blocks for the head's pairs never wait and whose blocks for the
+      // tail's pairs (the last of the grid) wait for the tail sweep (griddepcontrol.wait).  Everything behind it is ordinary.
+      const int upp = (p.L + kUnitRows - 1) / kUnitRows;                       // units per pair
+      const int rounds = (u0 + max_pairs - 1) / max_pairs;
+      int head = 0;
+      if (!(P.debug & 1024) && p.n > 1 && u0 > max_pairs && u0 % max_pairs != 0) {
+        const int h = ((u0 / max_pairs) * max_pairs) / upp;                    // pairs that fit the full rounds
+        const int ua = h * upp, ub = u0 - ua;
+        if (h > 0 && h < p.n && (ua + max_pairs - 1) / max_pairs + (ub + max_pairs - 1) / max_pairs == rounds && 2 * ub <= max_pairs + max_pairs / 2)
+          head = h;
+      }
+      auto sweep = [&](int n_base, int n_count) -> cudaError_t {
+        SweepParams Q = P;
+        Q.n_base = n_base; Q.n = n_count;
+        Q.units_dir0 = Q.total_units = n_count * upp;
+        k3<<<2 * min(Q.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(map0, map1, map0, map1, map0, map1, Q);
+        return cudaGetLastError();
+      };
+      if (head > 0) {
+        if ((e = sweep(0, head)) != cudaSuccess) return e;
+        if ((e = sweep(head, p.n - head)) != cudaSuccess) return e;
+        if ((e = colsum_reduce_run(p, w, flags, st, 0, p.n, head)) != cudaSuccess) return e;
+      } else {
+        if ((e = sweep(0, p.n)) != cudaSuccess) return e;
+        if ((e = colsum_reduce_run(p, w, flags, st, 0, p.n)) != cudaSuccess) return e;
+      }
+      P.units_dir0 = u0; P.total_units = u0;
       P.gate = 1;
       if (P.debug & 64) return cand_eval_lists_run(p, w, flags, 0, st);      // developer knob: no gated redo (inspect the single sweep)
     }

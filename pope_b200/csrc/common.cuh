@@ -146,7 +146,11 @@ cudaError_t gated_clear_run(void* ptr, size_t bytes, const int32_t* gate, cudaSt
 cudaError_t cand_eval_lists_run(const CoarseProblem& p, const CoarseScratch& w, const int32_t* flags, int mode, cudaStream_t st);
 // single-sweep tcgen05 path: column log-sum-exp from the per-32-row partial sums and their shifts (a log-sum-exp merge);
 // sets POPE_FLAG_ROBUST_PATH and the pair's flag when a column sum lost precision
-cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st);
+// (pairs [n_base, n_base + n_count) only: the single sweep may be launched in two parts)
+// wait_from >= 0: launched with programmatic stream serialisation, i.e. the kernel may start while the kernel in front of it
+// (the tail of a split single sweep) still runs; only the blocks of the pairs >= wait_from wait for that kernel
+cudaError_t colsum_reduce_run(const CoarseProblem& p, const CoarseScratch& w, int32_t* flags, cudaStream_t st, int n_base, int n_count,
+                              int wait_from = -1);
 // does coarse_tc_run need rowbest / colbest / cand_cnt cleared beforehand?  (not on the single-sweep launch sequence)
 bool coarse_tc_needs_clear(const CoarseProblem& p);
 // a thr large enough that a row's cells with p_row > thr fit its kCandSlots candidate slots
