@@ -148,3 +148,14 @@ def test_reference_arm_prints_the_contract_line():
     sys.path.insert(0, root)
     import bench
     assert line["config"] == bench.workload_config(64) and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
+
+
+def test_single_sweep_split_rule():
+    """The Python mirror of coarse_tc_run's head / tail rule (used for bench.py's launch count): 64 pairs at 480x640 are 1 216
+    units = 16 rounds of 74 CTA pairs + 32, so 62 + 2 pairs; 16 pairs at 960x1280 (1 200 units) would need a round more when cut
+    at a pair boundary; one pair, or a unit count that fills its rounds, is never cut."""
+    assert _lib.single_sweep_is_split(64, 4800) and _lib.single_sweep_is_split(32, 4800)
+    assert not _lib.single_sweep_is_split(16, 19200)
+    assert not _lib.single_sweep_is_split(1, 4800)
+    assert not _lib.single_sweep_is_split(74, 256)          # 74 units: exactly one round
+    assert not _lib.single_sweep_is_split(3, 4800)          # 57 units: fewer than one round
