@@ -160,6 +160,34 @@ def test_coarse_shift_rises_along_the_sweep(dtype):
         assert torch.allclose(out["mconf"], want["mconf"], rtol=1e-2 if dtype == torch.bfloat16 else 1e-4, atol=0)
 
 
+def test_coarse_split_sweep_equals_single_launch():
+    """When the static unit schedule's last round is part empty the single sweep runs as two launches (head + tail) with the
+    head's column merge beside the tail (csrc/coarse_tc.cu::coarse_tc_run).  Same arithmetic, so the results must equal the
+    one-launch form (developer bit 10) bit for bit -- also when a flagged pair sits in the head or in the tail."""
+    h, w = 40, 48                                   # 1920 cells: 8 units per pair; 24 pairs = 192 units = 2 rounds of 74 + 44
+    n = 24
+    assert _lib.single_sweep_is_split(n, h * w)
+    _need_tc("tcgen05", 256, h * w, h * w)
+    f0, f1 = synth.coarse_features(97, n, h * w, h * w, 256, sigma=1.1, dtype=torch.bfloat16)
+    fh0, fh1 = synth.hard_coarse_features(98, 2, h * w, h * w, 256, sigma=0.9, dtype=torch.bfloat16)
+    for variant in ("plain", "flagged"):
+        if variant == "flagged":                    # pair 3 lies in the head (18 pairs), pair 23 in the tail
+            f0[3], f1[3], f0[23], f1[23] = fh0[0], fh1[0], fh0[1], fh1[1]
+        outs = []
+        for knob in ("0", "1024"):
+            os.environ["POPE_TC_DEBUG"] = knob
+            try:
+                outs.append(_run_coarse(f0, f1, (h, w), (h, w), _lib.COARSE_TCGEN05, torch.bfloat16))
+            finally:
+                del os.environ["POPE_TC_DEBUG"]
+        assert bool(outs[0]["_flags"] & _lib.FLAG_ROBUST_PATH) == (variant == "flagged")
+        assert outs[0]["b_ids"].numel() > 10000
+        for k in outs[0]:
+            if k != "_flags":
+                assert torch.equal(outs[0][k], outs[1][k]), (variant, k)
+        assert outs[0]["_flags"] == outs[1]["_flags"]
+
+
 def test_coarse_mixed_batch_only_flagged_pairs_take_the_robust_launch():
     """A batch of ordinary pairs with one hard-set pair in the middle: the flag is raised, the result of every pair equals
     what the pair gives when it is run alone (the gated launch redoes the flagged pair only; the others keep the
