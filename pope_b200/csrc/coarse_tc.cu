@@ -1228,6 +1228,20 @@ static int debug_knob() {
   return dbg ? atoi(dbg) : 0;
 }
 
+// Head/tail cut of the single sweep (see coarse_tc_run): the number of leading pairs whose units fill whole rounds of the
+// static schedule, or 0 when the sweep should stay one launch.
+static int split_head(int n, int upp, int max_pairs, int debug) {
+  const int u0 = n * upp;
+  if ((debug & 1024) || n <= 1 || u0 <= max_pairs || u0 % max_pairs == 0) return 0;
+  const int rounds = (u0 + max_pairs - 1) / max_pairs;
+  const int h = ((u0 / max_pairs) * max_pairs) / upp;                          // pairs that fit the full rounds
+  const int ua = h * upp, ub = u0 - ua;
+  if (h > 0 && h < n && (ua + max_pairs - 1) / max_pairs + (ub + max_pairs - 1) / max_pairs == rounds &&
+      2 * ub <= max_pairs + max_pairs / 2)
+    return h;
+  return 0;
+}
+
 bool coarse_tc_needs_clear(const CoarseProblem& p) { return !(two_sweeps_possible(p) && !(debug_knob() & (8 | 16))); }
 
 bool coarse_tc_supported(const CoarseProblem& p) {
@@ -1271,12 +1285,25 @@ cudaError_t coarse_tc_split_run(const CoarseProblem& p, const CoarseScratch& w, 
   P.scale_log2 = p.scale_log2; P.log2_thr = p.log2_thr;
   P.lse_out0 = w.lse_r; P.lse_out1 = w.lse_c; P.lse_r = w.lse_r; P.lse_c = w.lse_c; P.rowbest = w.rowbest; P.colbest = w.colbest;
   P.cand_cnt = w.cand_cnt; P.cand = w.cand; P.flags = flags; P.colpart = w.colpart; P.cshift = w.cshift; P.pairflag = w.pairflag;
-  const int u0 = p.n * ((p.L + kUnitRows - 1) / kUnitRows);
-  P.units_dir0 = u0; P.total_units = u0;
+  const int upp = (p.L + kUnitRows - 1) / kUnitRows, max_pairs = sms / 2;
   if ((e = cudaMemsetAsync(w.pairflag, 0, sizeof(int) * p.n, st)) != cudaSuccess) return e;
-  k4<<<2 * min(u0, sms / 2), kThreads, kSmemAlloc, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], P);
-  if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if ((e = colsum_reduce_run(p, w, flags, st, 0, p.n)) != cudaSuccess) return e;
+  // head / tail launches with the head's column merge overlapped, as in coarse_tc_run
+  const int head = split_head(p.n, upp, max_pairs, P.debug);
+  auto sweep = [&](int n_base, int n_count) -> cudaError_t {
+    SweepParams Q = P;
+    Q.n_base = n_base; Q.n = n_count;
+    Q.units_dir0 = Q.total_units = n_count * upp;
+    k4<<<2 * min(Q.total_units, max_pairs), kThreads, kSmemAlloc, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], Q);
+    return cudaGetLastError();
+  };
+  if (head > 0) {
+    if ((e = sweep(0, head)) != cudaSuccess) return e;
+    if ((e = sweep(head, p.n - head)) != cudaSuccess) return e;
+    if ((e = colsum_reduce_run(p, w, flags, st, 0, p.n, head)) != cudaSuccess) return e;
+  } else {
+    if ((e = sweep(0, p.n)) != cudaSuccess) return e;
+    if ((e = colsum_reduce_run(p, w, flags, st, 0, p.n)) != cudaSuccess) return e;
+  }
   return cand_eval_lists_run(p, w, flags, 2, st);       // mode 2: 2^x lists; a no-op once the fallback flag is up
 }
 
@@ -1332,14 +1359,7 @@ cudaError_t coarse_tc_run(const CoarseProblem& p, const CoarseScratch& w, int32_
       // serialisation: ONE merge launch over all pairs, whose blocks for the head's pairs never wait and whose blocks for the
       // tail's pairs (the last of the grid) wait for the tail sweep (griddepcontrol.wait).  Everything behind it is ordinary.
       const int upp = (p.L + kUnitRows - 1) / kUnitRows;                       // units per pair
-      const int rounds = (u0 + max_pairs - 1) / max_pairs;
-      int head = 0;
-      if (!(P.debug & 1024) && p.n > 1 && u0 > max_pairs && u0 % max_pairs != 0) {
-        const int h = ((u0 / max_pairs) * max_pairs) / upp;                    // pairs that fit the full rounds
-        const int ua = h * upp, ub = u0 - ua;
-        if (h > 0 && h < p.n && (ua + max_pairs - 1) / max_pairs + (ub + max_pairs - 1) / max_pairs == rounds && 2 * ub <= max_pairs + max_pairs / 2)
-          head = h;
-      }
+      const int head = split_head(p.n, upp, max_pairs, P.debug);
       auto sweep = [&](int n_base, int n_count) -> cudaError_t {
         SweepParams Q = P;
         Q.n_base = n_base; Q.n = n_count;

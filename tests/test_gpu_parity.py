@@ -160,16 +160,18 @@ def test_coarse_shift_rises_along_the_sweep(dtype):
         assert torch.allclose(out["mconf"], want["mconf"], rtol=1e-2 if dtype == torch.bfloat16 else 1e-4, atol=0)
 
 
-def test_coarse_split_sweep_equals_single_launch():
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+def test_coarse_split_sweep_equals_single_launch(dtype):
     """When the static unit schedule's last round is part empty the single sweep runs as two launches (head + tail) with the
-    head's column merge beside the tail (csrc/coarse_tc.cu::coarse_tc_run).  Same arithmetic, so the results must equal the
-    one-launch form (developer bit 10) bit for bit -- also when a flagged pair sits in the head or in the tail."""
+    head's column merge beside the tail (csrc/coarse_tc.cu::coarse_tc_run, and coarse_tc_split_run for fp32 features).  Same
+    arithmetic, so the results must equal the one-launch form (developer bit 10) bit for bit -- also when a flagged pair
+    sits in the head or in the tail."""
     h, w = 40, 48                                   # 1920 cells: 8 units per pair; 24 pairs = 192 units = 2 rounds of 74 + 44
     n = 24
     assert _lib.single_sweep_is_split(n, h * w)
     _need_tc("tcgen05", 256, h * w, h * w)
-    f0, f1 = synth.coarse_features(97, n, h * w, h * w, 256, sigma=1.1, dtype=torch.bfloat16)
-    fh0, fh1 = synth.hard_coarse_features(98, 2, h * w, h * w, 256, sigma=0.9, dtype=torch.bfloat16)
+    f0, f1 = synth.coarse_features(97, n, h * w, h * w, 256, sigma=1.1, dtype=dtype)
+    fh0, fh1 = synth.hard_coarse_features(98, 2, h * w, h * w, 256, sigma=0.9, dtype=dtype)
     for variant in ("plain", "flagged"):
         if variant == "flagged":                    # pair 3 lies in the head (18 pairs), pair 23 in the tail
             f0[3], f1[3], f0[23], f1[23] = fh0[0], fh1[0], fh0[1], fh1[1]
@@ -177,7 +179,7 @@ def test_coarse_split_sweep_equals_single_launch():
         for knob in ("0", "1024"):
             os.environ["POPE_TC_DEBUG"] = knob
             try:
-                outs.append(_run_coarse(f0, f1, (h, w), (h, w), _lib.COARSE_TCGEN05, torch.bfloat16))
+                outs.append(_run_coarse(f0, f1, (h, w), (h, w), _lib.COARSE_TCGEN05, dtype))
             finally:
                 del os.environ["POPE_TC_DEBUG"]
         assert bool(outs[0]["_flags"] & _lib.FLAG_ROBUST_PATH) == (variant == "flagged")
