@@ -28,7 +28,7 @@ Workload (BASELINE.json configs[1]): a batch of 64 synthetic 480x640 pairs per G
   robust   : the same workload with features of token norm 49 (sigma 3.06: what the coarse transformer emits, SURVEY
              section 7; similarities reach +-135 in log2 units) -- the lazily shifted single sweep must keep it on the fast
              path (`flags` 0).
-  in_matcher / highres / retrieval / job_4096 : the other configurations of BASELINE.json (steps 3-5 of Matcher.forward
+  in_matcher / highres / single_pair / retrieval / job_4096 : the other configurations of BASELINE.json (steps 3-5 of Matcher.forward
              with the fine transformer in between; configs[3] 960x1280; configs[2] 1 query vs 256 crops; configs[4] a
              4096-pair job sharded over the ranks with a single gather).
   cpu_baseline : the oracle port (same op sequence as the reference, torch CPU) on a bounded sample, rank 0: the hot path
@@ -352,6 +352,37 @@ def in_matcher_figure(n_pairs: int, dev):
     return out
 
 
+def single_pair_block(impl, dev):
+    """BASELINE configs[0]'s shape on the GPU: ONE 480x640 pair per call, the way the reference's evaluation loop calls the
+    Matcher.  Latency of the hot path for that call, eager (ctypes launches from Python) and replayed from a CUDA graph (the
+    step has no host synchronisation, so it can be captured: tests/test_gpu_parity.py::test_hot_path_step_is_graph_capturable)."""
+    from pope_b200 import _lib, ops, synth
+    f0, f1 = synth.coarse_features(555, 1, L, L, C_COARSE, dtype=torch.bfloat16)
+    d0, d1 = f0.to(dev), f1.to(dev)
+    g = torch.Generator(device=dev).manual_seed(556)
+    ff0 = torch.randn(1, HC * FINE_STRIDE, WC * FINE_STRIDE, C_FINE, device=dev, generator=g).to(torch.bfloat16).permute(0, 3, 1, 2)
+    ff1 = torch.randn(1, HC * FINE_STRIDE, WC * FINE_STRIDE, C_FINE, device=dev, generator=g).to(torch.bfloat16).permute(0, 3, 1, 2)
+    ws = torch.empty(_lib.lib().pope_coarse_workspace_bytes_ex(1, L, L, C_COARSE, _lib.POPE_BF16), dtype=torch.uint8, device=dev)
+
+    def step():
+        return ops.match_pairs_device(d0, d1, ff0, ff1, (H, W_IMG), (HC, WC), (HC, WC), impl=impl, workspace=ws)
+
+    ms, res = _timed(step, 50, dev, warm=3)
+    out = {"workload": "1 pair at 480x640 per call (BASELINE configs[0]'s shape), bf16, inputs resident",
+           "eager": {"us_per_pair": ms * 1e3, "value": 1e3 / ms, "unit": UNIT}, "matches": res.total(), "flags": res.flags()}
+    try:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            gres = step()
+        gms, _ = _timed(graph.replay, 50, dev, warm=3)
+        out["graph"] = {"us_per_pair": gms * 1e3, "value": 1e3 / gms, "unit": UNIT, "matches": gres.total()}
+    except Exception as e:
+        out["graph"] = {"error": repr(e)[:200]}
+    return out
+
+
 def highres_block(n, impl, dev):
     """BASELINE configs[3]: 960x1280 pairs, 19 200 coarse tokens per image (the L x S matrix would be 1.47 GB per pair)."""
     from pope_b200 import _lib, synth
@@ -658,6 +689,7 @@ def main():
         for name, fn in (("robust", lambda: robust_block(n, ff0, ff1, impl, dev)),
                          ("in_matcher", (lambda: in_matcher_figure(args.in_matcher, dev)) if args.in_matcher > 0 else None),
                          ("highres", (lambda: highres_block(args.highres_pairs, impl, dev)) if args.highres_pairs > 0 else None),
+                         ("single_pair", lambda: single_pair_block(impl, dev)),
                          ("retrieval", lambda: retrieval_block(dev))):
             if fn is None:
                 continue

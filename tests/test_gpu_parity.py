@@ -692,6 +692,47 @@ def test_device_batch_runner_equals_sequential_steps():
             assert torch.equal(res[k][:m], want[k][:m]), k
 
 
+def test_hot_path_step_is_graph_capturable():
+    """ops.match_pairs_device has no host synchronisation, so a step can be captured into a CUDA graph and replayed on new
+    feature contents.  24 pairs at 40x48 cells take the head / tail sweep with the programmatically serialised merge launch
+    (csrc/coarse_tc.cu::coarse_tc_run), which must survive capture; the replays equal the eager calls bit for bit."""
+    n, h, w = 24, 40, 48
+    assert _lib.single_sweep_is_split(n, h * w)
+    _need_tc("tcgen05", 256, h * w, h * w)
+    sets = []
+    for seed in (201, 202):
+        f0, f1 = synth.coarse_features(seed, n, h * w, h * w, 256, sigma=1.0, dtype=torch.bfloat16)
+        ff0, ff1 = synth.fine_feature_maps(seed + 10, n, h * 4, w * 4, 128, dtype=torch.bfloat16, channels_last=True)
+        sets.append([t.to(DEV) for t in (f0, f1, ff0, ff1)])
+    keys = ("b_ids", "i_ids", "j_ids", "mconf", "mkpts1_f", "expec_f")
+    want = []
+    for s in sets:
+        r = ops.match_pairs_device(*s, (h * 8, w * 8), (h, w), (h, w))
+        m = r.total()
+        assert m > 5000 and r.flags() == 0
+        want.append((m, {k: r[k][:m].clone() for k in keys}))
+    static = [t.clone() for t in sets[0]]
+    ws = torch.empty(_lib.lib().pope_coarse_workspace_bytes_ex(n, h * w, h * w, 256, 1), dtype=torch.uint8, device=DEV)
+    side = torch.cuda.Stream(DEV)
+    side.wait_stream(torch.cuda.current_stream(DEV))
+    with torch.cuda.stream(side):                      # warm-up on the capture stream (first-use attribute calls)
+        ops.match_pairs_device(*static, (h * 8, w * 8), (h, w), (h, w), workspace=ws)
+    torch.cuda.current_stream(DEV).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        res = ops.match_pairs_device(*static, (h * 8, w * 8), (h, w), (h, w), workspace=ws)
+    for which in (1, 0, 1):
+        for dst, src in zip(static, sets[which]):
+            dst.copy_(src)
+        graph.replay()
+        torch.cuda.synchronize()
+        m, ref = want[which]
+        assert res.total() == m and res.flags() == 0
+        for k in keys:
+            assert torch.equal(res[k][:m], ref[k]), (which, k)
+
+
 def test_match_crops_equals_the_reference_pair_loop():
     """driver.match_crops against the loop of eval_linemod_json.py:103-122 / :146 restated with cv2 + numpy.  A stand-in
     matcher whose output is a deterministic function of its two input images makes the comparison non-vacuous (the real
