@@ -108,25 +108,28 @@ def dram_traffic_from_profiles():
     if not os.path.exists(TRAFFIC_CSV):
         return None, None, None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    with open(TRAFFIC_CSV) as f:
-        rows = list(csv.reader(f))
-    hdr = rows[0]
-    cols = {}
-    for k, name in enumerate(hdr):
-        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            if name.startswith(key):
-                cols[key] = (k, mult.get(name[name.index("[") + 1:name.index("]")], 1.0))
-    if len(cols) != 2:
+    try:
+        with open(TRAFFIC_CSV) as f:
+            rows = list(csv.reader(f))
+        hdr = rows[0]
+        cols = {}
+        for k, name in enumerate(hdr):
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                if name.startswith(key + " ["):
+                    cols[key] = (k, mult.get(name[name.index("[") + 1:name.index("]")], 1.0))
+        if len(cols) != 2 or hdr[0] != "kernel":
+            return None, None, None           # not the tools/ncu_extract.py table (e.g. ncu's raw page): no traffic figure
+        coarse = fine = 0.0
+        for r in rows[1:]:
+            if not r:
+                continue
+            byts = sum(float(r[k]) * m for k, m in cols.values())
+            if "fine_match_maps" in r[0]:
+                fine += byts
+            elif any(t in r[0] for t in ("sweep_tc", "colsum_reduce", "cand_eval", "count_emit")):
+                coarse += byts
+    except (OSError, ValueError, IndexError):
         return None, None, None
-    coarse = fine = 0.0
-    for r in rows[1:]:
-        if not r:
-            continue
-        byts = sum(float(r[k]) * m for k, m in cols.values())
-        if "fine_match_maps" in r[0]:
-            fine += byts
-        elif any(t in r[0] for t in ("sweep_tc", "colsum_reduce", "cand_eval", "count_emit")):
-            coarse += byts
     return (coarse or None), (fine or None), os.path.relpath(TRAFFIC_CSV, ROOT)
 
 

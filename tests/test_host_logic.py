@@ -159,3 +159,20 @@ def test_single_sweep_split_rule():
     assert not _lib.single_sweep_is_split(1, 4800)
     assert not _lib.single_sweep_is_split(74, 256)          # 74 units: exactly one round
     assert not _lib.single_sweep_is_split(3, 4800)          # 57 units: fewer than one round
+
+
+def test_bench_reads_the_committed_ncu_table(tmp_path, monkeypatch):
+    """bench.py takes `roofline.traffic` from the committed ncu table (tools/ncu_extract.py format): the committed file must
+    parse to plausible per-launch DRAM bytes, and a file in another format (ncu's raw page) must give None, not an exception
+    that takes the headline line down."""
+    import bench
+    coarse, fine, src = bench.dram_traffic_from_profiles()
+    assert src == "profiles/r2_ncu_step.csv"
+    assert 3e8 < coarse < 2e9 and 5e8 < fine < 2e9
+    raw = tmp_path / "raw.csv"
+    raw.write_text('"ID","Process ID","Kernel Name","dram__bytes_read.sum","dram__bytes_write.sum"\n'
+                   '"","","","Mbyte","Mbyte"\n"0","1","sweep_tc_kernel","310.9","168.7"\n')
+    monkeypatch.setattr(bench, "TRAFFIC_CSV", str(raw))
+    assert bench.dram_traffic_from_profiles() == (None, None, None)
+    monkeypatch.setattr(bench, "TRAFFIC_CSV", str(tmp_path / "absent.csv"))
+    assert bench.dram_traffic_from_profiles() == (None, None, None)
