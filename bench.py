@@ -610,27 +610,43 @@ def main():
         out = pl.alloc_outputs(n)
         if prev_aff is not None:
             os.sched_setaffinity(0, prev_aff)
-        for _ in range(2):
-            pl.run(h_f0, h_f1, h_ff0, h_ff1, out)
-        barrier()
+        def time_e2e(k, warm):
+            for _ in range(warm):
+                pl.run(h_f0, h_f1, h_ff0, h_ff1, out)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                pl.run(h_f0, h_f1, h_ff0, h_ff1, out)       # returns after the results are in host memory
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
         k_e2e = max(3, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            pl.run(h_f0, h_f1, h_ff0, h_ff1, out)       # returns after the results are in host memory
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        h2d = pl.last_h2d_bytes      # bulk copies + what the fine kernel reads in place from pinned memory (image 0's centre
-                                     # pixels, image 1's 5x5 windows)
+        dt = time_e2e(k_e2e, 2)
+        h2d = pl.last_h2d_bytes      # bulk copies + what crosses the link from pinned memory on demand (image 0's centre
+                                     # pixels, image 1's windows: in place or as their union, see `f1_mode`)
         d2h = sum(out[k].numel() * out[k].element_size() for k in ("i_ids", "j_ids", "mconf", "mkpts0_f", "mkpts1_f", "counts")) + 4 * ((n + chunk - 1) // chunk)
         e2e = {"value": world * n * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": k_e2e, "ms_per_step": 1e3 * dt / k_e2e, "matches": int(out["counts"].sum()),
-               "h2d_gbs_per_rank": h2d * k_e2e / dt / 1e9,
+               "h2d_gbs_per_rank": h2d * k_e2e / dt / 1e9, "f1_mode": pl.last_f1_mode,
                "api": "pope_pipeline_run (C ABI, pinned host buffers, chunk=%d pairs)" % chunk,
-               "note": "coarse features are copied; of the fine maps only the matched cells' pixels cross the link (read in place by "
-                       "the fine kernel), which is why the achieved rate sits below the bulk-copy ceiling"}
+               "note": "coarse features are copied; of the fine maps only the matched cells' pixels cross the link (image 0: "
+                       "centre pixels read in place by the fine kernel; image 1: `f1_mode`), which is why the achieved rate "
+                       "sits below the bulk-copy ceiling"}
+        # the three ways image 1's fine map can reach the device, same buffers, same box (POPE_PIPELINE_F1)
+        by_mode = {}
+        for mode in ("windows", "union", "bulk"):
+            os.environ["POPE_PIPELINE_F1"] = mode
+            try:
+                dtm = time_e2e(3, 1)
+                by_mode[mode] = {"value": world * n * 3 / dtm, "h2d_bytes_per_step": pl.last_h2d_bytes,
+                                 "h2d_gbs_per_rank": pl.last_h2d_bytes * 3 / dtm / 1e9}
+                assert pl.last_f1_mode == mode and int(out["counts"].sum()) == M
+            finally:
+                del os.environ["POPE_PIPELINE_F1"]
+        e2e["by_f1_mode"] = by_mode
         assert int(out["counts"].sum()) == M, (int(out["counts"].sum()), M)
         pl.close()
         del h_f0, h_f1, h_ff0, h_ff1

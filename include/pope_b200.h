@@ -189,6 +189,11 @@ int pope_pipeline_destroy(pope_pipeline_t* pl);
  * feat_f0 is page-locked, the centre pixels the fine kernel read directly from host memory (one Cf-vector per match;
  * the rest of image 0's fine map is never needed by this pipeline and is not transferred). */
 int64_t pope_pipeline_last_h2d_bytes(const pope_pipeline_t* pl);
+/* How image 1's fine map reached the device in the last pope_pipeline_run: 0 = whole map copied (pageable buffer, or
+ * POPE_PIPELINE_F1=bulk), 1 = the fine kernel read every match's 5x5 window in place (POPE_PIPELINE_F1=windows), 2 = the
+ * union of the matched cells' windows was fetched once per pixel into the device map (POPE_PIPELINE_F1=union); -1 for a
+ * null handle.  No counterpart in the reference (its loop copies whole images, eval_linemod_json.py:103-122). */
+int pope_pipeline_last_f1_mode(const pope_pipeline_t* pl);
 
 /* One-shot convenience: create + run + destroy. */
 int pope_match_pairs_host(const void* feat_c0, const void* feat_c1, const void* feat_f0, const void* feat_f1,

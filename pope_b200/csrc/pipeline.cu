@@ -40,6 +40,76 @@ __global__ void __launch_bounds__(256) slot_kernel(const int32_t* __restrict__ c
   }
 }
 
+// ---- union fetch of image 1's fine windows ---------------------------------------------------------------------------
+// The 5x5 windows of neighbouring matched cells overlap (window pitch = fine_stride < 5) and reads from page-locked host memory
+// are not kept in L2, so fetching window by window moves the shared pixels once per window.  Instead the chunk's matched
+// image-1 cells are marked in a byte map, and one kernel walks the fine map's pixels: a pixel that lies in the window of at
+// least one marked cell is copied ONCE from the host buffer to the same place of the slot's device map, which the fused fine
+// kernel then reads as after a bulk copy.  Bytes over the link: |union of the windows| <= min(sum of the windows, whole map).
+__global__ void __launch_bounds__(256) mark_cells_kernel(const int32_t* __restrict__ total, int64_t capacity,
+                                                        const int64_t* __restrict__ b_ids, const int64_t* __restrict__ j_ids,
+                                                        int S, uint8_t* __restrict__ cellmask) {
+  const int64_t M = min(int64_t(*total), capacity);
+  for (int64_t m = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; m < M; m += int64_t(gridDim.x) * blockDim.x)
+    cellmask[b_ids[m] * S + j_ids[m]] = 1;
+}
+
+__device__ __forceinline__ uint4 ld_host16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// LPP = lanes (16-byte vectors) per pixel: 16 for 128 bf16 channels, 32 for fp32.  A warp owns kIt x (32 / LPP) consecutive
+// pixels of the chunk's [n, Hf, Wf] map; all its loads are issued before the first store.
+template <int LPP>
+__global__ void __launch_bounds__(256) fetch_union_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                         const uint8_t* __restrict__ cellmask, int64_t n_pix, int Hf, int Wf,
+                                                         int hc, int wc, int stride, int half,
+                                                         unsigned long long* __restrict__ fetched) {
+  constexpr int PPI = 32 / LPP, kIt = 8;
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane / LPP, v = lane % LPP;
+  const int64_t warp = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t q0 = warp * (kIt * PPI);
+  uint4 r[kIt];
+  bool need[kIt];
+#pragma unroll
+  for (int k = 0; k < kIt; ++k) {
+    const int64_t q = q0 + k * PPI + sub;
+    need[k] = false;
+    if (q < n_pix) {
+      const int64_t b = q / (int64_t(Hf) * Wf);
+      const int rem = int(q - b * (int64_t(Hf) * Wf));
+      const int y = rem / Wf, x = rem - y * Wf;
+      // cells c with c * stride - half <= y <= c * stride + half
+      const int cy_lo = y > half ? (y - half + stride - 1) / stride : 0, cy_hi = min((y + half) / stride, hc - 1);
+      const int cx_lo = x > half ? (x - half + stride - 1) / stride : 0, cx_hi = min((x + half) / stride, wc - 1);
+      const uint8_t* cm = cellmask + b * (int64_t(hc) * wc);
+      for (int cy = cy_lo; cy <= cy_hi; ++cy)
+        for (int cx = cx_lo; cx <= cx_hi; ++cx) need[k] |= cm[cy * wc + cx] != 0;
+    }
+    if (need[k]) r[k] = ld_host16(src + (q * LPP + v));
+  }
+  int mine = 0;
+#pragma unroll
+  for (int k = 0; k < kIt; ++k) {
+    if (need[k]) {
+      dst[(q0 + k * PPI + sub) * LPP + v] = r[k];
+      mine += v == 0;
+    }
+  }
+  mine += __shfl_xor_sync(0xffffffffu, mine, 16);
+  if (lane == 0 && mine) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(fetched, (unsigned long long)s_cnt);
+}
+
+// default of POPE_PIPELINE_F1 for page-locked fine maps
+constexpr bool kF1UnionDefault = true;
+
 struct Slot {
   char *fc0 = nullptr, *fc1 = nullptr, *ff0 = nullptr, *ff1 = nullptr, *ws = nullptr, *win0 = nullptr, *win1 = nullptr;
   int64_t *b_ids = nullptr, *i_ids = nullptr, *j_ids = nullptr, *o_i = nullptr, *o_j = nullptr;
@@ -47,6 +117,7 @@ struct Slot {
         *o_mk0 = nullptr, *o_mk1 = nullptr;
   int32_t* counts = nullptr;
   int32_t* h_counts = nullptr;   // pinned staging for the flag word
+  uint8_t* cellmask = nullptr;   // [chunk, S] matched image-1 cells of the chunk (union fetch)
   cudaEvent_t uploaded = nullptr, computed = nullptr, drained = nullptr;
 };
 
@@ -59,8 +130,11 @@ struct pope_pipeline {
   int device, dtype, chunk, C, Cf, h0c, w0c, h1c, w1c, fstride, W, L, S, cap, esize, impl, border;
   float pixel_scale, fine_scale, temperature, thr;
   size_t ws_bytes;
+  int last_f1_mode = 0;            // how image 1's fine map reached the device in the last run: 0 bulk, 1 windows in place, 2 union fetch
   int64_t last_h2d_bytes = 0;      // bytes that crossed the host link towards the device in the last run
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_drain = nullptr;
+  unsigned long long* fetched = nullptr;     // device: pixels of image 1's fine map the union fetch has copied in this run
+  unsigned long long* h_fetched = nullptr;   // pinned staging for it
   Slot slot[2];
 };
 
@@ -75,13 +149,15 @@ extern "C" int pope_pipeline_destroy(pope_pipeline_t* pl) {
   cudaSetDevice(pl->device);
   for (Slot& s : pl->slot) {
     void* bufs[] = {s.fc0, s.fc1, s.ff0, s.ff1, s.ws, s.win0, s.win1, s.b_ids, s.i_ids, s.j_ids, s.o_i, s.o_j, s.mconf,
-                    s.mk0, s.mk1, s.expec, s.mk1f, s.o_conf, s.o_mk0, s.o_mk1, s.counts};
+                    s.mk0, s.mk1, s.expec, s.mk1f, s.o_conf, s.o_mk0, s.o_mk1, s.counts, s.cellmask};
     for (void* b : bufs) if (b) cudaFree(b);
     if (s.h_counts) cudaFreeHost(s.h_counts);
     if (s.uploaded) cudaEventDestroy(s.uploaded);
     if (s.computed) cudaEventDestroy(s.computed);
     if (s.drained) cudaEventDestroy(s.drained);
   }
+  if (pl->fetched) cudaFree(pl->fetched);
+  if (pl->h_fetched) cudaFreeHost(pl->h_fetched);
   if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
   if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
   if (pl->s_drain) cudaStreamDestroy(pl->s_drain);
@@ -116,7 +192,10 @@ extern "C" int pope_pipeline_create(pope_pipeline_t** out, int device, int dtype
     PL_CUDA(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
     PL_CUDA(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
     PL_CUDA(cudaStreamCreateWithFlags(&pl->s_drain, cudaStreamNonBlocking));
+    PL_CUDA(cudaMalloc(&pl->fetched, 8));
+    PL_CUDA(cudaMallocHost(&pl->h_fetched, 8));
     for (Slot& s : pl->slot) {
+      PL_CUDA(cudaMalloc(&s.cellmask, n * pl->S));
       PL_CUDA(cudaMalloc(&s.fc0, n * pl->L * C * e));
       PL_CUDA(cudaMalloc(&s.fc1, n * pl->S * C * e));
       PL_CUDA(cudaMalloc(&s.ff0, n * f0px * Cf * e));
@@ -174,14 +253,27 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
   // Image 1's 5x5 windows are read in place as well when its buffer is page-locked: M x 25 x 256 B per chunk (16.3 MB per
   // 480x640 pair at 2 544 matches) instead of the whole 19.7 MB map; the reads reach ~90 % of the link's copy rate, which
   // nets +5 % end to end (profiles/r2_history.md).  POPE_PIPELINE_WINDOWS_IN_PLACE=0 restores the bulk copy.
+  //   POPE_PIPELINE_F1=union  : the union of the matched cells' windows is fetched once per pixel into the slot's device map
+  //                             (fetch_union_kernel above), the fine kernel reads the device map;
+  //   POPE_PIPELINE_F1=windows: the fine kernel reads window by window in place;
+  //   POPE_PIPELINE_F1=bulk (or POPE_PIPELINE_WINDOWS_IN_PLACE=0): whole map copied.
+  bool f1_union = kF1UnionDefault;
   {
     const char* env = getenv("POPE_PIPELINE_WINDOWS_IN_PLACE");
-    if (!(env && env[0] == '0')) f1_dev_view = host_view(feat_f1);
+    const char* mode = getenv("POPE_PIPELINE_F1");
+    bool bulk = env && env[0] == '0';
+    if (mode && mode[0] == 'u') f1_union = true;
+    if (mode && mode[0] == 'w') f1_union = false;
+    if (mode && mode[0] == 'b') bulk = true;
+    if (!bulk) f1_dev_view = host_view(feat_f1);
+    if (!f1_dev_view || (Cf * e != 256 && Cf * e != 512)) f1_union = false;
   }
+  const int64_t n_pix1 = int64_t(Hf1) * Wf1;          // pixels of one image-1 fine map
   int64_t h2d = 0;
   int32_t flag_acc = 0;
   int n_chunks = (n_pairs + pl->chunk - 1) / pl->chunk;
   PL_CUDA(cudaSetDevice(pl->device));
+  if (f1_union) PL_CUDA(cudaMemsetAsync(pl->fetched, 0, 8, pl->s_comp));
   for (int k = 0; k < n_chunks; ++k) {
     Slot& s = pl->slot[k & 1];
     const int p0 = k * pl->chunk, n = (n_pairs - p0 < pl->chunk) ? n_pairs - p0 : pl->chunk;
@@ -206,8 +298,23 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
                            pl->pixel_scale, pl->temperature, pl->thr, pl->border, pl->impl, s.ws, pl->ws_bytes, s.b_ids,
                            s.i_ids, s.j_ids, s.mconf, s.mk0, s.mk1, s.counts, int64_t(capt), pl->s_comp);
     if (rc) goto fail;
+    if (f1_union) {
+      PL_CUDA(cudaMemsetAsync(s.cellmask, 0, size_t(n) * S, pl->s_comp));
+      mark_cells_kernel<<<64, 256, 0, pl->s_comp>>>(s.counts + n, int64_t(capt), s.b_ids, s.j_ids, int(S), s.cellmask);
+      const uint4* src = reinterpret_cast<const uint4*>(f1_dev_view + p0 * ff1_pair);
+      if (Cf * e == 256) {
+        const unsigned blocks = unsigned((n * n_pix1 + 8 * 16 - 1) / (8 * 16));        // 8 warps x 16 pixels per block
+        fetch_union_kernel<16><<<blocks, 256, 0, pl->s_comp>>>(src, reinterpret_cast<uint4*>(s.ff1), s.cellmask, n * n_pix1, Hf1,
+                                                             Wf1, pl->h1c, pl->w1c, pl->fstride, pl->W / 2, pl->fetched);
+      } else {
+        const unsigned blocks = unsigned((n * n_pix1 + 8 * 8 - 1) / (8 * 8));          // 8 warps x 8 pixels per block
+        fetch_union_kernel<32><<<blocks, 256, 0, pl->s_comp>>>(src, reinterpret_cast<uint4*>(s.ff1), s.cellmask, n * n_pix1, Hf1,
+                                                             Wf1, pl->h1c, pl->w1c, pl->fstride, pl->W / 2, pl->fetched);
+      }
+      PL_CUDA(cudaGetLastError());
+    }
     rc = pope_fine_match_maps(f0_dev_view ? static_cast<const void*>(f0_dev_view + p0 * ff0_pair) : s.ff0,
-                              f1_dev_view ? static_cast<const void*>(f1_dev_view + p0 * ff1_pair) : s.ff1, pl->dtype, n, pl->Cf, Hf0, Wf0, st0, Hf1, Wf1, st1, pl->w0c, pl->w1c,
+                              (f1_dev_view && !f1_union) ? static_cast<const void*>(f1_dev_view + p0 * ff1_pair) : s.ff1, pl->dtype, n, pl->Cf, Hf0, Wf0, st0, Hf1, Wf1, st1, pl->w0c, pl->w1c,
                               pl->fstride, pl->W, s.b_ids, s.i_ids, s.j_ids, int64_t(capt), s.counts + n, nullptr, s.mk1,
                               coord_scale, s.expec, s.mk1f, pl->s_comp);
     if (rc) goto fail;
@@ -225,6 +332,7 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
     PL_CUDA(cudaMemcpyAsync(s.h_counts + pl->chunk + 1, s.counts + n + 1, 4, cudaMemcpyDeviceToHost, pl->s_drain));
     PL_CUDA(cudaEventRecord(s.drained, pl->s_drain));
   }
+  if (f1_union) PL_CUDA(cudaMemcpyAsync(pl->h_fetched, pl->fetched, 8, cudaMemcpyDeviceToHost, pl->s_drain));   // (behind the last chunk's drain)
   PL_CUDA(cudaStreamSynchronize(pl->s_drain));
   for (int k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k) flag_acc |= pl->slot[k & 1].h_counts[pl->chunk + 1];
   if (flags) *flags = flag_acc;
@@ -232,8 +340,10 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
     int64_t m = 0;
     for (int p = 0; p < n_pairs; ++p) m += counts[p];
     h2d += m * int64_t(Cf * e);
-    if (f1_dev_view) h2d += m * int64_t(pl->W * pl->W) * int64_t(Cf * e);   // (upper bound: overlapping windows may hit L2)
+    if (f1_dev_view && !f1_union) h2d += m * int64_t(pl->W * pl->W) * int64_t(Cf * e);   // (upper bound: overlapping windows may hit L2)
   }
+  if (f1_union) h2d += int64_t(*pl->h_fetched) * int64_t(Cf * e);            // every pixel of the windows' union exactly once
+  pl->last_f1_mode = f1_union ? 2 : f1_dev_view ? 1 : 0;
   pl->last_h2d_bytes = h2d;
   return POPE_OK;
 fail:
@@ -261,3 +371,4 @@ extern "C" int pope_match_pairs_host(const void* feat_c0, const void* feat_c1, c
 }
 
 extern "C" int64_t pope_pipeline_last_h2d_bytes(const pope_pipeline_t* pl) { return pl ? pl->last_h2d_bytes : 0; }
+extern "C" int pope_pipeline_last_f1_mode(const pope_pipeline_t* pl) { return pl ? pl->last_f1_mode : -1; }

@@ -77,6 +77,7 @@ class Pipeline:
                                      out["counts"].data_ptr(), out["flags"].data_ptr())
         check(st, "pope_pipeline_run")
         self.last_h2d_bytes = int(lib().pope_pipeline_last_h2d_bytes(self._h))
+        self.last_f1_mode = ("bulk", "windows", "union")[int(lib().pope_pipeline_last_f1_mode(self._h))]
         return out
 
     def close(self):

@@ -559,23 +559,57 @@ def test_host_pipeline_equals_device_path():
     m = res.total()
     # pageable host buffers (bulk copies of everything) ...
     out = driver.match_pairs_host(f0, f1, ff0, ff1, (h * 8, w * 8), (h, w), (h, w), chunk_pairs=2, device=0)
-    # ... and page-locked ones: the fine kernel reads image 0's centre pixels and image 1's 5x5 windows in place over the host
-    # link, neither fine map is copied (POPE_PIPELINE_WINDOWS_IN_PLACE=0: image 1's map is copied in bulk as before)
+    # ... and page-locked ones: the fine kernel reads image 0's centre pixels in place over the host link; image 1's map is
+    # either read window by window in place ("windows"), fetched once per pixel of the windows' union into the device map
+    # ("union"), or copied whole ("bulk", also POPE_PIPELINE_WINDOWS_IN_PLACE=0)
     nhwc0, nhwc1 = ff0.permute(0, 2, 3, 1).contiguous().pin_memory(), ff1.permute(0, 2, 3, 1).contiguous().pin_memory()
     full = sum(t.numel() * t.element_size() for t in (f0, f1, nhwc0, nhwc1))
+    need = np.zeros((n, h * 4, w * 4), dtype=bool)             # pixels of image 1 inside the window of some matched cell
+    for b, j in zip(res["b_ids"][:m].tolist(), res["j_ids"][:m].tolist()):
+        cy, cx = divmod(j, w)
+        need[b, max(0, 4 * cy - 2):4 * cy + 3, max(0, 4 * cx - 2):4 * cx + 3] = True
+    assert 0 < need.sum() < m * 25
     outs = [out]
-    for in_place in ("1", "0"):
-        os.environ["POPE_PIPELINE_WINDOWS_IN_PLACE"] = in_place
+    for var, mode in (("POPE_PIPELINE_F1", "windows"), ("POPE_PIPELINE_F1", "bulk"), ("POPE_PIPELINE_F1", "union"),
+                      ("POPE_PIPELINE_WINDOWS_IN_PLACE", "0"), (None, None)):
+        if var:
+            os.environ[var] = mode
         try:
             pl = driver.Pipeline(torch.bfloat16, 2, (h * 8, w * 8), (h, w), (h, w), device=0)
             outs.append(pl.run(f0.pin_memory(), f1.pin_memory(), nhwc0, nhwc1))
             want = full - nhwc0.numel() * 2 + m * 128 * 2
-            if in_place == "1":
+            if var is None:
+                assert pl.last_f1_mode in ("windows", "union")          # the default is one of the two in-place forms
+            else:
+                assert pl.last_f1_mode == ("bulk" if mode == "0" else mode)
+            if pl.last_f1_mode == "windows":
                 want += -nhwc1.numel() * 2 + m * 25 * 128 * 2
-            assert pl.last_h2d_bytes == want
+            elif pl.last_f1_mode == "union":
+                want += -nhwc1.numel() * 2 + int(need.sum()) * 128 * 2
+            assert pl.last_h2d_bytes == want, (mode, pl.last_h2d_bytes, want)
             pl.close()
         finally:
-            del os.environ["POPE_PIPELINE_WINDOWS_IN_PLACE"]
+            if var:
+                del os.environ[var]
+    # fp32 maps (512-byte pixels: the other instantiation of the union fetch) against the bulk copy
+    g0, g1 = synth.coarse_features(73, 3, h * w, h * w, 256, sigma=0.85, dtype=torch.float32)
+    gg0, gg1 = synth.fine_feature_maps(74, 3, h * 4, w * 4, 128, dtype=torch.float32)
+    q0, q1 = gg0.permute(0, 2, 3, 1).contiguous().pin_memory(), gg1.permute(0, 2, 3, 1).contiguous().pin_memory()
+    got = {}
+    for mode in ("bulk", "union"):
+        os.environ["POPE_PIPELINE_F1"] = mode
+        try:
+            pl = driver.Pipeline(torch.float32, 2, (h * 8, w * 8), (h, w), (h, w), device=0)
+            got[mode] = pl.run(g0.pin_memory(), g1.pin_memory(), q0, q1)
+            assert pl.last_f1_mode == mode
+            pl.close()
+        finally:
+            del os.environ["POPE_PIPELINE_F1"]
+    assert int(got["bulk"]["counts"].sum()) > 0
+    assert torch.equal(got["bulk"]["counts"], got["union"]["counts"])
+    fa, fb = driver.flatten_slots(got["bulk"]), driver.flatten_slots(got["union"])
+    for k in ("i_ids", "j_ids", "mconf", "mkpts0_f", "mkpts1_f"):
+        assert torch.equal(fa[k], fb[k]), k
     for o in outs:
         assert int(o["counts"].sum()) == m
         cat = driver.flatten_slots(o)
