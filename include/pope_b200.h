@@ -168,9 +168,11 @@ int pope_running_topk(const float* scores, int R, int k, float* slot_scores, int
  * the library ever allocates and it is not shared between host threads.
  *   Inputs  : feat_c0 [n,L,C], feat_c1 [n,S,C]; feat_f0 [n,Hf0,Wf0,Cf], feat_f1 [n,Hf1,Wf1,Cf] (channels-last),
  *             Hf = fine_stride*h_c, Wf = fine_stride*w_c.  Host buffers should be page-locked for full PCIe speed;
- *             page-locked fine maps are not copied at all: the fine kernel reads the centre pixel of every matched cell of
- *             image 0 and the 5x5 window of its partner in image 1 in place over the host link (pageable maps are copied in
- *             bulk; POPE_PIPELINE_WINDOWS_IN_PLACE=0 in the environment restores the bulk copy of image 1's map).
+ *             page-locked fine maps are not copied whole: the fine kernel reads the centre pixel of every matched cell of
+ *             image 0 in place over the host link, and of image 1's map only the union of the matched cells' 5x5 windows is
+ *             fetched (every needed pixel once) into the device slot (pageable maps are copied in bulk; POPE_PIPELINE_F1 =
+ *             union | windows | bulk in the environment selects the form for image 1, see pope_pipeline_last_f1_mode;
+ *             POPE_PIPELINE_WINDOWS_IN_PLACE=0 is the older spelling of bulk).
  *   Outputs : per-pair slots of cap = min(L,S) entries: i_ids, j_ids int64[n][cap]; mconf float[n][cap];
  *             mkpts0_f, mkpts1_f float[n][cap][2]; counts int32[n]; flags (optional, may be NULL) int32[1] = OR of the
  *             POPE_FLAG_* bits of all chunks.  pope_pipeline_run returns after every copy has landed. */

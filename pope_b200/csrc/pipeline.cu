@@ -60,6 +60,10 @@ __device__ __forceinline__ uint4 ld_host16(const void* p) {
   return r;
 }
 
+// 16-byte loads in flight per thread (4 / 8 / 16 and chunks of 4 / 8 / 16 / 32 pairs measured: 2 735-2 822 pairs/s, all within
+// 3 %, best at 16 pairs per chunk -- the link, not the kernel's shape, sets the rate; profiles/r2_history.md)
+constexpr int kFetchIt = 8;
+
 // LPP = lanes (16-byte vectors) per pixel: 16 for 128 bf16 channels, 32 for fp32.  A warp owns kIt x (32 / LPP) consecutive
 // pixels of the chunk's [n, Hf, Wf] map; all its loads are issued before the first store.
 template <int LPP>
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(256) fetch_union_kernel(const uint4* __restric
                                                          const uint8_t* __restrict__ cellmask, int64_t n_pix, int Hf, int Wf,
                                                          int hc, int wc, int stride, int half,
                                                          unsigned long long* __restrict__ fetched) {
-  constexpr int PPI = 32 / LPP, kIt = 8;
+  constexpr int PPI = 32 / LPP, kIt = kFetchIt;
   __shared__ int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
@@ -302,15 +306,15 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
       PL_CUDA(cudaMemsetAsync(s.cellmask, 0, size_t(n) * S, pl->s_comp));
       mark_cells_kernel<<<64, 256, 0, pl->s_comp>>>(s.counts + n, int64_t(capt), s.b_ids, s.j_ids, int(S), s.cellmask);
       const uint4* src = reinterpret_cast<const uint4*>(f1_dev_view + p0 * ff1_pair);
-      if (Cf * e == 256) {
-        const unsigned blocks = unsigned((n * n_pix1 + 8 * 16 - 1) / (8 * 16));        // 8 warps x 16 pixels per block
-        fetch_union_kernel<16><<<blocks, 256, 0, pl->s_comp>>>(src, reinterpret_cast<uint4*>(s.ff1), s.cellmask, n * n_pix1, Hf1,
-                                                             Wf1, pl->h1c, pl->w1c, pl->fstride, pl->W / 2, pl->fetched);
-      } else {
-        const unsigned blocks = unsigned((n * n_pix1 + 8 * 8 - 1) / (8 * 8));          // 8 warps x 8 pixels per block
-        fetch_union_kernel<32><<<blocks, 256, 0, pl->s_comp>>>(src, reinterpret_cast<uint4*>(s.ff1), s.cellmask, n * n_pix1, Hf1,
-                                                             Wf1, pl->h1c, pl->w1c, pl->fstride, pl->W / 2, pl->fetched);
-      }
+      const int64_t np = int64_t(n) * n_pix1;
+      const int lpp = int(Cf * e / 16), ppw = kFetchIt * (32 / lpp);                   // pixels per warp
+      const unsigned blocks = unsigned((np + 8 * ppw - 1) / (8 * ppw));                // 8 warps per block
+      if (lpp == 16)
+        fetch_union_kernel<16><<<blocks, 256, 0, pl->s_comp>>>(src, reinterpret_cast<uint4*>(s.ff1), s.cellmask, np, Hf1, Wf1,
+                                                             pl->h1c, pl->w1c, pl->fstride, pl->W / 2, pl->fetched);
+      else
+        fetch_union_kernel<32><<<blocks, 256, 0, pl->s_comp>>>(src, reinterpret_cast<uint4*>(s.ff1), s.cellmask, np, Hf1, Wf1,
+                                                             pl->h1c, pl->w1c, pl->fstride, pl->W / 2, pl->fetched);
       PL_CUDA(cudaGetLastError());
     }
     rc = pope_fine_match_maps(f0_dev_view ? static_cast<const void*>(f0_dev_view + p0 * ff0_pair) : s.ff0,
