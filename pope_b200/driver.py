@@ -9,6 +9,7 @@ Pairs are independent, so ranks share nothing on the data path; the only cross-G
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Callable, Dict, Optional, Sequence
 
 import torch
@@ -130,6 +131,7 @@ class DeviceBatchRunner:
                         else [torch.cuda.current_stream(self.device)])
         self.workspaces = [None] * len(self.streams)
         self._k = 0
+        self._pending = []          # weak references to the results submitted since the last join()
 
     def fork(self) -> None:
         """the runner's streams wait for everything queued so far on the current stream (inputs being produced there)"""
@@ -139,11 +141,20 @@ class DeviceBatchRunner:
                 st.wait_stream(cur)
 
     def join(self) -> None:
-        """the current stream waits for every batch submitted so far"""
+        """the current stream waits for every batch submitted so far; results that are still alive are marked as in use
+        on the current stream (`Tensor.record_stream`), so that dropping one while a consumer queued here is still reading
+        it cannot hand its memory back to the batch stream's allocator pool early"""
         cur = torch.cuda.current_stream(self.device)
         for st in self.streams:
             if st != cur:
                 cur.wait_stream(st)
+        for ref, st in self._pending:
+            res = ref()
+            if res is not None and st != cur:
+                for key, v in res.items():
+                    if key != "workspace" and isinstance(v, torch.Tensor) and v.is_cuda:   # (the scratch stays with its stream)
+                        v.record_stream(cur)
+        self._pending.clear()
 
     def submit(self, feat_c0, feat_c1, feat_f0, feat_f1, hw0_i, hw0_c, hw1_c, after=None, **kw):
         """Queues one batch; returns (result, stream it was queued on).  `after(result)` runs inside the batch's stream
@@ -157,6 +168,7 @@ class DeviceBatchRunner:
             self.workspaces[k] = res["workspace"]
             if after is not None:
                 after(res)
+        self._pending.append((weakref.ref(res), self.streams[k]))
         return res, self.streams[k]
 
 
