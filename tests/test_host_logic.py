@@ -176,3 +176,27 @@ def test_bench_reads_the_committed_ncu_table(tmp_path, monkeypatch):
     assert bench.dram_traffic_from_profiles() == (None, None, None)
     monkeypatch.setattr(bench, "TRAFFIC_CSV", str(tmp_path / "absent.csv"))
     assert bench.dram_traffic_from_profiles() == (None, None, None)
+
+
+def test_union_fetch_cover_rule():
+    """The host pipeline's union fetch (csrc/pipeline.cu::fetch_union_kernel) copies a fine-map pixel iff it lies in the WxW
+    window (stride `stride`, zero padding W//2: fine_preprocess.py:40-43) of at least one matched coarse cell.  The kernel
+    finds the covering cells of pixel (y, x) as cy in [ceil((y - half) / stride), floor((y + half) / stride)] clipped to the
+    grid (same for x); this is that rule's Python mirror against windows painted cell by cell."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    for stride in (1, 2, 3, 4, 5, 8):
+        half, hc, wc = 2, 7, 9
+        hf, wf = hc * stride, wc * stride
+        marked = rng.random((hc, wc)) < 0.4
+        want = np.zeros((hf, wf), dtype=bool)
+        for cy, cx in zip(*np.nonzero(marked)):
+            want[max(0, cy * stride - half):cy * stride + half + 1, max(0, cx * stride - half):cx * stride + half + 1] = True
+        got = np.zeros_like(want)
+        for y in range(hf):
+            for x in range(wf):
+                cy_lo = (y - half + stride - 1) // stride if y > half else 0
+                cx_lo = (x - half + stride - 1) // stride if x > half else 0
+                cy_hi, cx_hi = min((y + half) // stride, hc - 1), min((x + half) // stride, wc - 1)
+                got[y, x] = marked[cy_lo:cy_hi + 1, cx_lo:cx_hi + 1].any()
+        assert np.array_equal(got, want), stride
