@@ -340,11 +340,11 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
   PL_CUDA(cudaStreamSynchronize(pl->s_drain));
   for (int k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; ++k) flag_acc |= pl->slot[k & 1].h_counts[pl->chunk + 1];
   if (flags) *flags = flag_acc;
-  if (f0_dev_view) {        // the centre pixels fetched by the fine kernel also crossed the host link
+  if (f0_dev_view || (f1_dev_view && !f1_union)) {   // what the fine kernel read in place also crossed the host link
     int64_t m = 0;
     for (int p = 0; p < n_pairs; ++p) m += counts[p];
-    h2d += m * int64_t(Cf * e);
-    if (f1_dev_view && !f1_union) h2d += m * int64_t(pl->W * pl->W) * int64_t(Cf * e);   // (upper bound: overlapping windows may hit L2)
+    if (f0_dev_view) h2d += m * int64_t(Cf * e);                                             // image 0: the centre pixels
+    if (f1_dev_view && !f1_union) h2d += m * int64_t(pl->W * pl->W) * int64_t(Cf * e);       // image 1: every window whole
   }
   if (f1_union) h2d += int64_t(*pl->h_fetched) * int64_t(Cf * e);            // every pixel of the windows' union exactly once
   pl->last_f1_mode = f1_union ? 2 : f1_dev_view ? 1 : 0;
