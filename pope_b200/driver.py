@@ -168,6 +168,8 @@ class DeviceBatchRunner:
             self.workspaces[k] = res["workspace"]
             if after is not None:
                 after(res)
+        if len(self._pending) >= 64:         # callers that never join(): forget the results that are gone
+            self._pending = [(r, st) for r, st in self._pending if r() is not None]
         self._pending.append((weakref.ref(res), self.streams[k]))
         return res, self.streams[k]
 
