@@ -254,13 +254,13 @@ extern "C" int pope_pipeline_run(pope_pipeline_t* pl, const void* feat_c0, const
     return nullptr;
   };
   f0_dev_view = host_view(feat_f0);
-  // Image 1's 5x5 windows are read in place as well when its buffer is page-locked: M x 25 x 256 B per chunk (16.3 MB per
-  // 480x640 pair at 2 544 matches) instead of the whole 19.7 MB map; the reads reach ~90 % of the link's copy rate, which
-  // nets +5 % end to end (profiles/r2_history.md).  POPE_PIPELINE_WINDOWS_IN_PLACE=0 restores the bulk copy.
-  //   POPE_PIPELINE_F1=union  : the union of the matched cells' windows is fetched once per pixel into the slot's device map
-  //                             (fetch_union_kernel above), the fine kernel reads the device map;
-  //   POPE_PIPELINE_F1=windows: the fine kernel reads window by window in place;
-  //   POPE_PIPELINE_F1=bulk (or POPE_PIPELINE_WINDOWS_IN_PLACE=0): whole map copied.
+  // Of image 1's map only the 5x5 windows of the matched cells are needed.  When its buffer is page-locked there are three
+  // ways to get them, POPE_PIPELINE_F1 in the environment (measured on 64 pairs at 480x640, one B200, profiles/r2_history.md):
+  //   union   (default): the union of the windows is fetched once per pixel into the slot's device map (fetch_union_kernel
+  //                      above) and the fine kernel reads the device map -- 12.5 MB per pair, 2 820 pairs/s end to end;
+  //   windows          : the fine kernel reads window by window in place over the link (M x 25 x 256 B = 16.3 MB per pair at
+  //                      2 544 matches: pixels shared by neighbouring windows cross the link twice) -- 2 269 pairs/s;
+  //   bulk (or POPE_PIPELINE_WINDOWS_IN_PLACE=0): the whole 19.7 MB map is copied -- 2 163 pairs/s.
   bool f1_union = kF1UnionDefault;
   {
     const char* env = getenv("POPE_PIPELINE_WINDOWS_IN_PLACE");
